@@ -1,0 +1,394 @@
+/*
+ * b200sched.h — C-ABI of libb200sched: the B200-native fit-and-pack core that sits
+ * behind Karpenter's provisioning scheduler as vendored by Azure/gpu-provisioner.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference
+ * tree, K/ = vendor/sigs.k8s.io/karpenter/pkg/):
+ *
+ *   b200s_encode            <- scheduling.NewScheduler's per-NodePool template build and the
+ *                              data the scheduler reads out of Pods / InstanceTypes
+ *                              (K/controllers/provisioning/scheduling/scheduler.go:116-182,
+ *                               :467-486; K/cloudprovider/types.go:105-121,181-219)
+ *   b200s_catalog_upload    <- CloudProvider.GetInstanceTypes consumer side
+ *                              (K/cloudprovider/types.go:84-88; call site
+ *                               K/controllers/provisioning/provisioner.go:252-271)
+ *   b200s_fit_matrix        <- filterInstanceTypesByRequirements over fresh NodeClaims
+ *                              (K/controllers/provisioning/scheduling/nodeclaim.go:373-441,
+ *                               reached through scheduler.go:587-675 and :143-158)
+ *   b200s_select_cheapest   <- InstanceTypes.OrderByPrice(reqs)[0]
+ *                              (K/cloudprovider/types.go:221-240)
+ *   b200s_solve             <- (*Scheduler).Solve
+ *                              (K/controllers/provisioning/scheduling/scheduler.go:377-432)
+ *   b200s_solve_batch       <- the per-candidate SimulateScheduling loop
+ *                              (K/controllers/disruption/helpers.go:52-143,
+ *                               singlenodeconsolidation.go:68-101)
+ *   b200s_create_select     <- instance.Provider.Create's vmSize pick
+ *                              (pkg/providers/instance/instance.go:76-95, :321-369)
+ *
+ * Conventions: every function returns 0 or a negative
+ * B200S_E* code and never aborts; the caller owns and allocates every output buffer
+ * and passes capacities; the library keeps no caller pointer after return; no
+ * callbacks; one CUDA stream per context; a context is not re-entrant.  Any non-zero
+ * return means "fall back to the vendored CPU Solve" on the Go side.  There is NO CPU
+ * backend in this library: b200s_init fails with B200S_ENODEVICE when no sm_100
+ * device is usable.
+ */
+#ifndef B200SCHED_H
+#define B200SCHED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200S_VERSION 100 /* 0.1.0 */
+
+/* ---- limits of the exact encoding (inputs beyond them are rejected, never approximated) ---- */
+#define B200S_MAX_KEYS 16        /* label keys that take part in requirements              */
+#define B200S_MAX_VALUES 64      /* distinct values per label key (one u64 word)           */
+#define B200S_MAX_RES 8          /* resource dimensions                                    */
+#define B200S_MAX_TEMPLATES 16   /* NodePools                                              */
+#define B200S_MAX_TAINTS 64      /* distinct taints over NodePools + existing nodes        */
+#define B200S_MAX_BOUNDED 4      /* label keys that carry Gt/Lt bounds anywhere            */
+#define B200S_MAX_ZC 64          /* zones x capacity-types                                 */
+
+/* ---- error codes ---- */
+#define B200S_OK 0
+#define B200S_EINVAL (-1)           /* malformed argument                                   */
+#define B200S_ENODEVICE (-2)        /* no usable sm_100 device / CUDA runtime failure at init */
+#define B200S_ECUDA (-3)            /* CUDA runtime error (see b200s_last_error)             */
+#define B200S_ENOTREPRESENTABLE (-4) /* input outside the exact encoding: use the CPU path   */
+#define B200S_ECAPACITY (-5)        /* caller-provided output capacity too small             */
+#define B200S_ENOMEM (-6)
+#define B200S_ESTATE (-7)           /* unknown catalog id / context misuse                   */
+
+/* ---- requirement operators (corev1.NodeSelectorOperator; K/scheduling/requirement.go:47-87) ---- */
+#define B200S_OP_IN 0
+#define B200S_OP_NOTIN 1
+#define B200S_OP_EXISTS 2
+#define B200S_OP_DOESNOTEXIST 3
+#define B200S_OP_GT 4
+#define B200S_OP_LT 5
+
+/* ---- taint effects / toleration operators (vendor/k8s.io/api/core/v1/toleration.go:38-57) ---- */
+#define B200S_EFFECT_NONE 0
+#define B200S_EFFECT_NOSCHEDULE 1
+#define B200S_EFFECT_PREFERNOSCHEDULE 2
+#define B200S_EFFECT_NOEXECUTE 3
+#define B200S_TOLOP_EMPTY 0  /* "" means Equal */
+#define B200S_TOLOP_EQUAL 1
+#define B200S_TOLOP_EXISTS 2
+#define B200S_TOLOP_OTHER 3  /* anything else never tolerates */
+
+/* =====================================================================================
+ * Level 1 — the semantic model.  This is what the cgo shim flattens Karpenter objects
+ * into: strings are interned to small integers, everything else keeps the reference's
+ * meaning (operators, sets, exact integer quantities).  The CPU oracle consumes exactly
+ * this structure too, so the encoder below is itself under test.
+ * ===================================================================================== */
+
+/* one NodeSelectorRequirement: key op values (K/scheduling/requirement.go:36-43) */
+typedef struct b200s_req {
+  int32_t key;        /* label key id, 0..n_keys-1                                        */
+  int32_t op;         /* B200S_OP_*                                                      */
+  int32_t val_off;    /* In/NotIn: range in req_values (value ids)                       */
+  int32_t val_cnt;
+  int64_t bound;      /* Gt/Lt: the integer operand (strconv.Atoi of values[0])          */
+  int32_t min_values; /* -1 = nil; anything else is rejected by the encoder              */
+  int32_t _pad;
+} b200s_req_t;
+
+typedef struct b200s_taint {
+  int32_t key, value; /* interned strings, 0 = "" */
+  int32_t effect;     /* B200S_EFFECT_* */
+} b200s_taint_t;
+
+typedef struct b200s_toleration {
+  int32_t key, value; /* interned strings, 0 = "" */
+  int32_t op;         /* B200S_TOLOP_* */
+  int32_t effect;     /* B200S_EFFECT_*, NONE = matches every effect */
+} b200s_toleration_t;
+
+typedef struct b200s_model {
+  /* label universe */
+  int32_t n_keys;
+  const uint8_t* key_wellknown; /* [n_keys] 1 if in v1.WellKnownLabels (K/apis/v1/labels.go:83-92) */
+  int32_t key_zone;             /* topology.kubernetes.io/zone, or -1 */
+  int32_t key_capacity_type;    /* karpenter.sh/capacity-type, or -1 */
+  int32_t n_vals;
+  const int32_t* val_key;       /* [n_vals] key each interned value belongs to */
+  const int64_t* val_int;       /* [n_vals] strconv.Atoi(value) when val_isint */
+  const uint8_t* val_isint;     /* [n_vals] */
+
+  /* resources: exact fixed-scale int64 (cpu in milli-units, the rest in base units) */
+  int32_t n_res;
+  int32_t res_cpu, res_memory;  /* indices used by the FFD order (queue.go:72-108) */
+
+  /* requirement / taint / toleration pools */
+  int32_t n_reqs;
+  const b200s_req_t* reqs;
+  int32_t n_req_values;
+  const int32_t* req_values;
+  int32_t n_taints;
+  const b200s_taint_t* taints;
+  int32_t n_tolerations;
+  const b200s_toleration_t* tolerations;
+
+  /* instance types (the GetInstanceTypes rows; K/cloudprovider/types.go:105-121) */
+  int32_t n_skus;
+  const int32_t* sku_req_off;   /* [n_skus+1] into reqs                                   */
+  const int64_t* sku_alloc;     /* [n_skus*n_res] Allocatable() (types.go:181-219)        */
+  const int64_t* sku_capacity;  /* [n_skus*n_res] Capacity (pool limits, scheduler.go:851) */
+  const int32_t* sku_off_off;   /* [n_skus+1] into offerings                              */
+  int32_t n_offerings;
+  const int32_t* off_req_off;   /* [n_offerings+1] into reqs                              */
+  const double* off_price;      /* [n_offerings]                                          */
+  const uint8_t* off_available; /* [n_offerings]                                          */
+
+  /* NodePools, unsorted: OrderByWeight (K/utils/nodepool/nodepool.go:121-131) is part of the path */
+  int32_t n_pools;
+  const int32_t* pool_req_off;    /* [n_pools+1] spec requirements + labels as In reqs     */
+  const int32_t* pool_taint_off;  /* [n_pools+1] into taints                               */
+  const int32_t* pool_weight;     /* [n_pools]                                             */
+  const int32_t* pool_name_rank;  /* [n_pools] rank of the pool name in ascending string order */
+  const int64_t* pool_daemon;     /* [n_pools*n_res] daemon overhead (scheduler.go:773-783) */
+  const uint8_t* pool_has_limit;  /* [n_pools*n_res] limits present per resource           */
+  const int64_t* pool_limit;      /* [n_pools*n_res]                                       */
+
+  /* pending pods */
+  int32_t n_pods;
+  const int32_t* pod_req_off;     /* [n_pods+1] NewPodRequirements (requirements.go:74-110) */
+  const int32_t* pod_tol_off;     /* [n_pods+1] into tolerations                           */
+  const int64_t* pod_requests;    /* [n_pods*n_res] RequestsForPods incl. pods:1 (resources.go:30-38) */
+  const int64_t* pod_ts;          /* [n_pods] creationTimestamp, seconds                   */
+  const uint64_t* pod_uid_hi;     /* [n_pods] UID as a 128-bit big-endian integer          */
+  const uint64_t* pod_uid_lo;
+
+  /* existing nodes, unsorted: sortExistingNodes (scheduler.go:729-742) is part of the path */
+  int32_t n_nodes;
+  const int32_t* node_req_off;    /* [n_nodes+1] node labels as In reqs                    */
+  const int32_t* node_taint_off;  /* [n_nodes+1]                                           */
+  const int64_t* node_available;  /* [n_nodes*n_res] remainingResources (existingnode.go:59) */
+  const uint8_t* node_initialized;/* [n_nodes]                                             */
+  const int32_t* node_name_rank;  /* [n_nodes]                                             */
+} b200s_model_t;
+
+/* =====================================================================================
+ * Level 0 — the device-facing structure-of-arrays encoding.  Label sets are one u64
+ * word per key, taints one u64 word, SKU sets ceil(S/64) words.  All pointers are HOST
+ * pointers; b200s_catalog_upload / b200s_fit_matrix / b200s_solve copy them to HBM.
+ * ===================================================================================== */
+
+/* per-key flag nibble inside a flags word: key k uses bits [4k, 4k+4) */
+#define B200S_RF_DEFINED 1u
+#define B200S_RF_COMPLEMENT 2u
+#define B200S_RF_HASGT 4u
+#define B200S_RF_HASLT 8u
+
+typedef struct b200s_catalog_soa {
+  int32_t n_skus;   /* S */
+  int32_t n_words;  /* W = ceil(S/64) */
+  int32_t n_res;    /* R */
+  int32_t n_keys;   /* K device key slots */
+  int32_t n_zones, n_cts, key_zone, key_ct; /* device key slots of zone / capacity-type, -1 if absent */
+  uint32_t wellknown;                 /* bit k: device key k is a well-known label             */
+  int32_t key_nvals[B200S_MAX_KEYS];  /* size of each key's value universe                     */
+  int32_t n_bounded;
+  int32_t bounded_key[B200S_MAX_BOUNDED]; /* device keys that may carry Gt/Lt                 */
+  /* value universe numerics: within(gt,lt) needs strconv.Atoi of the value */
+  const int64_t* val_int;    /* [K*64] */
+  const uint64_t* val_isint; /* [K] bit v: value v of key k parses as an integer */
+  /* bit-row tables, each row W words over SKUs */
+  int32_t n_rows;
+  const uint64_t* rows;      /* [n_rows*W] */
+  int32_t row_nonneg;        /* SKUs whose allocatable has no negative entry (resources.go:234-238) */
+  int32_t res_nd[B200S_MAX_RES];    /* distinct allocatable values per resource               */
+  int32_t res_dv0[B200S_MAX_RES];   /* offset of resource r in res_dv                         */
+  int32_t res_row0[B200S_MAX_RES];  /* row of "alloc[r] >= dv[r][0]"; row0+i for dv[r][i]     */
+  const int64_t* res_dv;     /* ascending distinct allocatable values, concatenated          */
+  int32_t n_dv;
+  int32_t key_row0[B200S_MAX_KEYS]; /* row of admit[k][0]; +v; then undef[k] at +nvals, dne[k] at +nvals+1 */
+  int32_t zc_row0;           /* row of offering-available[z*n_cts+c]                         */
+  const uint64_t* price;     /* [n_zones*n_cts*S] cheapest available offering price (float64 bits) per (zone,ct,SKU), B200S_PRICE_NONE if none */
+  const int64_t* alloc;      /* [R*S] raw allocatable, resource-major                        */
+  const int64_t* capacity;   /* [R*S] raw capacity, resource-major                           */
+} b200s_catalog_soa_t;
+
+#define B200S_PRICE_NONE 0x7FEFFFFFFFFFFFFFull /* math.MaxFloat64 (types.go:224-225) */
+
+typedef struct b200s_templates {
+  int32_t n_templates;       /* T, already in OrderByWeight order */
+  int32_t pool_index[B200S_MAX_TEMPLATES]; /* model pool each template came from */
+  uint64_t taints[B200S_MAX_TEMPLATES];
+  uint64_t req_mask[B200S_MAX_TEMPLATES][B200S_MAX_KEYS];
+  uint64_t req_flags[B200S_MAX_TEMPLATES];
+  int64_t req_gt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
+  int64_t req_lt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
+  int64_t daemon[B200S_MAX_TEMPLATES][B200S_MAX_RES];
+} b200s_templates_t;
+
+typedef struct b200s_pods_soa {
+  int32_t n_pods;            /* P */
+  int32_t n_res, n_keys, n_bounded;
+  const int64_t* requests;   /* [R*P] resource-major */
+  const uint64_t* req_mask;  /* [K*P] key-major */
+  const uint64_t* req_flags; /* [P] */
+  const int32_t* req_gt;     /* [NB*P] */
+  const int32_t* req_lt;     /* [NB*P] */
+  const uint64_t* tolerated; /* [P] bit t: pod tolerates taint t (taints.go:53-65) */
+  const int64_t* ts;         /* [P] */
+  const uint64_t* uid_hi;    /* [P] */
+  const uint64_t* uid_lo;    /* [P] */
+} b200s_pods_soa_t;
+
+typedef struct b200s_nodes_soa {
+  int32_t n_nodes;           /* E, already in sortExistingNodes order */
+  int32_t n_res, n_keys;
+  const int32_t* node_index; /* [E] model node each row came from */
+  const int64_t* available;  /* [R*E] resource-major */
+  const uint64_t* req_mask;  /* [K*E] key-major (node labels: single-value In sets) */
+  const uint64_t* req_flags; /* [E] */
+  const uint64_t* taints;    /* [E] */
+} b200s_nodes_soa_t;
+
+/* ---- per-template attempt code written by fit_matrix / solve (parity is on the code, never on message text) ---- */
+#define B200S_FIT_NONE 0x00          /* template not evaluated (an earlier one succeeded) or success */
+#define B200S_FIT_TAINT 0x01         /* did not tolerate taint (nodeclaim.go:116)                   */
+#define B200S_FIT_INCOMPATIBLE 0x02  /* incompatible requirements (nodeclaim.go:128)               */
+#define B200S_FIT_LIMITS 0x03        /* all instance types exceed nodepool limits (scheduler.go:603) */
+#define B200S_FIT_FILTER 0x80        /* InstanceTypeFilterError; low 6 bits are the flags below     */
+#define B200S_FF_REQUIREMENTS 0x01   /* requirementsMet        (nodeclaim.go:409) */
+#define B200S_FF_FITS 0x02           /* fits                   (:410)             */
+#define B200S_FF_OFFERING 0x04       /* hasOffering            (:411)             */
+#define B200S_FF_REQ_AND_FITS 0x08   /* requirementsAndFits    (:414)             */
+#define B200S_FF_REQ_AND_OFF 0x10    /* requirementsAndOffering(:415)             */
+#define B200S_FF_FITS_AND_OFF 0x20   /* fitsAndOffering        (:416)             */
+
+/* ---- where a pod ended up ---- */
+#define B200S_PLACE_UNSCHEDULED (-1)
+#define B200S_PLACE_NODE 0   /* index = row of the existing node (sorted order) */
+#define B200S_PLACE_CLAIM 1  /* index = position in Results.NewNodeClaims       */
+
+typedef struct b200s_solve_opts {
+  int32_t want_masks;        /* fill claim_mask */
+  int32_t reserved[7];
+} b200s_solve_opts_t;
+
+typedef struct b200s_result {
+  /* capacities, set by the caller */
+  int32_t cap_claims;        /* rows available in the claim_* arrays */
+  /* counts, set by the library */
+  int32_t n_claims;          /* len(Results.NewNodeClaims) */
+  int32_t n_unscheduled;     /* len(Results.PodErrors) */
+  int64_t fit_evals;         /* instance types passed through the filter loop by the device path */
+  /* per pod [P] */
+  int32_t* pod_place_kind;   /* B200S_PLACE_* */
+  int32_t* pod_place_index;
+  int32_t* pod_seq;          /* order in which pods were placed (Pods append order) */
+  uint8_t* pod_fit_code;     /* [P*T] last new-NodeClaim attempt per template */
+  /* per new NodeClaim, in Results.NewNodeClaims order [cap_claims] */
+  int32_t* claim_template;
+  int32_t* claim_npods;
+  int64_t* claim_requests;   /* [cap_claims*R] */
+  uint64_t* claim_mask;      /* [cap_claims*W] InstanceTypeOptions; may be NULL unless want_masks */
+  uint64_t* claim_req_mask;  /* [cap_claims*K] merged requirements (FinalizeScheduling applied) */
+  uint64_t* claim_req_flags; /* [cap_claims] */
+  int64_t* claim_req_gt;     /* [cap_claims*NB] */
+  int64_t* claim_req_lt;     /* [cap_claims*NB] */
+  int32_t* claim_sku;        /* OrderByPrice(reqs)[0] */
+  uint64_t* claim_price;     /* its price, float64 bits */
+  int32_t* claim_n_options;  /* len(InstanceTypeOptions) */
+} b200s_result_t;
+
+typedef struct b200s_ctx b200s_ctx_t;
+typedef struct b200s_encoded b200s_encoded_t;
+
+/* ---- lifecycle ---- */
+int b200s_version(void);
+int b200s_init(int device, b200s_ctx_t** out);
+void b200s_destroy(b200s_ctx_t* ctx);
+const char* b200s_last_error(const b200s_ctx_t* ctx);
+/* CUDA stream the context launches on (a cudaStream_t), for callers that time with events */
+void* b200s_stream(b200s_ctx_t* ctx);
+int b200s_synchronize(b200s_ctx_t* ctx);
+
+/* ---- host-side encoder: semantic model -> SoA (total or reject; no device needed) ---- */
+int b200s_encode(const b200s_model_t* model, b200s_encoded_t** out, char* err, size_t err_cap);
+void b200s_encoded_free(b200s_encoded_t* enc);
+const b200s_catalog_soa_t* b200s_encoded_catalog(const b200s_encoded_t* enc);
+const b200s_templates_t* b200s_encoded_templates(const b200s_encoded_t* enc);
+const b200s_pods_soa_t* b200s_encoded_pods(const b200s_encoded_t* enc);
+const b200s_nodes_soa_t* b200s_encoded_nodes(const b200s_encoded_t* enc);
+/* model key / value ids behind a device key slot and bit (for decoding results) */
+int b200s_encoded_key_model_id(const b200s_encoded_t* enc, int device_key);
+int b200s_encoded_value_model_id(const b200s_encoded_t* enc, int device_key, int bit);
+
+/* ---- device path ---- */
+int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* cat, uint64_t* catalog_id);
+int b200s_catalog_release(b200s_ctx_t* ctx, uint64_t catalog_id);
+
+/* Dense stage A.  For every pod, walk the templates in weight order exactly as
+ * addToNewNodeClaim does and record the first template whose filtered instance-type set
+ * is non-empty.  Outputs (caller-allocated HOST buffers):
+ *   tmpl_out  [P]    first feasible template or -1
+ *   mask_out  [P*W]  surviving instance types of that template (zeros if none)
+ *   code_out  [P*T]  per-template attempt code (B200S_FIT_*)
+ * Instance types evaluated = sum over pods of the |InstanceTypeOptions| of every
+ * template whose filter loop ran; returned through evals_out (may be NULL). */
+int b200s_fit_matrix(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods,
+                     const b200s_templates_t* templates, int32_t* tmpl_out, uint64_t* mask_out,
+                     uint8_t* code_out, int64_t* evals_out);
+
+/* argmin-price SKU of n SKU sets under per-set requirement rows (zone / capacity-type
+ * constraints are read from req_mask/req_flags/req_gt/req_lt, K-major like the pod SoA).
+ * sku_out[i] = -1 and price_out[i] = B200S_PRICE_NONE when set i is empty. */
+int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, const uint64_t* masks,
+                          const uint64_t* req_mask, const uint64_t* req_flags, const int64_t* req_gt,
+                          const int64_t* req_lt, int32_t* sku_out, uint64_t* price_out);
+
+/* Full Solve: stage A, FFD order, pack, finalize, cheapest SKU per NodeClaim. */
+int b200s_solve(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods,
+                const b200s_nodes_soa_t* existing, const b200s_templates_t* templates,
+                const b200s_solve_opts_t* opts, b200s_result_t* out);
+
+/* B independent Solves sharing one catalog and one template set (consolidation simulations).
+ * Problem b uses pods[b], existing[b] (may be NULL) and fills out[b]. */
+int b200s_solve_batch(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems,
+                      const b200s_pods_soa_t* const* pods, const b200s_nodes_soa_t* const* existing,
+                      const b200s_templates_t* templates, const b200s_solve_opts_t* opts,
+                      b200s_result_t* const* out);
+
+/* ---- resident (device-pointer) variants used for device-timed measurement ---- */
+typedef struct b200s_resident b200s_resident_t;
+int b200s_resident_create(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods,
+                          const b200s_nodes_soa_t* existing, const b200s_templates_t* templates,
+                          b200s_resident_t** out);
+void b200s_resident_free(b200s_ctx_t* ctx, b200s_resident_t* r);
+/* enqueue only, no host copies, no synchronisation */
+int b200s_resident_fit_matrix(b200s_ctx_t* ctx, b200s_resident_t* r);
+int b200s_resident_solve(b200s_ctx_t* ctx, b200s_resident_t* r);
+/* copy the resident results back (synchronises) */
+int b200s_resident_fetch_fit(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t* tmpl_out, uint64_t* mask_out,
+                             uint8_t* code_out, int64_t* evals_out);
+int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_result_t* out);
+/* number of kernels the last resident_* call enqueued */
+int b200s_resident_last_launches(const b200s_resident_t* r);
+
+/* ---- config 1: the vmSize pick of instance.Provider.Create (host only, no device) ----
+ * name: NodeClaim name; instance_types: the values of the node.kubernetes.io/instance-type
+ * requirement in the caller's order; prices: optional per-name price (NULL = keep the
+ * reference's values[0] rule); storage_bytes: spec.resources.requests["storage"].
+ * Outputs: chosen index, OS disk size in GB, 1 if the SKU is labelled gpu (instance.go:335-339). */
+#define B200S_CREATE_EBADNAME (-20)
+#define B200S_CREATE_ENOTYPE (-21)
+#define B200S_CREATE_ENOSTORAGE (-22)
+int b200s_create_select(const char* name, int32_t n_types, const char* const* instance_types,
+                        const double* prices, int64_t storage_bytes, int32_t* chosen, int32_t* disk_gb,
+                        int32_t* is_gpu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SCHED_H */

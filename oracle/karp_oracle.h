@@ -1,0 +1,61 @@
+/* karp_oracle.h — C entry points of the CPU oracle (TEST INFRASTRUCTURE; see karp_oracle.cpp).
+ * The oracle consumes the same semantic model (b200s_model_t) the product's encoder does and
+ * reports results in model terms: label values as a u64 per MODEL key whose bit i is the i-th
+ * value of that key in ascending value-id order. */
+#ifndef KARP_ORACLE_H
+#define KARP_ORACLE_H
+#include <stdint.h>
+#include "../include/b200sched.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oracle_opts {
+  int32_t stable_sort; /* 1: replace Go's pdqsort tie order by a stable sort (H1 sensitivity probe) */
+  int32_t reserved[7];
+} oracle_opts_t;
+
+typedef struct oracle_result {
+  int32_t cap_claims; /* in */
+  int32_t n_claims, n_unscheduled, n_templates;
+  int32_t template_pool[B200S_MAX_TEMPLATES]; /* model pool of each surviving template, weight order */
+  int64_t fit_evals, prefilter_evals, canadd_claim, canadd_node, new_claim_attempts, sorts, sorts_unsorted, price_ties;
+  int32_t value_overflow; /* a key had more than 64 values: claim_req_mask is truncated */
+  int32_t _pad;
+  int32_t* queue_order;     /* [P] FFD order (may be NULL) */
+  int32_t* node_order;      /* [E] model node index per sorted row (may be NULL) */
+  int32_t* node_npods;      /* [E] (may be NULL) */
+  int32_t* pod_place_kind;  /* [P] */
+  int32_t* pod_place_index; /* [P] */
+  int32_t* pod_seq;         /* [P] */
+  uint8_t* pod_fit_code;    /* [P*n_templates] */
+  int32_t* claim_template;  /* [cap] index into the surviving template list */
+  int32_t* claim_npods;
+  int64_t* claim_requests;  /* [cap*R] */
+  uint64_t* claim_mask;     /* [cap*W] */
+  int32_t* claim_n_options;
+  uint64_t* claim_req_mask; /* [cap*n_keys] */
+  uint8_t* claim_req_flags; /* [cap*n_keys] B200S_RF_* */
+  int64_t* claim_req_gt;    /* [cap*n_keys] */
+  int64_t* claim_req_lt;    /* [cap*n_keys] */
+  int32_t* claim_sku;
+  uint64_t* claim_price;
+} oracle_result_t;
+
+int oracle_version(void);
+int oracle_solve(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out);
+int oracle_fit_matrix(const b200s_model_t* model, int32_t pod_begin, int32_t pod_end, int32_t* tmpl_out,
+                      uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out, int32_t* n_templates_out);
+int oracle_go_sort_perm(const int64_t* keys, int32_t n, int32_t* perm_out);
+int oracle_req_algebra(const b200s_model_t* model, int32_t a0, int32_t a1, int32_t b0, int32_t b1,
+                       int32_t allow_wellknown, uint64_t* mask_out, uint8_t* flags_out, int64_t* gt_out,
+                       int64_t* lt_out);
+int oracle_tolerates(const b200s_model_t* model, int32_t taint0, int32_t taint1, int32_t tol0, int32_t tol1);
+int oracle_create_select(const char* name, int32_t n_types, const char* const* instance_types, const double* prices,
+                         int64_t storage_bytes, int32_t* chosen, int32_t* disk_gb, int32_t* is_gpu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

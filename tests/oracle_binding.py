@@ -1,0 +1,162 @@
+"""ctypes binding of the CPU oracle (oracle/karp_oracle.cpp).  Test infrastructure only: nothing in
+the product package imports this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_build", "libkarp_oracle.so")
+MAX_TEMPLATES = 16
+_P = C.POINTER
+
+
+class OracleOpts(C.Structure):
+    _fields_ = [("stable_sort", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class OracleResult(C.Structure):
+    _fields_ = [
+        ("cap_claims", C.c_int32), ("n_claims", C.c_int32), ("n_unscheduled", C.c_int32), ("n_templates", C.c_int32),
+        ("template_pool", C.c_int32 * MAX_TEMPLATES),
+        ("fit_evals", C.c_int64), ("prefilter_evals", C.c_int64), ("canadd_claim", C.c_int64),
+        ("canadd_node", C.c_int64), ("new_claim_attempts", C.c_int64), ("sorts", C.c_int64),
+        ("sorts_unsorted", C.c_int64), ("price_ties", C.c_int64),
+        ("value_overflow", C.c_int32), ("_pad", C.c_int32),
+        ("queue_order", _P(C.c_int32)), ("node_order", _P(C.c_int32)), ("node_npods", _P(C.c_int32)),
+        ("pod_place_kind", _P(C.c_int32)), ("pod_place_index", _P(C.c_int32)), ("pod_seq", _P(C.c_int32)),
+        ("pod_fit_code", _P(C.c_uint8)),
+        ("claim_template", _P(C.c_int32)), ("claim_npods", _P(C.c_int32)), ("claim_requests", _P(C.c_int64)),
+        ("claim_mask", _P(C.c_uint64)), ("claim_n_options", _P(C.c_int32)), ("claim_req_mask", _P(C.c_uint64)),
+        ("claim_req_flags", _P(C.c_uint8)), ("claim_req_gt", _P(C.c_int64)), ("claim_req_lt", _P(C.c_int64)),
+        ("claim_sku", _P(C.c_int32)), ("claim_price", _P(C.c_uint64)),
+    ]
+
+
+_lib = None
+
+
+def build() -> str:
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.oracle_solve.restype = C.c_int
+        _lib.oracle_fit_matrix.restype = C.c_int
+        _lib.oracle_go_sort_perm.restype = C.c_int
+        _lib.oracle_req_algebra.restype = C.c_int
+        _lib.oracle_tolerates.restype = C.c_int
+        _lib.oracle_create_select.restype = C.c_int
+    return _lib
+
+
+def _p(a: np.ndarray, ct):
+    return a.ctypes.data_as(_P(ct))
+
+
+@dataclass
+class SolveOut:
+    """Canonical, model-level view of a Solve result (the parity unit of SURVEY.md section 8d)."""
+    n_claims: int
+    n_unscheduled: int
+    n_templates: int
+    template_pool: np.ndarray
+    queue_order: np.ndarray
+    node_order: np.ndarray
+    node_npods: np.ndarray
+    pod_place_kind: np.ndarray
+    pod_place_index: np.ndarray
+    pod_seq: np.ndarray
+    pod_fit_code: np.ndarray       # [P, T]
+    claim_template: np.ndarray
+    claim_npods: np.ndarray
+    claim_requests: np.ndarray     # [N, R]
+    claim_mask: np.ndarray         # [N, W]
+    claim_n_options: np.ndarray
+    claim_req_mask: np.ndarray     # [N, n_keys] model keys
+    claim_req_flags: np.ndarray    # [N, n_keys]
+    claim_req_gt: np.ndarray
+    claim_req_lt: np.ndarray
+    claim_sku: np.ndarray
+    claim_price: np.ndarray
+    counters: Dict[str, int]
+
+
+def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None) -> SolveOut:
+    L = lib()
+    P, R, W, K, E = model.n_pods, model.n_res, model.n_words, len(model.key_names), int(model.c.n_nodes)
+    cap = cap_claims if cap_claims is not None else max(P, 1)
+    T = max(int(model.c.n_pools), 1)
+    res = OracleResult()
+    res.cap_claims = cap
+    arr = dict(
+        queue_order=np.zeros(P, np.int32), node_order=np.zeros(max(E, 1), np.int32),
+        node_npods=np.zeros(max(E, 1), np.int32), pod_place_kind=np.zeros(P, np.int32),
+        pod_place_index=np.zeros(P, np.int32), pod_seq=np.zeros(P, np.int32),
+        pod_fit_code=np.zeros(P * T, np.uint8), claim_template=np.zeros(cap, np.int32),
+        claim_npods=np.zeros(cap, np.int32), claim_requests=np.zeros(cap * R, np.int64),
+        claim_mask=np.zeros(cap * W, np.uint64), claim_n_options=np.zeros(cap, np.int32),
+        claim_req_mask=np.zeros(cap * K, np.uint64), claim_req_flags=np.zeros(cap * K, np.uint8),
+        claim_req_gt=np.zeros(cap * K, np.int64), claim_req_lt=np.zeros(cap * K, np.int64),
+        claim_sku=np.zeros(cap, np.int32), claim_price=np.zeros(cap, np.uint64))
+    ctypes_of = {np.dtype(np.int32): C.c_int32, np.dtype(np.int64): C.c_int64, np.dtype(np.uint64): C.c_uint64,
+                 np.dtype(np.uint8): C.c_uint8}
+    for k, a in arr.items():
+        setattr(res, k, _p(a, ctypes_of[a.dtype]))
+    opts = OracleOpts()
+    opts.stable_sort = 1 if stable_sort else 0
+    rc = L.oracle_solve(C.byref(model.c), C.byref(opts), C.byref(res))
+    if rc != 0:
+        raise RuntimeError(f"oracle_solve failed: {rc}")
+    N, Tn = res.n_claims, res.n_templates
+    return SolveOut(
+        n_claims=N, n_unscheduled=res.n_unscheduled, n_templates=Tn,
+        template_pool=np.array(res.template_pool[:Tn], dtype=np.int32),
+        queue_order=arr["queue_order"], node_order=arr["node_order"][:E], node_npods=arr["node_npods"][:E],
+        pod_place_kind=arr["pod_place_kind"], pod_place_index=arr["pod_place_index"], pod_seq=arr["pod_seq"],
+        pod_fit_code=arr["pod_fit_code"][:P * Tn].reshape(P, Tn) if Tn else np.zeros((P, 0), np.uint8),
+        claim_template=arr["claim_template"][:N], claim_npods=arr["claim_npods"][:N],
+        claim_requests=arr["claim_requests"][:N * R].reshape(N, R), claim_mask=arr["claim_mask"][:N * W].reshape(N, W),
+        claim_n_options=arr["claim_n_options"][:N], claim_req_mask=arr["claim_req_mask"][:N * K].reshape(N, K),
+        claim_req_flags=arr["claim_req_flags"][:N * K].reshape(N, K), claim_req_gt=arr["claim_req_gt"][:N * K].reshape(N, K),
+        claim_req_lt=arr["claim_req_lt"][:N * K].reshape(N, K), claim_sku=arr["claim_sku"][:N],
+        claim_price=arr["claim_price"][:N],
+        counters=dict(fit_evals=res.fit_evals, prefilter_evals=res.prefilter_evals, canadd_claim=res.canadd_claim,
+                      canadd_node=res.canadd_node, new_claim_attempts=res.new_claim_attempts, sorts=res.sorts,
+                      sorts_unsorted=res.sorts_unsorted, price_ties=res.price_ties,
+                      value_overflow=res.value_overflow))
+
+
+def fit_matrix(model, pod_begin: int = 0, pod_end: Optional[int] = None):
+    L = lib()
+    pod_end = model.n_pods if pod_end is None else pod_end
+    n, W = pod_end - pod_begin, model.n_words
+    T = max(int(model.c.n_pools), 1)
+    tmpl = np.zeros(n, np.int32)
+    mask = np.zeros(n * W, np.uint64)
+    code = np.zeros(n * T, np.uint8)
+    evals = C.c_int64(0)
+    nt = C.c_int32(0)
+    rc = L.oracle_fit_matrix(C.byref(model.c), pod_begin, pod_end, _p(tmpl, C.c_int32), _p(mask, C.c_uint64),
+                             _p(code, C.c_uint8), C.byref(evals), C.byref(nt))
+    if rc != 0:
+        raise RuntimeError(f"oracle_fit_matrix failed: {rc}")
+    Tn = nt.value
+    return tmpl, mask.reshape(n, W), code[:n * Tn].reshape(n, Tn), int(evals.value), Tn
+
+
+def go_sort_perm(keys: np.ndarray) -> np.ndarray:
+    keys = np.ascontiguousarray(keys, dtype=np.int64)
+    perm = np.zeros(len(keys), np.int32)
+    lib().oracle_go_sort_perm(_p(keys, C.c_int64), len(keys), _p(perm, C.c_int32))
+    return perm
