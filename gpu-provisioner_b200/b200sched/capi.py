@@ -1,0 +1,422 @@
+"""ctypes binding of libb200sched.so (include/b200sched.h).
+
+The library is the product: it is built in-tree by ``__graft_entry__.build()`` and loaded from this
+directory.  There is no Python or CPU fallback — a missing library or a missing sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .model import CModel, Model
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200sched.so")
+
+MAX_KEYS, MAX_RES, MAX_TEMPLATES, MAX_BOUNDED = 16, 8, 16, 4
+PRICE_NONE = 0x7FEFFFFFFFFFFFFF
+FIT_NONE, FIT_TAINT, FIT_INCOMPATIBLE, FIT_LIMITS, FIT_DROPPED, FIT_FILTER = 0x00, 0x01, 0x02, 0x03, 0x7F, 0x80
+PLACE_UNSCHEDULED, PLACE_NODE, PLACE_CLAIM = -1, 0, 1
+OK, EINVAL, ENODEVICE, ECUDA, ENOTREPRESENTABLE, ECAPACITY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
+CREATE_EBADNAME, CREATE_ENOTYPE, CREATE_ENOSTORAGE = -20, -21, -22
+
+_P = C.POINTER
+
+
+class CatalogSoA(C.Structure):
+    _fields_ = [
+        ("n_skus", C.c_int32), ("n_words", C.c_int32), ("n_res", C.c_int32), ("n_keys", C.c_int32),
+        ("n_zones", C.c_int32), ("n_cts", C.c_int32), ("key_zone", C.c_int32), ("key_ct", C.c_int32),
+        ("wellknown", C.c_uint32), ("key_nvals", C.c_int32 * MAX_KEYS), ("n_bounded", C.c_int32),
+        ("bounded_key", C.c_int32 * MAX_BOUNDED),
+        ("val_int", _P(C.c_int64)), ("val_isint", _P(C.c_uint64)),
+        ("n_rows", C.c_int32), ("rows", _P(C.c_uint64)), ("row_nonneg", C.c_int32),
+        ("res_nd", C.c_int32 * MAX_RES), ("res_dv0", C.c_int32 * MAX_RES), ("res_row0", C.c_int32 * MAX_RES),
+        ("res_dv", _P(C.c_int64)), ("n_dv", C.c_int32), ("key_row0", C.c_int32 * MAX_KEYS), ("zc_row0", C.c_int32),
+        ("price", _P(C.c_uint64)), ("alloc", _P(C.c_int64)), ("capacity", _P(C.c_int64)),
+    ]
+
+
+class Templates(C.Structure):
+    _fields_ = [
+        ("n_templates", C.c_int32), ("pool_index", C.c_int32 * MAX_TEMPLATES), ("taints", C.c_uint64 * MAX_TEMPLATES),
+        ("req_mask", (C.c_uint64 * MAX_KEYS) * MAX_TEMPLATES), ("req_flags", C.c_uint64 * MAX_TEMPLATES),
+        ("req_gt", (C.c_int64 * MAX_BOUNDED) * MAX_TEMPLATES), ("req_lt", (C.c_int64 * MAX_BOUNDED) * MAX_TEMPLATES),
+        ("daemon", (C.c_int64 * MAX_RES) * MAX_TEMPLATES), ("type_admit", _P(C.c_uint64)),
+    ]
+
+
+class PodsSoA(C.Structure):
+    _fields_ = [
+        ("n_pods", C.c_int32), ("n_res", C.c_int32), ("n_keys", C.c_int32), ("n_bounded", C.c_int32),
+        ("res_cpu", C.c_int32), ("res_memory", C.c_int32),
+        ("requests", _P(C.c_int64)), ("req_mask", _P(C.c_uint64)), ("req_flags", _P(C.c_uint64)),
+        ("req_gt", _P(C.c_int32)), ("req_lt", _P(C.c_int32)), ("tolerated", _P(C.c_uint64)), ("ts", _P(C.c_int64)),
+        ("uid_hi", _P(C.c_uint64)), ("uid_lo", _P(C.c_uint64)),
+    ]
+
+
+class NodesSoA(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("n_res", C.c_int32), ("n_keys", C.c_int32), ("node_index", _P(C.c_int32)),
+        ("available", _P(C.c_int64)), ("req_mask", _P(C.c_uint64)), ("req_flags", _P(C.c_uint64)),
+        ("taints", _P(C.c_uint64)),
+    ]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("want_masks", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ("cap_claims", C.c_int32), ("n_claims", C.c_int32), ("n_unscheduled", C.c_int32), ("fit_evals", C.c_int64),
+        ("pod_place_kind", _P(C.c_int32)), ("pod_place_index", _P(C.c_int32)), ("pod_seq", _P(C.c_int32)),
+        ("pod_fit_code", _P(C.c_uint8)),
+        ("claim_template", _P(C.c_int32)), ("claim_npods", _P(C.c_int32)), ("claim_requests", _P(C.c_int64)),
+        ("claim_mask", _P(C.c_uint64)), ("claim_req_mask", _P(C.c_uint64)), ("claim_req_flags", _P(C.c_uint64)),
+        ("claim_req_gt", _P(C.c_int64)), ("claim_req_lt", _P(C.c_int64)), ("claim_sku", _P(C.c_int32)),
+        ("claim_price", _P(C.c_uint64)), ("claim_n_options", _P(C.c_int32)),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libb200sched.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA library is the product; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.b200s_version.restype = C.c_int
+    L.b200s_init.argtypes = [C.c_int, _P(C.c_void_p)]
+    L.b200s_destroy.argtypes = [C.c_void_p]
+    L.b200s_destroy.restype = None
+    L.b200s_last_error.argtypes = [C.c_void_p]
+    L.b200s_last_error.restype = C.c_char_p
+    L.b200s_stream.argtypes = [C.c_void_p]
+    L.b200s_stream.restype = C.c_void_p
+    L.b200s_synchronize.argtypes = [C.c_void_p]
+    L.b200s_event_create.argtypes = [C.c_void_p]
+    L.b200s_event_create.restype = C.c_void_p
+    L.b200s_event_record.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_event_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_float)]
+    L.b200s_event_destroy.argtypes = [C.c_void_p]
+    L.b200s_event_destroy.restype = None
+    L.b200s_flush_l2.argtypes = [C.c_void_p, C.c_size_t]
+    L.b200s_encode.argtypes = [_P(CModel), _P(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.b200s_encoded_free.argtypes = [C.c_void_p]
+    L.b200s_encoded_free.restype = None
+    L.b200s_encoded_catalog.argtypes = [C.c_void_p]
+    L.b200s_encoded_catalog.restype = _P(CatalogSoA)
+    L.b200s_encoded_templates.argtypes = [C.c_void_p]
+    L.b200s_encoded_templates.restype = _P(Templates)
+    L.b200s_encoded_pods.argtypes = [C.c_void_p]
+    L.b200s_encoded_pods.restype = _P(PodsSoA)
+    L.b200s_encoded_nodes.argtypes = [C.c_void_p]
+    L.b200s_encoded_nodes.restype = _P(NodesSoA)
+    L.b200s_encoded_key_model_id.argtypes = [C.c_void_p, C.c_int]
+    L.b200s_encoded_value_model_id.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.b200s_catalog_upload.argtypes = [C.c_void_p, _P(CatalogSoA), _P(C.c_uint64)]
+    L.b200s_catalog_release.argtypes = [C.c_void_p, C.c_uint64]
+    L.b200s_fit_matrix.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(Templates), _P(C.c_int32), _P(C.c_uint64),
+                                   _P(C.c_uint8), _P(C.c_int64)]
+    L.b200s_select_cheapest.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(C.c_uint64), _P(C.c_uint64),
+                                        _P(C.c_uint64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int32), _P(C.c_uint64)]
+    L.b200s_solve.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates), _P(SolveOpts),
+                              _P(Result)]
+    L.b200s_solve_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(_P(PodsSoA)), _P(_P(NodesSoA)),
+                                    _P(Templates), _P(SolveOpts), _P(_P(Result))]
+    L.b200s_resident_create.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates),
+                                        _P(C.c_void_p)]
+    L.b200s_resident_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_resident_free.restype = None
+    L.b200s_resident_fit_matrix.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_resident_solve.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_resident_fetch_fit.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_int32), _P(C.c_uint64), _P(C.c_uint8),
+                                           _P(C.c_int64)]
+    L.b200s_resident_fetch_solve.argtypes = [C.c_void_p, C.c_void_p, _P(Result)]
+    L.b200s_resident_last_launches.argtypes = [C.c_void_p]
+    L.b200s_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
+                                      _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]
+    _lib = L
+    return L
+
+
+class B200SError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200sched error {code}: {msg}")
+        self.code = code
+
+
+class NotRepresentable(B200SError):
+    """The encoder rejected the input: the caller keeps the vendored CPU Solve for this batch."""
+
+
+def _p(a: np.ndarray, ct):
+    return a.ctypes.data_as(_P(ct))
+
+
+class Encoded:
+    """b200s_encode(model): the SoA views plus the decode maps."""
+
+    def __init__(self, model: Model):
+        L = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.b200s_encode(C.byref(model.c), C.byref(h), err, 512)
+        if rc == ENOTREPRESENTABLE:
+            raise NotRepresentable(rc, err.value.decode())
+        if rc != 0:
+            raise B200SError(rc, err.value.decode())
+        self.model = model
+        self.handle = h
+        self.catalog = L.b200s_encoded_catalog(h)
+        self.templates = L.b200s_encoded_templates(h)
+        self.pods = L.b200s_encoded_pods(h)
+        self.nodes = L.b200s_encoded_nodes(h)
+        c = self.catalog.contents
+        self.S, self.W, self.R, self.K, self.NB = c.n_skus, c.n_words, c.n_res, c.n_keys, c.n_bounded
+        self.T = self.templates.contents.n_templates
+        self.P = self.pods.contents.n_pods
+        self.E = self.nodes.contents.n_nodes
+        self.key_model = [L.b200s_encoded_key_model_id(h, k) for k in range(self.K)]
+        self.bounded_key = [c.bounded_key[b] for b in range(self.NB)]
+        self.pool_index = [self.templates.contents.pool_index[t] for t in range(self.T)]
+
+    def close(self):
+        if self.handle:
+            lib().b200s_encoded_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class FitOut:
+    tmpl: np.ndarray   # [P] device template index (weight order over all pools) or -1
+    mask: np.ndarray   # [P, W]
+    code: np.ndarray   # [P, T]
+    evals: int
+
+
+@dataclass
+class SolveRaw:
+    """b200s_result_t as numpy arrays, device-level indices (see tests/parity.py for the canonical form)."""
+    n_claims: int
+    n_unscheduled: int
+    fit_evals: int
+    pod_place_kind: np.ndarray
+    pod_place_index: np.ndarray
+    pod_seq: np.ndarray
+    pod_fit_code: np.ndarray
+    claim_template: np.ndarray
+    claim_npods: np.ndarray
+    claim_requests: np.ndarray
+    claim_mask: np.ndarray
+    claim_req_mask: np.ndarray
+    claim_req_flags: np.ndarray
+    claim_req_gt: np.ndarray
+    claim_req_lt: np.ndarray
+    claim_sku: np.ndarray
+    claim_price: np.ndarray
+    claim_n_options: np.ndarray
+
+
+class ResultBuffers:
+    def __init__(self, P: int, T: int, R: int, W: int, K: int, NB: int, cap: Optional[int] = None):
+        cap = max(P if cap is None else cap, 1)
+        P1, T1 = max(P, 1), max(T, 1)
+        self.dims = (P, T, R, W, K, NB, cap)
+        self.a = dict(
+            pod_place_kind=np.zeros(P1, np.int32), pod_place_index=np.zeros(P1, np.int32),
+            pod_seq=np.zeros(P1, np.int32), pod_fit_code=np.zeros(P1 * T1, np.uint8),
+            claim_template=np.zeros(cap, np.int32), claim_npods=np.zeros(cap, np.int32),
+            claim_requests=np.zeros(cap * R, np.int64), claim_mask=np.zeros(cap * W, np.uint64),
+            claim_req_mask=np.zeros(cap * max(K, 1), np.uint64), claim_req_flags=np.zeros(cap, np.uint64),
+            claim_req_gt=np.zeros(cap * max(NB, 1), np.int64), claim_req_lt=np.zeros(cap * max(NB, 1), np.int64),
+            claim_sku=np.zeros(cap, np.int32), claim_price=np.zeros(cap, np.uint64),
+            claim_n_options=np.zeros(cap, np.int32))
+        ct = {np.dtype(np.int32): C.c_int32, np.dtype(np.int64): C.c_int64, np.dtype(np.uint64): C.c_uint64,
+              np.dtype(np.uint8): C.c_uint8}
+        self.c = Result()
+        self.c.cap_claims = cap
+        for k, v in self.a.items():
+            setattr(self.c, k, _p(v, ct[v.dtype]))
+
+    def raw(self) -> SolveRaw:
+        P, T, R, W, K, NB, _ = self.dims
+        N = self.c.n_claims
+        a = self.a
+        return SolveRaw(
+            n_claims=N, n_unscheduled=self.c.n_unscheduled, fit_evals=self.c.fit_evals,
+            pod_place_kind=a["pod_place_kind"][:P].copy(), pod_place_index=a["pod_place_index"][:P].copy(),
+            pod_seq=a["pod_seq"][:P].copy(), pod_fit_code=a["pod_fit_code"][:P * T].reshape(P, T).copy(),
+            claim_template=a["claim_template"][:N].copy(), claim_npods=a["claim_npods"][:N].copy(),
+            claim_requests=a["claim_requests"][:N * R].reshape(N, R).copy(),
+            claim_mask=a["claim_mask"][:N * W].reshape(N, W).copy(),
+            claim_req_mask=a["claim_req_mask"][:N * K].reshape(N, K).copy(),
+            claim_req_flags=a["claim_req_flags"][:N].copy(),
+            claim_req_gt=a["claim_req_gt"][:N * NB].reshape(N, NB).copy(),
+            claim_req_lt=a["claim_req_lt"][:N * NB].reshape(N, NB).copy(),
+            claim_sku=a["claim_sku"][:N].copy(), claim_price=a["claim_price"][:N].copy(),
+            claim_n_options=a["claim_n_options"][:N].copy())
+
+
+class Context:
+    """b200s_init on one device.  Raises B200SError(ENODEVICE) when there is no sm_100 GPU."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.b200s_init(device, C.byref(h))
+        if rc != 0:
+            raise B200SError(rc, "b200s_init failed (no usable sm_100 device?)")
+        self.h = h
+        self.L = L
+
+    def close(self):
+        if self.h:
+            self.L.b200s_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise B200SError(rc, self.L.b200s_last_error(self.h).decode())
+
+    def upload_catalog(self, enc: Encoded) -> int:
+        cid = C.c_uint64(0)
+        self._check(self.L.b200s_catalog_upload(self.h, enc.catalog, C.byref(cid)))
+        return cid.value
+
+    def release_catalog(self, cid: int):
+        self._check(self.L.b200s_catalog_release(self.h, cid))
+
+    def fit_matrix(self, cid: int, enc: Encoded) -> FitOut:
+        P, W, T = enc.P, enc.W, enc.T
+        tmpl = np.zeros(max(P, 1), np.int32)
+        mask = np.zeros(max(P, 1) * W, np.uint64)
+        code = np.zeros(max(P, 1) * max(T, 1), np.uint8)
+        ev = C.c_int64(0)
+        self._check(self.L.b200s_fit_matrix(self.h, cid, enc.pods, enc.templates, _p(tmpl, C.c_int32),
+                                            _p(mask, C.c_uint64), _p(code, C.c_uint8), C.byref(ev)))
+        return FitOut(tmpl[:P], mask[:P * W].reshape(P, W), code[:P * T].reshape(P, T), int(ev.value))
+
+    def solve(self, cid: int, enc: Encoded) -> SolveRaw:
+        buf = ResultBuffers(enc.P, enc.T, enc.R, enc.W, enc.K, enc.NB)
+        opts = SolveOpts()
+        opts.want_masks = 1
+        nodes = enc.nodes if enc.E > 0 else None
+        self._check(self.L.b200s_solve(self.h, cid, enc.pods, nodes, enc.templates, C.byref(opts), C.byref(buf.c)))
+        return buf.raw()
+
+    def solve_batch(self, cid: int, encs: Sequence[Encoded]) -> List[SolveRaw]:
+        n = len(encs)
+        bufs = [ResultBuffers(e.P, e.T, e.R, e.W, e.K, e.NB) for e in encs]
+        pods = (_P(PodsSoA) * n)(*[e.pods for e in encs])
+        nodes = (_P(NodesSoA) * n)(*[e.nodes for e in encs])
+        outs = (_P(Result) * n)(*[C.pointer(b.c) for b in bufs])
+        opts = SolveOpts()
+        opts.want_masks = 1
+        self._check(self.L.b200s_solve_batch(self.h, cid, n, pods, nodes, encs[0].templates, C.byref(opts), outs))
+        return [b.raw() for b in bufs]
+
+    def select_cheapest(self, cid: int, enc: Encoded, masks: np.ndarray, req_mask: np.ndarray, req_flags: np.ndarray,
+                        req_gt: np.ndarray, req_lt: np.ndarray):
+        n = masks.shape[0]
+        masks = np.ascontiguousarray(masks, np.uint64)
+        req_mask = np.ascontiguousarray(req_mask, np.uint64)    # [K, n]
+        req_flags = np.ascontiguousarray(req_flags, np.uint64)
+        req_gt = np.ascontiguousarray(req_gt, np.int64)          # [NB, n]
+        req_lt = np.ascontiguousarray(req_lt, np.int64)
+        sku = np.zeros(max(n, 1), np.int32)
+        price = np.zeros(max(n, 1), np.uint64)
+        self._check(self.L.b200s_select_cheapest(self.h, cid, n, _p(masks, C.c_uint64), _p(req_mask, C.c_uint64),
+                                                 _p(req_flags, C.c_uint64), _p(req_gt, C.c_int64), _p(req_lt, C.c_int64),
+                                                 _p(sku, C.c_int32), _p(price, C.c_uint64)))
+        return sku[:n], price[:n]
+
+    # ---- resident (device-timed) path ----
+    def resident(self, cid: int, enc: Encoded) -> "Resident":
+        return Resident(self, cid, enc)
+
+    def event(self):
+        return self.L.b200s_event_create(self.h)
+
+    def record(self, ev):
+        self._check(self.L.b200s_event_record(self.h, ev))
+
+    def elapsed_ms(self, a, b) -> float:
+        ms = C.c_float(0)
+        self._check(self.L.b200s_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self, nbytes: int = 256 << 20):
+        self._check(self.L.b200s_flush_l2(self.h, nbytes))
+
+    def synchronize(self):
+        self._check(self.L.b200s_synchronize(self.h))
+
+
+class Resident:
+    def __init__(self, ctx: Context, cid: int, enc: Encoded):
+        self.ctx, self.enc = ctx, enc
+        h = C.c_void_p()
+        nodes = enc.nodes if enc.E > 0 else None
+        ctx._check(ctx.L.b200s_resident_create(ctx.h, cid, enc.pods, nodes, enc.templates, C.byref(h)))
+        self.h = h
+
+    def fit_matrix(self):
+        self.ctx._check(self.ctx.L.b200s_resident_fit_matrix(self.ctx.h, self.h))
+
+    def solve(self):
+        self.ctx._check(self.ctx.L.b200s_resident_solve(self.ctx.h, self.h))
+
+    def launches(self) -> int:
+        return self.ctx.L.b200s_resident_last_launches(self.h)
+
+    def fetch_fit(self) -> FitOut:
+        e = self.enc
+        tmpl = np.zeros(max(e.P, 1), np.int32)
+        mask = np.zeros(max(e.P, 1) * e.W, np.uint64)
+        code = np.zeros(max(e.P, 1) * max(e.T, 1), np.uint8)
+        ev = C.c_int64(0)
+        self.ctx._check(self.ctx.L.b200s_resident_fetch_fit(self.ctx.h, self.h, _p(tmpl, C.c_int32), _p(mask, C.c_uint64),
+                                                            _p(code, C.c_uint8), C.byref(ev)))
+        return FitOut(tmpl[:e.P], mask[:e.P * e.W].reshape(e.P, e.W), code[:e.P * e.T].reshape(e.P, e.T), int(ev.value))
+
+    def fetch_solve(self) -> SolveRaw:
+        e = self.enc
+        buf = ResultBuffers(e.P, e.T, e.R, e.W, e.K, e.NB)
+        self.ctx._check(self.ctx.L.b200s_resident_fetch_solve(self.ctx.h, self.h, C.byref(buf.c)))
+        return buf.raw()
+
+    def close(self):
+        if self.h:
+            self.ctx.L.b200s_resident_free(self.ctx.h, self.h)
+            self.h = None
+
+
+def create_select(name: str, instance_types: Sequence[str], storage_bytes: int, prices: Optional[Sequence[float]] = None):
+    """instance.Provider.Create's vmSize pick (pkg/providers/instance/instance.go:76-95, :321-369)."""
+    L = lib()
+    n = len(instance_types)
+    arr = (C.c_char_p * max(n, 1))(*[s.encode() for s in instance_types])
+    pr = None
+    if prices is not None:
+        pr = (C.c_double * max(n, 1))(*prices)
+    chosen, disk, gpu = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
+    rc = L.b200s_create_select(name.encode(), n, arr, pr, int(storage_bytes), C.byref(chosen), C.byref(disk), C.byref(gpu))
+    return rc, chosen.value, disk.value, gpu.value

@@ -64,7 +64,7 @@ _P = C.POINTER
 class CModel(C.Structure):
     _fields_ = [
         ("n_keys", C.c_int32), ("key_wellknown", _P(C.c_uint8)), ("key_zone", C.c_int32),
-        ("key_capacity_type", C.c_int32), ("n_vals", C.c_int32), ("val_key", _P(C.c_int32)),
+        ("key_capacity_type", C.c_int32), ("key_instance_type", C.c_int32), ("n_vals", C.c_int32), ("val_key", _P(C.c_int32)),
         ("val_int", _P(C.c_int64)), ("val_isint", _P(C.c_uint8)),
         ("n_res", C.c_int32), ("res_cpu", C.c_int32), ("res_memory", C.c_int32),
         ("n_reqs", C.c_int32), ("reqs", _P(Req)), ("n_req_values", C.c_int32), ("req_values", _P(C.c_int32)),
@@ -116,6 +116,7 @@ class Model:
         m.key_wellknown = _ptr(a["key_wellknown"], C.c_uint8)
         m.key_zone = kn.index(KEY_ZONE) if KEY_ZONE in kn else -1
         m.key_capacity_type = kn.index(KEY_CAPACITY_TYPE) if KEY_CAPACITY_TYPE in kn else -1
+        m.key_instance_type = kn.index(KEY_INSTANCE_TYPE) if KEY_INSTANCE_TYPE in kn else -1
         m.n_vals = len(a["val_key"])
         m.val_key = _ptr(a["val_key"], C.c_int32)
         m.val_int = _ptr(a["val_int"], C.c_int64)

@@ -1,0 +1,724 @@
+// api.cu — the C-ABI of libb200sched (include/b200sched.h): contexts, catalog upload, and the
+// host-buffer / resident entry points that enqueue the kernels of fit_kernels.cu and pack_kernels.cu
+// on the context's stream.  No CPU fallback lives here: without a usable sm_100 device b200s_init
+// fails and every other entry point needs a context.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace b200;
+
+namespace {
+
+struct Block {
+  void* ptr;
+  size_t size;
+  bool in_use;
+};
+
+struct Catalog {
+  KeyTab kt{};  // device pointers
+  std::vector<void*> bufs;
+  int S = 0, W = 0, R = 0, K = 0, NB = 0;
+};
+
+}  // namespace
+
+struct b200s_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_sm = 0;
+  int smem_limit = 0;
+  std::map<uint64_t, std::unique_ptr<Catalog>> catalogs;
+  uint64_t next_id = 1;
+  std::string err;
+  std::vector<Block> cache;  // grow-only device block cache so repeated calls do not hit cudaMalloc
+
+  void* alloc(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+    bytes = (bytes + 255) & ~(size_t)255;
+    Block* best = nullptr;
+    for (auto& b : cache)
+      if (!b.in_use && b.size >= bytes && b.size <= bytes * 2 + 4096 && (!best || b.size < best->size)) best = &b;
+    if (best) {
+      best->in_use = true;
+      return best->ptr;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    cache.push_back(Block{p, bytes, true});
+    return p;
+  }
+  void release(void* p) {
+    for (auto& b : cache)
+      if (b.ptr == p) b.in_use = false;
+  }
+};
+
+struct b200s_resident {
+  b200s_ctx* ctx = nullptr;
+  Catalog* cat = nullptr;
+  int P = 0, Ppad = 0, E = 0, T = 0, n_problems = 0;
+  std::vector<void*> owned;
+  PodsDev pods{};
+  int32_t* seg = nullptr;          // problem of each pod (batch only)
+  int32_t* row_problem = nullptr;  // problem of each claim row (batch only)
+  TmplDev* tmpl = nullptr;
+  uint64_t* type_admit = nullptr;
+  uint64_t* tmask = nullptr;
+  int32_t* alive = nullptr;
+  // nodes: pristine copies + the mutable state the pack works on
+  int64_t* n_avail0 = nullptr;
+  uint64_t* n_rmask0 = nullptr;
+  uint64_t* n_rflags0 = nullptr;
+  uint64_t* n_taints = nullptr;
+  // stage A
+  int32_t* a_tmpl = nullptr;
+  uint64_t* a_mask = nullptr;
+  uint8_t* a_code = nullptr;
+  unsigned long long* a_evals = nullptr;
+  // pack
+  PackArrays arr{};
+  PackProblem* problems = nullptr;
+  std::vector<PackProblem> problems_host;
+  ClaimOut cout{};
+  int32_t* sel_sku = nullptr;
+  uint64_t* sel_price = nullptr;
+  int32_t* sel_nopt = nullptr;
+  int last_launches = 0;
+  bool fit_done = false, solve_done = false;
+
+  template <class Tp>
+  Tp* dalloc(size_t n) {
+    void* p = ctx->alloc(n * sizeof(Tp));
+    if (p) owned.push_back(p);
+    return reinterpret_cast<Tp*>(p);
+  }
+};
+
+namespace {
+
+int fail(b200s_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    ctx->err = what;
+    if (e != cudaSuccess) {
+      ctx->err += ": ";
+      ctx->err += cudaGetErrorString(e);
+    }
+  }
+  cudaGetLastError();
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr, what)                                     \
+  do {                                                                \
+    cudaError_t e_ = (expr);                                          \
+    if (e_ != cudaSuccess) return fail(ctx, B200S_ECUDA, what, e_);   \
+  } while (0)
+
+template <class Tp>
+int upload(b200s_ctx* ctx, Tp* dst, const Tp* src, size_t n) {
+  if (n == 0) return 0;
+  if (!dst || !src) return fail(ctx, B200S_EINVAL, "null buffer");
+  CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, n * sizeof(Tp), cudaMemcpyHostToDevice, ctx->stream), "H2D copy");
+  return 0;
+}
+
+int check_shapes(b200s_ctx* ctx, const Catalog* cat, const b200s_pods_soa_t* pods, const b200s_nodes_soa_t* nodes) {
+  if (!pods) return fail(ctx, B200S_EINVAL, "pods is null");
+  if (pods->n_res != cat->R || pods->n_keys != cat->K || pods->n_bounded != cat->NB)
+    return fail(ctx, B200S_EINVAL, "pods SoA does not match the catalog's R/K/NB");
+  if (pods->res_cpu < 0 || pods->res_cpu >= cat->R || pods->res_memory < 0 || pods->res_memory >= cat->R)
+    return fail(ctx, B200S_EINVAL, "pods res_cpu/res_memory out of range");
+  if (nodes && nodes->n_nodes > 0 && (nodes->n_res != cat->R || nodes->n_keys != cat->K))
+    return fail(ctx, B200S_EINVAL, "nodes SoA does not match the catalog's R/K");
+  return 0;
+}
+
+void free_resident(b200s_resident* r) {
+  if (!r) return;
+  for (void* p : r->owned) r->ctx->release(p);
+  delete r;
+}
+
+// Builds every device buffer a fit / solve over `n_problems` pod sets needs.
+int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b200s_pods_soa_t* const* pods_in,
+                   const b200s_nodes_soa_t* const* nodes_in, const b200s_templates_t* tm, b200s_resident** out) {
+  auto it = ctx->catalogs.find(catalog_id);
+  if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
+  Catalog* cat = it->second.get();
+  if (!tm || tm->n_templates < 0 || tm->n_templates > MAXT) return fail(ctx, B200S_EINVAL, "bad templates");
+  if (n_problems < 1) return fail(ctx, B200S_EINVAL, "no problems");
+  const int R = cat->R, K = cat->K, NB = cat->NB, W = cat->W, T = tm->n_templates;
+  long long Ptot = 0, Etot = 0;
+  for (int b = 0; b < n_problems; b++) {
+    const b200s_nodes_soa_t* nd = nodes_in ? nodes_in[b] : nullptr;
+    int rc = check_shapes(ctx, cat, pods_in[b], nd);
+    if (rc) return rc;
+    Ptot += pods_in[b]->n_pods;
+    if (nd) Etot += nd->n_nodes;
+  }
+  if (Ptot > (1ll << 30) || Etot > (1ll << 30)) return fail(ctx, B200S_EINVAL, "problem too large");
+  std::unique_ptr<b200s_resident, void (*)(b200s_resident*)> r(new (std::nothrow) b200s_resident(), free_resident);
+  if (!r) return fail(ctx, B200S_ENOMEM, "host allocation");
+  r->ctx = ctx;
+  r->cat = cat;
+  r->P = (int)Ptot;
+  r->E = (int)Etot;
+  r->T = T;
+  r->n_problems = n_problems;
+  r->Ppad = ffd_padded(r->P);
+  const size_t P = (size_t)std::max<long long>(Ptot, 1), E = (size_t)std::max<long long>(Etot, 1);
+
+  // ---- pods (concatenated, resource/key-major over the total) ----
+  int64_t* d_req = r->dalloc<int64_t>((size_t)R * P);
+  uint64_t* d_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * P);
+  uint64_t* d_rflags = r->dalloc<uint64_t>(P);
+  int32_t* d_gt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * P);
+  int32_t* d_lt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * P);
+  uint64_t* d_tol = r->dalloc<uint64_t>(P);
+  int64_t* d_ts = r->dalloc<int64_t>(P);
+  uint64_t* d_uhi = r->dalloc<uint64_t>(P);
+  uint64_t* d_ulo = r->dalloc<uint64_t>(P);
+  if (!d_req || !d_rmask || !d_rflags || !d_gt || !d_lt || !d_tol || !d_ts || !d_uhi || !d_ulo)
+    return fail(ctx, B200S_ENOMEM, "device allocation (pods)");
+  {
+    size_t off = 0;
+    for (int b = 0; b < n_problems; b++) {
+      const b200s_pods_soa_t* ps = pods_in[b];
+      const size_t n = (size_t)ps->n_pods;
+      int rc = 0;
+      for (int x = 0; x < R && !rc; x++) rc = upload(ctx, d_req + (size_t)x * Ptot + off, ps->requests + (size_t)x * n, n);
+      for (int x = 0; x < K && !rc; x++) rc = upload(ctx, d_rmask + (size_t)x * Ptot + off, ps->req_mask + (size_t)x * n, n);
+      for (int x = 0; x < NB && !rc; x++) {
+        rc = upload(ctx, d_gt + (size_t)x * Ptot + off, ps->req_gt + (size_t)x * n, n);
+        if (!rc) rc = upload(ctx, d_lt + (size_t)x * Ptot + off, ps->req_lt + (size_t)x * n, n);
+      }
+      if (!rc) rc = upload(ctx, d_rflags + off, ps->req_flags, n);
+      if (!rc) rc = upload(ctx, d_tol + off, ps->tolerated, n);
+      if (!rc) rc = upload(ctx, d_ts + off, ps->ts, n);
+      if (!rc) rc = upload(ctx, d_uhi + off, ps->uid_hi, n);
+      if (!rc) rc = upload(ctx, d_ulo + off, ps->uid_lo, n);
+      if (rc) return rc;
+      off += n;
+    }
+  }
+  r->pods = PodsDev{(int32_t)Ptot, pods_in[0]->res_cpu, pods_in[0]->res_memory, d_req, d_rmask, d_rflags, d_gt, d_lt,
+                    d_tol, d_ts, d_uhi, d_ulo};
+
+  // ---- problems, segment ids ----
+  r->problems_host.resize(n_problems);
+  {
+    int po = 0, eo = 0;
+    std::vector<int32_t> seg, rowp;
+    if (n_problems > 1) { seg.resize(P); rowp.resize(P); }
+    for (int b = 0; b < n_problems; b++) {
+      PackProblem& pb = r->problems_host[b];
+      pb.pod_begin = po;
+      pb.pod_end = po + pods_in[b]->n_pods;
+      pb.node_begin = eo;
+      pb.node_end = eo + ((nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
+      pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0;
+      if (n_problems > 1)
+        for (int i = pb.pod_begin; i < pb.pod_end; i++) { seg[i] = b; rowp[i] = b; }
+      po = pb.pod_end;
+      eo = pb.node_end;
+    }
+    r->problems = r->dalloc<PackProblem>(n_problems);
+    if (!r->problems) return fail(ctx, B200S_ENOMEM, "device allocation (problems)");
+    if (n_problems > 1) {
+      r->seg = r->dalloc<int32_t>(P);
+      r->row_problem = r->dalloc<int32_t>(P);
+      if (!r->seg || !r->row_problem) return fail(ctx, B200S_ENOMEM, "device allocation (segments)");
+      int rc = upload(ctx, r->seg, seg.data(), (size_t)Ptot);
+      if (!rc) rc = upload(ctx, r->row_problem, rowp.data(), (size_t)Ptot);
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (segments)");  // host vectors go out of scope
+    }
+  }
+
+  // ---- templates ----
+  {
+    std::unique_ptr<TmplDev> h(new TmplDev());
+    std::memset(h.get(), 0, sizeof(TmplDev));
+    h->T = T;
+    for (int t = 0; t < T; t++) {
+      h->taints[t] = tm->taints[t];
+      h->rflags[t] = tm->req_flags[t];
+      for (int k = 0; k < MAXK; k++) h->rmask[t][k] = tm->req_mask[t][k];
+      for (int b = 0; b < MAXB; b++) { h->gt[t][b] = tm->req_gt[t][b]; h->lt[t][b] = tm->req_lt[t][b]; }
+      for (int x = 0; x < MAXR; x++) h->daemon[t][x] = tm->daemon[t][x];
+    }
+    r->tmpl = r->dalloc<TmplDev>(1);
+    r->tmask = r->dalloc<uint64_t>((size_t)std::max(T, 1) * W);
+    r->alive = r->dalloc<int32_t>(MAXT);
+    if (!r->tmpl || !r->tmask || !r->alive) return fail(ctx, B200S_ENOMEM, "device allocation (templates)");
+    CUDA_TRY(ctx, cudaMemcpyAsync(r->tmpl, h.get(), sizeof(TmplDev), cudaMemcpyHostToDevice, ctx->stream), "H2D templates");
+    if (tm->type_admit && T > 0) {
+      r->type_admit = r->dalloc<uint64_t>((size_t)T * W);
+      if (!r->type_admit) return fail(ctx, B200S_ENOMEM, "device allocation (type_admit)");
+      int rc = upload(ctx, r->type_admit, tm->type_admit, (size_t)T * W);
+      if (rc) return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (templates)");
+  }
+
+  // ---- existing nodes (concatenated; resource/key-major over the total) ----
+  r->n_avail0 = r->dalloc<int64_t>((size_t)R * E);
+  r->n_rmask0 = r->dalloc<uint64_t>((size_t)std::max(K, 1) * E);
+  r->n_rflags0 = r->dalloc<uint64_t>(E);
+  r->n_taints = r->dalloc<uint64_t>(E);
+  if (!r->n_avail0 || !r->n_rmask0 || !r->n_rflags0 || !r->n_taints) return fail(ctx, B200S_ENOMEM, "device allocation (nodes)");
+  {
+    size_t off = 0;
+    for (int b = 0; b < n_problems; b++) {
+      const b200s_nodes_soa_t* nd = nodes_in ? nodes_in[b] : nullptr;
+      if (!nd || nd->n_nodes == 0) continue;
+      const size_t n = (size_t)nd->n_nodes;
+      int rc = 0;
+      for (int x = 0; x < R && !rc; x++) rc = upload(ctx, r->n_avail0 + (size_t)x * Etot + off, nd->available + (size_t)x * n, n);
+      for (int x = 0; x < K && !rc; x++) rc = upload(ctx, r->n_rmask0 + (size_t)x * Etot + off, nd->req_mask + (size_t)x * n, n);
+      if (!rc) rc = upload(ctx, r->n_rflags0 + off, nd->req_flags, n);
+      if (!rc) rc = upload(ctx, r->n_taints + off, nd->taints, n);
+      if (rc) return rc;
+      off += n;
+    }
+  }
+
+  // ---- stage A outputs, sort, pack state, outputs ----
+  r->a_tmpl = r->dalloc<int32_t>(P);
+  r->a_mask = r->dalloc<uint64_t>(P * W);
+  r->a_code = r->dalloc<uint8_t>(P * (size_t)std::max(T, 1));
+  r->a_evals = r->dalloc<unsigned long long>(1);
+  PackArrays& A = r->arr;
+  A.c_mask = r->dalloc<uint64_t>(P * W);
+  A.c_req = r->dalloc<int64_t>(P * R);
+  A.c_rmask = r->dalloc<uint64_t>(P * (size_t)std::max(K, 1));
+  A.c_rflags = r->dalloc<uint64_t>(P);
+  A.c_gt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
+  A.c_lt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
+  A.c_tmpl = r->dalloc<int32_t>(P);
+  A.c_npods = r->dalloc<int32_t>(P);
+  A.ord = r->dalloc<int32_t>(P);
+  A.Etot = (int32_t)Etot;
+  A.n_avail = r->dalloc<int64_t>((size_t)R * E);
+  A.n_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * E);
+  A.n_rflags = r->dalloc<uint64_t>(E);
+  A.n_taints = r->n_taints;
+  A.n_npods = r->dalloc<int32_t>(E);
+  A.queue = r->dalloc<int32_t>((size_t)r->Ppad);
+  A.lastlen = r->dalloc<int32_t>(P);
+  A.a_tmpl = r->a_tmpl;
+  A.a_mask = r->a_mask;
+  A.pod_kind = r->dalloc<int32_t>(P);
+  A.pod_index = r->dalloc<int32_t>(P);
+  A.pod_seq = r->dalloc<int32_t>(P);
+  ClaimOut& O = r->cout;
+  O.tmpl = r->dalloc<int32_t>(P);
+  O.npods = r->dalloc<int32_t>(P);
+  O.req = r->dalloc<int64_t>(P * R);
+  O.mask = r->dalloc<uint64_t>(P * W);
+  O.rmask = r->dalloc<uint64_t>(P * (size_t)std::max(K, 1));
+  O.rflags = r->dalloc<uint64_t>(P);
+  O.gt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
+  O.lt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
+  O.pos_of_claim = r->dalloc<int32_t>(P);
+  r->sel_sku = r->dalloc<int32_t>(P);
+  r->sel_price = r->dalloc<uint64_t>(P);
+  r->sel_nopt = r->dalloc<int32_t>(P);
+  void* must[] = {r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
+                  A.c_tmpl, A.c_npods, A.ord, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
+                  A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
+                  r->sel_sku, r->sel_price, r->sel_nopt};
+  for (void* p : must)
+    if (!p) return fail(ctx, B200S_ENOMEM, "device allocation (state)");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (upload)");
+  *out = r.release();
+  return B200S_OK;
+}
+
+// stage A: template pre-filter + dense fit matrix
+int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
+  CUDA_TRY(ctx, cudaMemsetAsync(r->a_evals, 0, sizeof(unsigned long long), ctx->stream), "memset");
+  CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, ctx->stream),
+           "template_prefilter launch");
+  CUDA_TRY(ctx, launch_fit_matrix(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->a_tmpl, r->a_mask, r->a_code,
+                                  r->a_evals, ctx->n_sm, ctx->smem_limit, ctx->stream),
+           "fit_matrix launch");
+  *launches += r->P > 0 ? 2 : 1;
+  return 0;
+}
+
+int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
+  const Catalog* cat = r->cat;
+  const size_t E = (size_t)std::max(r->E, 1), P = (size_t)std::max(r->P, 1);
+  int rc = enqueue_fit(ctx, r, launches);
+  if (rc) return rc;
+  // fresh mutable state
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->arr.n_avail, r->n_avail0, (size_t)cat->R * E * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->arr.n_rmask, r->n_rmask0, (size_t)std::max(cat->K, 1) * E * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->arr.n_rflags, r->n_rflags0, E * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  CUDA_TRY(ctx, cudaMemsetAsync(r->arr.n_npods, 0, E * 4, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaMemsetAsync(r->arr.lastlen, 0, P * 4, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_kind, 0xFF, P * 4, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_index, 0xFF, P * 4, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_seq, 0xFF, P * 4, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->problems, r->problems_host.data(), sizeof(PackProblem) * r->n_problems,
+                                cudaMemcpyHostToDevice, ctx->stream), "H2D problems");
+  int nl = 0;
+  CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
+  *launches += nl;
+  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, ctx->smem_limit, ctx->stream),
+           "pack launch");
+  CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),
+           "pack_finalize launch");
+  CUDA_TRY(ctx, launch_select_cheapest(cat->kt, r->P, r->cout.mask, r->cout.rmask, (size_t)cat->K, 1, r->cout.rflags,
+                                       r->cout.gt, r->cout.lt, (size_t)cat->NB, 1, r->sel_sku, r->sel_price, r->sel_nopt,
+                                       r->problems, r->row_problem, ctx->stream),
+           "select_cheapest launch");
+  *launches += 3;
+  return 0;
+}
+
+int fetch_fit(b200s_ctx* ctx, b200s_resident* r, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out) {
+  const size_t P = (size_t)r->P;
+  if (P) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmpl_out, r->a_tmpl, P * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(mask_out, r->a_mask, P * r->cat->W * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+    if (r->T) CUDA_TRY(ctx, cudaMemcpyAsync(code_out, r->a_code, P * r->T, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  }
+  unsigned long long ev = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&ev, r->a_evals, 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (fetch fit)");
+  if (evals_out) *evals_out = (int64_t)ev;
+  return 0;
+}
+
+// copies problem b's results into out
+int fetch_problem(b200s_ctx* ctx, b200s_resident* r, int b, const PackProblem& pb, unsigned long long fit_evals,
+                  b200s_result_t* out) {
+  const Catalog* cat = r->cat;
+  const int R = cat->R, K = cat->K, NB = cat->NB, W = cat->W, T = r->T;
+  const size_t base = (size_t)pb.pod_begin, n = (size_t)(pb.pod_end - pb.pod_begin), nc = (size_t)pb.n_claims;
+  (void)b;
+  out->n_claims = pb.n_claims;
+  out->n_unscheduled = pb.n_unscheduled;
+  out->fit_evals = (int64_t)(pb.evals + fit_evals);
+  if ((int)nc > out->cap_claims) return fail(ctx, B200S_ECAPACITY, "cap_claims too small");
+  cudaStream_t s = ctx->stream;
+  if (n) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->pod_place_kind, r->arr.pod_kind + base, n * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->pod_place_index, r->arr.pod_index + base, n * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->pod_seq, r->arr.pod_seq + base, n * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    if (T) CUDA_TRY(ctx, cudaMemcpyAsync(out->pod_fit_code, r->a_code + base * T, n * T, cudaMemcpyDeviceToHost, s), "D2H");
+  }
+  if (nc) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_template, r->cout.tmpl + base, nc * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_npods, r->cout.npods + base, nc * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_requests, r->cout.req + base * R, nc * R * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    if (out->claim_mask)
+      CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_mask, r->cout.mask + base * W, nc * W * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    if (K) CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_req_mask, r->cout.rmask + base * K, nc * K * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_req_flags, r->cout.rflags + base, nc * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    if (NB) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_req_gt, r->cout.gt + base * NB, nc * NB * 8, cudaMemcpyDeviceToHost, s), "D2H");
+      CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_req_lt, r->cout.lt + base * NB, nc * NB * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_sku, r->sel_sku + base, nc * 4, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_price, r->sel_price + base, nc * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->claim_n_options, r->sel_nopt + base, nc * 4, cudaMemcpyDeviceToHost, s), "D2H");
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(s), "sync (fetch solve)");
+  // attempt codes are reported for pods left in PodErrors only (scheduler.go:411,419)
+  for (size_t i = 0; i < n; i++)
+    if (out->pod_place_kind[i] != B200S_PLACE_UNSCHEDULED)
+      for (int t = 0; t < T; t++)
+        if (out->pod_fit_code[i * T + t] != B200S_FIT_DROPPED) out->pod_fit_code[i * T + t] = B200S_FIT_NONE;
+  return 0;
+}
+
+int fetch_solve_all(b200s_ctx* ctx, b200s_resident* r, b200s_result_t* const* outs) {
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->problems_host.data(), r->problems, sizeof(PackProblem) * r->n_problems,
+                                cudaMemcpyDeviceToHost, ctx->stream), "D2H problems");
+  unsigned long long fit_ev = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&fit_ev, r->a_evals, 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (solve)");
+  for (int b = 0; b < r->n_problems; b++) {
+    int rc = fetch_problem(ctx, r, b, r->problems_host[b], r->n_problems == 1 ? fit_ev : 0ull, outs[b]);
+    if (rc) return rc;
+  }
+  if (r->n_problems > 1 && outs[0]) outs[0]->fit_evals += (int64_t)fit_ev;  // stage A ran once for the whole batch
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200s_version(void) { return B200S_VERSION; }
+
+int b200s_init(int device, b200s_ctx_t** out) {
+  if (!out) return B200S_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return B200S_ENODEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B200S_ENODEVICE;
+  if (prop.major != 10) return B200S_ENODEVICE;  // kernels are built for sm_100a only
+  if (cudaSetDevice(device) != cudaSuccess) return B200S_ENODEVICE;
+  std::unique_ptr<b200s_ctx> ctx(new (std::nothrow) b200s_ctx());
+  if (!ctx) return B200S_ENOMEM;
+  ctx->device = device;
+  ctx->n_sm = prop.multiProcessorCount;
+  ctx->smem_limit = (int)prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return B200S_ENODEVICE;
+  *out = ctx.release();
+  return B200S_OK;
+}
+
+void b200s_destroy(b200s_ctx_t* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->catalogs)
+    for (void* p : kv.second->bufs) cudaFree(p);
+  for (auto& b : ctx->cache) cudaFree(b.ptr);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* b200s_last_error(const b200s_ctx_t* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void* b200s_stream(b200s_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int b200s_synchronize(b200s_ctx_t* ctx) {
+  if (!ctx) return B200S_EINVAL;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "synchronize");
+  return B200S_OK;
+}
+
+void* b200s_event_create(b200s_ctx_t* ctx) {
+  if (!ctx) return nullptr;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+  return (void*)e;
+}
+int b200s_event_record(b200s_ctx_t* ctx, void* ev) {
+  if (!ctx || !ev) return B200S_EINVAL;
+  CUDA_TRY(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->stream), "event record");
+  return B200S_OK;
+}
+int b200s_event_elapsed_ms(b200s_ctx_t* ctx, void* a, void* b, float* ms) {
+  if (!ctx || !a || !b || !ms) return B200S_EINVAL;
+  CUDA_TRY(ctx, cudaEventSynchronize((cudaEvent_t)b), "event sync");
+  CUDA_TRY(ctx, cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b), "event elapsed");
+  return B200S_OK;
+}
+void b200s_event_destroy(void* ev) {
+  if (ev) cudaEventDestroy((cudaEvent_t)ev);
+}
+/* writes `bytes` of a pattern over a scratch buffer on the context's stream: the L2 flush the timing
+ * rules ask for between timed iterations */
+int b200s_flush_l2(b200s_ctx_t* ctx, size_t bytes) {
+  if (!ctx) return B200S_EINVAL;
+  void* p = ctx->alloc(bytes);
+  if (!p) return fail(ctx, B200S_ENOMEM, "flush buffer");
+  cudaError_t e = cudaMemsetAsync(p, 0x5A, bytes, ctx->stream);
+  ctx->release(p);
+  if (e != cudaSuccess) return fail(ctx, B200S_ECUDA, "flush memset", e);
+  return B200S_OK;
+}
+
+int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_t* catalog_id) {
+  if (!ctx || !c || !catalog_id) return B200S_EINVAL;
+  if (c->n_skus <= 0 || c->n_words != (c->n_skus + 63) / 64 || c->n_res <= 0 || c->n_res > MAXR || c->n_keys < 0 ||
+      c->n_keys > MAXK || c->n_bounded < 0 || c->n_bounded > MAXB || c->n_rows <= 0)
+    return fail(ctx, B200S_EINVAL, "bad catalog shape");
+  cudaSetDevice(ctx->device);
+  std::unique_ptr<Catalog> cat(new (std::nothrow) Catalog());
+  if (!cat) return B200S_ENOMEM;
+  auto put = [&](const void* src, size_t bytes) -> void* {
+    void* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(bytes, 8)) != cudaSuccess) return nullptr;
+    cat->bufs.push_back(d);
+    if (bytes && cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return nullptr;
+    return d;
+  };
+  const int S = c->n_skus, W = c->n_words, K = c->n_keys, ZC = std::max(c->n_zones * c->n_cts, 1);
+  KeyTab& kt = cat->kt;
+  kt.n_keys = K; kt.n_res = c->n_res; kt.n_words = W; kt.n_skus = S;
+  kt.key_zone = c->key_zone; kt.key_ct = c->key_ct; kt.n_zones = c->n_zones; kt.n_cts = c->n_cts;
+  kt.wellknown = c->wellknown;
+  kt.n_bounded = c->n_bounded;
+  for (int k = 0; k < MAXK; k++) { kt.nvals[k] = 0; kt.bslot[k] = -1; kt.isint[k] = 0; kt.key_row0[k] = 0; }
+  for (int k = 0; k < K; k++) { kt.nvals[k] = c->key_nvals[k]; kt.isint[k] = c->val_isint[k]; kt.key_row0[k] = c->key_row0[k]; }
+  for (int b = 0; b < c->n_bounded; b++) {
+    if (c->bounded_key[b] < 0 || c->bounded_key[b] >= K) return fail(ctx, B200S_EINVAL, "bad bounded key");
+    kt.bslot[c->bounded_key[b]] = (int8_t)b;
+  }
+  for (int r = 0; r < MAXR; r++) { kt.res_nd[r] = 0; kt.res_dv0[r] = 0; kt.res_row0[r] = 0; }
+  for (int r = 0; r < c->n_res; r++) { kt.res_nd[r] = c->res_nd[r]; kt.res_dv0[r] = c->res_dv0[r]; kt.res_row0[r] = c->res_row0[r]; }
+  kt.zc_row0 = c->zc_row0; kt.row_nonneg = c->row_nonneg; kt.n_rows = c->n_rows; kt.n_dv = c->n_dv;
+  kt.val_int = (const int64_t*)put(c->val_int, (size_t)std::max(K, 1) * 64 * 8);
+  kt.rows = (const uint64_t*)put(c->rows, (size_t)c->n_rows * W * 8);
+  kt.res_dv = (const int64_t*)put(c->res_dv, (size_t)c->n_dv * 8);
+  kt.price = (const uint64_t*)put(c->price, (size_t)ZC * S * 8);
+  if (!kt.val_int || !kt.rows || !kt.res_dv || !kt.price) {
+    for (void* p : cat->bufs) cudaFree(p);
+    return fail(ctx, B200S_ENOMEM, "catalog upload");
+  }
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (catalog)");
+  cat->S = S; cat->W = W; cat->R = c->n_res; cat->K = K; cat->NB = c->n_bounded;
+  *catalog_id = ctx->next_id++;
+  ctx->catalogs[*catalog_id] = std::move(cat);
+  return B200S_OK;
+}
+
+int b200s_catalog_release(b200s_ctx_t* ctx, uint64_t catalog_id) {
+  if (!ctx) return B200S_EINVAL;
+  auto it = ctx->catalogs.find(catalog_id);
+  if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : it->second->bufs) cudaFree(p);
+  ctx->catalogs.erase(it);
+  return B200S_OK;
+}
+
+int b200s_resident_create(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods,
+                          const b200s_nodes_soa_t* existing, const b200s_templates_t* templates, b200s_resident_t** out) {
+  if (!ctx || !out || !pods) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  const b200s_pods_soa_t* pp[1] = {pods};
+  const b200s_nodes_soa_t* nn[1] = {existing};
+  return build_resident(ctx, catalog_id, 1, pp, nn, templates, out);
+}
+
+void b200s_resident_free(b200s_ctx_t* ctx, b200s_resident_t* r) {
+  if (!ctx || !r) return;
+  cudaStreamSynchronize(ctx->stream);
+  free_resident(r);
+}
+
+int b200s_resident_fit_matrix(b200s_ctx_t* ctx, b200s_resident_t* r) {
+  if (!ctx || !r) return B200S_EINVAL;
+  r->last_launches = 0;
+  int rc = enqueue_fit(ctx, r, &r->last_launches);
+  if (!rc) r->fit_done = true;
+  return rc;
+}
+
+int b200s_resident_solve(b200s_ctx_t* ctx, b200s_resident_t* r) {
+  if (!ctx || !r) return B200S_EINVAL;
+  r->last_launches = 0;
+  int rc = enqueue_solve(ctx, r, &r->last_launches);
+  if (!rc) { r->fit_done = true; r->solve_done = true; }
+  return rc;
+}
+
+int b200s_resident_fetch_fit(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out,
+                             int64_t* evals_out) {
+  if (!ctx || !r || !r->fit_done) return B200S_ESTATE;
+  return fetch_fit(ctx, r, tmpl_out, mask_out, code_out, evals_out);
+}
+
+int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_result_t* out) {
+  if (!ctx || !r || !out || !r->solve_done) return B200S_ESTATE;
+  b200s_result_t* outs[1] = {out};
+  return fetch_solve_all(ctx, r, outs);
+}
+
+int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }
+
+int b200s_fit_matrix(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods, const b200s_templates_t* templates,
+                     int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out) {
+  if (!ctx || !pods || !templates || !tmpl_out || !mask_out || !code_out) return B200S_EINVAL;
+  b200s_resident_t* r = nullptr;
+  int rc = b200s_resident_create(ctx, catalog_id, pods, nullptr, templates, &r);
+  if (rc) return rc;
+  rc = b200s_resident_fit_matrix(ctx, r);
+  if (!rc) rc = fetch_fit(ctx, r, tmpl_out, mask_out, code_out, evals_out);
+  b200s_resident_free(ctx, r);
+  return rc;
+}
+
+int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, const uint64_t* masks, const uint64_t* req_mask,
+                          const uint64_t* req_flags, const int64_t* req_gt, const int64_t* req_lt, int32_t* sku_out,
+                          uint64_t* price_out) {
+  if (!ctx || n < 0 || !masks || !req_flags || !sku_out || !price_out) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  auto it = ctx->catalogs.find(catalog_id);
+  if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
+  Catalog* cat = it->second.get();
+  if (n == 0) return B200S_OK;
+  const size_t N = (size_t)n, K = (size_t)std::max(cat->K, 1), NB = (size_t)std::max(cat->NB, 1), W = (size_t)cat->W;
+  uint64_t* d_masks = (uint64_t*)ctx->alloc(N * W * 8);
+  uint64_t* d_rmask = (uint64_t*)ctx->alloc(N * K * 8);
+  uint64_t* d_rflags = (uint64_t*)ctx->alloc(N * 8);
+  int64_t* d_gt = (int64_t*)ctx->alloc(N * NB * 8);
+  int64_t* d_lt = (int64_t*)ctx->alloc(N * NB * 8);
+  int32_t* d_sku = (int32_t*)ctx->alloc(N * 4);
+  uint64_t* d_price = (uint64_t*)ctx->alloc(N * 8);
+  void* all[] = {d_masks, d_rmask, d_rflags, d_gt, d_lt, d_sku, d_price};
+  auto cleanup = [&]() {
+    for (void* p : all)
+      if (p) ctx->release(p);
+  };
+  for (void* p : all)
+    if (!p) { cleanup(); return fail(ctx, B200S_ENOMEM, "device allocation"); }
+  int rc = upload(ctx, d_masks, masks, N * W);
+  if (!rc && cat->K) rc = upload(ctx, d_rmask, req_mask, N * cat->K);   // key-major [K*n]
+  if (!rc) rc = upload(ctx, d_rflags, req_flags, N);
+  if (!rc && cat->NB) rc = upload(ctx, d_gt, req_gt, N * cat->NB);
+  if (!rc && cat->NB) rc = upload(ctx, d_lt, req_lt, N * cat->NB);
+  if (!rc) {
+    cudaError_t e = launch_select_cheapest(cat->kt, n, d_masks, d_rmask, 1, N, d_rflags, d_gt, d_lt, 1, N, d_sku, d_price,
+                                           nullptr, nullptr, nullptr, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "select_cheapest launch", e);
+  }
+  if (!rc && cudaMemcpyAsync(sku_out, d_sku, N * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
+  if (!rc && cudaMemcpyAsync(price_out, d_price, N * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, B200S_ECUDA, "sync");
+  cleanup();
+  return rc;
+}
+
+int b200s_solve_batch(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems, const b200s_pods_soa_t* const* pods,
+                      const b200s_nodes_soa_t* const* existing, const b200s_templates_t* templates,
+                      const b200s_solve_opts_t* opts, b200s_result_t* const* out) {
+  (void)opts;
+  if (!ctx || n_problems < 1 || !pods || !templates || !out) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  b200s_resident_t* r = nullptr;
+  int rc = build_resident(ctx, catalog_id, n_problems, pods, existing, templates, &r);
+  if (rc) return rc;
+  r->last_launches = 0;
+  rc = enqueue_solve(ctx, r, &r->last_launches);
+  if (!rc) rc = fetch_solve_all(ctx, r, out);
+  cudaStreamSynchronize(ctx->stream);
+  free_resident(r);
+  return rc;
+}
+
+int b200s_solve(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods, const b200s_nodes_soa_t* existing,
+                const b200s_templates_t* templates, const b200s_solve_opts_t* opts, b200s_result_t* out) {
+  if (!pods || !out) return B200S_EINVAL;
+  const b200s_pods_soa_t* pp[1] = {pods};
+  const b200s_nodes_soa_t* nn[1] = {existing};
+  b200s_result_t* oo[1] = {out};
+  return b200s_solve_batch(ctx, catalog_id, 1, pp, nn, templates, opts, oo);
+}
+
+}  // extern "C"

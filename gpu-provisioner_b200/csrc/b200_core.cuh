@@ -1,0 +1,456 @@
+// b200_core.cuh — the arithmetic of the fit-and-pack path on the bitset encoding, as plain
+// host/device functions.  Kernels (fit_kernels.cu, pack_kernels.cu) wrap these in lane-cooperative
+// code; the encoder (encoder.cpp) uses the same algebra on the host so that templates are built with
+// exactly the semantics the kernels evaluate.
+//
+// Encoding recap (include/b200sched.h, Level 0): a requirement on device key k is
+//   mask  : u64, bit v = v-th value of key k's universe (the In set, or the NotIn exclusion set)
+//   flags : DEFINED | COMPLEMENT | HASGT | HASLT
+//   gt/lt : integer bounds (only complement requirements carry them: requirement.go:186-189)
+// An undefined key reads as Exists (requirements.go:154-160).
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b200sched.h"
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b200 {
+
+constexpr uint32_t RF_DEF = B200S_RF_DEFINED, RF_CMPL = B200S_RF_COMPLEMENT, RF_GT = B200S_RF_HASGT,
+                   RF_LT = B200S_RF_HASLT;
+constexpr int MAXK = B200S_MAX_KEYS, MAXR = B200S_MAX_RES, MAXT = B200S_MAX_TEMPLATES, MAXB = B200S_MAX_BOUNDED;
+
+struct EReq {
+  uint64_t mask;
+  int64_t gt, lt;
+  uint32_t f;
+};
+
+// Per-catalog constants every kernel needs (lives in kernel-parameter / constant space).
+struct KeyTab {
+  int32_t n_keys, n_res, n_words, n_skus;
+  int32_t key_zone, key_ct, n_zones, n_cts;
+  uint32_t wellknown;
+  int32_t n_bounded;
+  int32_t nvals[MAXK];
+  int8_t bslot[MAXK];      // bounded slot of key k, or -1
+  uint64_t isint[MAXK];    // bit v: value v parses as an integer
+  const int64_t* val_int;  // [K*64]
+  // tables
+  const uint64_t* rows;    // [n_rows*W]
+  const int64_t* res_dv;   // ascending distinct allocatable values
+  int32_t res_nd[MAXR], res_dv0[MAXR], res_row0[MAXR];
+  int32_t key_row0[MAXK];
+  int32_t zc_row0, row_nonneg, n_rows, n_dv;
+  const uint64_t* price;   // [n_zc*S]
+};
+
+B2_HD int ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+
+B2_HD int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
+
+B2_HD int popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+
+B2_HD uint64_t universe_of(const KeyTab& kt, int k) {
+  int n = kt.nvals[k];
+  return n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+}
+
+// withinIntPtrs over the whole universe of key k (requirement.go:311-327): bit v set iff value v is
+// an integer strictly inside (gt, lt).  No bounds -> every value is within.
+B2_HD uint64_t within_mask(const KeyTab& kt, int k, uint32_t f, int64_t gt, int64_t lt) {
+  if (!(f & (RF_GT | RF_LT))) return ~0ull;
+  uint64_t m = 0, cand = kt.isint[k];
+  while (cand) {
+    int v = ctz64(cand);
+    cand &= cand - 1;
+    int64_t x = kt.val_int[k * 64 + v];
+    bool ok = true;
+    if ((f & RF_GT) && gt >= x) ok = false;
+    if ((f & RF_LT) && lt <= x) ok = false;
+    if (ok) m |= 1ull << v;
+  }
+  return m;
+}
+
+// Operator() in {NotIn, DoesNotExist} (requirement.go:267-278): the two operators requirements.go
+// :183 and :254-258 forgive.
+B2_HD bool forgiving(const EReq& q) { return (q.f & RF_CMPL) ? (q.mask != 0) : (q.mask == 0); }
+
+B2_HD void merge_bounds(const EReq& a, const EReq& b, uint32_t* f, int64_t* gt, int64_t* lt) {
+  bool ag = a.f & RF_GT, bg = b.f & RF_GT, al = a.f & RF_LT, bl = b.f & RF_LT;
+  *gt = ag ? (bg ? (a.gt > b.gt ? a.gt : b.gt) : a.gt) : b.gt;
+  *lt = al ? (bl ? (a.lt < b.lt ? a.lt : b.lt) : a.lt) : b.lt;
+  *f = ((ag || bg) ? RF_GT : 0u) | ((al || bl) ? RF_LT : 0u);
+}
+
+// Requirement.HasIntersection (requirement.go:197-231); both sides defined.
+B2_HD bool has_intersection(const KeyTab& kt, int k, const EReq& a, const EReq& b) {
+  uint32_t bf;
+  int64_t gt, lt;
+  merge_bounds(a, b, &bf, &gt, &lt);
+  if ((bf & RF_GT) && (bf & RF_LT) && gt >= lt) return false;
+  bool ca = a.f & RF_CMPL, cb = b.f & RF_CMPL;
+  if (ca && cb) return true;
+  uint64_t w = within_mask(kt, k, bf, gt, lt);
+  if (ca) return (b.mask & ~a.mask & w) != 0;
+  if (cb) return (a.mask & ~b.mask & w) != 0;
+  return (a.mask & b.mask & w) != 0;
+}
+
+// Requirement.Intersection (requirement.go:158-191); both sides defined.
+B2_HD EReq intersection(const KeyTab& kt, int k, const EReq& a, const EReq& b) {
+  uint32_t bf;
+  int64_t gt, lt;
+  merge_bounds(a, b, &bf, &gt, &lt);
+  EReq o;
+  if ((bf & RF_GT) && (bf & RF_LT) && gt >= lt) {  // -> DoesNotExist
+    o.mask = 0; o.gt = 0; o.lt = 0; o.f = RF_DEF;
+    return o;
+  }
+  bool ca = a.f & RF_CMPL, cb = b.f & RF_CMPL;
+  uint64_t values = (ca && cb) ? (a.mask | b.mask) : ca ? (b.mask & ~a.mask) : cb ? (a.mask & ~b.mask) : (a.mask & b.mask);
+  values &= within_mask(kt, k, bf, gt, lt);
+  o.mask = values;
+  if (ca && cb) {
+    o.f = RF_DEF | RF_CMPL | bf;
+    o.gt = (bf & RF_GT) ? gt : 0;
+    o.lt = (bf & RF_LT) ? lt : 0;
+  } else {
+    o.f = RF_DEF;
+    o.gt = 0; o.lt = 0;
+  }
+  return o;
+}
+
+// Requirements.Add for one key (requirements.go:127-134): either side may be undefined.
+B2_HD EReq add_req(const KeyTab& kt, int k, const EReq& existing, const EReq& incoming) {
+  if (!(incoming.f & RF_DEF)) return existing;
+  if (!(existing.f & RF_DEF)) return incoming;
+  return intersection(kt, k, incoming, existing);
+}
+
+// One key of Requirements.Compatible(state, pod, allow) (requirements.go:175-191, :248-268).
+B2_HD bool compatible_key(const KeyTab& kt, int k, const EReq& state, const EReq& pod, bool allowWellKnown) {
+  if (!(pod.f & RF_DEF)) return true;
+  if (!(state.f & RF_DEF)) {
+    if (allowWellKnown && ((kt.wellknown >> k) & 1u)) return true;
+    return forgiving(pod);
+  }
+  if (has_intersection(kt, k, state, pod)) return true;
+  return forgiving(pod) && forgiving(state);
+}
+
+// Values of key k a (defined) requirement admits, inside the universe.
+B2_HD uint64_t allowed_values(const KeyTab& kt, int k, const EReq& q) {
+  if (q.f & RF_CMPL) return ~q.mask & within_mask(kt, k, q.f, q.gt, q.lt) & universe_of(kt, k);
+  return q.mask;
+}
+
+// lower_bound over the ascending distinct allocatable values of one resource: index of the first
+// value >= x, or nd when x exceeds them all (then no instance type fits).
+B2_HD int fit_rank(const int64_t* dv, int nd, int64_t x) {
+  int lo = 0, hi = nd;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (dv[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---- one SKU word of the filter loop (nodeclaim.go:392-423), 64 instance types at a time ----------
+// Scratch a group prepares once per (state, pod) pair and every word then reads.
+struct EvalScratch {
+  uint64_t allowed[MAXK];  // admitted values per key of the merged requirements
+  int32_t fit_row[MAXR];   // table row per resource, or -1 when nothing fits
+  uint32_t defined;        // bit k: merged requirements define key k
+  uint32_t forgive;        // bit k: merged requirement k is NotIn / DoesNotExist
+  uint64_t zone_allowed, ct_allowed;  // offering filter (all ones when undefined)
+};
+
+struct WordEval {
+  uint64_t compat, fits, off;
+};
+
+B2_HD WordEval eval_word(const KeyTab& kt, const EvalScratch& sc, int w) {
+  const int W = kt.n_words;
+  const uint64_t* rows = kt.rows;
+  WordEval e;
+  // fits (nodeclaim.go:447-449 -> resources.go:232-245)
+  uint64_t fits = rows[(size_t)kt.row_nonneg * W + w];
+  for (int r = 0; r < kt.n_res; r++) {
+    int row = sc.fit_row[r];
+    fits &= row < 0 ? 0ull : rows[(size_t)row * W + w];
+  }
+  e.fits = fits;
+  // compatible (nodeclaim.go:443-445 -> requirements.go:248-268 -> requirement.go:197-231)
+  uint64_t compat = ~0ull;
+  uint32_t def = sc.defined;
+  while (def) {
+    int k = ctz32(def);
+    def &= def - 1;
+    int row0 = kt.key_row0[k], nv = kt.nvals[k];
+    uint64_t acc = rows[(size_t)(row0 + nv) * W + w];                            // SKUs that do not define k
+    if ((sc.forgive >> k) & 1u) acc |= rows[(size_t)(row0 + nv + 1) * W + w];    // both sides NotIn/DoesNotExist
+    uint64_t a = sc.allowed[k];
+    while (a) {
+      int v = ctz64(a);
+      a &= a - 1;
+      acc |= rows[(size_t)(row0 + v) * W + w];
+    }
+    compat &= acc;
+  }
+  e.compat = compat;
+  // offering scan (nodeclaim.go:400-406)
+  uint64_t off = 0;
+  uint64_t za = sc.zone_allowed & (kt.n_zones >= 64 ? ~0ull : ((1ull << kt.n_zones) - 1ull));
+  while (za) {
+    int z = ctz64(za);
+    za &= za - 1;
+    uint64_t ca = sc.ct_allowed & (kt.n_cts >= 64 ? ~0ull : ((1ull << kt.n_cts) - 1ull));
+    while (ca) {
+      int c = ctz64(ca);
+      ca &= ca - 1;
+      off |= rows[(size_t)(kt.zc_row0 + z * kt.n_cts + c) * W + w];
+    }
+  }
+  e.off = off;
+  return e;
+}
+
+// The six diagnostic flags over a candidate set (nodeclaim.go:409-416), from OR-reduced words.
+B2_HD uint8_t filter_flags(uint64_t anyC, uint64_t anyF, uint64_t anyO, uint64_t anyCFnO, uint64_t anyCOnF, uint64_t anyFOnC) {
+  return (uint8_t)(B200S_FIT_FILTER | (anyC ? B200S_FF_REQUIREMENTS : 0) | (anyF ? B200S_FF_FITS : 0) |
+                   (anyO ? B200S_FF_OFFERING : 0) | (anyCFnO ? B200S_FF_REQ_AND_FITS : 0) |
+                   (anyCOnF ? B200S_FF_REQ_AND_OFF : 0) | (anyFOnC ? B200S_FF_FITS_AND_OFF : 0));
+}
+
+// ---- requirement rows as the kernels store them -----------------------------------------------
+B2_HD EReq make_ereq(uint64_t mask, uint64_t flags_word, int k, int64_t gt, int64_t lt) {
+  EReq q;
+  q.mask = mask;
+  q.f = (uint32_t)((flags_word >> (4 * k)) & 0xFu);
+  q.gt = (q.f & RF_GT) ? gt : 0;
+  q.lt = (q.f & RF_LT) ? lt : 0;
+  return q;
+}
+
+// ---- Go sort.Slice on the in-flight NodeClaim order (scheduler.go:499) ---------------------------
+// ord[0..n) holds claim ids, cnt[id] = len(Pods).  Exact restatement of pdqsort_func
+// (Go 1.24 src/sort/zsortfunc.go) specialised to less(i,j) = cnt[ord[i]] < cnt[ord[j]].
+struct GoSort {
+  int32_t* ord;
+  const int32_t* cnt;
+  B2_HD bool less(int i, int j) const { return cnt[ord[i]] < cnt[ord[j]]; }
+  B2_HD void swap(int i, int j) const {
+    int32_t t = ord[i];
+    ord[i] = ord[j];
+    ord[j] = t;
+  }
+
+  B2_HD void insertion(int a, int b) const {
+    for (int i = a + 1; i < b; i++)
+      for (int j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
+  }
+  B2_HD void sift_down(int lo, int hi, int first) const {
+    int root = lo;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= hi) return;
+      if (child + 1 < hi && less(first + child, first + child + 1)) child++;
+      if (!less(first + root, first + child)) return;
+      swap(first + root, first + child);
+      root = child;
+    }
+  }
+  B2_HD void heap_sort(int a, int b) const {
+    int first = a, lo = 0, hi = b - a;
+    for (int i = (hi - 1) / 2; i >= 0; i--) sift_down(i, hi, first);
+    for (int i = hi - 1; i >= 0; i--) {
+      swap(first, first + i);
+      sift_down(lo, i, first);
+    }
+  }
+  B2_HD void order2(int& a, int& b, int& swaps) const {
+    if (less(b, a)) {
+      swaps++;
+      int t = a; a = b; b = t;
+    }
+  }
+  B2_HD int median(int a, int b, int c, int& swaps) const {
+    order2(a, b, swaps);
+    order2(b, c, swaps);
+    order2(a, b, swaps);
+    return b;
+  }
+  // hint: 0 unknown, 1 increasing, 2 decreasing
+  B2_HD int choose_pivot(int a, int b, int* hint) const {
+    int l = b - a, swaps = 0;
+    int i = a + l / 4 * 1, j = a + l / 4 * 2, k = a + l / 4 * 3;
+    if (l >= 8) {
+      if (l >= 50) {
+        i = median(i - 1, i, i + 1, swaps);
+        j = median(j - 1, j, j + 1, swaps);
+        k = median(k - 1, k, k + 1, swaps);
+      }
+      j = median(i, j, k, swaps);
+    }
+    *hint = swaps == 0 ? 1 : swaps == 12 ? 2 : 0;
+    return j;
+  }
+  B2_HD void reverse_range(int a, int b) const {
+    int i = a, j = b - 1;
+    while (i < j) { swap(i, j); i++; j--; }
+  }
+  B2_HD bool partial_insertion(int a, int b) const {
+    int i = a + 1;
+    for (int s = 0; s < 5; s++) {
+      while (i < b && !less(i, i - 1)) i++;
+      if (i == b) return true;
+      if (b - a < 50) return false;
+      swap(i, i - 1);
+      if (i - a >= 2)
+        for (int j = i - 1; j >= 1; j--) {
+          if (!less(j, j - 1)) break;
+          swap(j, j - 1);
+        }
+      if (b - i >= 2)
+        for (int j = i + 1; j < b; j++) {
+          if (!less(j, j - 1)) break;
+          swap(j, j - 1);
+        }
+    }
+    return false;
+  }
+  B2_HD void break_patterns(int a, int b) const {
+    int length = b - a;
+    if (length >= 8) {
+      uint64_t random = (uint64_t)length;
+      int bl = 0;
+      for (unsigned x = (unsigned)length; x; x >>= 1) bl++;
+      unsigned modulus = 1u << bl;
+      int idx = a + (length / 4) * 2 - 1;
+      for (int i = 0; i < 3; i++) {
+        random ^= random << 13;
+        random ^= random >> 7;
+        random ^= random << 17;
+        int other = (int)((unsigned)random & (modulus - 1));
+        if (other >= length) other -= length;
+        swap(idx - 1 + i, a + other);
+      }
+    }
+  }
+  B2_HD int partition_equal(int a, int b, int pivot) const {
+    swap(a, pivot);
+    int i = a + 1, j = b - 1;
+    for (;;) {
+      while (i <= j && !less(a, i)) i++;
+      while (i <= j && less(a, j)) j--;
+      if (i > j) break;
+      swap(i, j);
+      i++; j--;
+    }
+    return i;
+  }
+  B2_HD int partition(int a, int b, int pivot, bool* already) const {
+    swap(a, pivot);
+    int i = a + 1, j = b - 1;
+    while (i <= j && less(i, a)) i++;
+    while (i <= j && !less(j, a)) j--;
+    if (i > j) {
+      swap(j, a);
+      *already = true;
+      return j;
+    }
+    swap(i, j);
+    i++; j--;
+    for (;;) {
+      while (i <= j && less(i, a)) i++;
+      while (i <= j && !less(j, a)) j--;
+      if (i > j) break;
+      swap(i, j);
+      i++; j--;
+    }
+    swap(j, a);
+    *already = false;
+    return j;
+  }
+
+  // pdqsort_func(data, 0, n, bits.Len(n)).  The Go routine recurses into the smaller side and then
+  // keeps looping on the larger one; here the larger side's loop state is parked on an explicit stack
+  // while the smaller side runs, which is the same order of operations with depth <= log2(n).
+  B2_HD void sort(int n) const {
+    struct Frame { int a, b, limit; bool wasBalanced, wasPartitioned; };
+    Frame stack[36];
+    int sp = 0;
+    int limit0 = 0;
+    for (unsigned x = (unsigned)n; x; x >>= 1) limit0++;
+    stack[sp++] = Frame{0, n, limit0, true, true};
+    while (sp > 0) {
+      Frame fr = stack[--sp];
+      int a = fr.a, b = fr.b, limit = fr.limit;
+      bool wasBalanced = fr.wasBalanced, wasPartitioned = fr.wasPartitioned;
+      for (;;) {
+        int length = b - a;
+        if (length <= 12) { insertion(a, b); break; }
+        if (limit == 0) { heap_sort(a, b); break; }
+        if (!wasBalanced) { break_patterns(a, b); limit--; }
+        int hint;
+        int pivot = choose_pivot(a, b, &hint);
+        if (hint == 2) {
+          reverse_range(a, b);
+          pivot = (b - 1) - (pivot - a);
+          hint = 1;
+        }
+        if (wasBalanced && wasPartitioned && hint == 1) {
+          if (partial_insertion(a, b)) break;
+        }
+        if (a > 0 && !less(a - 1, pivot)) {
+          a = partition_equal(a, b, pivot);
+          continue;
+        }
+        bool already;
+        int mid = partition(a, b, pivot, &already);
+        wasPartitioned = already;
+        int leftLen = mid - a, rightLen = b - mid;
+        int balanceThreshold = length / 8;
+        if (leftLen < rightLen) {
+          wasBalanced = leftLen >= balanceThreshold;
+          stack[sp++] = Frame{mid + 1, b, limit, wasBalanced, wasPartitioned};  // resume here afterwards
+          b = mid;  // pdqsort_func(data, a, mid, limit)
+        } else {
+          wasBalanced = rightLen >= balanceThreshold;
+          stack[sp++] = Frame{a, mid, limit, wasBalanced, wasPartitioned};
+          a = mid + 1;  // pdqsort_func(data, mid+1, b, limit)
+        }
+        wasBalanced = true;
+        wasPartitioned = true;
+      }
+    }
+  }
+};
+
+}  // namespace b200

@@ -1,0 +1,80 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (fit_kernels.cu, pack_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.cuh"
+
+namespace b200 {
+
+// One Solve inside a (possibly batched) launch.  Pods of problem b are the entries
+// [pod_begin, pod_end) of the FFD-sorted index array (problem id is the leading sort key).
+struct PackProblem {
+  int32_t pod_begin, pod_end;
+  int32_t node_begin, node_end;
+  // outputs
+  int32_t n_claims, n_unscheduled;
+  unsigned long long evals;
+};
+
+// Mutable state of all problems of a launch (device pointers).
+struct PackArrays {
+  // in-flight NodeClaims; problem b owns rows [pod_begin, pod_end) (a claim holds at least one pod)
+  uint64_t* c_mask;    // [Ptot*W]  InstanceTypeOptions
+  int64_t* c_req;      // [Ptot*R]  Spec.Resources.Requests
+  uint64_t* c_rmask;   // [Ptot*K]  Requirements
+  uint64_t* c_rflags;  // [Ptot]
+  int64_t* c_gt;       // [Ptot*NB]
+  int64_t* c_lt;       // [Ptot*NB]
+  int32_t* c_tmpl;     // [Ptot]
+  int32_t* c_npods;    // [Ptot]    len(Pods)
+  int32_t* ord;        // [Ptot]    s.newNodeClaims order, local claim ids
+  // existing nodes (mutable copies), resource/key-major with stride Etot
+  int32_t Etot;
+  int64_t* n_avail;    // [R*Etot]
+  uint64_t* n_rmask;   // [K*Etot]
+  uint64_t* n_rflags;  // [Etot]
+  const uint64_t* n_taints;
+  int32_t* n_npods;    // [Etot]
+  // queue (the FFD-sorted index array is used in place as the ring buffer)
+  int32_t* queue;      // [Ppad]
+  int32_t* lastlen;    // [Ptot]
+  // stage A results
+  const int32_t* a_tmpl;   // [Ptot]
+  const uint64_t* a_mask;  // [Ptot*W]
+  // per pod outputs
+  int32_t* pod_kind;   // [Ptot]
+  int32_t* pod_index;  // [Ptot] local claim id / node row
+  int32_t* pod_seq;    // [Ptot]
+};
+
+// final, ordered NodeClaim rows (what b200s_result_t carries)
+struct ClaimOut {
+  int32_t* tmpl;
+  int32_t* npods;
+  int64_t* req;      // [*R]
+  uint64_t* mask;    // [*W]
+  uint64_t* rmask;   // [*K]
+  uint64_t* rflags;
+  int64_t* gt;       // [*NB]
+  int64_t* lt;
+  int32_t* pos_of_claim;  // [Ptot] position in Results.NewNodeClaims of local claim id
+};
+
+cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
+                                      int32_t* alive, cudaStream_t stream);
+int fit_tables_fit_in_smem(const KeyTab& kt, int T, int smem_limit);
+cudaError_t launch_fit_matrix(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
+                              const PodsDev& pods, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out,
+                              unsigned long long* evals, int n_sm, int smem_limit, cudaStream_t stream);
+int ffd_padded(int P);
+cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, int32_t* idx, int* launches, cudaStream_t stream);
+cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* masks, const uint64_t* rmask, size_t rms,
+                                   size_t rks, const uint64_t* rflags, const int64_t* rgt, const int64_t* rlt, size_t bms,
+                                   size_t bks, int32_t* sku_out, uint64_t* price_out, int32_t* nopt_out,
+                                   const PackProblem* problems, const int32_t* row_problem, cudaStream_t stream);
+cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
+                        PackProblem* problems, int n_problems, int smem_limit, cudaStream_t stream);
+cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
+                                 int n_problems, ClaimOut out, cudaStream_t stream);
+
+}  // namespace b200

@@ -117,6 +117,9 @@ typedef struct b200s_model {
   const uint8_t* key_wellknown; /* [n_keys] 1 if in v1.WellKnownLabels (K/apis/v1/labels.go:83-92) */
   int32_t key_zone;             /* topology.kubernetes.io/zone, or -1 */
   int32_t key_capacity_type;    /* karpenter.sh/capacity-type, or -1 */
+  int32_t key_instance_type;    /* node.kubernetes.io/instance-type, or -1.  Its values name SKUs, so it is
+                                   exempt from the 64-values-per-key limit: every SKU must carry
+                                   `In {its own name}`, NodePools may constrain it, pods may not. */
   int32_t n_vals;
   const int32_t* val_key;       /* [n_vals] key each interned value belongs to */
   const int64_t* val_int;       /* [n_vals] strconv.Atoi(value) when val_isint */
@@ -227,11 +230,13 @@ typedef struct b200s_templates {
   int64_t req_gt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
   int64_t req_lt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
   int64_t daemon[B200S_MAX_TEMPLATES][B200S_MAX_RES];
+  const uint64_t* type_admit; /* [T*W] SKUs each template's instance-type requirement admits; NULL = all */
 } b200s_templates_t;
 
 typedef struct b200s_pods_soa {
   int32_t n_pods;            /* P */
   int32_t n_res, n_keys, n_bounded;
+  int32_t res_cpu, res_memory; /* resource rows the FFD order sorts on (queue.go:72-108) */
   const int64_t* requests;   /* [R*P] resource-major */
   const uint64_t* req_mask;  /* [K*P] key-major */
   const uint64_t* req_flags; /* [P] */
@@ -258,6 +263,8 @@ typedef struct b200s_nodes_soa {
 #define B200S_FIT_TAINT 0x01         /* did not tolerate taint (nodeclaim.go:116)                   */
 #define B200S_FIT_INCOMPATIBLE 0x02  /* incompatible requirements (nodeclaim.go:128)               */
 #define B200S_FIT_LIMITS 0x03        /* all instance types exceed nodepool limits (scheduler.go:603) */
+#define B200S_FIT_DROPPED 0x7F       /* template had no instance types after NewScheduler's pre-filter and
+                                        does not exist for the scheduler (scheduler.go:147-156)       */
 #define B200S_FIT_FILTER 0x80        /* InstanceTypeFilterError; low 6 bits are the flags below     */
 #define B200S_FF_REQUIREMENTS 0x01   /* requirementsMet        (nodeclaim.go:409) */
 #define B200S_FF_FITS 0x02           /* fits                   (:410)             */
@@ -313,6 +320,13 @@ const char* b200s_last_error(const b200s_ctx_t* ctx);
 /* CUDA stream the context launches on (a cudaStream_t), for callers that time with events */
 void* b200s_stream(b200s_ctx_t* ctx);
 int b200s_synchronize(b200s_ctx_t* ctx);
+
+/* ---- device timing on the context's stream (CUDA events) and the L2 flush the timing rules need ---- */
+void* b200s_event_create(b200s_ctx_t* ctx);
+int b200s_event_record(b200s_ctx_t* ctx, void* ev);
+int b200s_event_elapsed_ms(b200s_ctx_t* ctx, void* start, void* stop, float* ms);
+void b200s_event_destroy(void* ev);
+int b200s_flush_l2(b200s_ctx_t* ctx, size_t bytes);
 
 /* ---- host-side encoder: semantic model -> SoA (total or reject; no device needed) ---- */
 int b200s_encode(const b200s_model_t* model, b200s_encoded_t** out, char* err, size_t err_cap);

@@ -1,0 +1,339 @@
+// emul.cpp — TEST-ONLY host emulation of the device algorithm.
+//
+// Runs the arithmetic the kernels run (b200_core.cuh: requirement algebra on bitsets, table lookups,
+// eval_word, GoSort) with plain serial control flow, on the SoA the product encoder emits.  It lets
+// the CPU test suite (no GPU in the authoring container) check encoder + tables + algebra + sort port
+// against the oracle; the lane-cooperative wrappers and the kernels themselves are only exercised by
+// the `-m gpu` tests.  Never linked into libb200sched.so and never measured.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../gpu-provisioner_b200/csrc/b200_core.cuh"
+
+using namespace b200;
+
+namespace {
+
+KeyTab keytab_from(const b200s_catalog_soa_t* c) {
+  KeyTab kt{};
+  kt.n_keys = c->n_keys; kt.n_res = c->n_res; kt.n_words = c->n_words; kt.n_skus = c->n_skus;
+  kt.key_zone = c->key_zone; kt.key_ct = c->key_ct; kt.n_zones = c->n_zones; kt.n_cts = c->n_cts;
+  kt.wellknown = c->wellknown; kt.n_bounded = c->n_bounded;
+  for (int k = 0; k < MAXK; k++) { kt.nvals[k] = 0; kt.bslot[k] = -1; kt.isint[k] = 0; }
+  for (int k = 0; k < c->n_keys; k++) { kt.nvals[k] = c->key_nvals[k]; kt.isint[k] = c->val_isint[k]; kt.key_row0[k] = c->key_row0[k]; }
+  for (int b = 0; b < c->n_bounded; b++) kt.bslot[c->bounded_key[b]] = (int8_t)b;
+  for (int r = 0; r < c->n_res; r++) { kt.res_nd[r] = c->res_nd[r]; kt.res_dv0[r] = c->res_dv0[r]; kt.res_row0[r] = c->res_row0[r]; }
+  kt.val_int = c->val_int; kt.rows = c->rows; kt.res_dv = c->res_dv; kt.price = c->price;
+  kt.zc_row0 = c->zc_row0; kt.row_nonneg = c->row_nonneg; kt.n_rows = c->n_rows; kt.n_dv = c->n_dv;
+  return kt;
+}
+
+struct ReqRow {  // one requirement set, row-major
+  uint64_t mask[MAXK];
+  uint64_t flags;
+  int64_t gt[MAXB], lt[MAXB];
+};
+
+EReq get(const KeyTab& kt, const ReqRow& r, int k) {
+  int b = kt.bslot[k];
+  return make_ereq(r.mask[k], r.flags, k, b >= 0 ? r.gt[b] : 0, b >= 0 ? r.lt[b] : 0);
+}
+
+void put(const KeyTab& kt, ReqRow& r, int k, const EReq& q) {
+  r.mask[k] = q.mask;
+  r.flags = (r.flags & ~(0xFull << (4 * k))) | ((uint64_t)(q.f & 0xFu) << (4 * k));
+  int b = kt.bslot[k];
+  if (b >= 0) { r.gt[b] = (q.f & RF_GT) ? q.gt : 0; r.lt[b] = (q.f & RF_LT) ? q.lt : 0; }
+}
+
+ReqRow pod_row(const KeyTab& kt, const b200s_pods_soa_t* p, int i) {
+  ReqRow r{};
+  for (int k = 0; k < kt.n_keys; k++) r.mask[k] = p->req_mask[(size_t)k * p->n_pods + i];
+  r.flags = p->req_flags[i];
+  for (int b = 0; b < kt.n_bounded; b++) { r.gt[b] = p->req_gt[(size_t)b * p->n_pods + i]; r.lt[b] = p->req_lt[(size_t)b * p->n_pods + i]; }
+  return r;
+}
+
+ReqRow tmpl_row(const KeyTab& kt, const b200s_templates_t* tm, int t) {
+  ReqRow r{};
+  for (int k = 0; k < kt.n_keys; k++) r.mask[k] = tm->req_mask[t][k];
+  r.flags = tm->req_flags[t];
+  for (int b = 0; b < kt.n_bounded; b++) { r.gt[b] = tm->req_gt[t][b]; r.lt[b] = tm->req_lt[t][b]; }
+  return r;
+}
+
+constexpr int ST_OK = 0, ST_TAINT = 1, ST_INCOMPATIBLE = 2, ST_FILTER = 3;
+
+// serial twin of device_types.cuh::group_can_add
+int can_add(const KeyTab& kt, const ReqRow& st, const int64_t* st_req, uint64_t st_taints, const ReqRow& pd,
+            const int64_t* pd_req, uint64_t pd_tol, bool check_taints, const uint64_t* cand, uint64_t* out, uint8_t* code,
+            int64_t* visited, ReqRow* merged) {
+  if (check_taints && (st_taints & ~pd_tol)) return ST_TAINT;
+  EvalScratch sc{};
+  bool ok = true;
+  uint32_t def = 0, forg = 0;
+  ReqRow m{};
+  for (int k = 0; k < kt.n_keys; k++) {
+    EReq s = get(kt, st, k), p = get(kt, pd, k);
+    ok = ok && compatible_key(kt, k, s, p, true);
+    EReq q = add_req(kt, k, s, p);
+    put(kt, m, k, q);
+    sc.allowed[k] = 0;
+    if (q.f & RF_DEF) {
+      sc.allowed[k] = allowed_values(kt, k, q);
+      def |= 1u << k;
+      if (forgiving(q)) forg |= 1u << k;
+    }
+  }
+  if (!ok) return ST_INCOMPATIBLE;
+  for (int r = 0; r < kt.n_res; r++) {
+    int64_t x = st_req[r] + pd_req[r];
+    int i = fit_rank(kt.res_dv + kt.res_dv0[r], kt.res_nd[r], x);
+    sc.fit_row[r] = i < kt.res_nd[r] ? kt.res_row0[r] + i : -1;
+  }
+  sc.defined = def;
+  sc.forgive = forg;
+  sc.zone_allowed = (kt.key_zone >= 0 && ((def >> kt.key_zone) & 1u)) ? sc.allowed[kt.key_zone] : ~0ull;
+  sc.ct_allowed = (kt.key_ct >= 0 && ((def >> kt.key_ct) & 1u)) ? sc.allowed[kt.key_ct] : ~0ull;
+  uint64_t any = 0, aC = 0, aF = 0, aO = 0, aCF = 0, aCO = 0, aFO = 0;
+  for (int w = 0; w < kt.n_words; w++) {
+    uint64_t c = cand[w];
+    *visited += popc64(c);
+    WordEval e = eval_word(kt, sc, w);
+    out[w] = c & e.compat & e.fits & e.off;
+    any |= out[w];
+    aC |= c & e.compat; aF |= c & e.fits; aO |= c & e.off;
+    aCF |= c & e.compat & e.fits & ~e.off;
+    aCO |= c & e.compat & e.off & ~e.fits;
+    aFO |= c & e.fits & e.off & ~e.compat;
+  }
+  if (merged) *merged = m;
+  if (any) return ST_OK;
+  *code = filter_flags(aC, aF, aO, aCF, aCO, aFO);
+  return ST_FILTER;
+}
+
+uint64_t tailmask(int S, int w) {
+  int W = (S + 63) / 64;
+  if (w != W - 1 || (S & 63) == 0) return ~0ull;
+  return (1ull << (S & 63)) - 1ull;
+}
+
+void prefilter(const KeyTab& kt, const b200s_templates_t* tm, std::vector<uint64_t>* tmask, std::vector<int>* alive) {
+  const int W = kt.n_words, T = tm->n_templates;
+  tmask->assign((size_t)std::max(T, 1) * W, 0);
+  alive->assign(MAXT, 0);
+  std::vector<int64_t> zero(MAXR, 0);
+  for (int t = 0; t < T; t++) {
+    std::vector<uint64_t> cand(W), out(W);
+    for (int w = 0; w < W; w++) cand[w] = tailmask(kt.n_skus, w) & (tm->type_admit ? tm->type_admit[(size_t)t * W + w] : ~0ull);
+    ReqRow st = tmpl_row(kt, tm, t), pd{};
+    uint8_t code = 0;
+    int64_t vis = 0;
+    int s = can_add(kt, st, zero.data(), 0, pd, zero.data(), 0, false, cand.data(), out.data(), &code, &vis, nullptr);
+    if (s == ST_OK) {
+      for (int w = 0; w < W; w++) (*tmask)[(size_t)t * W + w] = out[w];
+      (*alive)[t] = 1;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int emul_fit_matrix(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, const b200s_pods_soa_t* pods,
+                    int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out) {
+  KeyTab kt = keytab_from(cat);
+  const int W = kt.n_words, T = tm->n_templates, P = pods->n_pods, R = kt.n_res;
+  std::vector<uint64_t> tmask;
+  std::vector<int> alive;
+  prefilter(kt, tm, &tmask, &alive);
+  int64_t evals = 0;
+  std::vector<uint64_t> out(W);
+  std::vector<int64_t> preq(R);
+  for (int p = 0; p < P; p++) {
+    ReqRow pd = pod_row(kt, pods, p);
+    for (int r = 0; r < R; r++) preq[r] = pods->requests[(size_t)r * P + p];
+    int chosen = -1;
+    for (int w = 0; w < W; w++) mask_out[(size_t)p * W + w] = 0;
+    for (int t = 0; t < T; t++) {
+      uint8_t code = alive[t] ? B200S_FIT_NONE : B200S_FIT_DROPPED;
+      if (alive[t] && chosen < 0) {
+        ReqRow st = tmpl_row(kt, tm, t);
+        int s = can_add(kt, st, tm->daemon[t], tm->taints[t], pd, preq.data(), pods->tolerated[p], true,
+                        &tmask[(size_t)t * W], out.data(), &code, &evals, nullptr);
+        if (s == ST_OK) {
+          chosen = t;
+          code = B200S_FIT_NONE;
+          for (int w = 0; w < W; w++) mask_out[(size_t)p * W + w] = out[w];
+        } else if (s == ST_TAINT) code = B200S_FIT_TAINT;
+        else if (s == ST_INCOMPATIBLE) code = B200S_FIT_INCOMPATIBLE;
+      }
+      code_out[(size_t)p * T + t] = code;
+    }
+    tmpl_out[p] = chosen;
+  }
+  if (evals_out) *evals_out = evals;
+  return 0;
+}
+
+int emul_go_sort(const int32_t* cnt, int32_t n, int32_t* ord) {
+  GoSort gs{ord, cnt};
+  gs.sort(n);
+  return 0;
+}
+
+// Serial twin of ffd sort + pack_kernel + finalize + select_cheapest.
+int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, const b200s_pods_soa_t* pods,
+               const b200s_nodes_soa_t* nodes, b200s_result_t* out) {
+  KeyTab kt = keytab_from(cat);
+  const int W = kt.n_words, T = tm->n_templates, P = pods->n_pods, R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded;
+  const int E = nodes ? nodes->n_nodes : 0;
+  std::vector<int32_t> a_tmpl(std::max(P, 1));
+  std::vector<uint64_t> a_mask((size_t)std::max(P, 1) * W);
+  std::vector<uint8_t> a_code((size_t)std::max(P, 1) * std::max(T, 1));
+  int64_t evals = 0;
+  emul_fit_matrix(cat, tm, pods, a_tmpl.data(), a_mask.data(), a_code.data(), &evals);
+  // FFD order (queue.go:72-108)
+  std::vector<int> q(P);
+  for (int i = 0; i < P; i++) q[i] = i;
+  auto req = [&](int r, int p) { return pods->requests[(size_t)r * P + p]; };
+  std::sort(q.begin(), q.end(), [&](int a, int b) {
+    if (req(pods->res_cpu, a) != req(pods->res_cpu, b)) return req(pods->res_cpu, a) > req(pods->res_cpu, b);
+    if (req(pods->res_memory, a) != req(pods->res_memory, b)) return req(pods->res_memory, a) > req(pods->res_memory, b);
+    if (pods->ts[a] != pods->ts[b]) return pods->ts[a] < pods->ts[b];
+    if (pods->uid_hi[a] != pods->uid_hi[b]) return pods->uid_hi[a] < pods->uid_hi[b];
+    if (pods->uid_lo[a] != pods->uid_lo[b]) return pods->uid_lo[a] < pods->uid_lo[b];
+    return a < b;
+  });
+  struct Claim { ReqRow reqs; std::vector<int64_t> req; std::vector<uint64_t> mask; int tmpl; };
+  std::vector<Claim> claims;
+  std::vector<int32_t> npods, ord;
+  struct Node { ReqRow reqs; std::vector<int64_t> avail; uint64_t taints; };
+  std::vector<Node> nd(E);
+  for (int e = 0; e < E; e++) {
+    nd[e].reqs = ReqRow{};
+    for (int k = 0; k < K; k++) nd[e].reqs.mask[k] = nodes->req_mask[(size_t)k * E + e];
+    nd[e].reqs.flags = nodes->req_flags[e];
+    nd[e].avail.resize(R);
+    for (int r = 0; r < R; r++) nd[e].avail[r] = nodes->available[(size_t)r * E + e];
+    nd[e].taints = nodes->taints[e];
+  }
+  std::vector<int> lastlen(P, 0);
+  std::vector<int> pod_claim(P, -1);
+  size_t head = 0;
+  int seq = 0;
+  std::vector<int64_t> preq(R);
+  std::vector<uint64_t> outw(W);
+  for (int p = 0; p < P; p++) { out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED; out->pod_place_index[p] = -1; out->pod_seq[p] = -1; }
+  for (;;) {
+    size_t len = q.size() - head;
+    if (len == 0) break;
+    int p = q[head];
+    if (lastlen[p] == (int)len) break;
+    head++;
+    ReqRow pd = pod_row(kt, pods, p);
+    uint64_t tol = pods->tolerated[p];
+    for (int r = 0; r < R; r++) preq[r] = req(r, p);
+    bool placed = false;
+    for (int e = 0; e < E && !placed; e++) {  // addToExistingNode
+      if (nd[e].taints & ~tol) continue;
+      bool fits = true;
+      for (int r = 0; r < R; r++) if (nd[e].avail[r] < 0 || preq[r] > nd[e].avail[r]) fits = false;
+      if (!fits) continue;
+      bool ok = true;
+      for (int k = 0; k < K; k++) ok = ok && compatible_key(kt, k, get(kt, nd[e].reqs, k), get(kt, pd, k), false);
+      if (!ok) continue;
+      for (int k = 0; k < K; k++) put(kt, nd[e].reqs, k, add_req(kt, k, get(kt, nd[e].reqs, k), get(kt, pd, k)));
+      for (int r = 0; r < R; r++) nd[e].avail[r] -= preq[r];
+      out->pod_place_kind[p] = B200S_PLACE_NODE; out->pod_place_index[p] = e; out->pod_seq[p] = seq++;
+      placed = true;
+    }
+    if (placed) continue;
+    if (!ord.empty()) { GoSort gs{ord.data(), npods.data()}; gs.sort((int)ord.size()); }
+    for (size_t i = 0; i < ord.size() && !placed; i++) {  // addToInflightNode
+      Claim& c = claims[ord[i]];
+      uint8_t code; ReqRow merged;
+      int s = can_add(kt, c.reqs, c.req.data(), tm->taints[c.tmpl], pd, preq.data(), tol, true, c.mask.data(), outw.data(), &code, &evals, &merged);
+      if (s == ST_OK) {
+        c.reqs = merged; c.mask = outw;
+        for (int r = 0; r < R; r++) c.req[r] += preq[r];
+        npods[ord[i]]++;
+        pod_claim[p] = ord[i];
+        out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
+        placed = true;
+      }
+    }
+    if (placed) continue;
+    int t = a_tmpl[p];
+    if (t >= 0) {  // addToNewNodeClaim
+      Claim c;
+      ReqRow st = tmpl_row(kt, tm, t);
+      c.reqs = ReqRow{};
+      for (int k = 0; k < K; k++) put(kt, c.reqs, k, add_req(kt, k, get(kt, st, k), get(kt, pd, k)));
+      c.req.resize(R);
+      for (int r = 0; r < R; r++) c.req[r] = tm->daemon[t][r] + preq[r];
+      c.mask.assign(a_mask.begin() + (size_t)p * W, a_mask.begin() + (size_t)(p + 1) * W);
+      c.tmpl = t;
+      claims.push_back(c);
+      npods.push_back(1);
+      ord.push_back((int)claims.size() - 1);
+      pod_claim[p] = (int)claims.size() - 1;
+      out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
+    } else {
+      q.push_back(p);
+      lastlen[p] = (int)(q.size() - head);
+      out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED;
+    }
+  }
+  int n = (int)claims.size();
+  if (n > out->cap_claims) return B200S_ECAPACITY;
+  out->n_claims = n;
+  out->n_unscheduled = (int)(q.size() - head);
+  out->fit_evals = evals;
+  std::vector<int> pos(n);
+  for (int i = 0; i < n; i++) pos[ord[i]] = i;
+  for (int p = 0; p < P; p++) {
+    if (out->pod_place_kind[p] == B200S_PLACE_CLAIM) out->pod_place_index[p] = pos[pod_claim[p]];
+    for (int t = 0; t < T; t++) {
+      uint8_t c = a_code[(size_t)p * T + t];
+      out->pod_fit_code[(size_t)p * T + t] = (out->pod_place_kind[p] == B200S_PLACE_UNSCHEDULED || c == B200S_FIT_DROPPED) ? c : (uint8_t)B200S_FIT_NONE;
+    }
+  }
+  const int ZC = kt.n_zones * kt.n_cts;
+  for (int i = 0; i < n; i++) {
+    const Claim& c = claims[ord[i]];
+    out->claim_template[i] = c.tmpl;
+    out->claim_npods[i] = npods[ord[i]];
+    for (int r = 0; r < R; r++) out->claim_requests[(size_t)i * R + r] = c.req[r];
+    if (out->claim_mask) for (int w = 0; w < W; w++) out->claim_mask[(size_t)i * W + w] = c.mask[w];
+    for (int k = 0; k < K; k++) out->claim_req_mask[(size_t)i * K + k] = c.reqs.mask[k];
+    out->claim_req_flags[i] = c.reqs.flags;
+    for (int b = 0; b < NB; b++) { out->claim_req_gt[(size_t)i * NB + b] = c.reqs.gt[b]; out->claim_req_lt[(size_t)i * NB + b] = c.reqs.lt[b]; }
+    // OrderByPrice head (types.go:221-240)
+    uint64_t za = ~0ull, ca = ~0ull;
+    if (kt.key_zone >= 0) { EReq qz = get(kt, c.reqs, kt.key_zone); if (qz.f & RF_DEF) za = allowed_values(kt, kt.key_zone, qz); }
+    if (kt.key_ct >= 0) { EReq qc = get(kt, c.reqs, kt.key_ct); if (qc.f & RF_DEF) ca = allowed_values(kt, kt.key_ct, qc); }
+    uint64_t best = ~0ull; int bs = -1, cnt = 0;
+    for (int s = 0; s < kt.n_skus; s++) {
+      if (!((c.mask[s / 64] >> (s % 64)) & 1ull)) continue;
+      cnt++;
+      uint64_t pr = B200S_PRICE_NONE;
+      for (int zc = 0; zc < ZC; zc++) {
+        int z = zc / kt.n_cts, ct = zc % kt.n_cts;
+        if (!((za >> z) & 1ull) || !((ca >> ct) & 1ull)) continue;
+        pr = std::min(pr, kt.price[(size_t)zc * kt.n_skus + s]);
+      }
+      if (pr < best) { best = pr; bs = s; }
+    }
+    out->claim_sku[i] = bs;
+    out->claim_price[i] = bs >= 0 ? best : B200S_PRICE_NONE;
+    out->claim_n_options[i] = cnt;
+  }
+  return 0;
+}
+
+}  // extern "C"
