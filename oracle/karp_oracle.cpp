@@ -495,6 +495,7 @@ struct Counters {
   int64_t canadd_claim = 0, canadd_node = 0, new_claim_attempts = 0;
   int64_t sorts = 0, sorts_unsorted = 0;
   int64_t price_ties = 0;
+  int64_t newclaim_evals = 0;
 };
 
 struct FilterError {
@@ -723,7 +724,9 @@ struct Scheduler {
       std::vector<const InstanceType*> upd;
       FilterError fe;
       C.new_claim_attempts++;
+      int64_t before = C.fit_evals;
       AddErr e = ClaimCanAdd(nc, pod, tolerations, &r, &upd, &fe);
+      C.newclaim_evals += C.fit_evals - before;
       if (e != ErrNone) {
         podFitCode[(size_t)pod.index * T + i] =
             e == ErrTaint ? B200S_FIT_TAINT : e == ErrIncompatible ? B200S_FIT_INCOMPATIBLE : fe.code();
@@ -1001,6 +1004,7 @@ int oracle_solve(const b200s_model_t* M, const oracle_opts_t* opts, oracle_resul
   out->sorts = S.C.sorts;
   out->sorts_unsorted = S.C.sorts_unsorted;
   out->price_ties = S.C.price_ties;
+  out->newclaim_evals = S.C.newclaim_evals;
   out->value_overflow = overflow;
   g_model = nullptr;
   return 0;

@@ -20,7 +20,8 @@ typedef struct oracle_result {
   int32_t cap_claims; /* in */
   int32_t n_claims, n_unscheduled, n_templates;
   int32_t template_pool[B200S_MAX_TEMPLATES]; /* model pool of each surviving template, weight order */
-  int64_t fit_evals, prefilter_evals, canadd_claim, canadd_node, new_claim_attempts, sorts, sorts_unsorted, price_ties;
+  int64_t fit_evals, prefilter_evals, canadd_claim, canadd_node, new_claim_attempts, sorts, sorts_unsorted, price_ties,
+      newclaim_evals; /* part of fit_evals spent in addToNewNodeClaim's template walk */
   int32_t value_overflow; /* a key had more than 64 values: claim_req_mask is truncated */
   int32_t _pad;
   int32_t* queue_order;     /* [P] FFD order (may be NULL) */

@@ -26,7 +26,7 @@ class OracleResult(C.Structure):
         ("template_pool", C.c_int32 * MAX_TEMPLATES),
         ("fit_evals", C.c_int64), ("prefilter_evals", C.c_int64), ("canadd_claim", C.c_int64),
         ("canadd_node", C.c_int64), ("new_claim_attempts", C.c_int64), ("sorts", C.c_int64),
-        ("sorts_unsorted", C.c_int64), ("price_ties", C.c_int64),
+        ("sorts_unsorted", C.c_int64), ("price_ties", C.c_int64), ("newclaim_evals", C.c_int64),
         ("value_overflow", C.c_int32), ("_pad", C.c_int32),
         ("queue_order", _P(C.c_int32)), ("node_order", _P(C.c_int32)), ("node_npods", _P(C.c_int32)),
         ("pod_place_kind", _P(C.c_int32)), ("pod_place_index", _P(C.c_int32)), ("pod_seq", _P(C.c_int32)),
@@ -57,6 +57,8 @@ def lib():
         _lib.oracle_req_algebra.restype = C.c_int
         _lib.oracle_tolerates.restype = C.c_int
         _lib.oracle_create_select.restype = C.c_int
+        _lib.oracle_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
+                                              _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]
     return _lib
 
 
@@ -133,7 +135,7 @@ def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None) ->
         claim_price=arr["claim_price"][:N],
         counters=dict(fit_evals=res.fit_evals, prefilter_evals=res.prefilter_evals, canadd_claim=res.canadd_claim,
                       canadd_node=res.canadd_node, new_claim_attempts=res.new_claim_attempts, sorts=res.sorts,
-                      sorts_unsorted=res.sorts_unsorted, price_ties=res.price_ties,
+                      sorts_unsorted=res.sorts_unsorted, price_ties=res.price_ties, newclaim_evals=res.newclaim_evals,
                       value_overflow=res.value_overflow))
 
 

@@ -1,0 +1,185 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C-ABI of libb200sched.so and is
+compared bit for bit with the CPU oracle; at BASELINE.json's full sizes, where the reference-shaped oracle would
+take minutes, size-independent properties are checked instead."""
+import numpy as np
+import pytest
+
+import fuzz_models
+import oracle_binding as ob
+import parity
+from b200sched import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _fit_parity(ctx, model, what):
+    enc = capi.Encoded(model)
+    cid = ctx.upload_catalog(enc)
+    try:
+        fit = ctx.fit_matrix(cid, enc)
+    finally:
+        ctx.release_catalog(cid)
+    o_tmpl, o_mask, o_code, o_evals, _ = ob.fit_matrix(model)
+    cf = parity.canon_fit(enc, fit)
+    assert np.array_equal(cf["tmpl"], o_tmpl), what
+    assert np.array_equal(cf["mask"], o_mask), what
+    assert np.array_equal(cf["code"], o_code), what
+    assert fit.evals == o_evals, what
+
+
+def _solve_parity(ctx, model, what):
+    enc = capi.Encoded(model)
+    cid = ctx.upload_catalog(enc)
+    try:
+        raw = ctx.solve(cid, enc)
+    finally:
+        ctx.release_catalog(cid)
+    o = ob.solve(model)
+    parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(model, o), what)
+    return raw, o
+
+
+@pytest.mark.parametrize("kind,P,S", [("c2", 1500, 100), ("c3", 2500, 200), ("c3", 1200, 700), ("c2", 300, 1300),
+                                      ("c3", 777, 2500), ("c3", 500, 5000)])
+def test_fit_matrix_matches_oracle(gpu_ctx, kind, P, S):
+    _fit_parity(gpu_ctx, synth.config(kind, P, S), f"fit {kind} {P}x{S}")
+
+
+@pytest.mark.parametrize("kind,P,S", [("c2", 1500, 100), ("c3", 2500, 200), ("c3", 1200, 700), ("c2", 300, 1300),
+                                      ("c3", 777, 2500)])
+def test_solve_matches_oracle(gpu_ctx, kind, P, S):
+    raw, o = _solve_parity(gpu_ctx, synth.config(kind, P, S), f"solve {kind} {P}x{S}")
+    assert o.counters["price_ties"] == 0
+
+
+def test_fuzzed_models_match_oracle(gpu_ctx):
+    ran = 0
+    for seed in range(150):
+        m = fuzz_models.random_model(seed)
+        try:
+            enc = capi.Encoded(m)
+        except capi.NotRepresentable:
+            continue
+        del enc
+        _fit_parity(gpu_ctx, m, f"fuzz fit seed {seed}")
+        _solve_parity(gpu_ctx, m, f"fuzz solve seed {seed}")
+        ran += 1
+    assert ran >= 120
+
+
+def test_config2_full_size_bit_identical(gpu_ctx):
+    """BASELINE.json configs[1]: 10k pods x 500 SKUs — NodeClaim -> SKU selections identical to the oracle."""
+    m = synth.c2()
+    raw, o = _solve_parity(gpu_ctx, m, "config 2")
+    assert raw.n_claims == o.n_claims and np.array_equal(raw.claim_sku, o.claim_sku)
+    _fit_parity(gpu_ctx, m, "config 2 fit")
+
+
+def test_empty_and_ragged_inputs(gpu_ctx):
+    # no pods
+    m = synth.config("c2", 0, 50)
+    raw, o = _solve_parity(gpu_ctx, m, "no pods")
+    assert raw.n_claims == 0
+    # one pod, 1 SKU; S not a multiple of 64; a pod nothing can hold
+    for P, S in ((1, 1), (3, 65), (130, 129)):
+        _solve_parity(gpu_ctx, synth.config("c3", P, S), f"ragged {P}x{S}")
+    b = synth.new_builder()
+    synth.add_catalog(b, 40)
+    synth.add_pools(b, "c2")
+    b.add_pod([], [10_000_000, 1 << 20, 0, 0, 1])            # cpu beyond every SKU
+    b.add_pod([], [100, 1 << 20, 0, 0, 1])
+    raw, o = _solve_parity(gpu_ctx, b.build(), "unschedulable pod")
+    assert raw.n_unscheduled == 1 and raw.pod_fit_code[0, 0] & 0x80
+
+
+def test_select_cheapest_matches_oracle_selection(gpu_ctx):
+    m = synth.config("c3", 3000, 300)
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    try:
+        raw = gpu_ctx.solve(cid, enc)
+        N = raw.n_claims
+        gt = raw.claim_req_gt.T.copy() if enc.NB else np.zeros((1, N), np.int64)
+        lt = raw.claim_req_lt.T.copy() if enc.NB else np.zeros((1, N), np.int64)
+        sku, price = gpu_ctx.select_cheapest(cid, enc, raw.claim_mask, raw.claim_req_mask.T.copy(), raw.claim_req_flags, gt, lt)
+    finally:
+        gpu_ctx.release_catalog(cid)
+    o = ob.solve(m)
+    assert np.array_equal(sku, o.claim_sku) and np.array_equal(price, o.claim_price)
+
+
+def test_batched_solve_equals_individual_solves(gpu_ctx):
+    """solve_batch (one CTA per independent simulation, consolidation-style) == one solve per problem."""
+    base = synth.config("c3", 64, 300)
+    enc0 = capi.Encoded(base)
+    cid = gpu_ctx.upload_catalog(enc0)
+    try:
+        models = [synth.config("c3", 40 + 13 * i, 300, seed_pods=0xB2000002 + i) for i in range(9)]
+        encs = [capi.Encoded(m) for m in models]
+        batch = gpu_ctx.solve_batch(cid, encs)
+        for i, (m, e, r) in enumerate(zip(models, encs, batch)):
+            single = gpu_ctx.solve(cid, e)
+            a, b = parity.canon_device(e, r), parity.canon_device(e, single)
+            parity.assert_same(a, b, f"batch item {i}")
+            parity.assert_same(a, parity.canon_oracle(m, ob.solve(m)), f"batch item {i} vs oracle")
+    finally:
+        gpu_ctx.release_catalog(cid)
+
+
+def test_existing_nodes(gpu_ctx):
+    for seed in (3, 8, 21, 55, 89, 144):
+        m = fuzz_models.random_model(1000 + seed, with_nodes=True, max_pods=120)
+        try:
+            capi.Encoded(m)
+        except capi.NotRepresentable:
+            continue
+        raw, o = _solve_parity(gpu_ctx, m, f"nodes seed {seed}")
+
+
+def test_config3_full_size_properties(gpu_ctx):
+    """BASELINE.json configs[2]: 100k pods x 1k SKUs with taints / tolerations / selector bitsets.  The dense fit
+    matrix is compared with the oracle on a 4 000-pod sample of rows; the whole solve is checked through
+    invariants that do not depend on size."""
+    m = synth.c3()
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    try:
+        fit = gpu_ctx.fit_matrix(cid, enc)
+        raw = gpu_ctx.solve(cid, enc)
+        raw2 = gpu_ctx.solve(cid, enc)
+    finally:
+        gpu_ctx.release_catalog(cid)
+    cf = parity.canon_fit(enc, fit)
+    lo, hi = 48_000, 52_000
+    o_tmpl, o_mask, o_code, _, _ = ob.fit_matrix(m, lo, hi)
+    assert np.array_equal(cf["tmpl"][lo:hi], o_tmpl) and np.array_equal(cf["mask"][lo:hi], o_mask)
+    assert np.array_equal(cf["code"][lo:hi], o_code)
+    # determinism / idempotence
+    parity.assert_same(parity.canon_device(enc, raw), parity.canon_device(enc, raw2), "repeat solve")
+    P, R = enc.P, enc.R
+    req = m.arrays["pod_requests"]
+    placed = raw.pod_place_kind == capi.PLACE_CLAIM
+    assert placed.sum() + raw.n_unscheduled == P
+    # every pod placed exactly once, placement order is a permutation
+    seq = raw.pod_seq[placed]
+    assert sorted(seq.tolist()) == list(range(len(seq)))
+    # claim accounting: pod counts and summed requests
+    N = raw.n_claims
+    counts = np.bincount(raw.pod_place_index[placed], minlength=N)
+    assert np.array_equal(counts, raw.claim_npods)
+    sums = np.zeros((N, R), np.int64)
+    np.add.at(sums, raw.pod_place_index[placed], req[placed])
+    assert np.array_equal(sums, raw.claim_requests)   # daemon overhead is zero in this config
+    # every surviving instance type really holds the claim's pods; the selected SKU is in the set and cheapest
+    alloc = m.arrays["sku_alloc"]
+    for c in range(0, N, max(1, N // 300)):
+        bits = np.unpackbits(raw.claim_mask[c].view(np.uint8), bitorder="little")[:enc.S].astype(bool)
+        assert bits.sum() == raw.claim_n_options[c] and bits[raw.claim_sku[c]]
+        assert (alloc[bits] >= raw.claim_requests[c]).all()
+        pods = np.nonzero(placed & (raw.pod_place_index == c))[0]
+        for p in pods[:5]:  # a claim's options are a subset of what each of its pods could start a claim with
+            if fit.tmpl[p] == raw.claim_template[c]:
+                assert (raw.claim_mask[c] & ~fit.mask[p]).sum() == 0
+    # claims are in Results.NewNodeClaims order: non-decreasing pod count except for the last modification
+    d = np.diff(raw.claim_npods)
+    assert (d < 0).sum() <= 1
