@@ -312,6 +312,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   A.c_tmpl = r->dalloc<int32_t>(P);
   A.c_npods = r->dalloc<int32_t>(P);
   A.ord = r->dalloc<int32_t>(P);
+  A.ord_key = r->dalloc<int32_t>(P);
   A.Etot = (int32_t)Etot;
   A.n_avail = r->dalloc<int64_t>((size_t)R * E);
   A.n_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * E);
@@ -339,7 +340,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sel_price = r->dalloc<uint64_t>(P);
   r->sel_nopt = r->dalloc<int32_t>(P);
   void* must[] = {r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
-                  A.c_tmpl, A.c_npods, A.ord, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
+                  A.c_tmpl, A.c_npods, A.ord, A.ord_key, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
                   A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
                   r->sel_sku, r->sel_price, r->sel_nopt};
   for (void* p : must)

@@ -259,16 +259,20 @@ B2_HD EReq make_ereq(uint64_t mask, uint64_t flags_word, int k, int64_t gt, int6
 }
 
 // ---- Go sort.Slice on the in-flight NodeClaim order (scheduler.go:499) ---------------------------
-// ord[0..n) holds claim ids, cnt[id] = len(Pods).  Exact restatement of pdqsort_func
-// (Go 1.24 src/sort/zsortfunc.go) specialised to less(i,j) = cnt[ord[i]] < cnt[ord[j]].
+// ord[i] = claim id at position i of s.newNodeClaims, key[i] = len(Pods) of that claim (kept by
+// position so a comparison is two adjacent-array reads).  Exact restatement of pdqsort_func
+// (Go 1.24 src/sort/zsortfunc.go) specialised to less(i,j) = key[i] < key[j]; swaps move both arrays.
 struct GoSort {
   int32_t* ord;
-  const int32_t* cnt;
-  B2_HD bool less(int i, int j) const { return cnt[ord[i]] < cnt[ord[j]]; }
+  int32_t* key;
+  B2_HD bool less(int i, int j) const { return key[i] < key[j]; }
   B2_HD void swap(int i, int j) const {
     int32_t t = ord[i];
     ord[i] = ord[j];
     ord[j] = t;
+    t = key[i];
+    key[i] = key[j];
+    key[j] = t;
   }
 
   B2_HD void insertion(int a, int b) const {

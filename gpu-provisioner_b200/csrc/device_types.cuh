@@ -73,9 +73,12 @@ __device__ __forceinline__ EReq pod_req(const KeyTab& kt, const PodRef& p, int k
 
 template <int G>
 __device__ __forceinline__ unsigned group_mask() {
-  if (G == 32) return 0xffffffffu;
-  unsigned lane = threadIdx.x & 31u;
-  return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+  if constexpr (G == 32) {
+    return 0xffffffffu;
+  } else {
+    unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~(unsigned)(G - 1));
+  }
 }
 
 // NodeClaim.CanAdd for one (state, pod) pair, cooperatively by a group of G lanes

@@ -28,6 +28,7 @@ struct PackArrays {
   int32_t* c_tmpl;     // [Ptot]
   int32_t* c_npods;    // [Ptot]    len(Pods)
   int32_t* ord;        // [Ptot]    s.newNodeClaims order, local claim ids
+  int32_t* ord_key;    // [Ptot]    len(Pods) by position (spill area of the shared-memory copy)
   // existing nodes (mutable copies), resource/key-major with stride Etot
   int32_t Etot;
   int64_t* n_avail;    // [R*Etot]

@@ -19,6 +19,7 @@
 namespace b200 {
 
 constexpr int PACK_THREADS = 512;
+constexpr int ORD_SMEM_CAP = 8192;  // NodeClaims whose order / count-by-position arrays stay in shared memory
 constexpr int KIND_INC = 1, KIND_APPEND = 2;
 constexpr int MODE_NONE = 0, MODE_ROT_INC = 1, MODE_ROT_APPEND = 2;
 
@@ -29,17 +30,20 @@ struct PackShared {
   int64_t zero_b[MAXB];
   int32_t p_gt[MAXB], p_lt[MAXB];
   uint64_t p_flags, p_tol;
-  int32_t pod, best, n_claims, head, len, seq, dirty_pos, dirty_kind, mode, rot_from, rot_to, rot_x;
+  int32_t pod, best, n_claims, head, len, seq, dirty_pos, dirty_kind, mode, rot_from, rot_to, rot_x, rot_k, ord_global,
+      n_pushed;
   unsigned long long evals;
 };
 
 __host__ __device__ inline size_t pack_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t pack_smem_bytes(int G, int W, int n_rows, int n_dv, int tables_in_smem, size_t* scratch_off,
-                                                  size_t* tables_off) {
+                                                  size_t* tables_off, size_t* ord_off = nullptr) {
   size_t o = pack_align16(sizeof(PackShared));
   if (scratch_off) *scratch_off = o;
   o += pack_align16(sizeof(EvalScratch) * (PACK_THREADS / G));
+  if (ord_off) *ord_off = o;
+  o += pack_align16((size_t)ORD_SMEM_CAP * 8);  // ord[] + key[]
   if (tables_off) *tables_off = o;
   if (tables_in_smem) o += pack_align16((size_t)n_rows * W * 8 + (size_t)n_dv * 8);
   return o;
@@ -67,9 +71,11 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = PACK_THREADS / G;
   PackShared& S = *reinterpret_cast<PackShared*>(smem);
-  size_t scratch_off, tables_off;
-  pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, tables_in_smem, &scratch_off, &tables_off);
+  size_t scratch_off, tables_off, ord_off;
+  pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, tables_in_smem, &scratch_off, &tables_off, &ord_off);
   EvalScratch* scratch = reinterpret_cast<EvalScratch*>(smem + scratch_off);
+  int32_t* s_ord = reinterpret_cast<int32_t*>(smem + ord_off);
+  int32_t* s_key = s_ord + ORD_SMEM_CAP;
   const int tid = threadIdx.x, g = tid / G, gl = tid & (G - 1);
   const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words, P = pods.P;
 
@@ -85,7 +91,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
   int64_t* c_lt = A.c_lt + (size_t)base * NB;
   int32_t* c_tmpl = A.c_tmpl + base;
   int32_t* c_npods = A.c_npods + base;
-  int32_t* ord = A.ord + base;
+  int32_t* g_ord = A.ord + base;      // the order array's home (and its spill area past ORD_SMEM_CAP claims)
+  int32_t* g_key = A.ord_key + base;
   int32_t* queue = A.queue + base;
 
   {
@@ -104,6 +111,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
   if (tid < MAXB) S.zero_b[tid] = 0;
   if (tid == 0) {
     S.n_claims = 0; S.head = 0; S.len = n_pods; S.seq = 0; S.dirty_pos = -1; S.dirty_kind = 0; S.evals = 0;
+    S.ord_global = 0; S.n_pushed = 0;
   }
   unsigned long long my_evals = 0;
   __syncthreads();
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
       int p = -1;
       if (S.len > 0) {
         int cand = queue[S.head];
-        if (A.lastlen[cand] != S.len) {
+        if (S.n_pushed == 0 || A.lastlen[cand] != S.len) {  // lastLen is zero until a pod has been pushed back
           p = cand;
           S.head = S.head + 1 == n_pods ? 0 : S.head + 1;
           S.len--;
@@ -175,11 +183,20 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
     }
 
     // ---- sort.Slice(newNodeClaims, len(Pods) ascending) with Go's exact tie order ----
+    // the order (claim ids) and the pod counts by position live in shared memory up to ORD_SMEM_CAP claims
+    if (!S.ord_global && S.n_claims >= ORD_SMEM_CAP) {
+      for (int i = tid; i < S.n_claims; i += PACK_THREADS) { g_ord[i] = s_ord[i]; g_key[i] = s_key[i]; }
+      __syncthreads();
+      if (tid == 0) S.ord_global = 1;
+      __syncthreads();
+    }
+    int32_t* ord = S.ord_global ? g_ord : s_ord;
+    int32_t* key = S.ord_global ? g_key : s_key;
     if (tid == 0) {
       int mode = MODE_NONE;
       const int n = S.n_claims;
       if (S.dirty_pos >= 0 && n > 1) {
-        GoSort gs{ord, c_npods};
+        GoSort gs{ord, key};
         const int pos = S.dirty_pos;
         bool sorted = S.dirty_kind == KIND_INC ? (pos == n - 1 || !gs.less(pos + 1, pos)) : !gs.less(n - 1, n - 2);
         if (!sorted) {
@@ -188,12 +205,12 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
           if (n >= 50 && hint == 1) {
             // pdqsort takes partialInsertionSort: the single displaced element is re-inserted next to
             // its equals (see DESIGN.md "tie order"); done by all threads as a rotate
-            const int cx = c_npods[ord[pos]];
+            const int cx = key[pos];
             if (S.dirty_kind == KIND_INC) {
               int lo = pos + 1, hi = n;  // first index > pos whose count >= cx
               while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if (c_npods[ord[mid]] < cx) lo = mid + 1; else hi = mid;
+                if (key[mid] < cx) lo = mid + 1; else hi = mid;
               }
               mode = MODE_ROT_INC;
               S.rot_from = pos;
@@ -202,13 +219,14 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
               int lo = 0, hi = n - 1;  // first index whose count > cx
               while (lo < hi) {
                 int mid = (lo + hi) >> 1;
-                if (c_npods[ord[mid]] <= cx) lo = mid + 1; else hi = mid;
+                if (key[mid] <= cx) lo = mid + 1; else hi = mid;
               }
               mode = MODE_ROT_APPEND;
               S.rot_from = n - 1;
               S.rot_to = lo;
             }
             S.rot_x = ord[pos];
+            S.rot_k = cx;
           } else {
             gs.sort(n);
           }
@@ -218,27 +236,29 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
       S.mode = mode;
     }
     __syncthreads();
-    if (S.mode == MODE_ROT_INC) {  // ord[from+1 .. to] move one slot left, X lands at `to`
+    if (S.mode == MODE_ROT_INC) {  // [from+1 .. to] move one slot left, X lands at `to`
       const int from = S.rot_from, to = S.rot_to;
       for (int cb = from + 1; cb <= to; cb += PACK_THREADS) {
         int i = cb + tid;
-        int v = i <= to ? ord[i] : 0;
+        int v = 0, kv = 0;
+        if (i <= to) { v = ord[i]; kv = key[i]; }
         __syncthreads();
-        if (i <= to) ord[i - 1] = v;
+        if (i <= to) { ord[i - 1] = v; key[i - 1] = kv; }
         __syncthreads();
       }
-      if (tid == 0) ord[to] = S.rot_x;
+      if (tid == 0) { ord[to] = S.rot_x; key[to] = S.rot_k; }
       __syncthreads();
-    } else if (S.mode == MODE_ROT_APPEND) {  // ord[to .. from-1] move one slot right, X lands at `to`
+    } else if (S.mode == MODE_ROT_APPEND) {  // [to .. from-1] move one slot right, X lands at `to`
       const int from = S.rot_from, to = S.rot_to;
       for (int ce = from - 1; ce >= to; ce -= PACK_THREADS) {
         int i = ce - tid;
-        int v = i >= to ? ord[i] : 0;
+        int v = 0, kv = 0;
+        if (i >= to) { v = ord[i]; kv = key[i]; }
         __syncthreads();
-        if (i >= to) ord[i + 1] = v;
+        if (i >= to) { ord[i + 1] = v; key[i + 1] = kv; }
         __syncthreads();
       }
-      if (tid == 0) ord[to] = S.rot_x;
+      if (tid == 0) { ord[to] = S.rot_x; key[to] = S.rot_k; }
       __syncthreads();
     }
 
@@ -285,6 +305,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
           for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += S.p_req[r];
           if (gl == 0) {
             c_npods[c]++;
+            key[found]++;
             A.pod_kind[p] = B200S_PLACE_CLAIM;
             A.pod_index[p] = c;
             A.pod_seq[p] = S.seq++;
@@ -314,6 +335,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
           c_tmpl[c] = t;
           c_npods[c] = 1;
           ord[n] = c;
+          key[n] = 1;
           S.n_claims = n + 1;
           S.dirty_pos = n;
           S.dirty_kind = KIND_APPEND;
@@ -327,6 +349,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
       if (tail >= n_pods) tail -= n_pods;
       queue[tail] = p;
       S.len++;
+      S.n_pushed++;
       A.lastlen[p] = S.len;
       A.pod_kind[p] = B200S_PLACE_UNSCHEDULED;
       A.pod_index[p] = -1;
@@ -334,6 +357,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
     __syncthreads();
   }
 
+  if (!S.ord_global)
+    for (int i = tid; i < S.n_claims; i += PACK_THREADS) g_ord[i] = s_ord[i];
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
   if ((tid & 31) == 0 && my_evals) atomicAdd(&S.evals, my_evals);
   __syncthreads();
@@ -371,7 +396,7 @@ __global__ void __launch_bounds__(256) pack_finalize_kernel(KeyTab kt, PodsDev p
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_pods; i += blockDim.x) {
-    int p = A.queue[base + i];  // the ring still holds exactly this problem's pods
+    int p = base + i;  // pods of a problem are a contiguous index range (the queue ring is NOT a permutation any more)
     if (A.pod_kind[p] == B200S_PLACE_CLAIM) A.pod_index[p] = out.pos_of_claim[base + A.pod_index[p]];
   }
   (void)pods;

@@ -181,7 +181,9 @@ int emul_fit_matrix(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm,
 }
 
 int emul_go_sort(const int32_t* cnt, int32_t n, int32_t* ord) {
-  GoSort gs{ord, cnt};
+  std::vector<int32_t> key(n);
+  for (int i = 0; i < n; i++) key[i] = cnt[ord[i]];
+  GoSort gs{ord, key.data()};
   gs.sort(n);
   return 0;
 }
@@ -253,7 +255,12 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
       placed = true;
     }
     if (placed) continue;
-    if (!ord.empty()) { GoSort gs{ord.data(), npods.data()}; gs.sort((int)ord.size()); }
+    if (!ord.empty()) {
+      std::vector<int32_t> key(ord.size());
+      for (size_t i = 0; i < ord.size(); i++) key[i] = npods[ord[i]];
+      GoSort gs{ord.data(), key.data()};
+      gs.sort((int)ord.size());
+    }
     for (size_t i = 0; i < ord.size() && !placed; i++) {  // addToInflightNode
       Claim& c = claims[ord[i]];
       uint8_t code; ReqRow merged;
