@@ -83,10 +83,9 @@ class ClockSampler:
 def algorithmic_bytes_fit(enc) -> int:
     """Compulsory traffic of one dense fit-matrix launch with this repo's layout (DESIGN.md "Algorithmic bytes"):
     every pod row read once, every output written once, catalog tables read once."""
-    c = enc.catalog.contents
-    pod_row = enc.R * 8 + enc.K * 8 + 8 + 8 + enc.NB * 8          # requests, key masks, flags, tolerated, bounds
-    out_row = enc.W * 8 + 4 + enc.T                                # mask, template, per-template codes
-    tables = c.n_rows * enc.W * 8 + c.n_dv * 8
+    pod_row = 4 + 4                                                # signature id + request-class id
+    out_row = enc.W * 8 + 4 + enc.T                                # mask, first feasible template, per-template codes
+    tables = (enc.NS * 2 + enc.NQ) * enc.T * enc.W * 8 + enc.NS * enc.T  # class rows C, O, F + status, read once
     return enc.P * (pod_row + out_row) + tables
 
 
@@ -218,7 +217,7 @@ def main():
     peak, peak_src = peaks()
     ab = algorithmic_bytes_fit(enc)
     achieved = ab / (ms_fit * 1e-3) / 1e9
-    h2d = enc.P * (enc.R * 8 + enc.K * 8 + 8 + 8 + enc.NB * 8 + 8 + 16)
+    h2d = enc.P * (4 + 4 + 8 + 16) + enc.NS * (enc.K * 8 + 16 + enc.NB * 8) + enc.NQ * enc.R * 8
     d2h = enc.P * (12 + enc.T) + raw.n_claims * (8 + enc.R * 8 + enc.W * 8 + enc.K * 8 + 8 + enc.NB * 16 + 16)
 
     # CPU baseline: a bounded sample — one dense pass + one Solve of this config, already timed above on this host

@@ -53,10 +53,11 @@ class Templates(C.Structure):
 class PodsSoA(C.Structure):
     _fields_ = [
         ("n_pods", C.c_int32), ("n_res", C.c_int32), ("n_keys", C.c_int32), ("n_bounded", C.c_int32),
-        ("res_cpu", C.c_int32), ("res_memory", C.c_int32),
-        ("requests", _P(C.c_int64)), ("req_mask", _P(C.c_uint64)), ("req_flags", _P(C.c_uint64)),
-        ("req_gt", _P(C.c_int32)), ("req_lt", _P(C.c_int32)), ("tolerated", _P(C.c_uint64)), ("ts", _P(C.c_int64)),
-        ("uid_hi", _P(C.c_uint64)), ("uid_lo", _P(C.c_uint64)),
+        ("res_cpu", C.c_int32), ("res_memory", C.c_int32), ("n_sigs", C.c_int32), ("n_reqcls", C.c_int32),
+        ("sig_id", _P(C.c_int32)), ("req_id", _P(C.c_int32)), ("ts", _P(C.c_int64)), ("uid_hi", _P(C.c_uint64)),
+        ("uid_lo", _P(C.c_uint64)),
+        ("sig_mask", _P(C.c_uint64)), ("sig_flags", _P(C.c_uint64)), ("sig_gt", _P(C.c_int32)), ("sig_lt", _P(C.c_int32)),
+        ("sig_tolerated", _P(C.c_uint64)), ("rq_requests", _P(C.c_int64)),
     ]
 
 
@@ -145,6 +146,7 @@ def lib():
                                            _P(C.c_int64)]
     L.b200s_resident_fetch_solve.argtypes = [C.c_void_p, C.c_void_p, _P(Result)]
     L.b200s_resident_last_launches.argtypes = [C.c_void_p]
+    L.b200s_resident_pack_profile.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint64)]
     L.b200s_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
                                       _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]
     _lib = L
@@ -187,6 +189,8 @@ class Encoded:
         self.S, self.W, self.R, self.K, self.NB = c.n_skus, c.n_words, c.n_res, c.n_keys, c.n_bounded
         self.T = self.templates.contents.n_templates
         self.P = self.pods.contents.n_pods
+        self.NS = self.pods.contents.n_sigs
+        self.NQ = self.pods.contents.n_reqcls
         self.E = self.nodes.contents.n_nodes
         self.key_model = [L.b200s_encoded_key_model_id(h, k) for k in range(self.K)]
         self.bounded_key = [c.bounded_key[b] for b in range(self.NB)]
@@ -386,6 +390,12 @@ class Resident:
 
     def launches(self) -> int:
         return self.ctx.L.b200s_resident_last_launches(self.h)
+
+    def pack_profile(self):
+        out = (C.c_uint64 * 8)()
+        self.ctx._check(self.ctx.L.b200s_resident_pack_profile(self.ctx.h, self.h, out))
+        names = ["start", "nodes", "scan", "commit", "normalise", "-", "--", "steps"]
+        return dict(zip(names, [int(x) for x in out]))
 
     def fetch_fit(self) -> FitOut:
         e = self.enc

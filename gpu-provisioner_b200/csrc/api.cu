@@ -84,6 +84,12 @@ struct b200s_resident {
   uint64_t* n_rmask0 = nullptr;
   uint64_t* n_rflags0 = nullptr;
   uint64_t* n_taints = nullptr;
+  // class tables (per signature x template, per request vector x template)
+  uint8_t* sg_status = nullptr;
+  uint64_t* sgC = nullptr;
+  uint64_t* sgO = nullptr;
+  uint64_t* rqF = nullptr;
+  int32_t* tm_count = nullptr;
   // stage A
   int32_t* a_tmpl = nullptr;
   uint64_t* a_mask = nullptr;
@@ -140,6 +146,7 @@ int check_shapes(b200s_ctx* ctx, const Catalog* cat, const b200s_pods_soa_t* pod
   if (!pods) return fail(ctx, B200S_EINVAL, "pods is null");
   if (pods->n_res != cat->R || pods->n_keys != cat->K || pods->n_bounded != cat->NB)
     return fail(ctx, B200S_EINVAL, "pods SoA does not match the catalog's R/K/NB");
+  if (pods->n_pods > 0 && (pods->n_sigs <= 0 || pods->n_reqcls <= 0)) return fail(ctx, B200S_EINVAL, "pods without class tables");
   if (pods->res_cpu < 0 || pods->res_cpu >= cat->R || pods->res_memory < 0 || pods->res_memory >= cat->R)
     return fail(ctx, B200S_EINVAL, "pods res_cpu/res_memory out of range");
   if (nodes && nodes->n_nodes > 0 && (nodes->n_res != cat->R || nodes->n_keys != cat->K))
@@ -182,41 +189,57 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->Ppad = ffd_padded(r->P);
   const size_t P = (size_t)std::max<long long>(Ptot, 1), E = (size_t)std::max<long long>(Etot, 1);
 
-  // ---- pods (concatenated, resource/key-major over the total) ----
-  int64_t* d_req = r->dalloc<int64_t>((size_t)R * P);
-  uint64_t* d_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * P);
-  uint64_t* d_rflags = r->dalloc<uint64_t>(P);
-  int32_t* d_gt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * P);
-  int32_t* d_lt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * P);
-  uint64_t* d_tol = r->dalloc<uint64_t>(P);
+  // ---- pods: per-pod ids / tie-break keys concatenated; class tables concatenated with id offsets ----
+  long long NStot = 0, NQtot = 0;
+  for (int b = 0; b < n_problems; b++) { NStot += pods_in[b]->n_sigs; NQtot += pods_in[b]->n_reqcls; }
+  const size_t NS = (size_t)std::max<long long>(NStot, 1), NQ = (size_t)std::max<long long>(NQtot, 1);
+  int32_t* d_sig = r->dalloc<int32_t>(P);
+  int32_t* d_rq = r->dalloc<int32_t>(P);
   int64_t* d_ts = r->dalloc<int64_t>(P);
   uint64_t* d_uhi = r->dalloc<uint64_t>(P);
   uint64_t* d_ulo = r->dalloc<uint64_t>(P);
-  if (!d_req || !d_rmask || !d_rflags || !d_gt || !d_lt || !d_tol || !d_ts || !d_uhi || !d_ulo)
+  uint64_t* d_smask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * NS);
+  uint64_t* d_sflags = r->dalloc<uint64_t>(NS);
+  int32_t* d_sgt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * NS);
+  int32_t* d_slt = r->dalloc<int32_t>((size_t)std::max(NB, 1) * NS);
+  uint64_t* d_stol = r->dalloc<uint64_t>(NS);
+  int64_t* d_rq_req = r->dalloc<int64_t>((size_t)R * NQ);
+  if (!d_sig || !d_rq || !d_ts || !d_uhi || !d_ulo || !d_smask || !d_sflags || !d_sgt || !d_slt || !d_stol || !d_rq_req)
     return fail(ctx, B200S_ENOMEM, "device allocation (pods)");
   {
-    size_t off = 0;
+    size_t off = 0, soff = 0, qoff = 0;
+    std::vector<int32_t> tmp;
     for (int b = 0; b < n_problems; b++) {
       const b200s_pods_soa_t* ps = pods_in[b];
-      const size_t n = (size_t)ps->n_pods;
+      const size_t n = (size_t)ps->n_pods, ns = (size_t)ps->n_sigs, nq = (size_t)ps->n_reqcls;
       int rc = 0;
-      for (int x = 0; x < R && !rc; x++) rc = upload(ctx, d_req + (size_t)x * Ptot + off, ps->requests + (size_t)x * n, n);
-      for (int x = 0; x < K && !rc; x++) rc = upload(ctx, d_rmask + (size_t)x * Ptot + off, ps->req_mask + (size_t)x * n, n);
-      for (int x = 0; x < NB && !rc; x++) {
-        rc = upload(ctx, d_gt + (size_t)x * Ptot + off, ps->req_gt + (size_t)x * n, n);
-        if (!rc) rc = upload(ctx, d_lt + (size_t)x * Ptot + off, ps->req_lt + (size_t)x * n, n);
+      if (n_problems == 1) {
+        rc = upload(ctx, d_sig, ps->sig_id, n);
+        if (!rc) rc = upload(ctx, d_rq, ps->req_id, n);
+      } else {  // class ids of problem b are shifted by the classes of the problems before it
+        tmp.resize(2 * n);
+        for (size_t i = 0; i < n; i++) { tmp[i] = ps->sig_id[i] + (int32_t)soff; tmp[n + i] = ps->req_id[i] + (int32_t)qoff; }
+        rc = upload(ctx, d_sig + off, tmp.data(), n);
+        if (!rc) rc = upload(ctx, d_rq + off, tmp.data() + n, n);
+        if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "sync (ids)");
       }
-      if (!rc) rc = upload(ctx, d_rflags + off, ps->req_flags, n);
-      if (!rc) rc = upload(ctx, d_tol + off, ps->tolerated, n);
       if (!rc) rc = upload(ctx, d_ts + off, ps->ts, n);
       if (!rc) rc = upload(ctx, d_uhi + off, ps->uid_hi, n);
       if (!rc) rc = upload(ctx, d_ulo + off, ps->uid_lo, n);
+      for (int x = 0; x < K && !rc; x++) rc = upload(ctx, d_smask + (size_t)x * NStot + soff, ps->sig_mask + (size_t)x * ns, ns);
+      for (int x = 0; x < NB && !rc; x++) {
+        rc = upload(ctx, d_sgt + (size_t)x * NStot + soff, ps->sig_gt + (size_t)x * ns, ns);
+        if (!rc) rc = upload(ctx, d_slt + (size_t)x * NStot + soff, ps->sig_lt + (size_t)x * ns, ns);
+      }
+      if (!rc) rc = upload(ctx, d_sflags + soff, ps->sig_flags, ns);
+      if (!rc) rc = upload(ctx, d_stol + soff, ps->sig_tolerated, ns);
+      for (int x = 0; x < R && !rc; x++) rc = upload(ctx, d_rq_req + (size_t)x * NQtot + qoff, ps->rq_requests + (size_t)x * nq, nq);
       if (rc) return rc;
-      off += n;
+      off += n; soff += ns; qoff += nq;
     }
   }
-  r->pods = PodsDev{(int32_t)Ptot, pods_in[0]->res_cpu, pods_in[0]->res_memory, d_req, d_rmask, d_rflags, d_gt, d_lt,
-                    d_tol, d_ts, d_uhi, d_ulo};
+  r->pods = PodsDev{(int32_t)Ptot, (int32_t)NStot, (int32_t)NQtot, pods_in[0]->res_cpu, pods_in[0]->res_memory, d_sig, d_rq,
+                    d_ts, d_uhi, d_ulo, d_smask, d_sflags, d_sgt, d_slt, d_stol, d_rq_req};
 
   // ---- problems, segment ids ----
   r->problems_host.resize(n_problems);
@@ -231,6 +254,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
       pb.node_begin = eo;
       pb.node_end = eo + ((nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
       pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0;
+      for (int i = 0; i < 8; i++) pb.prof[i] = 0;
       if (n_problems > 1)
         for (int i = pb.pod_begin; i < pb.pod_end; i++) { seg[i] = b; rowp[i] = b; }
       po = pb.pod_end;
@@ -298,6 +322,12 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   }
 
   // ---- stage A outputs, sort, pack state, outputs ----
+  const size_t T1 = (size_t)std::max(T, 1);
+  r->sg_status = r->dalloc<uint8_t>(NS * T1);
+  r->sgC = r->dalloc<uint64_t>(NS * T1 * W);
+  r->sgO = r->dalloc<uint64_t>(NS * T1 * W);
+  r->rqF = r->dalloc<uint64_t>(NQ * T1 * W);
+  r->tm_count = r->dalloc<int32_t>(MAXT);
   r->a_tmpl = r->dalloc<int32_t>(P);
   r->a_mask = r->dalloc<uint64_t>(P * W);
   r->a_code = r->dalloc<uint8_t>(P * (size_t)std::max(T, 1));
@@ -305,14 +335,17 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   PackArrays& A = r->arr;
   A.c_mask = r->dalloc<uint64_t>(P * W);
   A.c_req = r->dalloc<int64_t>(P * R);
+  A.c_hi = r->dalloc<int64_t>(P * R);
   A.c_rmask = r->dalloc<uint64_t>(P * (size_t)std::max(K, 1));
   A.c_rflags = r->dalloc<uint64_t>(P);
   A.c_gt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
   A.c_lt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
   A.c_tmpl = r->dalloc<int32_t>(P);
   A.c_npods = r->dalloc<int32_t>(P);
+  A.c_nopt = r->dalloc<int32_t>(P);
   A.ord = r->dalloc<int32_t>(P);
   A.ord_key = r->dalloc<int32_t>(P);
+  A.ord_snap = r->dalloc<int32_t>(P);
   A.Etot = (int32_t)Etot;
   A.n_avail = r->dalloc<int64_t>((size_t)R * E);
   A.n_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * E);
@@ -339,8 +372,8 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sel_sku = r->dalloc<int32_t>(P);
   r->sel_price = r->dalloc<uint64_t>(P);
   r->sel_nopt = r->dalloc<int32_t>(P);
-  void* must[] = {r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
-                  A.c_tmpl, A.c_npods, A.ord, A.ord_key, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
+  void* must[] = {r->sg_status, r->sgC, r->sgO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
+                  A.c_tmpl, A.c_npods, A.c_nopt, A.ord, A.ord_key, A.ord_snap, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
                   A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
                   r->sel_sku, r->sel_price, r->sel_nopt};
   for (void* p : must)
@@ -350,15 +383,18 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   return B200S_OK;
 }
 
-// stage A: template pre-filter + dense fit matrix
+// stage A: template pre-filter, class tables, dense fit matrix
 int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, cudaMemsetAsync(r->a_evals, 0, sizeof(unsigned long long), ctx->stream), "memset");
   CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, ctx->stream),
            "template_prefilter launch");
-  CUDA_TRY(ctx, launch_fit_matrix(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->a_tmpl, r->a_mask, r->a_code,
-                                  r->a_evals, ctx->n_sm, ctx->smem_limit, ctx->stream),
-           "fit_matrix launch");
-  *launches += r->P > 0 ? 2 : 1;
+  CUDA_TRY(ctx, launch_class_tables(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->sg_status, r->sgC, r->sgO,
+                                    r->rqF, r->tm_count, ctx->n_sm, ctx->smem_limit, ctx->stream),
+           "class_tables launch");
+  CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->rqF, r->tm_count, r->a_tmpl,
+                                 r->a_mask, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
+           "fit_dense launch");
+  *launches += 1 + (r->T > 0 ? 1 : 0) + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);
   return 0;
 }
 
@@ -571,7 +607,15 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
     kt.bslot[c->bounded_key[b]] = (int8_t)b;
   }
   for (int r = 0; r < MAXR; r++) { kt.res_nd[r] = 0; kt.res_dv0[r] = 0; kt.res_row0[r] = 0; }
-  for (int r = 0; r < c->n_res; r++) { kt.res_nd[r] = c->res_nd[r]; kt.res_dv0[r] = c->res_dv0[r]; kt.res_row0[r] = c->res_row0[r]; }
+  kt.max_p2 = 0;
+  for (int r = 0; r < MAXR; r++) kt.res_p2[r] = 0;
+  for (int r = 0; r < c->n_res; r++) {
+    kt.res_nd[r] = c->res_nd[r]; kt.res_dv0[r] = c->res_dv0[r]; kt.res_row0[r] = c->res_row0[r];
+    int p2 = 0;
+    for (int x = 1; x <= c->res_nd[r]; x <<= 1) p2 = x;
+    kt.res_p2[r] = p2;
+    kt.max_p2 = std::max(kt.max_p2, p2);
+  }
   kt.zc_row0 = c->zc_row0; kt.row_nonneg = c->row_nonneg; kt.n_rows = c->n_rows; kt.n_dv = c->n_dv;
   kt.val_int = (const int64_t*)put(c->val_int, (size_t)std::max(K, 1) * 64 * 8);
   kt.rows = (const uint64_t*)put(c->rows, (size_t)c->n_rows * W * 8);
@@ -642,6 +686,17 @@ int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_resu
 }
 
 int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }
+
+/* diagnostic: SM cycles thread 0 of problem 0's pack CTA spent per phase in the last solve
+ * (step start, existing nodes, in-flight scan, commit + next pod, order normalisation) and the step count */
+int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[8]) {
+  if (!ctx || !r || !out || !r->solve_done) return B200S_ESTATE;
+  CUDA_TRY(ctx, cudaMemcpyAsync(r->problems_host.data(), r->problems, sizeof(PackProblem) * r->n_problems,
+                                cudaMemcpyDeviceToHost, ctx->stream), "D2H problems");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+  for (int i = 0; i < 8; i++) out[i] = r->problems_host[0].prof[i];
+  return B200S_OK;
+}
 
 int b200s_fit_matrix(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods, const b200s_templates_t* templates,
                      int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out) {

@@ -45,6 +45,8 @@ struct KeyTab {
   const uint64_t* rows;    // [n_rows*W]
   const int64_t* res_dv;   // ascending distinct allocatable values
   int32_t res_nd[MAXR], res_dv0[MAXR], res_row0[MAXR];
+  int32_t res_p2[MAXR];    // largest power of two <= res_nd[r] (0 when the resource has no values)
+  int32_t max_p2;          // max over resources
   int32_t key_row0[MAXK];
   int32_t zc_row0, row_nonneg, n_rows, n_dv;
   const uint64_t* price;   // [n_zc*S]
@@ -195,49 +197,72 @@ struct WordEval {
   uint64_t compat, fits, off;
 };
 
-B2_HD WordEval eval_word(const KeyTab& kt, const EvalScratch& sc, int w) {
+// fits (nodeclaim.go:447-449 -> resources.go:232-245)
+B2_HD uint64_t eval_fits_word(const KeyTab& kt, const int32_t* fit_row, int w) {
   const int W = kt.n_words;
   const uint64_t* rows = kt.rows;
-  WordEval e;
-  // fits (nodeclaim.go:447-449 -> resources.go:232-245)
   uint64_t fits = rows[(size_t)kt.row_nonneg * W + w];
   for (int r = 0; r < kt.n_res; r++) {
-    int row = sc.fit_row[r];
+    int row = fit_row[r];
     fits &= row < 0 ? 0ull : rows[(size_t)row * W + w];
   }
-  e.fits = fits;
-  // compatible (nodeclaim.go:443-445 -> requirements.go:248-268 -> requirement.go:197-231)
+  return fits;
+}
+
+// SKUs whose requirement on key k intersects a requirement that admits `allowed` (requirement.go:197-231 for a
+// concrete SKU set), or that do not define k, or — when the requirement is NotIn/DoesNotExist — that say
+// DoesNotExist (requirements.go:253-258)
+B2_HD uint64_t eval_key_word(const KeyTab& kt, int k, uint64_t allowed, bool forgive, int w) {
+  const int W = kt.n_words;
+  const uint64_t* rows = kt.rows;
+  int row0 = kt.key_row0[k], nv = kt.nvals[k];
+  uint64_t acc = rows[(size_t)(row0 + nv) * W + w];
+  if (forgive) acc |= rows[(size_t)(row0 + nv + 1) * W + w];
+  while (allowed) {
+    int v = ctz64(allowed);
+    allowed &= allowed - 1;
+    acc |= rows[(size_t)(row0 + v) * W + w];
+  }
+  return acc;
+}
+
+// compatible (nodeclaim.go:443-445 -> requirements.go:248-268)
+B2_HD uint64_t eval_compat_word(const KeyTab& kt, const EvalScratch& sc, int w) {
   uint64_t compat = ~0ull;
   uint32_t def = sc.defined;
   while (def) {
     int k = ctz32(def);
     def &= def - 1;
-    int row0 = kt.key_row0[k], nv = kt.nvals[k];
-    uint64_t acc = rows[(size_t)(row0 + nv) * W + w];                            // SKUs that do not define k
-    if ((sc.forgive >> k) & 1u) acc |= rows[(size_t)(row0 + nv + 1) * W + w];    // both sides NotIn/DoesNotExist
-    uint64_t a = sc.allowed[k];
-    while (a) {
-      int v = ctz64(a);
-      a &= a - 1;
-      acc |= rows[(size_t)(row0 + v) * W + w];
-    }
-    compat &= acc;
+    compat &= eval_key_word(kt, k, sc.allowed[k], (sc.forgive >> k) & 1u, w);
   }
-  e.compat = compat;
-  // offering scan (nodeclaim.go:400-406)
+  return compat;
+}
+
+// offering scan (nodeclaim.go:400-406): some Available offering whose zone and capacity type are admitted
+B2_HD uint64_t eval_off_word(const KeyTab& kt, uint64_t zone_allowed, uint64_t ct_allowed, int w) {
+  const int W = kt.n_words;
+  const uint64_t* rows = kt.rows;
   uint64_t off = 0;
-  uint64_t za = sc.zone_allowed & (kt.n_zones >= 64 ? ~0ull : ((1ull << kt.n_zones) - 1ull));
+  uint64_t za = zone_allowed & (kt.n_zones >= 64 ? ~0ull : ((1ull << kt.n_zones) - 1ull));
+  const uint64_t cmask = kt.n_cts >= 64 ? ~0ull : ((1ull << kt.n_cts) - 1ull);
   while (za) {
     int z = ctz64(za);
     za &= za - 1;
-    uint64_t ca = sc.ct_allowed & (kt.n_cts >= 64 ? ~0ull : ((1ull << kt.n_cts) - 1ull));
+    uint64_t ca = ct_allowed & cmask;
     while (ca) {
       int c = ctz64(ca);
       ca &= ca - 1;
       off |= rows[(size_t)(kt.zc_row0 + z * kt.n_cts + c) * W + w];
     }
   }
-  e.off = off;
+  return off;
+}
+
+B2_HD WordEval eval_word(const KeyTab& kt, const EvalScratch& sc, int w) {
+  WordEval e;
+  e.fits = eval_fits_word(kt, sc.fit_row, w);
+  e.compat = eval_compat_word(kt, sc, w);
+  e.off = eval_off_word(kt, sc.zone_allowed, sc.ct_allowed, w);
   return e;
 }
 

@@ -7,18 +7,22 @@
 
 namespace b200 {
 
+// Dictionary-encoded pods (include/b200sched.h b200s_pods_soa_t): two class ids per pod, class tables
+// for requirement signatures (key-major over NS) and request vectors (resource-major over NQ).
 struct PodsDev {
-  int32_t P;
+  int32_t P, NS, NQ;
   int32_t res_cpu, res_mem;
-  const int64_t* req;      // [R*P]
-  const uint64_t* rmask;   // [K*P]
-  const uint64_t* rflags;  // [P]
-  const int32_t* gt;       // [NB*P]
-  const int32_t* lt;       // [NB*P]
-  const uint64_t* tol;     // [P]
-  const int64_t* ts;
+  const int32_t* sig_id;    // [P]
+  const int32_t* req_id;    // [P]
+  const int64_t* ts;        // [P]
   const uint64_t* uid_hi;
   const uint64_t* uid_lo;
+  const uint64_t* sig_mask;  // [K*NS]
+  const uint64_t* sig_flags; // [NS]
+  const int32_t* sig_gt;     // [NB*NS]
+  const int32_t* sig_lt;     // [NB*NS]
+  const uint64_t* sig_tol;   // [NS]
+  const int64_t* rq_req;     // [R*NQ]
 };
 
 // NodeClaimTemplates, weight order; lives in global memory, copied to shared memory by each CTA.
@@ -179,6 +183,296 @@ __device__ __forceinline__ void group_store_merged(const KeyTab& kt, const State
   flo = __reduce_or_sync(gm, flo);
   fhi = __reduce_or_sync(gm, fhi);
   if (gl == 0) *dflags = (uint64_t)flo | ((uint64_t)fhi << 32);
+}
+
+// Requirement part of CanAdd for a (template, signature) pair, without resources: taints, Compatible, and the
+// two SKU sets the filter loop derives from the merged requirements — C = cand & compatible(merged),
+// O = cand & hasOffering(merged).  The resource side (fits) depends only on the request vector and is
+// tabulated separately, so the filter result of a fresh NodeClaim is C & O & F (nodeclaim.go:392-423).
+template <int G, int WPL>
+__device__ __forceinline__ int group_label_masks(const KeyTab& kt, EvalScratch* sc, const StateRef& st, const PodRef& pd,
+                                                 const uint64_t (&cand)[WPL], uint64_t (&C)[WPL], uint64_t (&O)[WPL]) {
+  const unsigned gm = group_mask<G>();
+  const int gl = threadIdx.x & (G - 1);
+  const int K = kt.n_keys, W = kt.n_words;
+  if (st.taints & ~pd.tol) return ST_TAINT;
+  bool ok = true;
+  uint32_t my_def = 0, my_forg = 0;
+  for (int k = gl; k < K; k += G) {
+    EReq s = state_req(kt, st, k);
+    EReq p = pod_req(kt, pd, k);
+    ok = ok && compatible_key(kt, k, s, p, true);
+    EReq m = add_req(kt, k, s, p);
+    uint64_t a = 0;
+    if (m.f & RF_DEF) {
+      a = allowed_values(kt, k, m);
+      my_def |= 1u << k;
+      if (forgiving(m)) my_forg |= 1u << k;
+    }
+    sc->allowed[k] = a;
+  }
+  unsigned bad = __ballot_sync(gm, !ok) & gm;
+  uint32_t def = __reduce_or_sync(gm, my_def);
+  uint32_t forg = __reduce_or_sync(gm, my_forg);
+  if (bad) return ST_INCOMPATIBLE;
+  __syncwarp(gm);
+  if (gl == 0) {
+    sc->defined = def;
+    sc->forgive = forg;
+  }
+  __syncwarp(gm);
+  const uint64_t za = (kt.key_zone >= 0 && ((def >> kt.key_zone) & 1u)) ? sc->allowed[kt.key_zone] : ~0ull;
+  const uint64_t ca = (kt.key_ct >= 0 && ((def >> kt.key_ct) & 1u)) ? sc->allowed[kt.key_ct] : ~0ull;
+#pragma unroll
+  for (int i = 0; i < WPL; i++) {
+    int w = gl + i * G;
+    C[i] = 0;
+    O[i] = 0;
+    if (w < W) {
+      C[i] = cand[i] & eval_compat_word(kt, *sc, w);
+      O[i] = cand[i] & eval_off_word(kt, za, ca, w);
+    }
+  }
+  __syncwarp(gm);
+  return ST_OK;
+}
+
+// NodeClaim.CanAdd against an IN-FLIGHT claim (scheduler.go:552-584 -> nodeclaim.go:114-163), specialised
+// on the keys the pod defines.  Invariant of a claim's InstanceTypeOptions (by induction over Add): every
+// remaining SKU already satisfies compatible() for the claim's requirement on each key, has an offering the
+// claim's zone / capacity-type requirements admit, and fits the claim's requests.  Adding a pod changes the
+// merged requirement only on keys the pod defines, so only those keys' SKU rows (and the offering rows when
+// the pod touches zone or capacity type) have to be re-evaluated, plus the resource rows for the new total.
+// The diagnostic flags are not needed here: addToInflightNode discards the error.  All lanes run the scalar
+// key algebra redundantly (it is uniform across the group), which avoids any cross-lane traffic.
+template <int G, int WPL>
+__device__ __forceinline__ bool group_inflight(const KeyTab& kt, const StateRef& st, const int64_t* hi, const PodRef& pd,
+                                               uint32_t podkeys, const uint64_t (&cand)[WPL], uint64_t (&out)[WPL],
+                                               int* n_visited) {
+  const unsigned gm = group_mask<G>();
+  const int gl = threadIdx.x & (G - 1);
+  const int R = kt.n_res, W = kt.n_words;
+  *n_visited = 0;
+  if (st.taints & ~pd.tol) return false;  // nodeclaim.go:116
+  // resource rows of the new total (nodeclaim.go:144), one resource per lane, then broadcast.  A total above
+  // the largest Allocatable() the claim's instance types ever had cannot fit (cheap exact reject).
+  int my_row = 0;
+  bool over = false;
+  if (gl < R) {
+    int64_t x = st.req[(size_t)gl * st.rs] + pd.req[(size_t)gl * pd.rs];
+    over = x > hi[gl];
+    if (!over) {
+      int nd = kt.res_nd[gl];
+      int i = fit_rank(kt.res_dv + kt.res_dv0[gl], nd, x);
+      my_row = i < nd ? kt.res_row0[gl] + i : -1;
+      over = my_row < 0;
+    }
+  }
+  if (__ballot_sync(gm, over) & gm) return false;
+  uint64_t keep[WPL];
+  int visited = 0;
+#pragma unroll
+  for (int i = 0; i < WPL; i++) {
+    keep[i] = cand[i];
+    visited += popc64(cand[i]);
+  }
+  for (int r = 0; r < R; r++) {
+    int row = __shfl_sync(gm, my_row, r, G);
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+      int w = gl + i * G;
+      if (w < W) keep[i] &= kt.rows[(size_t)row * W + w];
+    }
+  }
+  // keys the pod defines (nodeclaim.go:125-131): Compatible, merge, and the merged key's SKU rows
+  bool ok = true, touch_off = false;
+  uint32_t keys = podkeys;
+  while (keys) {
+    int k = ctz32(keys);
+    keys &= keys - 1;
+    EReq s = state_req(kt, st, k);
+    EReq p = pod_req(kt, pd, k);
+    ok = ok && compatible_key(kt, k, s, p, true);
+    EReq m = add_req(kt, k, s, p);
+    uint64_t a = allowed_values(kt, k, m);
+    bool fg = forgiving(m);
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+      int w = gl + i * G;
+      if (w < W) keep[i] &= eval_key_word(kt, k, a, fg, w);
+    }
+    touch_off = touch_off || k == kt.key_zone || k == kt.key_ct;
+  }
+  if (!ok) return false;  // incompatible requirements (uniform across the group)
+  if (touch_off) {
+    uint64_t za = ~0ull, ca = ~0ull;
+    if (kt.key_zone >= 0) {
+      EReq m = add_req(kt, kt.key_zone, state_req(kt, st, kt.key_zone), pod_req(kt, pd, kt.key_zone));
+      if (m.f & RF_DEF) za = allowed_values(kt, kt.key_zone, m);
+    }
+    if (kt.key_ct >= 0) {
+      EReq m = add_req(kt, kt.key_ct, state_req(kt, st, kt.key_ct), pod_req(kt, pd, kt.key_ct));
+      if (m.f & RF_DEF) ca = allowed_values(kt, kt.key_ct, m);
+    }
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+      int w = gl + i * G;
+      if (w < W) keep[i] &= eval_off_word(kt, za, ca, w);
+    }
+  }
+  unsigned any = 0;
+#pragma unroll
+  for (int i = 0; i < WPL; i++) {
+    out[i] = keep[i];
+    any |= keep[i] ? 1u : 0u;
+  }
+  any = __reduce_or_sync(gm, any);
+  *n_visited = (int)__reduce_add_sync(gm, (unsigned)visited);
+  return any != 0;
+}
+
+// The same in-flight CanAdd as group_inflight, decided by ONE thread (used by the scan, 512 claims per pass): only
+// the yes/no answer is needed there, so the SKU words are walked until the first one that keeps an instance type.
+constexpr int MAX_FAST_KEYS = 4;  // pod-defined keys handled from registers; more than that re-derives per word
+
+// Returns 0 when CanAdd fails before the filter loop (taints, Compatible), 1 when the filter loop leaves no
+// instance type, 2 when the pod fits.  `ract` has bit r set for the resources the pod actually requests: a
+// resource with a zero request leaves the claim's total unchanged, and the claim's instance types already fit
+// that total, so its row is skipped (exact by the invariant above).  Written branch-free over resources and
+// words so that the independent table lookups overlap.
+__device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef& st, const int64_t* hi, const uint64_t* cmask,
+                                               const PodRef& pd, uint32_t podkeys, uint32_t ract) {
+  const int W = kt.n_words;
+  if (st.taints & ~pd.tol) return 0;
+  // keys the pod defines: Compatible + merged admitted values (nodeclaim.go:125-131)
+  int kk[MAX_FAST_KEYS];
+  uint64_t ka[MAX_FAST_KEYS];
+  uint32_t kfg = 0;
+  int nk = 0;
+  bool touch_off = false;
+  uint64_t za = ~0ull, ca = ~0ull;
+  if (podkeys) {
+    uint32_t keys = podkeys;
+    while (keys) {
+      int k = ctz32(keys);
+      keys &= keys - 1;
+      EReq s = state_req(kt, st, k);
+      EReq p = pod_req(kt, pd, k);
+      if (!compatible_key(kt, k, s, p, true)) return 0;
+      EReq m = add_req(kt, k, s, p);
+      uint64_t a = allowed_values(kt, k, m);
+#pragma unroll
+      for (int j = 0; j < MAX_FAST_KEYS; j++)
+        if (j == nk) { kk[j] = k; ka[j] = a; }
+      if (nk < MAX_FAST_KEYS && forgiving(m)) kfg |= 1u << nk;
+      nk++;
+      touch_off = touch_off || k == kt.key_zone || k == kt.key_ct;
+    }
+    if (touch_off) {
+      if (kt.key_zone >= 0) {
+        EReq m = add_req(kt, kt.key_zone, state_req(kt, st, kt.key_zone), pod_req(kt, pd, kt.key_zone));
+        if (m.f & RF_DEF) za = allowed_values(kt, kt.key_zone, m);
+      }
+      if (kt.key_ct >= 0) {
+        EReq m = add_req(kt, kt.key_ct, state_req(kt, st, kt.key_ct), pod_req(kt, pd, kt.key_ct));
+        if (m.f & RF_DEF) ca = allowed_values(kt, kt.key_ct, m);
+      }
+    }
+  }
+  // new totals, headroom, and the rank of each requested resource (interleaved branch-free lower_bound)
+  int64_t x[MAXR];
+  int lo[MAXR];
+  bool dead = false;
+#pragma unroll
+  for (int r = 0; r < MAXR; r++) {
+    x[r] = 0;
+    lo[r] = 0;
+    if ((ract >> r) & 1u) {
+      x[r] = st.req[(size_t)r * st.rs] + pd.req[(size_t)r * pd.rs];
+      dead = dead || x[r] > hi[r];
+    }
+  }
+  if (dead) return 1;
+  for (int step = kt.max_p2; step > 0; step >>= 1) {
+#pragma unroll
+    for (int r = 0; r < MAXR; r++) {
+      if (((ract >> r) & 1u) && step <= kt.res_p2[r]) {
+        int mid = lo[r] + step;
+        if (mid <= kt.res_nd[r] && kt.res_dv[kt.res_dv0[r] + mid - 1] < x[r]) lo[r] = mid;
+      }
+    }
+  }
+  int rowoff[MAXR];
+#pragma unroll
+  for (int r = 0; r < MAXR; r++) {
+    rowoff[r] = 0;
+    if ((ract >> r) & 1u) {
+      dead = dead || lo[r] >= kt.res_nd[r];
+      rowoff[r] = (kt.res_row0[r] + lo[r]) * W;
+    }
+  }
+  if (dead) return 1;
+  bool any = false;
+  if (!podkeys) {
+#pragma unroll 4
+    for (int w = 0; w < W; w++) {
+      uint64_t m = cmask[w];
+#pragma unroll
+      for (int r = 0; r < MAXR; r++)
+        if ((ract >> r) & 1u) m &= kt.rows[rowoff[r] + w];
+      any = any || m != 0;
+    }
+    return any ? 2 : 1;
+  }
+  for (int w = 0; w < W && !any; w++) {
+    uint64_t m = cmask[w];
+    if (m == 0) continue;
+#pragma unroll
+    for (int r = 0; r < MAXR; r++)
+      if ((ract >> r) & 1u) m &= kt.rows[rowoff[r] + w];
+    if (m == 0) continue;
+    if (nk <= MAX_FAST_KEYS) {
+#pragma unroll
+      for (int j = 0; j < MAX_FAST_KEYS; j++)
+        if (j < nk) m &= eval_key_word(kt, kk[j], ka[j], (kfg >> j) & 1u, w);
+    } else {
+      uint32_t keys = podkeys;
+      while (keys) {
+        int k = ctz32(keys);
+        keys &= keys - 1;
+        EReq mm = add_req(kt, k, state_req(kt, st, k), pod_req(kt, pd, k));
+        m &= eval_key_word(kt, k, allowed_values(kt, k, mm), forgiving(mm), w);
+      }
+    }
+    if (m && touch_off) m &= eval_off_word(kt, za, ca, w);
+    any = m != 0;
+  }
+  return any ? 2 : 1;
+}
+
+// NodeClaim.Add's requirement update (nodeclaim.go:173) for the keys the pod defines; the rest are unchanged.
+template <int G>
+__device__ __forceinline__ void group_store_merged_keys(const KeyTab& kt, const StateRef& st, const PodRef& pd,
+                                                        uint32_t podkeys, uint64_t* dmask, uint64_t* dflags, int64_t* dgt,
+                                                        int64_t* dlt) {
+  const int gl = threadIdx.x & (G - 1);
+  uint64_t flags = st.flags;
+  uint32_t keys = podkeys;
+  while (keys) {
+    int k = ctz32(keys);
+    keys &= keys - 1;
+    EReq m = add_req(kt, k, state_req(kt, st, k), pod_req(kt, pd, k));
+    flags = (flags & ~(0xFull << (4 * k))) | ((uint64_t)(m.f & 0xFu) << (4 * k));
+    if (gl == 0) {
+      dmask[k] = m.mask;
+      int b = kt.bslot[k];
+      if (b >= 0) {
+        dgt[b] = (m.f & RF_GT) ? m.gt : 0;
+        dlt[b] = (m.f & RF_LT) ? m.lt : 0;
+      }
+    }
+  }
+  if (gl == 0) *dflags = flags;
 }
 
 __device__ __forceinline__ uint64_t tail_mask(int S, int w) {

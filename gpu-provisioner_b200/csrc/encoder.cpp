@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "b200_core.cuh"
@@ -35,10 +36,10 @@ struct b200s_encoded {
   b200s_pods_soa_t pods{};
   b200s_nodes_soa_t nodes{};
   // owned storage
-  std::vector<int64_t> val_int, res_dv, alloc_rm, cap_rm, pod_requests, pod_ts, node_available;
-  std::vector<uint64_t> val_isint, rows, price, type_admit, pod_req_mask, pod_req_flags, pod_tolerated, pod_uid_hi,
-      pod_uid_lo, node_req_mask, node_req_flags, node_taints;
-  std::vector<int32_t> pod_gt, pod_lt, node_index;
+  std::vector<int64_t> val_int, res_dv, alloc_rm, cap_rm, rq_requests, pod_ts, node_available;
+  std::vector<uint64_t> val_isint, rows, price, type_admit, sig_mask, sig_flags, sig_tolerated, pod_uid_hi, pod_uid_lo,
+      node_req_mask, node_req_flags, node_taints;
+  std::vector<int32_t> sig_gt, sig_lt, pod_sig, pod_reqcls, node_index;
   // decode maps
   std::vector<int> devkey_model;               // device key slot -> model key
   std::vector<std::vector<int>> devkey_values; // device key slot -> model value ids by bit
@@ -473,14 +474,21 @@ void do_encode(Ctx& c) {
   N.req_flags = E->node_req_flags.data();
   N.taints = E->node_taints.data();
 
-  // ---- pods ----
+  // ---- pods: dictionary-encode requirement signatures and request vectors ----
+  // Replicas of one workload share both, so the pod arrays shrink to two ids per pod and the kernels
+  // evaluate each distinct signature / request vector once.  Exact: a class is a bit-for-bit equal row.
+  struct VecHash {
+    size_t operator()(const std::vector<uint64_t>& v) const {
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (uint64_t x : v) { h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; }
+      return (size_t)h;
+    }
+  };
+  std::unordered_map<std::vector<uint64_t>, int32_t, VecHash> sig_of, rq_of;
+  std::vector<std::vector<uint64_t>> sig_rows, rq_rows;
   const size_t Pz = (size_t)std::max(P, 1);
-  E->pod_requests.assign((size_t)R * Pz, 0);
-  E->pod_req_mask.assign((size_t)std::max(K, 1) * Pz, 0);
-  E->pod_req_flags.assign(Pz, 0);
-  E->pod_gt.assign((size_t)std::max(NB, 1) * Pz, 0);
-  E->pod_lt.assign((size_t)std::max(NB, 1) * Pz, 0);
-  E->pod_tolerated.assign(Pz, 0);
+  E->pod_sig.assign(Pz, 0);
+  E->pod_reqcls.assign(Pz, 0);
   E->pod_ts.assign(M->pod_ts, M->pod_ts + P);
   E->pod_ts.resize(Pz);
   E->pod_uid_hi.assign(M->pod_uid_hi, M->pod_uid_hi + P);
@@ -488,28 +496,40 @@ void do_encode(Ctx& c) {
   E->pod_uid_lo.assign(M->pod_uid_lo, M->pod_uid_lo + P);
   E->pod_uid_lo.resize(Pz);
   std::vector<long double> sums(R, 0);
+  std::vector<uint64_t> row;
+  // memo of the signature of an identical raw requirement + toleration list (cheap path for replicas)
   for (int p = 0; p < P; p++) {
+    row.assign((size_t)R, 0);
     for (int r = 0; r < R; r++) {
       int64_t q = M->pod_requests[(size_t)p * R + r];
       if (q < 0) reject("pod %d has a negative request", p);
-      E->pod_requests[(size_t)r * P + p] = q;
+      row[r] = (uint64_t)q;
       sums[r] += (long double)q;
     }
+    auto itq = rq_of.find(row);
+    if (itq == rq_of.end()) {
+      itq = rq_of.emplace(row, (int32_t)rq_rows.size()).first;
+      rq_rows.push_back(row);
+    }
+    E->pod_reqcls[p] = itq->second;
+
     ReqSet rs;
     int r0 = M->pod_req_off[p], r1 = M->pod_req_off[p + 1];
-    if (r1 > r0) {
-      build_set(r0, r1, &rs, "a pod", nullptr);
-      uint64_t f;
-      encode_ereq(rs, K, kt, &E->pod_req_mask[p], (size_t)P, &f);
-      E->pod_req_flags[p] = f;
-      for (int k = 0; k < K; k++) {
-        if (rs.q[k].f & (RF_GT | RF_LT)) {
-          int b = kt.bslot[k];
-          E->pod_gt[(size_t)b * P + p] = (int32_t)rs.q[k].gt;
-          E->pod_lt[(size_t)b * P + p] = (int32_t)rs.q[k].lt;
-        }
+    if (r1 > r0) build_set(r0, r1, &rs, "a pod", nullptr);
+    row.assign((size_t)K + 2 + 2 * (size_t)NB, 0);
+    uint64_t f = 0;
+    for (int k = 0; k < K; k++) {
+      row[k] = rs.q[k].mask;
+      f |= (uint64_t)(rs.q[k].f & 0xFu) << (4 * k);
+      if (rs.q[k].f & (RF_GT | RF_LT)) {
+        int b = kt.bslot[k];
+        row[(size_t)K + 2 + b] = (uint64_t)(int64_t)(int32_t)rs.q[k].gt;
+        row[(size_t)K + 2 + NB + b] = (uint64_t)(int64_t)(int32_t)rs.q[k].lt;
+        if ((rs.q[k].f & RF_CMPL) && rs.q[k].mask != 0 && NE > 0)
+          reject("pod %d combines NotIn with Gt/Lt on one key while existing nodes are present", p);
       }
     }
+    row[K] = f;
     uint64_t tol = 0;
     int t0 = M->pod_tol_off[p], t1 = M->pod_tol_off[p + 1];
     for (size_t ti = 0; ti < taint_u.size(); ti++) {
@@ -517,25 +537,53 @@ void do_encode(Ctx& c) {
       for (int i = t0; i < t1 && !ok; i++) ok = tolerates_taint(M->tolerations[i], taint_u[ti]);
       if (ok) tol |= 1ull << ti;
     }
-    E->pod_tolerated[p] = tol;
+    row[(size_t)K + 1] = tol;
+    auto its = sig_of.find(row);
+    if (its == sig_of.end()) {
+      its = sig_of.emplace(row, (int32_t)sig_rows.size()).first;
+      sig_rows.push_back(row);
+    }
+    E->pod_sig[p] = its->second;
   }
   for (int r = 0; r < R; r++) {
     long double mx = 0;
     for (int t = 0; t < M->n_pools; t++) mx = std::max(mx, (long double)T.daemon[t][r]);
     if (sums[r] + mx > 9.0e18L) reject("accumulated requests of resource %d could overflow int64", r);
   }
+  const size_t NS = sig_rows.size(), NQ = rq_rows.size(), NS1 = std::max<size_t>(NS, 1), NQ1 = std::max<size_t>(NQ, 1);
+  E->sig_mask.assign((size_t)std::max(K, 1) * NS1, 0);
+  E->sig_flags.assign(NS1, 0);
+  E->sig_tolerated.assign(NS1, 0);
+  E->sig_gt.assign((size_t)std::max(NB, 1) * NS1, 0);
+  E->sig_lt.assign((size_t)std::max(NB, 1) * NS1, 0);
+  for (size_t i = 0; i < NS; i++) {
+    const auto& rw = sig_rows[i];
+    for (int k = 0; k < K; k++) E->sig_mask[(size_t)k * NS + i] = rw[k];
+    E->sig_flags[i] = rw[K];
+    E->sig_tolerated[i] = rw[(size_t)K + 1];
+    for (int b = 0; b < NB; b++) {
+      E->sig_gt[(size_t)b * NS + i] = (int32_t)(int64_t)rw[(size_t)K + 2 + b];
+      E->sig_lt[(size_t)b * NS + i] = (int32_t)(int64_t)rw[(size_t)K + 2 + NB + b];
+    }
+  }
+  E->rq_requests.assign((size_t)R * NQ1, 0);
+  for (size_t i = 0; i < NQ; i++)
+    for (int r = 0; r < R; r++) E->rq_requests[(size_t)r * NQ + i] = (int64_t)rq_rows[i][r];
   b200s_pods_soa_t& Pd = E->pods;
   Pd.n_pods = P; Pd.n_res = R; Pd.n_keys = K; Pd.n_bounded = NB;
   Pd.res_cpu = M->res_cpu; Pd.res_memory = M->res_memory;
-  Pd.requests = E->pod_requests.data();
-  Pd.req_mask = E->pod_req_mask.data();
-  Pd.req_flags = E->pod_req_flags.data();
-  Pd.req_gt = E->pod_gt.data();
-  Pd.req_lt = E->pod_lt.data();
-  Pd.tolerated = E->pod_tolerated.data();
+  Pd.n_sigs = (int32_t)NS; Pd.n_reqcls = (int32_t)NQ;
+  Pd.sig_id = E->pod_sig.data();
+  Pd.req_id = E->pod_reqcls.data();
   Pd.ts = E->pod_ts.data();
   Pd.uid_hi = E->pod_uid_hi.data();
   Pd.uid_lo = E->pod_uid_lo.data();
+  Pd.sig_mask = E->sig_mask.data();
+  Pd.sig_flags = E->sig_flags.data();
+  Pd.sig_gt = E->sig_gt.data();
+  Pd.sig_lt = E->sig_lt.data();
+  Pd.sig_tolerated = E->sig_tolerated.data();
+  Pd.rq_requests = E->rq_requests.data();
 }
 
 }  // namespace

@@ -1,8 +1,12 @@
 // fit_kernels.cu — sm_100a kernels of the dense side of the path:
 //   template_prefilter_kernel  NewScheduler's per-NodePool instance-type pre-filter (scheduler.go:143-158)
-//   fit_matrix_kernel          addToNewNodeClaim's template walk for every pending pod (scheduler.go:587-675,
-//                              nodeclaim.go:114-163, :373-441): per-pod feasibility mask over SKUs, the first
-//                              feasible template, the per-template attempt codes
+//   class_tables_kernel        the filter loop of a fresh NodeClaim (nodeclaim.go:114-163, :373-441) factored by
+//                              what it depends on: per (requirement signature, template) the SKU sets
+//                              C = compatible, O = hasOffering and the taint / Compatible status; per (request
+//                              vector, template) the SKU set F = fits
+//   fit_dense_kernel           addToNewNodeClaim's template walk for every pending pod (scheduler.go:587-675):
+//                              per-pod feasibility mask C & O & F over SKUs, the first feasible template, the
+//                              per-template attempt codes (six diagnostic flags on failure) — a pure stream
 //   ffd_* kernels              NewQueue's order (queue.go:37-43, :72-108): bitonic sort of pod indices on
 //                              (cpu desc, memory desc, creationTimestamp asc, UID asc) — a total order
 //   select_cheapest_kernel     OrderByPrice(reqs)[0] (cloudprovider/types.go:221-240) per SKU set
@@ -24,6 +28,8 @@ __device__ __forceinline__ void copy_words(void* dst, const void* src, size_t by
   const uint64_t* s = reinterpret_cast<const uint64_t*>(src);
   for (size_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) d[i] = s[i];
 }
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Carves the catalog tables (bit rows + distinct values) into shared memory and repoints kt at them.
 __device__ __forceinline__ unsigned char* stage_tables(KeyTab& kt, unsigned char* smem, int tables_in_smem) {
@@ -83,137 +89,187 @@ __global__ void __launch_bounds__(32 * MAXT) template_prefilter_kernel(KeyTab kt
 }
 
 // -------------------------------------------------------------------------------------------------
-// dense stage A
+// class tables: one lane group per (signature, template) and per (request vector, template)
 // -------------------------------------------------------------------------------------------------
-constexpr int FIT_THREADS = 256;
-constexpr int FIT_TILE = 128;  // pods staged per CTA iteration
-
-struct FitSmemLayout {
-  size_t tmpl, scratch, tmask, alive, tile, tables, total;
-};
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-__host__ __device__ inline FitSmemLayout fit_layout(int G, int R, int K, int NB, int T, int W, int n_rows, int n_dv,
-                                                    int tables_in_smem) {
-  FitSmemLayout L;
-  size_t o = 0;
-  L.tmpl = o; o += align16(sizeof(TmplDev));
-  L.scratch = o; o += align16(sizeof(EvalScratch) * (FIT_THREADS / G));
-  L.tmask = o; o += align16((size_t)T * W * 8);
-  L.alive = o; o += align16((size_t)MAXT * 4);
-  L.tile = o;
-  // per pod: R requests, K masks, flags, tolerated (8 B each) + 2*NB int32 bounds
-  o += align16((size_t)FIT_TILE * ((size_t)(R + K + 2) * 8 + (size_t)NB * 8));
-  L.tables = o;
-  if (tables_in_smem) o += align16((size_t)n_rows * W * 8 + (size_t)n_dv * 8);
-  L.total = o;
-  return L;
-}
+constexpr int CLS_THREADS = 256;
 
 template <int G, int WPL>
-__global__ void __launch_bounds__(FIT_THREADS) fit_matrix_kernel(KeyTab kt, const TmplDev* __restrict__ tg,
-                                                                 const uint64_t* __restrict__ tmask_g,
-                                                                 const int32_t* __restrict__ alive_g, PodsDev pods,
-                                                                 int32_t* __restrict__ tmpl_out,
-                                                                 uint64_t* __restrict__ mask_out,
-                                                                 uint8_t* __restrict__ code_out,
-                                                                 unsigned long long* __restrict__ evals,
-                                                                 int tables_in_smem) {
+__global__ void __launch_bounds__(CLS_THREADS) class_tables_kernel(KeyTab kt, const TmplDev* __restrict__ tg,
+                                                                   const uint64_t* __restrict__ tmask_g,
+                                                                   const int32_t* __restrict__ alive_g, PodsDev pods,
+                                                                   uint8_t* __restrict__ sg_status,
+                                                                   uint64_t* __restrict__ sgC, uint64_t* __restrict__ sgO,
+                                                                   uint64_t* __restrict__ rqF, int tables_in_smem) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int NG = FIT_THREADS / G;
-  const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
-  const int T = tg->T;
-  const FitSmemLayout L = fit_layout(G, R, K, NB, T, W, kt.n_rows, kt.n_dv, tables_in_smem);
-  TmplDev* tm = reinterpret_cast<TmplDev*>(smem + L.tmpl);
-  EvalScratch* scratch = reinterpret_cast<EvalScratch*>(smem + L.scratch);
-  uint64_t* tmask = reinterpret_cast<uint64_t*>(smem + L.tmask);
-  int32_t* alive = reinterpret_cast<int32_t*>(smem + L.alive);
-  // tile arrays (SoA inside the tile, stride FIT_TILE)
-  int64_t* t_req = reinterpret_cast<int64_t*>(smem + L.tile);
-  uint64_t* t_mask = reinterpret_cast<uint64_t*>(t_req + (size_t)R * FIT_TILE);
-  uint64_t* t_flags = t_mask + (size_t)K * FIT_TILE;
-  uint64_t* t_tol = t_flags + FIT_TILE;
-  int32_t* t_gt = reinterpret_cast<int32_t*>(t_tol + FIT_TILE);
-  int32_t* t_lt = t_gt + (size_t)NB * FIT_TILE;
-
+  constexpr int NG = CLS_THREADS / G;
+  TmplDev* tm = reinterpret_cast<TmplDev*>(smem);
+  EvalScratch* scratch = reinterpret_cast<EvalScratch*>(smem + align16(sizeof(TmplDev)));
+  unsigned char* tab = smem + align16(sizeof(TmplDev)) + align16(sizeof(EvalScratch) * NG);
   copy_words(tm, tg, sizeof(TmplDev));
-  copy_words(tmask, tmask_g, (size_t)T * W * 8);
-  if (threadIdx.x < MAXT) alive[threadIdx.x] = threadIdx.x < T ? alive_g[threadIdx.x] : 0;
-  stage_tables(kt, smem + L.tables, tables_in_smem);
+  stage_tables(kt, tab, tables_in_smem);
   __syncthreads();
-
+  const int T = tm->T, W = kt.n_words, R = kt.n_res;
   const int g = threadIdx.x / G, gl = threadIdx.x & (G - 1);
-  const int P = pods.P;
-  const int n_tiles = (P + FIT_TILE - 1) / FIT_TILE;
-  unsigned long long my_evals = 0;
-
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int p0 = tile * FIT_TILE;
-    const int np = min(FIT_TILE, P - p0);
-    // coalesced SoA tile load: each array row is np contiguous words in HBM
-    for (int i = threadIdx.x; i < (R + K + 2) * FIT_TILE; i += FIT_THREADS) {
-      int row = i / FIT_TILE, j = i - row * FIT_TILE;
-      if (j < np) {
-        uint64_t v;
-        if (row < R) v = (uint64_t)pods.req[(size_t)row * P + p0 + j];
-        else if (row < R + K) v = pods.rmask[(size_t)(row - R) * P + p0 + j];
-        else if (row == R + K) v = pods.rflags[p0 + j];
-        else v = pods.tol[p0 + j];
-        reinterpret_cast<uint64_t*>(t_req)[i] = v;
-      }
-    }
-    for (int i = threadIdx.x; i < 2 * NB * FIT_TILE; i += FIT_THREADS) {
-      int row = i / FIT_TILE, j = i - row * FIT_TILE;
-      if (j < np) t_gt[i] = row < NB ? pods.gt[(size_t)row * P + p0 + j] : pods.lt[(size_t)(row - NB) * P + p0 + j];
-    }
-    __syncthreads();
-
-    for (int j = g; j < np; j += NG) {
-      const int p = p0 + j;
-      PodRef pd{t_mask + j, FIT_TILE, t_flags[j], t_gt + j, t_lt + j, FIT_TILE, t_req + j, FIT_TILE, t_tol[j]};
-      int chosen = -1;
-      uint64_t keep[WPL];
+  const unsigned gm = group_mask<G>();
+  const long long n_sig = (long long)pods.NS * T, n_items = n_sig + (long long)pods.NQ * T;
+  for (long long item = (long long)blockIdx.x * NG + g; item < n_items; item += (long long)gridDim.x * NG) {
+    if (item < n_sig) {
+      const int sig = (int)(item / T), t = (int)(item % T);
+      uint8_t status = B200S_FIT_DROPPED;
+      uint64_t C[WPL], O[WPL];
 #pragma unroll
-      for (int i = 0; i < WPL; i++) keep[i] = 0;
-      for (int t = 0; t < T; t++) {
-        uint8_t code = alive[t] ? B200S_FIT_NONE : B200S_FIT_DROPPED;
-        if (alive[t] && chosen < 0) {
-          StateRef st{tm->rmask[t], 1, tm->rflags[t], tm->gt[t], tm->lt[t], 1, tm->daemon[t], 1, tm->taints[t]};
-          uint64_t cand[WPL], out[WPL];
+      for (int i = 0; i < WPL; i++) { C[i] = 0; O[i] = 0; }
+      if (alive_g[t]) {
+        StateRef st{tm->rmask[t], 1, tm->rflags[t], tm->gt[t], tm->lt[t], 1, tm->daemon[t], 1, tm->taints[t]};
+        PodRef pd{pods.sig_mask + sig, (size_t)pods.NS, pods.sig_flags[sig], pods.sig_gt + sig, pods.sig_lt + sig,
+                  (size_t)pods.NS, nullptr, 0, pods.sig_tol[sig]};
+        uint64_t cand[WPL];
 #pragma unroll
-          for (int i = 0; i < WPL; i++) {
-            int w = gl + i * G;
-            cand[i] = w < W ? tmask[(size_t)t * W + w] : 0ull;
-          }
-          int visited;
-          int stt = group_can_add<G, WPL>(kt, &scratch[g], st, pd, true, cand, out, &code, &visited);
-          if (gl == 0) my_evals += (unsigned long long)visited;
-          if (stt == ST_OK) {
-            chosen = t;
-            code = B200S_FIT_NONE;
-#pragma unroll
-            for (int i = 0; i < WPL; i++) keep[i] = out[i];
-          } else if (stt == ST_TAINT) {
-            code = B200S_FIT_TAINT;
-          } else if (stt == ST_INCOMPATIBLE) {
-            code = B200S_FIT_INCOMPATIBLE;
-          }
+        for (int i = 0; i < WPL; i++) {
+          int w = gl + i * G;
+          cand[i] = w < W ? tmask_g[(size_t)t * W + w] : 0ull;
         }
-        if (gl == 0) code_out[(size_t)p * T + t] = code;
+        int stt = group_label_masks<G, WPL>(kt, &scratch[g], st, pd, cand, C, O);
+        status = stt == ST_OK ? B200S_FIT_NONE : stt == ST_TAINT ? B200S_FIT_TAINT : B200S_FIT_INCOMPATIBLE;
       }
-      if (gl == 0) tmpl_out[p] = chosen;
+      if (gl == 0) sg_status[item] = status;
 #pragma unroll
       for (int i = 0; i < WPL; i++) {
         int w = gl + i * G;
-        if (w < W) mask_out[(size_t)p * W + w] = keep[i];
+        if (w < W) {
+          sgC[(size_t)item * W + w] = C[i];
+          sgO[(size_t)item * W + w] = O[i];
+        }
+      }
+    } else {
+      const long long j = item - n_sig;
+      const int q = (int)(j / T), t = (int)(j % T);
+      // F = template's instance types that fit daemon overhead + the request vector (nodeclaim.go:144,447-449)
+      int my_row = 0;
+      if (gl < R) {
+        int64_t x = tm->daemon[t][gl] + pods.rq_req[(size_t)gl * pods.NQ + q];
+        int nd = kt.res_nd[gl];
+        int i = fit_rank(kt.res_dv + kt.res_dv0[gl], nd, x);
+        my_row = i < nd ? kt.res_row0[gl] + i : -1;
+      }
+      uint64_t F[WPL];
+#pragma unroll
+      for (int i = 0; i < WPL; i++) {
+        int w = gl + i * G;
+        F[i] = w < W ? (tmask_g[(size_t)t * W + w] & kt.rows[(size_t)kt.row_nonneg * W + w]) : 0ull;
+      }
+      for (int r = 0; r < R; r++) {
+        int row = __shfl_sync(gm, my_row, r, G);
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+          int w = gl + i * G;
+          if (w < W) F[i] &= row < 0 ? 0ull : kt.rows[(size_t)row * W + w];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < WPL; i++) {
+        int w = gl + i * G;
+        if (w < W) rqF[(size_t)j * W + w] = F[i];
       }
     }
-    __syncthreads();
   }
-  // one atomic per warp
+}
+
+// -------------------------------------------------------------------------------------------------
+// dense stage A: stream the pods, combine the class rows
+// -------------------------------------------------------------------------------------------------
+constexpr int FIT_THREADS = 256;
+
+template <int G, int WPL>
+__global__ void __launch_bounds__(FIT_THREADS) fit_dense_kernel(int P, int T, int W, const int32_t* __restrict__ sig_id,
+                                                                const int32_t* __restrict__ req_id,
+                                                                const uint8_t* __restrict__ sg_status,
+                                                                const uint64_t* __restrict__ sgC,
+                                                                const uint64_t* __restrict__ sgO,
+                                                                const uint64_t* __restrict__ rqF,
+                                                                const int32_t* __restrict__ tm_count,
+                                                                int32_t* __restrict__ tmpl_out,
+                                                                uint64_t* __restrict__ mask_out,
+                                                                uint8_t* __restrict__ code_out,
+                                                                unsigned long long* __restrict__ evals) {
+  constexpr int NG = FIT_THREADS / G;
+  const unsigned gm = group_mask<G>();
+  const int gl = threadIdx.x & (G - 1);
+  unsigned long long my_evals = 0;
+  for (int p = blockIdx.x * NG + threadIdx.x / G; p < P; p += gridDim.x * NG) {
+    const int sig = sig_id[p], rq = req_id[p];
+    int chosen = -1;
+    uint64_t keep[WPL];
+#pragma unroll
+    for (int i = 0; i < WPL; i++) keep[i] = 0;
+    uint32_t code_lo = 0, code_hi = 0;  // byte t of the pair = attempt code of template t (T <= 16... 8 per word)
+    uint32_t code_2 = 0, code_3 = 0;
+    for (int t = 0; t < T; t++) {
+      uint32_t code = sg_status[(size_t)sig * T + t];
+      if (chosen >= 0 && code != B200S_FIT_DROPPED) code = B200S_FIT_NONE;  // templates after the first success are never tried
+      if (code == B200S_FIT_NONE && chosen < 0) {  // addToNewNodeClaim stops at the first template that works
+        const size_t cb = ((size_t)sig * T + t) * W, fb = ((size_t)rq * T + t) * W;
+        uint64_t c[WPL], o[WPL], f[WPL];
+        unsigned any = 0;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+          int w = gl + i * G;
+          c[i] = 0; o[i] = 0; f[i] = 0;
+          if (w < W) {
+            c[i] = sgC[cb + w];
+            o[i] = sgO[cb + w];
+            f[i] = rqF[fb + w];
+          }
+          any |= (c[i] & o[i] & f[i]) ? 1u : 0u;
+        }
+        any = __reduce_or_sync(gm, any);
+        if (gl == 0) my_evals += (unsigned long long)tm_count[t];
+        if (any) {
+          chosen = t;
+#pragma unroll
+          for (int i = 0; i < WPL; i++) keep[i] = c[i] & o[i] & f[i];
+        } else {  // InstanceTypeFilterError: the six flags (nodeclaim.go:409-416)
+          uint32_t bits = 0;
+#pragma unroll
+          for (int i = 0; i < WPL; i++)
+            bits |= (c[i] ? 2u : 0u) | (f[i] ? 4u : 0u) | (o[i] ? 8u : 0u) | ((c[i] & f[i] & ~o[i]) ? 16u : 0u) |
+                    ((c[i] & o[i] & ~f[i]) ? 32u : 0u) | ((f[i] & o[i] & ~c[i]) ? 64u : 0u);
+          bits = __reduce_or_sync(gm, bits);
+          code = filter_flags(bits & 2u, bits & 4u, bits & 8u, bits & 16u, bits & 32u, bits & 64u);
+        }
+      }
+      const uint32_t sh = (uint32_t)(t & 3) * 8u;
+      if (t < 4) code_lo |= code << sh;
+      else if (t < 8) code_hi |= code << sh;
+      else if (t < 12) code_2 |= code << sh;
+      else code_3 |= code << sh;
+    }
+    if (gl == 0) tmpl_out[p] = chosen;
+    if (gl < T) {
+      uint32_t word = gl < 4 ? code_lo : gl < 8 ? code_hi : gl < 12 ? code_2 : code_3;
+      code_out[(size_t)p * T + gl] = (uint8_t)(word >> ((gl & 3) * 8));
+    }
+    if (G < MAXT && gl + G < T) {
+      int t = gl + G;
+      uint32_t word = t < 4 ? code_lo : t < 8 ? code_hi : t < 12 ? code_2 : code_3;
+      code_out[(size_t)p * T + t] = (uint8_t)(word >> ((t & 3) * 8));
+    }
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+      int w = gl + i * G;
+      if (w < W) mask_out[(size_t)p * W + w] = keep[i];
+    }
+  }
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
   if ((threadIdx.x & 31) == 0 && my_evals) atomicAdd(evals, my_evals);
+}
+
+__global__ void template_count_kernel(int T, int W, const uint64_t* __restrict__ tmask, int32_t* __restrict__ tm_count) {
+  int t = threadIdx.x;
+  if (t >= T) return;
+  int n = 0;
+  for (int w = 0; w < W; w++) n += __popcll(tmask[(size_t)t * W + w]);
+  tm_count[t] = n;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -228,10 +284,13 @@ __device__ __forceinline__ bool ffd_less(const PodsDev& pods, const int32_t* __r
     int sa = seg[a], sb = seg[b];
     if (sa != sb) return sa < sb;
   }
-  int64_t ca = pods.req[(size_t)pods.res_cpu * P + a], cb = pods.req[(size_t)pods.res_cpu * P + b];
-  if (ca != cb) return ca > cb;
-  int64_t ma = pods.req[(size_t)pods.res_mem * P + a], mb = pods.req[(size_t)pods.res_mem * P + b];
-  if (ma != mb) return ma > mb;
+  const int qa = pods.req_id[a], qb = pods.req_id[b];
+  if (qa != qb) {  // equal request classes have equal cpu and memory
+    int64_t ca = pods.rq_req[(size_t)pods.res_cpu * pods.NQ + qa], cb = pods.rq_req[(size_t)pods.res_cpu * pods.NQ + qb];
+    if (ca != cb) return ca > cb;
+    int64_t ma = pods.rq_req[(size_t)pods.res_mem * pods.NQ + qa], mb = pods.rq_req[(size_t)pods.res_mem * pods.NQ + qb];
+    if (ma != mb) return ma > mb;
+  }
   int64_t ta = pods.ts[a], tb = pods.ts[b];
   if (ta != tb) return ta < tb;
   uint64_t ha = pods.uid_hi[a], hb = pods.uid_hi[b];
@@ -388,36 +447,51 @@ cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const
   return cudaGetLastError();
 }
 
-int fit_tables_fit_in_smem(const KeyTab& kt, int T, int smem_limit) {
-  int G, WPL;
-  pick_group(kt.n_words, &G, &WPL);
-  FitSmemLayout L = fit_layout(G, kt.n_res, kt.n_keys, kt.n_bounded, T, kt.n_words, kt.n_rows, kt.n_dv, 1);
-  return L.total <= (size_t)smem_limit;
+static size_t class_smem_bytes(const KeyTab& kt, int G, int in_smem) {
+  size_t o = align16(sizeof(TmplDev)) + align16(sizeof(EvalScratch) * (CLS_THREADS / G));
+  if (in_smem) o += align16((size_t)kt.n_rows * kt.n_words * 8 + (size_t)kt.n_dv * 8);
+  return o;
 }
 
-cudaError_t launch_fit_matrix(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
-                              const PodsDev& pods, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out,
-                              unsigned long long* evals, int n_sm, int smem_limit, cudaStream_t stream) {
+cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
+                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* rqF,
+                                int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
-  if (pods.P == 0) return cudaSuccess;
+  if (T > 0) template_count_kernel<<<1, MAXT, 0, stream>>>(T, kt.n_words, tmask, tm_count);
+  long long items = ((long long)pods.NS + pods.NQ) * T;
+  if (items == 0) return cudaGetLastError();
   int G, WPL;
   pick_group(kt.n_words, &G, &WPL);
-  int in_smem = fit_tables_fit_in_smem(kt, T, smem_limit);
-  FitSmemLayout L = fit_layout(G, kt.n_res, kt.n_keys, kt.n_bounded, T, kt.n_words, kt.n_rows, kt.n_dv, in_smem);
-  int n_tiles = (pods.P + FIT_TILE - 1) / FIT_TILE;
+  int in_smem = class_smem_bytes(kt, G, 1) <= (size_t)smem_limit;
+  size_t bytes = class_smem_bytes(kt, G, in_smem);
   cudaError_t err = cudaSuccess;
-#define CALL(G, WPL)                                                                                              \
-  do {                                                                                                            \
-    auto kern = fit_matrix_kernel<G, WPL>;                                                                        \
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);                  \
-    if (err != cudaSuccess) return err;                                                                           \
-    int per_sm = 1;                                                                                               \
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FIT_THREADS, L.total);                     \
-    if (err != cudaSuccess) return err;                                                                           \
-    if (per_sm < 1) per_sm = 1;                                                                                   \
-    int grid = n_tiles < n_sm * per_sm ? n_tiles : n_sm * per_sm;                                                 \
-    kern<<<grid, FIT_THREADS, L.total, stream>>>(kt, tg, tmask, alive, pods, tmpl_out, mask_out, code_out, evals, \
-                                                 in_smem);                                                        \
+#define CALL(G_, WPL_)                                                                                      \
+  do {                                                                                                      \
+    auto kern = class_tables_kernel<G_, WPL_>;                                                              \
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);              \
+    if (err != cudaSuccess) return err;                                                                     \
+    long long need = (items + (CLS_THREADS / G_) - 1) / (CLS_THREADS / G_);                                 \
+    int grid = (int)(need < (long long)n_sm * 4 ? need : (long long)n_sm * 4);                              \
+    kern<<<grid, CLS_THREADS, bytes, stream>>>(kt, tg, tmask, alive, pods, sg_status, sgC, sgO, rqF, in_smem); \
+  } while (0)
+  DISPATCH_GROUP(kt.n_words, CALL);
+#undef CALL
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const uint8_t* sg_status, const uint64_t* sgC,
+                             const uint64_t* sgO, const uint64_t* rqF, const int32_t* tm_count, int32_t* tmpl_out,
+                             uint64_t* mask_out, uint8_t* code_out, unsigned long long* evals, int n_sm,
+                             cudaStream_t stream) {
+  if (kt.n_words > 128) return cudaErrorInvalidValue;
+  if (pods.P == 0) return cudaSuccess;
+#define CALL(G_, WPL_)                                                                                          \
+  do {                                                                                                          \
+    long long need = ((long long)pods.P + (FIT_THREADS / G_) - 1) / (FIT_THREADS / G_);                         \
+    int grid = (int)(need < (long long)n_sm * 8 ? need : (long long)n_sm * 8);                                  \
+    fit_dense_kernel<G_, WPL_><<<grid, FIT_THREADS, 0, stream>>>(pods.P, T, kt.n_words, pods.sig_id, pods.req_id, \
+                                                                 sg_status, sgC, sgO, rqF, tm_count, tmpl_out,  \
+                                                                 mask_out, code_out, evals);                    \
   } while (0)
   DISPATCH_GROUP(kt.n_words, CALL);
 #undef CALL

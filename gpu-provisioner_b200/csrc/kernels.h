@@ -14,6 +14,8 @@ struct PackProblem {
   // outputs
   int32_t n_claims, n_unscheduled;
   unsigned long long evals;
+  // SM cycles thread 0 spent per phase (pop, pod row, nodes, sort, pre-filter, evaluate, commit, steps)
+  unsigned long long prof[8];
 };
 
 // Mutable state of all problems of a launch (device pointers).
@@ -21,14 +23,17 @@ struct PackArrays {
   // in-flight NodeClaims; problem b owns rows [pod_begin, pod_end) (a claim holds at least one pod)
   uint64_t* c_mask;    // [Ptot*W]  InstanceTypeOptions
   int64_t* c_req;      // [Ptot*R]  Spec.Resources.Requests
+  int64_t* c_hi;       // [Ptot*R]  upper bound of Allocatable over the claim's instance types (pre-filter only)
   uint64_t* c_rmask;   // [Ptot*K]  Requirements
   uint64_t* c_rflags;  // [Ptot]
   int64_t* c_gt;       // [Ptot*NB]
   int64_t* c_lt;       // [Ptot*NB]
   int32_t* c_tmpl;     // [Ptot]
   int32_t* c_npods;    // [Ptot]    len(Pods)
+  int32_t* c_nopt;     // [Ptot]    len(InstanceTypeOptions)
   int32_t* ord;        // [Ptot]    s.newNodeClaims order, local claim ids
   int32_t* ord_key;    // [Ptot]    len(Pods) by position (spill area of the shared-memory copy)
+  int32_t* ord_snap;   // [Ptot]    order before the last full pdqsort (so the final normalisation can be undone)
   // existing nodes (mutable copies), resource/key-major with stride Etot
   int32_t Etot;
   int64_t* n_avail;    // [R*Etot]
@@ -63,10 +68,13 @@ struct ClaimOut {
 
 cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
                                       int32_t* alive, cudaStream_t stream);
-int fit_tables_fit_in_smem(const KeyTab& kt, int T, int smem_limit);
-cudaError_t launch_fit_matrix(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
-                              const PodsDev& pods, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out,
-                              unsigned long long* evals, int n_sm, int smem_limit, cudaStream_t stream);
+cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
+                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* rqF,
+                                int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream);
+cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const uint8_t* sg_status, const uint64_t* sgC,
+                             const uint64_t* sgO, const uint64_t* rqF, const int32_t* tm_count, int32_t* tmpl_out,
+                             uint64_t* mask_out, uint8_t* code_out, unsigned long long* evals, int n_sm,
+                             cudaStream_t stream);
 int ffd_padded(int P);
 cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, int32_t* idx, int* launches, cudaStream_t stream);
 cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* masks, const uint64_t* rmask, size_t rms,

@@ -18,30 +18,38 @@
 
 namespace b200 {
 
-constexpr int PACK_THREADS = 512;
+constexpr int PACK_THREADS = 256;
 constexpr int ORD_SMEM_CAP = 8192;  // NodeClaims whose order / count-by-position arrays stay in shared memory
-constexpr int KIND_INC = 1, KIND_APPEND = 2;
-constexpr int MODE_NONE = 0, MODE_ROT_INC = 1, MODE_ROT_APPEND = 2;
+constexpr int MODE_NONE = 0;
 
 struct PackShared {
   TmplDev tm;
-  int64_t p_req[MAXR];
-  uint64_t p_mask[MAXK];
+  // pod rows, double buffered: the next pod's row is fetched while the current one commits
+  int64_t p_req[2][MAXR];
+  uint64_t p_mask[2][MAXK];
+  int32_t p_gt[2][MAXB], p_lt[2][MAXB];
+  uint64_t p_flags[2], p_tol[2];
+  uint32_t p_keys[2];  // bit k: the pod's requirements define key k
+  uint32_t p_ract[2];  // bit r: the pod requests resource r (non-zero)
+  int32_t p_id[2];     // pod index, -1 when the queue is done
   int64_t zero_b[MAXB];
-  int32_t p_gt[MAXB], p_lt[MAXB];
-  uint64_t p_flags, p_tol;
-  int32_t pod, best, n_claims, head, len, seq, dirty_pos, dirty_kind, mode, rot_from, rot_to, rot_x, rot_k, ord_global,
-      n_pushed;
+  int32_t best[2];
+  int32_t hit_c[PACK_THREADS / 32];  // claim id behind each warp's first feasible index of the current scan
+  int32_t n_claims, head, len, seq, n_pushed, ord_global;
+  int32_t mode, rot_src, rot_dst, rot_orig;   // order normalisation left for the whole CTA after this step's commit
+  int32_t undo_mode, undo_src, undo_dst;      // how to take the last normalisation back (see the end of the kernel)
   unsigned long long evals;
 };
+
+constexpr int MODE_ROTATE = 1, MODE_GENERIC = 2;
 
 __host__ __device__ inline size_t pack_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t pack_smem_bytes(int G, int W, int n_rows, int n_dv, int tables_in_smem, size_t* scratch_off,
                                                   size_t* tables_off, size_t* ord_off = nullptr) {
+  (void)G;
   size_t o = pack_align16(sizeof(PackShared));
   if (scratch_off) *scratch_off = o;
-  o += pack_align16(sizeof(EvalScratch) * (PACK_THREADS / G));
   if (ord_off) *ord_off = o;
   o += pack_align16((size_t)ORD_SMEM_CAP * 8);  // ord[] + key[]
   if (tables_off) *tables_off = o;
@@ -64,20 +72,176 @@ __device__ __forceinline__ bool node_can_add(const KeyTab& kt, const PackArrays&
   return true;
 }
 
+// Moves the element at position src of (ord, key) to position dst, shifting what lies between by one slot;
+// all threads of the CTA take part (uniform arguments).
+__device__ __forceinline__ void cta_rotate(int32_t* ord, int32_t* key, int src, int dst) {
+  const int tid = threadIdx.x;
+  const int x = ord[src], kx = key[src];
+  __syncthreads();
+  if (src < dst) {
+    for (int cb = src + 1; cb <= dst; cb += PACK_THREADS) {
+      int i = cb + tid, v = 0, kv = 0;
+      if (i <= dst) { v = ord[i]; kv = key[i]; }
+      __syncthreads();
+      if (i <= dst) { ord[i - 1] = v; key[i - 1] = kv; }
+      __syncthreads();
+    }
+  } else {
+    for (int ce = src - 1; ce >= dst; ce -= PACK_THREADS) {
+      int i = ce - tid, v = 0, kv = 0;
+      if (i >= dst) { v = ord[i]; kv = key[i]; }
+      __syncthreads();
+      if (i >= dst) { ord[i + 1] = v; key[i + 1] = kv; }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) { ord[dst] = x; key[dst] = kx; }
+  __syncthreads();
+}
+
+// The same move by one warp (no CTA barrier): used inside the commit phase while the other warps do their part.
+__device__ __forceinline__ void warp_rotate(int32_t* ord, int32_t* key, int src, int dst) {
+  const int lane = threadIdx.x & 31;
+  const int x = ord[src], kx = key[src];
+  __syncwarp();
+  if (src < dst) {
+    for (int cb = src + 1; cb <= dst; cb += 32) {
+      int i = cb + lane, v = 0, kv = 0;
+      if (i <= dst) { v = ord[i]; kv = key[i]; }
+      __syncwarp();
+      if (i <= dst) { ord[i - 1] = v; key[i - 1] = kv; }
+      __syncwarp();
+    }
+  } else {
+    for (int ce = src - 1; ce >= dst; ce -= 32) {
+      int i = ce - lane, v = 0, kv = 0;
+      if (i >= dst) { v = ord[i]; kv = key[i]; }
+      __syncwarp();
+      if (i >= dst) { ord[i + 1] = v; key[i + 1] = kv; }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) { ord[dst] = x; key[dst] = kx; }
+  __syncwarp();
+}
+
+// What Go's sort.Slice will do to an order that was sorted before one element changed (position pos got one more
+// pod, or a new claim with one pod was appended at pos = n-1).  Run by ONE WARP right after the change:
+//   * still sorted                                   -> identity
+//   * n >= 50 and choosePivot sees no inversion      -> partialInsertionSort re-inserts the element next to its
+//                                                       equals (zsortfunc.go partialInsertionSort_func): the warp
+//                                                       shifts the run it passes over, 32 slots per step
+//   * otherwise                                      -> the full pdqsort (lane 0), order saved first for the undo
+// choosePivot_func with n >= 50 reports "increasing" iff none of its order2 calls swaps, i.e. iff the three
+// adjacent triples around n/4, n/2, 3n/4 are non-decreasing and so are their middles: 9 keys, read by 9 lanes.
+constexpr int WARP_SHIFT_LIMIT = 1024;  // slots one warp shifts before handing the rest to the whole CTA
+
+__device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int32_t* key, int32_t* snap, int n, int pos,
+                                               bool appended) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) S.mode = MODE_NONE;
+  if (n <= 1) return;
+  const bool sorted = appended ? !(key[n - 1] < key[n - 2]) : (pos == n - 1 || !(key[pos + 1] < key[pos]));
+  if (sorted) return;
+  bool increasing = false;
+  if (n >= 50) {
+    const int q = n / 4;
+    int v = 0;
+    if (lane < 9) v = key[q * (lane / 3 + 1) + (lane % 3) - 1];
+    const int up = __shfl_down_sync(0xffffffffu, v, 1);
+    const int mid_next = __shfl_down_sync(0xffffffffu, v, 3);
+    bool bad = false;
+    if (lane < 9 && (lane % 3) != 2) bad = up < v;                  // inside a triple
+    if (lane == 1 || lane == 4) bad = bad || mid_next < v;          // middle of triple t vs middle of triple t+1
+    increasing = __ballot_sync(0xffffffffu, bad) == 0;
+  }
+  if (!increasing) {
+    if (lane == 0) {
+      for (int i = 0; i < n; i++) snap[i] = ord[i];  // rare path; lets the last normalisation be taken back
+      GoSort gs{ord, key};
+      gs.sort(n);
+      S.mode = MODE_GENERIC;
+    }
+    __syncwarp();
+    return;
+  }
+  // re-insertion: the displaced element X walks over the run of smaller (when it grew) or larger (when it was
+  // appended) keys; the run moves one slot the other way
+  const int x = ord[pos], kx = key[pos];
+  __syncwarp();
+  int dst = -1, hole = pos, moved = 0;
+  if (!appended) {
+    for (int b0 = pos + 1; dst < 0 && moved < WARP_SHIFT_LIMIT; b0 += 32) {
+      const int i = b0 + lane;
+      int v = 0, kv = 0;
+      bool stop = true;
+      if (i < n) { v = ord[i]; kv = key[i]; stop = !(kv < kx); }
+      const unsigned sb = __ballot_sync(0xffffffffu, stop);
+      const int cnt = sb ? __ffs(sb) - 1 : 32;
+      __syncwarp();
+      if (lane < cnt) { ord[i - 1] = v; key[i - 1] = kv; }
+      __syncwarp();
+      hole = b0 + cnt - 1;
+      moved += cnt;
+      if (sb) dst = hole;
+    }
+  } else {
+    for (int t0 = pos - 1; dst < 0 && moved < WARP_SHIFT_LIMIT; t0 -= 32) {
+      const int i = t0 - lane;
+      int v = 0, kv = 0;
+      bool stop = true;
+      if (i >= 0) { v = ord[i]; kv = key[i]; stop = !(kx < kv); }
+      const unsigned sb = __ballot_sync(0xffffffffu, stop);
+      const int cnt = sb ? __ffs(sb) - 1 : 32;
+      __syncwarp();
+      if (lane < cnt) { ord[i + 1] = v; key[i + 1] = kv; }
+      __syncwarp();
+      hole = t0 - cnt + 1;
+      moved += cnt;
+      if (sb) dst = hole;
+    }
+  }
+  if (lane == 0) {
+    ord[hole] = x;
+    key[hole] = kx;
+    if (dst >= 0) {  // done: remember how to take it back
+      S.undo_mode = hole != pos ? MODE_ROTATE : MODE_NONE;
+      S.undo_src = hole;
+      S.undo_dst = pos;
+    } else {  // long run: X sits at `hole`, the whole CTA finishes the move after the barrier
+      int lo, hi;
+      if (!appended) {
+        lo = hole + 1; hi = n;  // first index > hole whose count >= kx
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (key[mid] < kx) lo = mid + 1; else hi = mid; }
+        S.rot_dst = lo - 1;
+      } else {
+        lo = 0; hi = hole;      // first index whose count > kx
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (key[mid] <= kx) lo = mid + 1; else hi = mid; }
+        S.rot_dst = lo;
+      }
+      S.rot_src = hole;
+      S.rot_orig = pos;
+      S.mode = MODE_ROTATE;
+    }
+  }
+  __syncwarp();
+}
+
 template <int G, int WPL>
-__global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const TmplDev* __restrict__ tg, PodsDev pods,
-                                                               PackArrays A, PackProblem* __restrict__ problems,
-                                                               int tables_in_smem) {
+__global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
+                                                               const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
+                                                               PackProblem* __restrict__ problems, int tables_in_smem) {
+  // kt stays in the constant bank (never modified): the bit-row tables are read through L1 from global memory,
+  // they are read-only and a few tens of KB
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int NG = PACK_THREADS / G;
+  constexpr int NW = PACK_THREADS / 32;
   PackShared& S = *reinterpret_cast<PackShared*>(smem);
   size_t scratch_off, tables_off, ord_off;
   pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, tables_in_smem, &scratch_off, &tables_off, &ord_off);
-  EvalScratch* scratch = reinterpret_cast<EvalScratch*>(smem + scratch_off);
   int32_t* s_ord = reinterpret_cast<int32_t*>(smem + ord_off);
   int32_t* s_key = s_ord + ORD_SMEM_CAP;
-  const int tid = threadIdx.x, g = tid / G, gl = tid & (G - 1);
-  const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words, P = pods.P;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gl = tid & (G - 1);
+  const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
 
   PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
@@ -85,14 +249,17 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
   // this problem's slices
   uint64_t* c_mask = A.c_mask + (size_t)base * W;
   int64_t* c_req = A.c_req + (size_t)base * R;
+  int64_t* c_hi = A.c_hi + (size_t)base * R;
   uint64_t* c_rmask = A.c_rmask + (size_t)base * K;
   uint64_t* c_rflags = A.c_rflags + base;
   int64_t* c_gt = A.c_gt + (size_t)base * NB;
   int64_t* c_lt = A.c_lt + (size_t)base * NB;
   int32_t* c_tmpl = A.c_tmpl + base;
   int32_t* c_npods = A.c_npods + base;
+  int32_t* c_nopt = A.c_nopt + base;
   int32_t* g_ord = A.ord + base;      // the order array's home (and its spill area past ORD_SMEM_CAP claims)
   int32_t* g_key = A.ord_key + base;
+  int32_t* g_snap = A.ord_snap + base;
   int32_t* queue = A.queue + base;
 
   {
@@ -100,26 +267,30 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
     const uint64_t* s = reinterpret_cast<const uint64_t*>(tg);
     for (int i = tid; i < (int)(sizeof(TmplDev) / 8); i += PACK_THREADS) d[i] = s[i];
   }
-  if (tables_in_smem) {
-    size_t row_words = (size_t)kt.n_rows * W, dv_words = (size_t)kt.n_dv;
-    uint64_t* d = reinterpret_cast<uint64_t*>(smem + tables_off);
-    for (size_t i = tid; i < row_words; i += PACK_THREADS) d[i] = kt.rows[i];
-    for (size_t i = tid; i < dv_words; i += PACK_THREADS) d[row_words + i] = (uint64_t)kt.res_dv[i];
-    kt.rows = d;
-    kt.res_dv = reinterpret_cast<const int64_t*>(d + row_words);
-  }
   if (tid < MAXB) S.zero_b[tid] = 0;
   if (tid == 0) {
-    S.n_claims = 0; S.head = 0; S.len = n_pods; S.seq = 0; S.dirty_pos = -1; S.dirty_kind = 0; S.evals = 0;
-    S.ord_global = 0; S.n_pushed = 0;
+    S.n_claims = 0; S.head = 0; S.len = n_pods; S.seq = 0; S.evals = 0;
+    S.ord_global = 0; S.n_pushed = 0; S.mode = MODE_NONE; S.undo_mode = MODE_NONE;
+    S.best[0] = INT_MAX; S.best[1] = INT_MAX;
   }
   unsigned long long my_evals = 0;
+  unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tick = clock64();
+#define PROF(i)                                       \
+  do {                                                \
+    if (tid == 0) {                                   \
+      long long now_ = clock64();                     \
+      prof[i] += (unsigned long long)(now_ - tick);   \
+      tick = now_;                                    \
+    }                                                 \
+  } while (0)
   __syncthreads();
 
-  for (;;) {
-    // ---- Queue.Pop (queue.go:46-60) ----
-    if (tid == 0) {
-      int p = -1;
+  // Queue.Pop (queue.go:46-60) + the pod's row (updateCachedPodData's products, scheduler.go:467-486) through
+  // its signature / request-class ids, by warp 0 into buffer `buf`.
+  auto pop_and_load = [&](int buf) {
+    int p = -1;
+    if (lane == 0) {
       if (S.len > 0) {
         int cand = queue[S.head];
         if (S.n_pushed == 0 || A.lastlen[cand] != S.len) {  // lastLen is zero until a pod has been pushed back
@@ -128,38 +299,118 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
           S.len--;
         }
       }
-      S.pod = p;
-      S.best = INT_MAX;
+      S.p_id[buf] = p;
     }
-    __syncthreads();
-    const int p = S.pod;
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p < 0) return;
+    const int sig = pods.sig_id[p], rq = pods.req_id[p];
+    int64_t myreq = 0;
+    if (lane < R) myreq = pods.rq_req[(size_t)lane * pods.NQ + rq];
+    const unsigned ract = __ballot_sync(0xffffffffu, myreq != 0);
+    if (lane < 8) {
+      if (lane < R) S.p_req[buf][lane] = myreq;
+      if (lane == 0) S.p_ract[buf] = ract;
+    } else if (lane < 24) {
+      if (lane - 8 < K) S.p_mask[buf][lane - 8] = pods.sig_mask[(size_t)(lane - 8) * pods.NS + sig];
+    } else if (lane < 28) {
+      if (lane - 24 < NB) {
+        S.p_gt[buf][lane - 24] = pods.sig_gt[(size_t)(lane - 24) * pods.NS + sig];
+        S.p_lt[buf][lane - 24] = pods.sig_lt[(size_t)(lane - 24) * pods.NS + sig];
+      }
+    } else if (lane == 28) {
+      uint64_t f = pods.sig_flags[sig];
+      uint32_t keys = 0;
+      for (int k = 0; k < K; k++) keys |= (uint32_t)((f >> (4 * k)) & 1ull) << k;
+      S.p_flags[buf] = f;
+      S.p_keys[buf] = keys;
+      S.p_tol[buf] = pods.sig_tol[sig];
+    }
+  };
+
+  if (warp == 0) pop_and_load(0);
+  __syncthreads();
+  int cur = 0;
+
+  for (;;) {
+    const int p = S.p_id[cur];
     if (p < 0) break;
-    // ---- pod row -> shared memory (updateCachedPodData's products, scheduler.go:467-486) ----
-    if (tid < R) S.p_req[tid] = pods.req[(size_t)tid * P + p];
-    if (tid >= 32 && tid < 32 + K) S.p_mask[tid - 32] = pods.rmask[(size_t)(tid - 32) * P + p];
-    if (tid >= 64 && tid < 64 + NB) {
-      S.p_gt[tid - 64] = pods.gt[(size_t)(tid - 64) * P + p];
-      S.p_lt[tid - 64] = pods.lt[(size_t)(tid - 64) * P + p];
-    }
-    if (tid == 96) { S.p_flags = pods.rflags[p]; S.p_tol = pods.tol[p]; }
-    __syncthreads();
-    const PodRef pd{S.p_mask, 1, S.p_flags, S.p_gt, S.p_lt, 1, S.p_req, 1, S.p_tol};
+    const PodRef pd{S.p_mask[cur], 1, S.p_flags[cur], S.p_gt[cur], S.p_lt[cur], 1, S.p_req[cur], 1, S.p_tol[cur]};
+    const uint32_t podkeys = S.p_keys[cur], ract = S.p_ract[cur];
+    prof[7] += tid == 0;
+    PROF(0);
 
     // ---- addToExistingNode ----
     int found = INT_MAX;
     for (int eb = 0; eb < E; eb += PACK_THREADS) {
       int e = eb + tid;
-      if (e < E && node_can_add(kt, A, E0 + e, pd, S.zero_b)) atomicMin(&S.best, e);
+      if (e < E && node_can_add(kt, A, E0 + e, pd, S.zero_b)) atomicMin(&S.best[cur], e);
       __syncthreads();
-      found = S.best;
+      found = S.best[cur];
       __syncthreads();
       if (found != INT_MAX) break;
     }
-    if (found != INT_MAX) {
+    const bool on_node = found != INT_MAX;
+    PROF(1);
+
+    int32_t* ord = S.ord_global ? g_ord : s_ord;
+    int32_t* key = S.ord_global ? g_key : s_key;
+    const int n = S.n_claims;
+    if (!on_node) {
+      // ---- addToInflightNode ----
+      // One thread per in-flight claim, s.newNodeClaims order: warp w takes claims [32(w + it*NW), +32) in
+      // pass `it` and stops as soon as the CTA-wide best index lies before its next block, so every index below
+      // the final minimum has been evaluated and rejected (scheduler.go:566-575).
+      if (tid == 0) S.undo_mode = MODE_NONE;  // the reference sorts here too: the last normalisation stands
+      // Round 0 looks at the first 64 claims with two warps (most pods land there); only if none takes the pod
+      // do all warps walk the rest, 512 claims per pass.
+      auto scan_block = [&](int b0) -> bool {
+        const int idx = b0 + lane;
+        int code = 0, c = -1;
+        if (idx < n) {
+          c = ord[idx];
+          StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
+                      c_req + (size_t)c * R, 1, S.tm.taints[c_tmpl[c]]};
+          code = thread_inflight(kt, st, c_hi + (size_t)c * R, c_mask + (size_t)c * W, pd, podkeys, ract);
+          if (code) my_evals += (unsigned long long)c_nopt[c];
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, code == 2);
+        if (!hit) return false;
+        const int first = __ffs(hit) - 1;
+        const int hc = __shfl_sync(0xffffffffu, c, first);
+        if (lane == 0) {
+          S.hit_c[warp] = hc;
+          atomicMin(&S.best[cur], b0 + first);
+        }
+        return true;
+      };
+      constexpr int ROUND0 = 64;
+      if (warp < ROUND0 / 32 && warp * 32 < n) scan_block(warp * 32);
+      __syncthreads();
+      if (S.best[cur] == INT_MAX && n > ROUND0) {
+        for (int it = 0;; it++) {
+          const int b0 = ROUND0 + (it * NW + warp) * 32;
+          int best_now = 0;
+          if (lane == 0) best_now = *(volatile int32_t*)&S.best[cur];
+          best_now = __shfl_sync(0xffffffffu, best_now, 0);  // one read per warp keeps the loop exit uniform
+          if (b0 >= n || b0 > best_now) break;
+          if (scan_block(b0)) break;  // later blocks of this warp come later in order
+        }
+        __syncthreads();
+      }
+      found = S.best[cur];
+    }
+    PROF(2);
+
+    // ---- commit: exactly one of (node, in-flight claim, new claim, push back).  Warp 0 handles the queue and the
+    // next pod's row, the first lane group of warp 1 the claim state, warp 2 the claim order. ----
+    if (tid == 0) S.best[cur ^ 1] = INT_MAX;
+    const int t_new = (!on_node && found == INT_MAX) ? A.a_tmpl[p] : -1;
+    if (on_node) {
       const int row = E0 + found;  // ExistingNode.Add (existingnode.go:111-119)
-      if (tid < R) A.n_avail[(size_t)tid * A.Etot + row] -= S.p_req[tid];
-      if (tid >= 32 && tid < 64) {
-        int k = tid - 32;
+      if (warp == 1) {
+        if (lane < R) A.n_avail[(size_t)lane * A.Etot + row] -= pd.req[lane];
+      } else if (warp == 2) {
+        const int k = lane;
         uint32_t nib_lo = 0, nib_hi = 0;
         if (k < K) {
           StateRef st{A.n_rmask + row, (size_t)A.Etot, A.n_rflags[row], S.zero_b, S.zero_b, 1, nullptr, 0, 0};
@@ -178,171 +429,92 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
         A.pod_index[p] = found;
         A.pod_seq[p] = S.seq++;
       }
-      __syncthreads();
-      continue;
-    }
-
-    // ---- sort.Slice(newNodeClaims, len(Pods) ascending) with Go's exact tie order ----
-    // the order (claim ids) and the pod counts by position live in shared memory up to ORD_SMEM_CAP claims
-    if (!S.ord_global && S.n_claims >= ORD_SMEM_CAP) {
-      for (int i = tid; i < S.n_claims; i += PACK_THREADS) { g_ord[i] = s_ord[i]; g_key[i] = s_key[i]; }
-      __syncthreads();
-      if (tid == 0) S.ord_global = 1;
-      __syncthreads();
-    }
-    int32_t* ord = S.ord_global ? g_ord : s_ord;
-    int32_t* key = S.ord_global ? g_key : s_key;
-    if (tid == 0) {
-      int mode = MODE_NONE;
-      const int n = S.n_claims;
-      if (S.dirty_pos >= 0 && n > 1) {
-        GoSort gs{ord, key};
-        const int pos = S.dirty_pos;
-        bool sorted = S.dirty_kind == KIND_INC ? (pos == n - 1 || !gs.less(pos + 1, pos)) : !gs.less(n - 1, n - 2);
-        if (!sorted) {
-          int hint = 0;
-          if (n >= 50) gs.choose_pivot(0, n, &hint);
-          if (n >= 50 && hint == 1) {
-            // pdqsort takes partialInsertionSort: the single displaced element is re-inserted next to
-            // its equals (see DESIGN.md "tie order"); done by all threads as a rotate
-            const int cx = key[pos];
-            if (S.dirty_kind == KIND_INC) {
-              int lo = pos + 1, hi = n;  // first index > pos whose count >= cx
-              while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (key[mid] < cx) lo = mid + 1; else hi = mid;
-              }
-              mode = MODE_ROT_INC;
-              S.rot_from = pos;
-              S.rot_to = lo - 1;
-            } else {
-              int lo = 0, hi = n - 1;  // first index whose count > cx
-              while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (key[mid] <= cx) lo = mid + 1; else hi = mid;
-              }
-              mode = MODE_ROT_APPEND;
-              S.rot_from = n - 1;
-              S.rot_to = lo;
-            }
-            S.rot_x = ord[pos];
-            S.rot_k = cx;
-          } else {
-            gs.sort(n);
-          }
-        }
-      }
-      S.dirty_pos = -1;
-      S.mode = mode;
-    }
-    __syncthreads();
-    if (S.mode == MODE_ROT_INC) {  // [from+1 .. to] move one slot left, X lands at `to`
-      const int from = S.rot_from, to = S.rot_to;
-      for (int cb = from + 1; cb <= to; cb += PACK_THREADS) {
-        int i = cb + tid;
-        int v = 0, kv = 0;
-        if (i <= to) { v = ord[i]; kv = key[i]; }
-        __syncthreads();
-        if (i <= to) { ord[i - 1] = v; key[i - 1] = kv; }
-        __syncthreads();
-      }
-      if (tid == 0) { ord[to] = S.rot_x; key[to] = S.rot_k; }
-      __syncthreads();
-    } else if (S.mode == MODE_ROT_APPEND) {  // [to .. from-1] move one slot right, X lands at `to`
-      const int from = S.rot_from, to = S.rot_to;
-      for (int ce = from - 1; ce >= to; ce -= PACK_THREADS) {
-        int i = ce - tid;
-        int v = 0, kv = 0;
-        if (i >= to) { v = ord[i]; kv = key[i]; }
-        __syncthreads();
-        if (i >= to) { ord[i + 1] = v; key[i + 1] = kv; }
-        __syncthreads();
-      }
-      if (tid == 0) { ord[to] = S.rot_x; key[to] = S.rot_k; }
-      __syncthreads();
-    }
-
-    // ---- addToInflightNode ----
-    const int n = S.n_claims;
-    found = INT_MAX;
-    for (int cb = 0; cb < n; cb += NG) {
-      const int idx = cb + g;
-      uint64_t out[WPL];
-      int c = -1;
-      if (idx < n) {
-        c = ord[idx];
-        const int t = c_tmpl[c];
-        StateRef st{c_rmask + (size_t)c * K, 1, c_rflags[c], c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
-                    c_req + (size_t)c * R, 1, S.tm.taints[t]};
-        uint64_t cand[WPL];
+    } else if (found != INT_MAX) {
+      const int c = S.hit_c[found < 64 ? (found >> 5) : (((found - 64) >> 5) % NW)];  // not ord[found]: warp 2 reorders ord
+      if (warp == 1 && lane < G) {  // NodeClaim.Add (nodeclaim.go:168-180): the full surviving set, by one lane group
+        StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
+                    c_req + (size_t)c * R, 1, 0};
+        uint64_t cand[WPL], out[WPL];
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
           int w = gl + i * G;
           cand[i] = w < W ? c_mask[(size_t)c * W + w] : 0ull;
         }
-        uint8_t code;
         int visited;
-        int stt = group_can_add<G, WPL>(kt, &scratch[g], st, pd, true, cand, out, &code, &visited);
-        if (gl == 0) {
-          my_evals += (unsigned long long)visited;
-          if (stt == ST_OK) atomicMin(&S.best, idx);
-        }
-      }
-      __syncthreads();
-      found = S.best;
-      __syncthreads();
-      if (found != INT_MAX) {
-        if (idx == found) {  // NodeClaim.Add (nodeclaim.go:168-180)
-          StateRef st{c_rmask + (size_t)c * K, 1, c_rflags[c], c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
-                      c_req + (size_t)c * R, 1, 0};
-          group_store_merged<G>(kt, st, pd, c_rmask + (size_t)c * K, 1, &c_rflags[c], c_gt + (size_t)c * NB,
-                                c_lt + (size_t)c * NB, 1);
+        group_inflight<G, WPL>(kt, st, c_hi + (size_t)c * R, pd, podkeys, cand, out, &visited);
+        if (podkeys)
+          group_store_merged_keys<G>(kt, st, pd, podkeys, c_rmask + (size_t)c * K, &c_rflags[c], c_gt + (size_t)c * NB,
+                                     c_lt + (size_t)c * NB);
+        int cnt = 0;
 #pragma unroll
-          for (int i = 0; i < WPL; i++) {
-            int w = gl + i * G;
-            if (w < W) c_mask[(size_t)c * W + w] = out[i];
-          }
-          for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += S.p_req[r];
-          if (gl == 0) {
-            c_npods[c]++;
-            key[found]++;
-            A.pod_kind[p] = B200S_PLACE_CLAIM;
-            A.pod_index[p] = c;
-            A.pod_seq[p] = S.seq++;
-            S.dirty_pos = found;
-            S.dirty_kind = KIND_INC;
-          }
+        for (int i = 0; i < WPL; i++) {
+          int w = gl + i * G;
+          if (w < W) c_mask[(size_t)c * W + w] = out[i];
+          cnt += popc64(out[i]);
         }
-        break;
+        cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
+        for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += pd.req[r];
+        if (gl == 0) {
+          c_nopt[c] = cnt;
+          c_npods[c]++;
+        }
+      } else if (warp == 2) {  // the claim moved one pod up: what sort.Slice will do with that
+        if (lane == 0) key[found]++;
+        __syncwarp();
+        warp_normalise(S, ord, key, g_snap, n, found, false);
       }
-    }
-    if (found != INT_MAX) {
-      __syncthreads();
-      continue;
-    }
-
-    // ---- addToNewNodeClaim: the template walk was done for every pod by stage A ----
-    const int t = A.a_tmpl[p];
-    if (t >= 0) {
-      const int c = n;  // NewNodeClaim + Add (nodeclaim.go:83-109, :168-180)
-      if (g == 0) {
+      if (tid == 0) {
+        A.pod_kind[p] = B200S_PLACE_CLAIM;
+        A.pod_index[p] = c;
+        A.pod_seq[p] = S.seq++;
+      }
+    } else if (t_new >= 0) {
+      // ---- addToNewNodeClaim: the template walk was done for every pod by stage A ----
+      const int t = t_new, c = n;
+      if (warp == 1 && lane < G) {  // NewNodeClaim + Add (nodeclaim.go:83-109, :168-180)
         StateRef st{S.tm.rmask[t], 1, S.tm.rflags[t], S.tm.gt[t], S.tm.lt[t], 1, S.tm.daemon[t], 1, 0};
         group_store_merged<G>(kt, st, pd, c_rmask + (size_t)c * K, 1, &c_rflags[c], c_gt + (size_t)c * NB,
                               c_lt + (size_t)c * NB, 1);
-        for (int w = gl; w < W; w += G) c_mask[(size_t)c * W + w] = A.a_mask[(size_t)p * W + w];
-        for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] = S.tm.daemon[t][r] + S.p_req[r];
+        int cnt = 0;
+        for (int w = gl; w < W; w += G) {
+          uint64_t m = A.a_mask[(size_t)p * W + w];
+          c_mask[(size_t)c * W + w] = m;
+          cnt += popc64(m);
+        }
+        cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
+        for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] = S.tm.daemon[t][r] + pd.req[r];
+        // largest Allocatable() among the claim's instance types, per resource: the highest table row
+        // "alloc >= dv[i]" that still meets the mask (the mask only shrinks afterwards, so this stays an upper bound)
+        for (int r = 0; r < R; r++) {
+          int lo = 0, hi = kt.res_nd[r] - 1;  // row 0 always meets a non-empty mask
+          while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            unsigned hit = 0;
+            for (int w = gl; w < W; w += G)
+              hit |= (A.a_mask[(size_t)p * W + w] & kt.rows[(size_t)(kt.res_row0[r] + mid) * W + w]) ? 1u : 0u;
+            hit = __reduce_or_sync(group_mask<G>(), hit);
+            if (hit) lo = mid; else hi = mid - 1;
+          }
+          if (gl == 0) c_hi[(size_t)c * R + r] = kt.res_dv[kt.res_dv0[r] + lo];
+        }
         if (gl == 0) {
           c_tmpl[c] = t;
           c_npods[c] = 1;
+          c_nopt[c] = cnt;
+        }
+      } else if (warp == 2) {
+        if (lane == 0) {
           ord[n] = c;
           key[n] = 1;
           S.n_claims = n + 1;
-          S.dirty_pos = n;
-          S.dirty_kind = KIND_APPEND;
-          A.pod_kind[p] = B200S_PLACE_CLAIM;
-          A.pod_index[p] = c;
-          A.pod_seq[p] = S.seq++;
         }
+        __syncwarp();
+        warp_normalise(S, ord, key, g_snap, n + 1, n, true);
+      }
+      if (tid == 0) {
+        A.pod_kind[p] = B200S_PLACE_CLAIM;
+        A.pod_index[p] = c;
+        A.pod_seq[p] = S.seq++;
       }
     } else if (tid == 0) {  // Queue.Push (queue.go:63-66); the pod stays in PodErrors
       int tail = S.head + S.len;
@@ -354,11 +526,51 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
       A.pod_kind[p] = B200S_PLACE_UNSCHEDULED;
       A.pod_index[p] = -1;
     }
+    if (warp == 0) {
+      __syncwarp();
+      pop_and_load(cur ^ 1);
+    }
     __syncthreads();
+    PROF(3);
+
+    // ---- what is left of the order normalisation: long rotates and the full pdqsort's bookkeeping ----
+    if (S.mode != MODE_NONE) {
+      const int mode = S.mode, src = S.rot_src, dst = S.rot_dst, orig = S.rot_orig;
+      prof[5] += tid == 0;
+      prof[6] += (tid == 0 && mode == MODE_GENERIC);
+      if (mode == MODE_ROTATE) cta_rotate(ord, key, src, dst);
+      if (tid == 0) {
+        S.undo_mode = mode;
+        S.undo_src = dst;
+        S.undo_dst = orig;
+        S.mode = MODE_NONE;
+      }
+      __syncthreads();
+    }
+    if (!S.ord_global && S.n_claims >= ORD_SMEM_CAP) {  // spill the order arrays to global memory
+      for (int i = tid; i < S.n_claims; i += PACK_THREADS) { g_ord[i] = s_ord[i]; g_key[i] = s_key[i]; }
+      __syncthreads();
+      if (tid == 0) S.ord_global = 1;
+      __syncthreads();
+    }
+    PROF(4);
+    cur ^= 1;
   }
 
-  if (!S.ord_global)
-    for (int i = tid; i < S.n_claims; i += PACK_THREADS) g_ord[i] = s_ord[i];
+  // Results.NewNodeClaims is the order after the LAST sort the reference ran plus the modification that followed it:
+  // if no later add() reached the sort, the eager normalisation of that last modification has to be taken back.
+  {
+    int32_t* ord = S.ord_global ? g_ord : s_ord;
+    int32_t* key = S.ord_global ? g_key : s_key;
+    const int um = S.undo_mode, n = S.n_claims;
+    __syncthreads();
+    if (um == MODE_ROTATE) cta_rotate(ord, key, S.undo_src, S.undo_dst);
+    else if (um == MODE_GENERIC)
+      for (int i = tid; i < n; i += PACK_THREADS) ord[i] = g_snap[i];
+    __syncthreads();
+    if (!S.ord_global)
+      for (int i = tid; i < n; i += PACK_THREADS) g_ord[i] = s_ord[i];
+  }
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
   if ((tid & 31) == 0 && my_evals) atomicAdd(&S.evals, my_evals);
   __syncthreads();
@@ -366,6 +578,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(KeyTab kt, const 
     pb.n_claims = S.n_claims;
     pb.n_unscheduled = S.len;
     pb.evals = S.evals;
+    for (int i = 0; i < 8; i++) pb.prof[i] = prof[i];
   }
 }
 
@@ -418,7 +631,8 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   int G, WPL;
   pick_group_pack(kt.n_words, &G, &WPL);
   size_t so, to;
-  int in_smem = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, 1, &so, &to) <= (size_t)smem_limit;
+  (void)smem_limit;
+  int in_smem = 0;  // tables stay in global memory / L1 for this kernel
   size_t bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                            \

@@ -233,19 +233,29 @@ typedef struct b200s_templates {
   const uint64_t* type_admit; /* [T*W] SKUs each template's instance-type requirement admits; NULL = all */
 } b200s_templates_t;
 
+/* Pods are dictionary-encoded: replicas of one workload share a requirement signature (requirement
+ * set + tolerated taints) and a request vector, so a pod row is two class ids (8 bytes) plus the FFD
+ * tie-break keys.  The class tables are tiny next to the pod arrays and stay L2-resident. */
 typedef struct b200s_pods_soa {
   int32_t n_pods;            /* P */
   int32_t n_res, n_keys, n_bounded;
   int32_t res_cpu, res_memory; /* resource rows the FFD order sorts on (queue.go:72-108) */
-  const int64_t* requests;   /* [R*P] resource-major */
-  const uint64_t* req_mask;  /* [K*P] key-major */
-  const uint64_t* req_flags; /* [P] */
-  const int32_t* req_gt;     /* [NB*P] */
-  const int32_t* req_lt;     /* [NB*P] */
-  const uint64_t* tolerated; /* [P] bit t: pod tolerates taint t (taints.go:53-65) */
-  const int64_t* ts;         /* [P] */
+  int32_t n_sigs;            /* NS distinct requirement signatures */
+  int32_t n_reqcls;          /* NQ distinct request vectors        */
+  /* per pod */
+  const int32_t* sig_id;     /* [P] */
+  const int32_t* req_id;     /* [P] */
+  const int64_t* ts;         /* [P] creationTimestamp, seconds */
   const uint64_t* uid_hi;    /* [P] */
   const uint64_t* uid_lo;    /* [P] */
+  /* signature table, key-major over NS */
+  const uint64_t* sig_mask;  /* [K*NS] */
+  const uint64_t* sig_flags; /* [NS]   */
+  const int32_t* sig_gt;     /* [NB*NS] */
+  const int32_t* sig_lt;     /* [NB*NS] */
+  const uint64_t* sig_tolerated; /* [NS] bit t: tolerates taint t (taints.go:53-65) */
+  /* request-class table, resource-major over NQ */
+  const int64_t* rq_requests; /* [R*NQ] RequestsForPods incl. pods:1 (resources.go:30-38) */
 } b200s_pods_soa_t;
 
 typedef struct b200s_nodes_soa {
@@ -389,6 +399,9 @@ int b200s_resident_fetch_fit(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t* tmp
 int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_result_t* out);
 /* number of kernels the last resident_* call enqueued */
 int b200s_resident_last_launches(const b200s_resident_t* r);
+/* diagnostic: SM cycles per phase of the last solve's pack kernel (pop, pod row, existing nodes, sort,
+ * pre-filter, evaluate, commit) and, in out[7], the number of pod steps */
+int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[8]);
 
 /* ---- config 1: the vmSize pick of instance.Provider.Create (host only, no device) ----
  * name: NodeClaim name; instance_types: the values of the node.kubernetes.io/instance-type

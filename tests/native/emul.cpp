@@ -50,11 +50,15 @@ void put(const KeyTab& kt, ReqRow& r, int k, const EReq& q) {
 
 ReqRow pod_row(const KeyTab& kt, const b200s_pods_soa_t* p, int i) {
   ReqRow r{};
-  for (int k = 0; k < kt.n_keys; k++) r.mask[k] = p->req_mask[(size_t)k * p->n_pods + i];
-  r.flags = p->req_flags[i];
-  for (int b = 0; b < kt.n_bounded; b++) { r.gt[b] = p->req_gt[(size_t)b * p->n_pods + i]; r.lt[b] = p->req_lt[(size_t)b * p->n_pods + i]; }
+  const int sig = p->sig_id[i], ns = p->n_sigs;
+  for (int k = 0; k < kt.n_keys; k++) r.mask[k] = p->sig_mask[(size_t)k * ns + sig];
+  r.flags = p->sig_flags[sig];
+  for (int b = 0; b < kt.n_bounded; b++) { r.gt[b] = p->sig_gt[(size_t)b * ns + sig]; r.lt[b] = p->sig_lt[(size_t)b * ns + sig]; }
   return r;
 }
+
+int64_t pod_request(const b200s_pods_soa_t* p, int r, int i) { return p->rq_requests[(size_t)r * p->n_reqcls + p->req_id[i]]; }
+uint64_t pod_tolerated(const b200s_pods_soa_t* p, int i) { return p->sig_tolerated[p->sig_id[i]]; }
 
 ReqRow tmpl_row(const KeyTab& kt, const b200s_templates_t* tm, int t) {
   ReqRow r{};
@@ -156,14 +160,14 @@ int emul_fit_matrix(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm,
   std::vector<int64_t> preq(R);
   for (int p = 0; p < P; p++) {
     ReqRow pd = pod_row(kt, pods, p);
-    for (int r = 0; r < R; r++) preq[r] = pods->requests[(size_t)r * P + p];
+    for (int r = 0; r < R; r++) preq[r] = pod_request(pods, r, p);
     int chosen = -1;
     for (int w = 0; w < W; w++) mask_out[(size_t)p * W + w] = 0;
     for (int t = 0; t < T; t++) {
       uint8_t code = alive[t] ? B200S_FIT_NONE : B200S_FIT_DROPPED;
       if (alive[t] && chosen < 0) {
         ReqRow st = tmpl_row(kt, tm, t);
-        int s = can_add(kt, st, tm->daemon[t], tm->taints[t], pd, preq.data(), pods->tolerated[p], true,
+        int s = can_add(kt, st, tm->daemon[t], tm->taints[t], pd, preq.data(), pod_tolerated(pods, p), true,
                         &tmask[(size_t)t * W], out.data(), &code, &evals, nullptr);
         if (s == ST_OK) {
           chosen = t;
@@ -202,7 +206,7 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
   // FFD order (queue.go:72-108)
   std::vector<int> q(P);
   for (int i = 0; i < P; i++) q[i] = i;
-  auto req = [&](int r, int p) { return pods->requests[(size_t)r * P + p]; };
+  auto req = [&](int r, int p) { return pod_request(pods, r, p); };
   std::sort(q.begin(), q.end(), [&](int a, int b) {
     if (req(pods->res_cpu, a) != req(pods->res_cpu, b)) return req(pods->res_cpu, a) > req(pods->res_cpu, b);
     if (req(pods->res_memory, a) != req(pods->res_memory, b)) return req(pods->res_memory, a) > req(pods->res_memory, b);
@@ -238,7 +242,7 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
     if (lastlen[p] == (int)len) break;
     head++;
     ReqRow pd = pod_row(kt, pods, p);
-    uint64_t tol = pods->tolerated[p];
+    uint64_t tol = pod_tolerated(pods, p);
     for (int r = 0; r < R; r++) preq[r] = req(r, p);
     bool placed = false;
     for (int e = 0; e < E && !placed; e++) {  // addToExistingNode

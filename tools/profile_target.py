@@ -27,5 +27,10 @@ for i in range(iters):
     (res.fit_matrix if mode == "fit" else res.solve)()
     ctx.record(ev1)
     print(f"{mode} {kind} {P}x{S} iter {i}: {ctx.elapsed_ms(ev0, ev1):.4f} ms", flush=True)
+    if mode == "solve":
+        pr = res.pack_profile()
+        steps = max(pr["steps"], 1)
+        print("   cycles/step:", {k: round(v / steps, 1) for k, v in pr.items() if k not in ("steps", "-", "--")}, "steps", steps,
+              "cta-normalisations", pr["-"], "of which full pdqsort", pr["--"], flush=True)
 res.close()
 ctx.close()
