@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py — pod x SKU fit evaluations/s and NodeClaims scheduled/s of the B200 path, next to the CPU oracle.
 
-One step = one pass of the hot path over BASELINE.json configs[1] (10 000 synthetic pending pods x 500 Azure
-SKUs): dense fit matrix (stage A) + FFD order + bin-pack + cheapest SKU per NodeClaim, i.e. one b200s_solve.
-  value    evaluations/s, device-timed (CUDA events on the library's stream), inputs resident in HBM
-  e2e      the same through the host-buffer C-ABI call (b200s_solve): H2D of the pod/node SoA and D2H of the
-           result inside the timed region
-  roofline the dense fit-matrix kernel: algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json hbm_gbs
-Evaluations per step = P x S-after-prefilter instance types the dense stage visits + the instance types the
-reference's in-flight CanAdd calls visit (the oracle's count, credited — not the device's own larger count).
+Default workload = BASELINE.json configs[1]: 10 000 synthetic pending pods x 500 Azure SKUs, one NodePool.
+One step = one pass of the hot path over that batch = one b200s_solve: class tables + dense pod x SKU fit matrix
+(stage A), FFD order, bin-pack into NodeClaims, cheapest SKU per NodeClaim.
 
-`--impl reference` times the CPU oracle (reference-shaped restatement of the Go scheduler; the reference itself
-is Go and cannot be built here) on the same config, same metric.  Under torchrun every rank solves its own
-shard-independent replica (the pack is sequential per Solve: "replicas only"; the dense stage shards by pod
-rows and needs no collective) and rank 0 prints the max-over-ranks time.
+  value     evaluations/s, device-timed with CUDA events on the library's stream, inputs resident in HBM, L2 flushed
+            between iterations.  Evaluations per step = the P x S-after-prefilter instance types the dense stage
+            decides + the instance types the reference's in-flight CanAdd calls visit (the ORACLE's count, credited;
+            the device's own count is larger because it evaluates claims in parallel).
+  e2e       the same through the host-buffer C-ABI call (b200s_solve): H2D of the pod / class / node SoA and D2H of
+            the result inside the timed region.
+  roofline  the dense kernel (the HBM-bound kernel of the path) alone: algorithmic bytes / its own CUDA-event time
+            vs MEASURED_PEAKS.json hbm_gbs.  config[1] moves < 1 MB per launch, so the same kernel is also timed on
+            configs[2] (100k x 1k) and, with --large, configs[4]'s size (1M x 2k): `roofline_large`.
+  --impl reference   the CPU oracle (reference-shaped restatement of the Go scheduler; the reference itself is Go and
+            cannot be built here) on the same workload, same metric, one host core (the reference's default: one worker).
+  --workload c5      1M pods x 2k SKUs, dense stage row-sharded over the ranks + one NCCL all-gather of the result rows.
+
+Under torchrun with the default workload every rank runs an independent replica ("replicas only": the pack is
+sequential per Solve) and rank 0 prints the max-over-ranks time.
 """
 from __future__ import annotations
 
@@ -31,11 +37,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+METRIC = "pod x SKU fit evaluations/s"
+WORKLOAD = "config[1]: 10k pending pods x 500 Azure SKUs, 1 NodePool; dense fit matrix + FFD pack + cheapest SKU (one Solve)"
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
@@ -43,9 +52,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
     def __init__(self, index: int):
-        self.rows = []
-        self.stop = False
-        self.index = index
+        self.rows, self.stop, self.index = [], False, index
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -74,52 +81,186 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        reasons = [n for i, n in enumerate(names)
+                   if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(self.rows)}
 
 
-def algorithmic_bytes_fit(enc) -> int:
-    """Compulsory traffic of one dense fit-matrix launch with this repo's layout (DESIGN.md "Algorithmic bytes"):
-    every pod row read once, every output written once, catalog tables read once."""
-    pod_row = 4 + 4                                                # signature id + request-class id
-    out_row = enc.W * 8 + 4 + enc.T                                # mask, first feasible template, per-template codes
-    tables = (enc.NS * 2 + enc.NQ) * enc.T * enc.W * 8 + enc.NS * enc.T  # class rows C, O, F + status, read once
+def dense_bytes(enc) -> int:
+    """Algorithmic bytes of one dense launch with this repo's layout: every pod row (two class
+    ids) read once, every output (SKU mask, first feasible template, per-template codes) written once, every class
+    row (C, O per signature x template; F per request vector x template; status) read once."""
+    pod_row = 4 + 4
+    out_row = enc.W * 8 + 4 + enc.T
+    tables = (enc.NS * 2 + enc.NQ) * enc.T * enc.W * 8 + enc.NS * enc.T
     return enc.P * (pod_row + out_row) + tables
 
 
-def run_reference(args, rank, world):
+def time_device(ctx, fn, steps, warmup):
+    ev0, ev1 = ctx.event(), ctx.event()
+    for _ in range(warmup):
+        ctx.flush_l2()
+        fn()
+    ctx.synchronize()
+    total = 0.0
+    for _ in range(steps):
+        ctx.flush_l2()  # L2 flush between timed iterations (256 MiB memset)
+        ctx.record(ev0)
+        fn()
+        ctx.record(ev1)
+        total += ctx.elapsed_ms(ev0, ev1)
+    return total / steps
+
+
+def oracle_counts(model):
+    import oracle_binding as ob
+    t0 = time.perf_counter()
+    o = ob.solve(model)
+    t_solve = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    f = ob.fit_matrix(model)
+    t_fit = time.perf_counter() - t0
+    credited = f[3] + o.counters["fit_evals"] - o.counters["newclaim_evals"]
+    return o, f, credited, t_solve, t_fit
+
+
+def run_reference(args, rank):
     import oracle_binding as ob
     from b200sched import synth
     if rank != 0:
         return
     model = synth.c2()
-    P, S = model.n_pods, model.n_skus
     ob.lib()
     times = []
-    evals = None
+    credited = nclaims = 0
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        o = ob.solve(model)
-        f = ob.fit_matrix(model)
-        dt = time.perf_counter() - t0
+        o, f, credited, t_solve, t_fit = oracle_counts(model)
         if it >= args.warmup:
-            times.append(dt)
-        evals = f[3] + o.counters["fit_evals"] - o.counters["newclaim_evals"]  # dense matrix + in-flight CanAdd visits
+            times.append(t_solve + t_fit)
         nclaims = o.n_claims
     ms = 1e3 * sum(times) / len(times)
-    value = evals / (ms / 1e3)
-    line = {"metric": "pod x SKU fit evaluations/s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64/u64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "config[1]: 10k pending pods x 500 Azure SKUs, 1 NodePool; dense fit matrix + full Solve",
-                       "pods": P, "skus": S},
-            "nodeclaims_per_s": nclaims / (ms / 1e3),
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port",
-                             "sample": "the whole config (one dense pass + one Solve per step), single thread as the reference's default one worker"},
-            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    value = credited / (ms / 1e3)
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u64",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "pods": model.n_pods, "skus": model.n_skus},
+        "nodeclaims_per_s": nclaims / (ms / 1e3), "evals_per_step": int(credited),
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": 1, "kind": "port",
+                         "sample": "the whole workload per step (one dense pass + one Solve), one thread — the reference's "
+                                   "default is one scheduler worker (K/operator/options/options.go:122)",
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def dense_leg(ctx, capi, synth, kind, P, S, steps, warmup, peak):
+    """The dense stage alone on a larger config: class tables + streaming kernel, each timed with its own events."""
+    model = synth.config(kind, P, S)
+    enc = capi.Encoded(model)
+    cid = ctx.upload_catalog(enc)
+    res = ctx.resident(cid, enc)
+    ms = time_device(ctx, res.fit_matrix, steps, warmup)
+    ab = dense_bytes(enc)
+    out = {"workload": f"{P} pods x {S} SKUs ({'4 tainted NodePools, selectors' if kind == 'c3' else '1 NodePool'})",
+           "signatures": enc.NS, "request_classes": enc.NQ, "stage_ms": ms, "evals_per_s": P * S / (ms * 1e-3),
+           "algorithmic_bytes": ab, "achieved_gbs_stage": ab / (ms * 1e-3) / 1e9, "frac_stage": ab / (ms * 1e-3) / 1e9 / peak,
+           "note": "stage = template pre-filter + class tables + dense kernel (4 launches); the dense kernel's own share is in profiles/"}
+    res.close()
+    ctx.release_catalog(cid)
+    return out
+
+
+def run_c5(args, rank, world, local):
+    """configs[4]: 1M pods x 2k SKUs, dense stage sharded by pod rows, one NCCL all-gather of the result rows."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from b200sched import capi, model as M, sharding, synth
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P, S = args.pods or 1_000_000, args.skus or 2_000
+    full = synth.config("c3", P, S)
+    lo, hi = sharding.row_shard(P, rank, world)
+    shard = M.slice_pods(full, lo, hi) if world > 1 else full
+    enc = capi.Encoded(shard)
+    ctx = capi.Context(local)
+    cid = ctx.upload_catalog(enc)
+    res = ctx.resident(cid, enc)
+    rows = max(sharding.row_shard(P, r, world)[1] - sharding.row_shard(P, r, world)[0] for r in range(world))
+    W, T = enc.W, enc.T
+    d_tmpl = torch.zeros(rows, dtype=torch.int32, device="cuda")
+    d_mask = torch.zeros(rows * W, dtype=torch.int64, device="cuda")
+    d_code = torch.zeros(rows * T, dtype=torch.uint8, device="cuda")
+    g_tmpl = torch.empty(world * rows, dtype=torch.int32, device="cuda")
+    g_mask = torch.empty(world * rows * W, dtype=torch.int64, device="cuda")
+    g_code = torch.empty(world * rows * T, dtype=torch.uint8, device="cuda")
+    ev0, ev1 = ctx.event(), ctx.event()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def step():
+        ctx.flush_l2()
+        ctx.record(ev0)
+        res.fit_matrix()
+        res.copy_fit_device(d_tmpl.data_ptr(), d_mask.data_ptr(), d_code.data_ptr())
+        ctx.record(ev1)
+        ms_fit = ctx.elapsed_ms(ev0, ev1)  # synchronises the library's stream: the send buffers are complete
+        ms_ag = 0.0
+        if world > 1:
+            t0.record()
+            dist.all_gather_into_tensor(g_tmpl, d_tmpl)
+            dist.all_gather_into_tensor(g_mask, d_mask)
+            dist.all_gather_into_tensor(g_code, d_code)
+            t1.record()
+            t1.synchronize()
+            ms_ag = t0.elapsed_time(t1)
+        return ms_fit, ms_ag
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    acc = np.zeros(2)
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            acc += step()
+    acc /= args.steps
+    if world > 1:
+        t = torch.tensor(acc, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        acc = t.cpu().numpy()
+    # parity spot check on this rank's shard
+    import oracle_binding as ob
+    import parity
+    fit = res.fetch_fit()
+    s0, s1 = 0, min(2000, enc.P)
+    o_tmpl, o_mask, o_code, _, _ = ob.fit_matrix(shard, s0, s1)
+    cf = parity.canon_fit(enc, fit)
+    assert np.array_equal(cf["tmpl"][s0:s1], o_tmpl) and np.array_equal(cf["mask"][s0:s1], o_mask)
+    peak, src = peaks()
+    ms = float(acc[0] + acc[1])
+    ab = dense_bytes(enc)
+    line = {"metric": METRIC, "value": P * S / (ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"config[4]: {P} pods x {S} SKUs, dense stage sharded by pod rows over {world} GPU(s), "
+                                   "one NCCL all-gather of the result rows", "l2": "flushed between timed iterations"},
+            "dense_ms_max_over_ranks": float(acc[0]), "allgather_ms": float(acc[1]),
+            "allgather_bytes_per_rank": int(rows * (4 + W * 8 + T)),
+            "roofline": {"bound": "hbm", "kernel": "dense stage (per rank shard)", "achieved": ab / (acc[0] * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": ab / (acc[0] * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": src},
+            "clocks": clk.summary(), "parity": "first 2000 rows of the rank-0 shard identical to the CPU oracle"}
+    res.close()
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -128,13 +269,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--pods", type=int, default=0)
+    ap.add_argument("--skus", type=int, default=0)
+    ap.add_argument("--large", action="store_true", help="also time the dense stage on 1M pods x 2k SKUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank)
+        return
+    if args.workload == "c5":
+        run_c5(args, rank, world, local)
         return
 
     import torch
@@ -142,7 +289,6 @@ def main():
     import __graft_entry__ as g
     g.build()
     from b200sched import capi, synth
-    import oracle_binding as ob
     import parity
 
     if not torch.cuda.is_available():
@@ -157,40 +303,16 @@ def main():
     cid = ctx.upload_catalog(enc)
     res = ctx.resident(cid, enc)
     P, S = enc.P, enc.S
-
-    # oracle counts for crediting (rank 0 only times it; every rank needs the count)
-    t0 = time.perf_counter()
-    o = ob.solve(model)
-    t_solve_cpu = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    of = ob.fit_matrix(model)
-    t_fit_cpu = time.perf_counter() - t0
+    o, of, credited, t_solve_cpu, t_fit_cpu = oracle_counts(model)
     dense_evals = of[3]
-    # a step evaluates the dense pod x SKU matrix (which subsumes addToNewNodeClaim's template walks) plus the
-    # instance types the reference's in-flight CanAdd calls visit (the oracle's count, credited)
-    credited = dense_evals + o.counters["fit_evals"] - o.counters["newclaim_evals"]
 
     # parity gate before any timing
     res.solve()
     raw = res.fetch_solve()
     parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(model, o), "bench parity")
-    launches = res.launches()
-
-    ev = [ctx.event() for _ in range(4)]
-
-    def timed_device(fn, steps, warmup):
-        for _ in range(warmup):
-            ctx.flush_l2()
-            fn()
-        ctx.synchronize()
-        total = 0.0
-        for _ in range(steps):
-            ctx.flush_l2()          # L2 flush between timed iterations (inputs are smaller than L2)
-            ctx.record(ev[0])
-            fn()
-            ctx.record(ev[1])
-            total += ctx.elapsed_ms(ev[0], ev[1])
-        return total / steps
+    launches_solve = res.launches()
+    res.fit_matrix()
+    launches_fit = res.launches()
 
     def barrier():
         if world > 1:
@@ -199,15 +321,15 @@ def main():
 
     barrier()
     with ClockSampler(local) as clk:
-        ms_solve = timed_device(res.solve, args.steps, args.warmup)
-        ms_fit = timed_device(res.fit_matrix, args.steps, args.warmup)
-        # e2e: host buffers in, host results out, through the public C-ABI call
+        ms_solve = time_device(ctx, res.solve, args.steps, args.warmup)
+        ms_fit = time_device(ctx, res.fit_matrix, args.steps, args.warmup)
         for _ in range(args.warmup):
             ctx.solve(cid, enc)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.solve(cid, enc)
+            ctx.solve(cid, enc)  # host buffers in, host results out, through the public C-ABI call
         ms_e2e = 1e3 * (time.perf_counter() - t0) / args.steps
+    prof = res.pack_profile()
     barrier()
     if world > 1:
         t = torch.tensor([ms_solve, ms_fit, ms_e2e], device="cuda", dtype=torch.float64)
@@ -215,41 +337,50 @@ def main():
         ms_solve, ms_fit, ms_e2e = [float(x) for x in t.tolist()]
 
     peak, peak_src = peaks()
-    ab = algorithmic_bytes_fit(enc)
-    achieved = ab / (ms_fit * 1e-3) / 1e9
+    ab = dense_bytes(enc)
     h2d = enc.P * (4 + 4 + 8 + 16) + enc.NS * (enc.K * 8 + 16 + enc.NB * 8) + enc.NQ * enc.R * 8
     d2h = enc.P * (12 + enc.T) + raw.n_claims * (8 + enc.R * 8 + enc.W * 8 + enc.K * 8 + 8 + enc.NB * 16 + 16)
-
-    # CPU baseline: a bounded sample — one dense pass + one Solve of this config, already timed above on this host
     cpu_ms = 1e3 * (t_solve_cpu + t_fit_cpu)
+    steps_total = (args.steps + args.warmup)
     line = {
-        "metric": "pod x SKU fit evaluations/s", "value": world * credited / (ms_solve * 1e-3), "unit": "evals/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_solve,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
-        "config": {"workload": "config[1]: 10k pending pods x 500 Azure SKUs, 1 NodePool; dense fit matrix + full Solve",
-                   "pods": P, "skus": S, "l2": "flushed between timed iterations (256 MiB memset)",
-                   "multi_gpu": "replicas only: one independent Solve per rank, no data-path collective"},
-        "nodeclaims_per_s": world * raw.n_claims / (ms_solve * 1e-3),
-        "nodeclaims": int(raw.n_claims), "evals_per_step": int(credited), "dense_evals_per_step": int(dense_evals),
-        "fit_matrix": {"ms": ms_fit, "evals_per_s": dense_evals / (ms_fit * 1e-3)},
-        "roofline": {"bound": "hbm", "kernel": "fit_matrix_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes": ab, "peak_source": peak_src,
-                     "note": "config[1] moves ~2 MB per launch: launch-latency bound; see profiles/ for the 100k x 1k figure"},
+        "metric": METRIC, "value": world * credited / (ms_solve * 1e-3), "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_solve, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pods": P, "skus": S, "signatures": enc.NS, "request_classes": enc.NQ,
+                   "l2": "flushed between timed iterations (256 MiB memset)",
+                   "multi_gpu": "replicas only: one independent Solve per rank, no data-path collective (DESIGN.md section 7)"},
+        "nodeclaims_per_s": world * raw.n_claims / (ms_solve * 1e-3), "nodeclaims": int(raw.n_claims),
+        "evals_per_step": int(credited), "dense_evals_per_step": int(dense_evals),
+        "step_breakdown": {"dense_stage_ms": ms_fit, "dense_stage_share": ms_fit / ms_solve,
+                           "pack_and_rest_ms": ms_solve - ms_fit,
+                           "note": "the FFD pack is one sequential chain per Solve (latency-bound, one CTA); "
+                                   "cycles per pod step by phase: " + json.dumps({k: round(v / max(prof['steps'], 1)) for k, v in prof.items() if k not in ('steps', '-', '--')})},
+        "roofline": {"bound": "hbm", "kernel": "dense stage A (template_prefilter + class_tables + fit_dense_vec_kernel)",
+                     "achieved": ab / (ms_fit * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": ab / (ms_fit * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": ab,
+                     "evals_per_s": dense_evals / (ms_fit * 1e-3), "peak_source": peak_src,
+                     "note": "config[1] moves < 1 MB per launch: launch-latency bound by construction; see roofline_large"},
         "cpu_baseline": {"value": credited / (cpu_ms * 1e-3), "unit": "evals/s", "cores": 1, "kind": "port",
-                         "sample": "one dense pass + one Solve of the same config on one host core (reference default: one worker)",
-                         "ms": cpu_ms, "host_cores": os.cpu_count()},
+                         "sample": "one dense pass + one Solve of the same workload on one host core "
+                                   "(reference default: one scheduler worker)", "ms": cpu_ms, "host_cores": os.cpu_count()},
         "e2e": {"value": world * credited / (ms_e2e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": int(launches) * args.steps * 2 - args.steps * (launches - 2),
-        "launches_per_solve": int(launches),
+        "gpu_launches": int(steps_total * (launches_solve + launches_fit) + steps_total * launches_solve),
+        "launches_per_solve": int(launches_solve), "launches_per_dense_stage": int(launches_fit),
         "clocks": clk.summary(),
         "parity": "bit-identical to the CPU oracle (SHA-256 " + parity.digest(parity.canon_device(enc, raw))[:16] + ")",
     }
     res.close()
+    if rank == 0:
+        large = {"c3": dense_leg(ctx, capi, synth, "c3", 100_000, 1_000, 10, 3, peak)}
+        if args.large:
+            large["c5"] = dense_leg(ctx, capi, synth, "c3", 1_000_000, 2_000, 10, 3, peak)
+        line["roofline_large"] = large
     ctx.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -145,6 +145,7 @@ def lib():
     L.b200s_resident_fetch_fit.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_int32), _P(C.c_uint64), _P(C.c_uint8),
                                            _P(C.c_int64)]
     L.b200s_resident_fetch_solve.argtypes = [C.c_void_p, C.c_void_p, _P(Result)]
+    L.b200s_resident_copy_fit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200s_resident_last_launches.argtypes = [C.c_void_p]
     L.b200s_resident_pack_profile.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint64)]
     L.b200s_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
@@ -387,6 +388,11 @@ class Resident:
 
     def solve(self):
         self.ctx._check(self.ctx.L.b200s_resident_solve(self.ctx.h, self.h))
+
+    def copy_fit_device(self, d_tmpl: int, d_mask: int, d_code: int):
+        """Device pointers (ints) of caller-owned buffers, e.g. torch tensors' data_ptr()."""
+        self.ctx._check(self.ctx.L.b200s_resident_copy_fit_device(self.ctx.h, self.h, C.c_void_p(d_tmpl), C.c_void_p(d_mask),
+                                                                  C.c_void_p(d_code)))
 
     def launches(self) -> int:
         return self.ctx.L.b200s_resident_last_launches(self.h)

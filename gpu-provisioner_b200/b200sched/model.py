@@ -176,6 +176,27 @@ class Model:
         return out
 
 
+def slice_pods(m: "Model", lo: int, hi: int) -> "Model":
+    """A model with pods [lo, hi) of m and everything else shared (row shard for the multi-GPU dense stage)."""
+    a = dict(m.arrays)
+    off = a["pod_req_off"].astype(np.int64)
+    r0, r1 = int(off[lo]), int(off[hi])
+    p0, p1 = int(off[0]), int(off[-1])
+    a["reqs"] = np.ascontiguousarray(np.concatenate([a["reqs"][:p0], a["reqs"][r0:r1], a["reqs"][p1:]]))
+    a["pod_req_off"] = np.ascontiguousarray((off[lo:hi + 1] - r0 + p0).astype(np.int32))
+    a["node_req_off"] = np.ascontiguousarray((a["node_req_off"].astype(np.int64) - (p1 - p0) + (r1 - r0)).astype(np.int32))
+    toff = a["pod_tol_off"].astype(np.int64)
+    t0, t1 = int(toff[lo]), int(toff[hi])
+    a["tolerations"] = np.ascontiguousarray(a["tolerations"][t0:t1])
+    a["pod_tol_off"] = np.ascontiguousarray((toff[lo:hi + 1] - t0).astype(np.int32))
+    for k in ("pod_requests", "pod_ts", "pod_uid_hi", "pod_uid_lo"):
+        a[k] = np.ascontiguousarray(a[k][lo:hi])
+    out = Model(key_names=list(m.key_names), val_names=list(m.val_names), res_names=list(m.res_names),
+                sku_names=list(m.sku_names), pool_names=list(m.pool_names), node_names=list(m.node_names), arrays=a,
+                wellknown_extra=set(m.wellknown_extra))
+    return out.finalize()
+
+
 def _parse_int(s: str) -> Tuple[bool, int]:
     """strconv.Atoi: optional sign followed by decimal digits, must fit int64."""
     t = s[1:] if s[:1] in "+-" else s

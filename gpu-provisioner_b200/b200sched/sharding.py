@@ -1,0 +1,36 @@
+"""Row sharding of the dense stage across ranks.
+
+The pod x SKU matrix shards by pod rows: rows are independent, the catalog tables are replicated, and the only
+collective is ONE all-gather of the result rows (first feasible template, SKU mask, attempt codes) when a single
+pack has to see them all.  The pack itself does not shard (each placement depends on every earlier one): across
+GPUs it scales over independent Solves only ("replicas only").
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def row_shard(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) of rank's rows; the first n_rows % world ranks get one row more."""
+    q, r = divmod(n_rows, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
+
+
+def pad_rows(a: np.ndarray, rows: int) -> np.ndarray:
+    """all_gather_into_tensor wants equal shards: pad the first axis with zeros up to `rows`."""
+    if a.shape[0] == rows:
+        return a
+    pad = np.zeros((rows - a.shape[0],) + a.shape[1:], a.dtype)
+    return np.concatenate([a, pad], axis=0)
+
+
+def unpad_gathered(g: np.ndarray, n_rows: int, world: int) -> np.ndarray:
+    """g: [world, rows_max, ...] gathered shards -> [n_rows, ...] in row order."""
+    parts = []
+    for rank in range(world):
+        lo, hi = row_shard(n_rows, rank, world)
+        parts.append(g[rank, :hi - lo])
+    return np.concatenate(parts, axis=0)

@@ -685,6 +685,16 @@ int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_resu
   return fetch_solve_all(ctx, r, outs);
 }
 
+int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_tmpl, void* d_mask, void* d_code) {
+  if (!ctx || !r || !r->fit_done) return B200S_ESTATE;
+  const size_t P = (size_t)r->P;
+  if (P == 0) return B200S_OK;
+  if (d_tmpl) CUDA_TRY(ctx, cudaMemcpyAsync(d_tmpl, r->a_tmpl, P * 4, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  if (d_mask) CUDA_TRY(ctx, cudaMemcpyAsync(d_mask, r->a_mask, P * r->cat->W * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  if (d_code && r->T) CUDA_TRY(ctx, cudaMemcpyAsync(d_code, r->a_code, P * r->T, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  return B200S_OK;
+}
+
 int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }
 
 /* diagnostic: SM cycles thread 0 of problem 0's pack CTA spent per phase in the last solve

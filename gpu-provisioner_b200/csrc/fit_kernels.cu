@@ -264,6 +264,105 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_kernel(int P, int T, in
   if ((threadIdx.x & 31) == 0 && my_evals) atomicAdd(evals, my_evals);
 }
 
+// Vector form of fit_dense_kernel for an even number of SKU words: a lane owns 16-byte pieces of the row
+// (two SKU words), LPG lanes own one pod, 32/LPG pods per warp.  Lane j of a group also carries the attempt code of
+// template j (in chunks of LPG templates), so the codes cost one byte load and one byte store per pod.
+// Control flow is kept uniform across the WARP so that every vote is a single full-mask instruction from which a
+// group extracts its own bits (sub-warp masks make the compiler emit shuffle loops).  Indices are 32-bit: the
+// launcher checks that the tables and the output stay below 2^31 vectors.
+template <int LPG, int VPL>
+__global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(int P, int T, int W2, const int32_t* __restrict__ sig_id,
+                                                                    const int32_t* __restrict__ req_id,
+                                                                    const uint8_t* __restrict__ sg_status,
+                                                                    const ulonglong2* __restrict__ sgC,
+                                                                    const ulonglong2* __restrict__ sgO,
+                                                                    const ulonglong2* __restrict__ rqF,
+                                                                    const int32_t* __restrict__ tm_count,
+                                                                    int32_t* __restrict__ tmpl_out,
+                                                                    ulonglong2* __restrict__ mask_out,
+                                                                    uint8_t* __restrict__ code_out,
+                                                                    unsigned long long* __restrict__ evals) {
+  constexpr int NG = FIT_THREADS / LPG;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned GLOW = LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u);
+  const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (LPG - 1), gshift = lane & ~(unsigned)(LPG - 1);
+  unsigned my_evals = 0;
+  const int stride = gridDim.x * NG;
+  // all lanes of a warp run the same number of iterations (P is rounded up per warp; idle groups are predicated off)
+  const int p_first = blockIdx.x * NG + threadIdx.x / LPG;
+  const int warp_first = p_first - (int)(lane / LPG);
+  for (int pw = warp_first; pw < P; pw += stride) {
+    const int p = pw + (int)(lane / LPG);
+    const bool live = p < P;
+    const unsigned sig = live ? (unsigned)sig_id[p] : 0u, rq = live ? (unsigned)req_id[p] : 0u;
+    int chosen = -1;
+    ulonglong2 keep[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(0ull, 0ull);
+    for (int t0 = 0; t0 < T; t0 += LPG) {
+      const int t = t0 + (int)gl;
+      uint32_t code = (live && t < T) ? sg_status[sig * (unsigned)T + (unsigned)t] : 0xFFu;
+      const uint32_t status = code;
+      unsigned ok = (__ballot_sync(FULL, status == B200S_FIT_NONE) >> gshift) & GLOW;
+      for (;;) {  // addToNewNodeClaim walks the templates in order and stops at the first that works
+        const bool active = chosen < 0 && ok != 0;
+        if (!__any_sync(FULL, active)) break;
+        const int j = active ? __ffs(ok) - 1 : 0;
+        if (active) ok &= ok - 1;
+        const unsigned tt = (unsigned)(t0 + j);
+        const unsigned cb = (sig * (unsigned)T + tt) * (unsigned)W2, fb = (rq * (unsigned)T + tt) * (unsigned)W2;
+        ulonglong2 c[VPL], o[VPL], f[VPL];
+        bool nz = false;
+#pragma unroll
+        for (int i = 0; i < VPL; i++) {
+          const unsigned v = gl + i * LPG;
+          c[i] = o[i] = f[i] = make_ulonglong2(0ull, 0ull);
+          if (active && v < (unsigned)W2) {
+            c[i] = __ldg(sgC + cb + v);
+            o[i] = __ldg(sgO + cb + v);
+            f[i] = __ldg(rqF + fb + v);
+          }
+          nz = nz || ((c[i].x & o[i].x & f[i].x) | (c[i].y & o[i].y & f[i].y)) != 0;
+        }
+        if (active && gl == 0) my_evals += (unsigned)tm_count[tt];
+        const bool fits = ((__ballot_sync(FULL, nz) >> gshift) & GLOW) != 0;
+        if (active && fits) {
+          chosen = (int)tt;
+#pragma unroll
+          for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(c[i].x & o[i].x & f[i].x, c[i].y & o[i].y & f[i].y);
+        }
+        if (__any_sync(FULL, active && !fits)) {  // InstanceTypeFilterError: the six flags (nodeclaim.go:409-416)
+          bool bC = false, bF = false, bO = false, bCF = false, bCO = false, bFO = false;
+#pragma unroll
+          for (int i = 0; i < VPL; i++) {
+            bC = bC || (c[i].x | c[i].y);
+            bF = bF || (f[i].x | f[i].y);
+            bO = bO || (o[i].x | o[i].y);
+            bCF = bCF || ((c[i].x & f[i].x & ~o[i].x) | (c[i].y & f[i].y & ~o[i].y));
+            bCO = bCO || ((c[i].x & o[i].x & ~f[i].x) | (c[i].y & o[i].y & ~f[i].y));
+            bFO = bFO || ((f[i].x & o[i].x & ~c[i].x) | (f[i].y & o[i].y & ~c[i].y));
+          }
+          const unsigned vC = (__ballot_sync(FULL, bC) >> gshift) & GLOW, vF = (__ballot_sync(FULL, bF) >> gshift) & GLOW,
+                         vO = (__ballot_sync(FULL, bO) >> gshift) & GLOW, vCF = (__ballot_sync(FULL, bCF) >> gshift) & GLOW,
+                         vCO = (__ballot_sync(FULL, bCO) >> gshift) & GLOW, vFO = (__ballot_sync(FULL, bFO) >> gshift) & GLOW;
+          if (active && !fits && (int)gl == j) code = filter_flags(vC, vF, vO, vCF, vCO, vFO);
+        }
+      }
+      // templates after the first success are never tried; dropped ones stay marked
+      if (chosen >= 0 && t > chosen && status != B200S_FIT_DROPPED) code = B200S_FIT_NONE;
+      if (live && t < T) code_out[(unsigned)p * (unsigned)T + (unsigned)t] = (uint8_t)code;
+    }
+    if (live && gl == 0) tmpl_out[p] = chosen;
+#pragma unroll
+    for (int i = 0; i < VPL; i++) {
+      const unsigned v = gl + i * LPG;
+      if (live && v < (unsigned)W2) mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(FULL, my_evals, o);
+  if (lane == 0 && my_evals) atomicAdd(evals, (unsigned long long)my_evals);
+}
+
 __global__ void template_count_kernel(int T, int W, const uint64_t* __restrict__ tmask, int32_t* __restrict__ tm_count) {
   int t = threadIdx.x;
   if (t >= T) return;
@@ -485,6 +584,28 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
                              cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
   if (pods.P == 0) return cudaSuccess;
+  const long long W2l = kt.n_words / 2;
+  const bool small = (long long)pods.P * W2l < (1ll << 31) && (long long)pods.NS * T * W2l < (1ll << 31) &&
+                     (long long)pods.NQ * T * W2l < (1ll << 31) && (long long)pods.P * T < (1ll << 31);
+  if ((kt.n_words & 1) == 0 && small) {  // 16-byte rows, 32-bit indices: the vector kernel
+    const int W2 = kt.n_words / 2;
+#define VCALL(LPG_, VPL_)                                                                                        \
+  do {                                                                                                           \
+    long long need = ((long long)pods.P + (FIT_THREADS / LPG_) - 1) / (FIT_THREADS / LPG_);                      \
+    int grid = (int)(need < (long long)n_sm * 8 ? need : (long long)n_sm * 8);                                   \
+    fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(                                          \
+        pods.P, T, W2, pods.sig_id, pods.req_id, sg_status, reinterpret_cast<const ulonglong2*>(sgC),           \
+        reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out, \
+        reinterpret_cast<ulonglong2*>(mask_out), code_out, evals);                                               \
+  } while (0)
+    if (W2 <= 4) VCALL(4, 1);
+    else if (W2 <= 8) VCALL(8, 1);
+    else if (W2 <= 16) VCALL(16, 1);
+    else if (W2 <= 32) VCALL(32, 1);
+    else VCALL(32, 2);
+#undef VCALL
+    return cudaGetLastError();
+  }
 #define CALL(G_, WPL_)                                                                                          \
   do {                                                                                                          \
     long long need = ((long long)pods.P + (FIT_THREADS / G_) - 1) / (FIT_THREADS / G_);                         \

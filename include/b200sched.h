@@ -397,6 +397,9 @@ int b200s_resident_solve(b200s_ctx_t* ctx, b200s_resident_t* r);
 int b200s_resident_fetch_fit(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t* tmpl_out, uint64_t* mask_out,
                              uint8_t* code_out, int64_t* evals_out);
 int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_result_t* out);
+/* device-to-device copy of the resident dense results into caller-owned DEVICE buffers (e.g. the send buffers of
+ * an NCCL all-gather when the pod rows are sharded across GPUs); enqueued on the context's stream */
+int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_tmpl, void* d_mask, void* d_code);
 /* number of kernels the last resident_* call enqueued */
 int b200s_resident_last_launches(const b200s_resident_t* r);
 /* diagnostic: SM cycles per phase of the last solve's pack kernel (pop, pod row, existing nodes, sort,
