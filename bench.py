@@ -263,13 +263,88 @@ def run_c5(args, rank, world, local):
         dist.destroy_process_group()
 
 
+def run_c4(args, rank, world, local):
+    """configs[3], consolidation re-pack: 50k running pods on loosely packed nodes; a batch of single-node
+    consolidation simulations (one CTA per simulation, b200s_solve_batch) plus one multi-node re-pack."""
+    import __graft_entry__ as g
+    g.build()
+    import oracle_binding as ob
+    import parity
+    from b200sched import capi, model as M, synth
+    if rank != 0:
+        return
+    P, S, B = args.pods or 50_000, args.skus or 500, args.batch
+    ctx = capi.Context(local)
+    t0 = time.perf_counter()
+
+    def device_solve(m):  # the loose initial packing is itself produced by the device path
+        e = capi.Encoded(m)
+        cid0 = ctx.upload_catalog(e)
+        r = ctx.solve(cid0, e)
+        ctx.release_catalog(cid0)
+
+        class R:
+            pass
+        out = R()
+        out.claim_sku, out.claim_requests = r.claim_sku, r.claim_requests
+        out.pod_place_index = np.where(r.pod_place_kind == capi.PLACE_CLAIM, r.pod_place_index, -1)
+        return out
+
+    model, node_of_pod, util = synth.c4(P, S, solve=device_solve)
+    E = int(model.c.n_nodes)
+    sims = synth.c4_simulations(model, node_of_pod, util, B)
+    encs = [capi.Encoded(m) for _, m in sims]
+    t_build = time.perf_counter() - t0
+    cid = ctx.upload_catalog(encs[0])
+    # parity of a sample of simulations against the oracle, and the reference arm's time on the same sample
+    t0 = time.perf_counter()
+    oracle_out = [ob.solve(m) for _, m in sims[:32]]
+    t_cpu = (time.perf_counter() - t0) / len(oracle_out)
+    for _ in range(args.warmup):
+        outs = ctx.solve_batch(cid, encs)
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            outs = ctx.solve_batch(cid, encs)
+        ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    for (i, m), e, r, o in zip(sims[:32], encs[:32], outs[:32], oracle_out):
+        parity.assert_same(parity.canon_device(e, r), parity.canon_oracle(m, o), f"c4 simulation of node {i}")
+    removable = sum(1 for r in outs if r.n_claims == 0 and r.n_unscheduled == 0)
+    # multi-node re-pack: every pod of the candidates at once against the remaining nodes
+    cand = np.array([i for i, _ in sims])
+    keep_nodes = np.setdiff1d(np.arange(E), cand)
+    pods = np.nonzero(np.isin(node_of_pod, cand))[0]
+    multi = M.subset(model, pods, keep_nodes)
+    em = capi.Encoded(multi)
+    rm = ctx.solve(cid, em)
+    om = ob.solve(multi)
+    parity.assert_same(parity.canon_device(em, rm), parity.canon_oracle(multi, om), "c4 multi-node re-pack")
+    evals_cpu = sum(o.counters["fit_evals"] for o in oracle_out) / len(oracle_out)
+    line = {"metric": "consolidation simulations/s", "value": B / (ms * 1e-3), "unit": "simulations/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
+            "config": {"workload": f"config[3]: {P} running pods on {E} loosely packed nodes ({S} SKUs); {B} single-node "
+                                   "consolidation simulations per step through b200s_solve_batch (host buffers in and out), "
+                                   "plus one multi-node re-pack", "build_s": t_build},
+            "nodes_before": E, "single_node_removable": int(removable), "batch": B,
+            "multi_node_repack": {"pods": int(len(pods)), "candidates": int(len(cand)), "new_nodeclaims": int(rm.n_claims),
+                                  "unschedulable": int(rm.n_unscheduled), "nodes_after": int(E - len(cand) + rm.n_claims)},
+            "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "simulations/s", "cores": 1, "kind": "port",
+                             "sample": "32 of the same simulations on one host core", "evals_per_simulation": evals_cpu},
+            "e2e": {"value": B / (ms * 1e-3), "unit": "simulations/s"},
+            "clocks": clk.summary(), "parity": "32 simulations + the multi-node re-pack bit-identical to the CPU oracle"}
+    ctx.close()
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--pods", type=int, default=0)
     ap.add_argument("--skus", type=int, default=0)
     ap.add_argument("--large", action="store_true", help="also time the dense stage on 1M pods x 2k SKUs")
@@ -282,6 +357,9 @@ def main():
         return
     if args.workload == "c5":
         run_c5(args, rank, world, local)
+        return
+    if args.workload == "c4":
+        run_c4(args, rank, world, local)
         return
 
     import torch

@@ -197,6 +197,47 @@ def slice_pods(m: "Model", lo: int, hi: int) -> "Model":
     return out.finalize()
 
 
+def _csr_take(off: np.ndarray, idx: np.ndarray):
+    """Rows idx of a CSR offsets array -> (flat element indices, new offsets starting at 0)."""
+    off = off.astype(np.int64)
+    lens = off[idx + 1] - off[idx]
+    new_off = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    flat = np.repeat(off[idx] - new_off[:-1], lens) + np.arange(int(new_off[-1]), dtype=np.int64)
+    return flat, new_off
+
+
+def subset(m: "Model", pod_idx, node_idx) -> "Model":
+    """A model with the given pods and existing nodes of m (catalog, pools, universes shared): the input of one
+    consolidation simulation (K/controllers/disruption/helpers.go:52-143)."""
+    a = dict(m.arrays)
+    pod_idx = np.asarray(pod_idx, dtype=np.int64)
+    node_idx = np.asarray(node_idx, dtype=np.int64)
+    p0 = int(a["pod_req_off"][0])
+    pflat, poff = _csr_take(a["pod_req_off"], pod_idx)
+    nflat, noff = _csr_take(a["node_req_off"], node_idx)
+    head = a["reqs"][:p0]
+    a["reqs"] = np.ascontiguousarray(np.concatenate([head, a["reqs"][pflat], a["reqs"][nflat]]))
+    a["pod_req_off"] = np.ascontiguousarray((poff + p0).astype(np.int32))
+    a["node_req_off"] = np.ascontiguousarray((noff + p0 + len(pflat)).astype(np.int32))
+    tflat, toff = _csr_take(a["pod_tol_off"], pod_idx)
+    a["tolerations"] = np.ascontiguousarray(a["tolerations"][tflat])
+    a["pod_tol_off"] = np.ascontiguousarray(toff.astype(np.int32))
+    for k in ("pod_requests", "pod_ts", "pod_uid_hi", "pod_uid_lo"):
+        a[k] = np.ascontiguousarray(a[k][pod_idx])
+    # taints: pools first, then nodes
+    n_pool_t = int(a["pool_taint_off"][-1])
+    ntflat, ntoff = _csr_take(a["node_taint_off"], node_idx)
+    a["taints"] = np.ascontiguousarray(np.concatenate([a["taints"][:n_pool_t], a["taints"][ntflat]]))
+    a["node_taint_off"] = np.ascontiguousarray((ntoff + n_pool_t).astype(np.int32))
+    for k in ("node_available", "node_initialized", "node_name_rank"):
+        a[k] = np.ascontiguousarray(a[k][node_idx])
+    out = Model(key_names=list(m.key_names), val_names=list(m.val_names), res_names=list(m.res_names),
+                sku_names=list(m.sku_names), pool_names=list(m.pool_names),
+                node_names=[m.node_names[i] for i in node_idx], arrays=a, wellknown_extra=set(m.wellknown_extra))
+    return out.finalize()
+
+
 def _parse_int(s: str) -> Tuple[bool, int]:
     """strconv.Atoi: optional sign followed by decimal digits, must fit int64."""
     t = s[1:] if s[:1] in "+-" else s

@@ -336,3 +336,58 @@ def c3(n_pods: int = 100_000, n_skus: int = 1_000) -> M.Model:
 
 def c5(n_pods: int = 1_000_000, n_skus: int = 2_000) -> M.Model:
     return config("c3", n_pods, n_skus)
+
+
+def c4(n_pods: int = 50_000, n_skus: int = 500, cap: float = 0.6, solve=None):
+    """configs[3], consolidation re-pack: `n_pods` RUNNING pods on nodes produced by a deliberately loose packing
+    (a Solve against instance types shrunk to `cap` of their allocatable), to be re-packed onto fewer NodeClaims.
+
+    `solve(model)` must return an object with claim_sku, claim_requests, pod_place_index (the CPU oracle's solve in
+    tests, the device path in the bench).  Returns (model with the nodes as existing nodes and ALL pods, node_of_pod,
+    utilisation per node).  A single-node consolidation simulation for candidate i is
+    model.subset(pods on node i, all nodes but i)."""
+    b = new_builder()
+    add_catalog(b, n_skus)
+    add_pools(b, "c2")
+    pods = bulk_pods(b, n_pods, "c2", SEED_PODS + 4)
+    loose = build_model(b, pods)
+    real_alloc = loose.arrays["sku_alloc"].copy()
+    shrunk = (real_alloc.astype(np.float64) * cap).astype(np.int64)
+    shrunk[:, 4] = real_alloc[:, 4]  # the pods-per-node capacity is not shrunk
+    loose.arrays["sku_alloc"] = np.ascontiguousarray(shrunk)
+    loose.finalize()
+    r = solve(loose)
+    placed = r.pod_place_index >= 0
+    n_nodes = int(r.claim_sku.shape[0])
+    # second model: same catalog / pools / pods, the claims become existing nodes on their selected SKU
+    b2 = new_builder()
+    add_catalog(b2, n_skus)
+    add_pools(b2, "c2")
+    pods2 = bulk_pods(b2, n_pods, "c2", SEED_PODS + 4)
+    zone_u = sm64(SEED_NODES, 1, n_nodes) % np.uint64(len(ZONES))
+    ct_u = sm64(SEED_NODES, 2, n_nodes) % np.uint64(len(CAPACITY_TYPES))
+    util = np.zeros(n_nodes)
+    for i in range(n_nodes):
+        s = int(r.claim_sku[i])
+        sku = b2.skus[s]
+        labels = {M.KEY_INSTANCE_TYPE: sku["name"], M.KEY_NODEPOOL: "default", M.KEY_OS: "linux",
+                  M.KEY_ZONE: ZONES[int(zone_u[i])], M.KEY_CAPACITY_TYPE: CAPACITY_TYPES[int(ct_u[i])]}
+        avail = real_alloc[s] - r.claim_requests[i]
+        util[i] = float(r.claim_requests[i][0]) / max(float(real_alloc[s][0]), 1.0)
+        b2.add_node(f"node-{i:06d}", labels, [int(x) for x in avail])
+    model = build_model(b2, pods2)
+    node_of_pod = np.where(placed, r.pod_place_index, -1).astype(np.int64)
+    return model, node_of_pod, util
+
+
+def c4_simulations(model: M.Model, node_of_pod: np.ndarray, util: np.ndarray, n_candidates: int):
+    """Single-node consolidation candidates, lowest utilisation first (singlenodeconsolidation.go:68-101): one
+    simulation per candidate = its pods against every other node."""
+    E = int(model.c.n_nodes)
+    order = np.argsort(util, kind="stable")[:n_candidates]
+    all_nodes = np.arange(E)
+    sims = []
+    for i in order:
+        pods = np.nonzero(node_of_pod == i)[0]
+        sims.append((int(i), M.subset(model, pods, all_nodes[all_nodes != i])))
+    return sims

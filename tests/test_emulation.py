@@ -170,3 +170,14 @@ def test_golden_digests():
         o = ob.solve(m)
         assert parity.digest(parity.canon_oracle(m, o)) == g["digest"], name
         assert [o.n_claims, o.n_unscheduled, o.counters["fit_evals"]] == [g["n_claims"], g["n_unscheduled"], g["fit_evals"]]
+
+
+def test_config4_generator_and_simulations_on_the_host_emulation():
+    from b200sched import model as M
+    model, node_of_pod, util = synth.c4(1500, 120, solve=ob.solve)
+    assert (node_of_pod >= 0).sum() > 1400
+    for i, sim in synth.c4_simulations(model, node_of_pod, util, 6):
+        o = ob.solve(sim)
+        enc = capi.Encoded(sim)
+        parity.assert_same(parity.canon_device(enc, parity.emul_solve(enc)), parity.canon_oracle(sim, o), f"node {i}")
+        assert sim.n_pods == int((node_of_pod == i).sum()) and int(sim.c.n_nodes) == int(model.c.n_nodes) - 1

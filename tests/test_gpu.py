@@ -183,3 +183,25 @@ def test_config3_full_size_properties(gpu_ctx):
     # claims are in Results.NewNodeClaims order: non-decreasing pod count except for the last modification
     d = np.diff(raw.claim_npods)
     assert (d < 0).sum() <= 1
+
+
+def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
+    """BASELINE.json configs[3] at a size the oracle finishes quickly: running pods on loosely packed nodes, a batch of
+    single-node consolidation simulations (one CTA each) and the multi-node re-pack, all bit-identical to the oracle."""
+    from b200sched import model as M
+    model, node_of_pod, util = synth.c4(4000, 300, solve=ob.solve)
+    sims = synth.c4_simulations(model, node_of_pod, util, 24)
+    encs = [capi.Encoded(m) for _, m in sims]
+    cid = gpu_ctx.upload_catalog(encs[0])
+    try:
+        outs = gpu_ctx.solve_batch(cid, encs)
+        for (i, m), e, r in zip(sims, encs, outs):
+            parity.assert_same(parity.canon_device(e, r), parity.canon_oracle(m, ob.solve(m)), f"simulation of node {i}")
+        E = int(model.c.n_nodes)
+        cand = np.array([i for i, _ in sims])
+        multi = M.subset(model, np.nonzero(np.isin(node_of_pod, cand))[0], np.setdiff1d(np.arange(E), cand))
+        em = capi.Encoded(multi)
+        parity.assert_same(parity.canon_device(em, gpu_ctx.solve(cid, em)), parity.canon_oracle(multi, ob.solve(multi)),
+                           "multi-node re-pack")
+    finally:
+        gpu_ctx.release_catalog(cid)
