@@ -331,6 +331,70 @@ __device__ __forceinline__ bool group_inflight(const KeyTab& kt, const StateRef&
   return any != 0;
 }
 
+// group_inflight for a pod WITHOUT requirement keys (no nodeSelector / affinity), the common case: only the resource
+// rows can change the claim's instance types.  Written so that all 32 lanes of the warp stay converged — no early
+// exits, full-mask shuffles and votes only (sub-warp masks compile to shuffle loops) — with `live` predicating the
+// groups that have no claim to look at.  Lane gl < R of a group owns resource gl, lane w owns SKU word w (+ i*G).
+// Returns whether the pod fits; out[] is the claim's new InstanceTypeOptions when it does.
+template <int G, int WPL>
+__device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, bool live, const int64_t* creq, const int64_t* chi,
+                                                      const uint64_t* cmask, bool tolerated, const int64_t* preq,
+                                                      uint32_t ract, uint64_t (&out)[WPL]) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (G - 1), gbase = lane & ~(unsigned)(G - 1);
+  const int R = kt.n_res, W = kt.n_words;
+  // all loads first (independent): my resource's total and bound, my SKU words
+  int64_t x = 0, hi = 0;
+  const bool mine = live && gl < (unsigned)R && ((ract >> gl) & 1u);
+  if (mine) {
+    x = creq[gl] + preq[gl];
+    hi = chi[gl];
+  }
+  uint64_t keep[WPL];
+#pragma unroll
+  for (int i = 0; i < WPL; i++) {
+    const int w = (int)gl + i * G;
+    keep[i] = (live && w < W) ? cmask[w] : 0ull;
+  }
+  // rank of the new total among the distinct allocatable values (branch-free lower_bound)
+  int row = -1;  // -1: this lane contributes no row
+  bool dead = !tolerated;
+  if (mine) {
+    const int nd = kt.res_nd[gl];
+    const int64_t* dv = kt.res_dv + kt.res_dv0[gl];
+    int lo = 0;
+    for (int step = kt.res_p2[gl]; step > 0; step >>= 1) {
+      const int mid = lo + step;
+      if (mid <= nd && dv[mid - 1] < x) lo = mid;
+    }
+    dead = dead || x > hi || lo >= nd;
+    row = kt.res_row0[gl] + lo;
+  }
+  const unsigned deadb = __ballot_sync(FULL, dead);
+  const bool gdead = ((deadb >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0;
+#pragma unroll
+  for (int r = 0; r < MAXR; r++) {
+    if (r < R) {  // uniform
+      const int rr = __shfl_sync(FULL, row, (int)gbase + r);
+      if (rr >= 0) {
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+          const int w = (int)gl + i * G;
+          if (w < W) keep[i] &= kt.rows[(size_t)rr * W + w];
+        }
+      }
+    }
+  }
+  bool nz = false;
+#pragma unroll
+  for (int i = 0; i < WPL; i++) {
+    out[i] = keep[i];
+    nz = nz || keep[i] != 0;
+  }
+  const unsigned nzb = __ballot_sync(FULL, nz && live && !gdead);
+  return ((nzb >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0;
+}
+
 // The same in-flight CanAdd as group_inflight, decided by ONE thread (used by the scan, 512 claims per pass): only
 // the yes/no answer is needed there, so the SKU words are walked until the first one that keeps an instance type.
 constexpr int MAX_FAST_KEYS = 4;  // pod-defined keys handled from registers; more than that re-derives per word

@@ -355,6 +355,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     int32_t* ord = S.ord_global ? g_ord : s_ord;
     int32_t* key = S.ord_global ? g_key : s_key;
     const int n = S.n_claims;
+    uint64_t out0[WPL];
+    int my_idx0 = -1, my_c0 = -1;
     if (!on_node) {
       // ---- addToInflightNode ----
       // One thread per in-flight claim, s.newNodeClaims order: warp w takes claims [32(w + it*NW), +32) in
@@ -383,10 +385,39 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
         return true;
       };
-      constexpr int ROUND0 = 64;
-      if (warp < ROUND0 / 32 && warp * 32 < n) scan_block(warp * 32);
-      __syncthreads();
-      if (S.best[cur] == INT_MAX && n > ROUND0) {
+      // Round 0: the first NW*(32/G) claims, one lane group each.  Selector-less pods take the tuned convergent
+      // path and the winning group keeps the claim's new instance types for the commit; other pods use one thread
+      // per claim like the later rounds.
+      constexpr int GPW = 32 / G, GROUP_ROUNDS = 2;
+      const int ROUND0 = podkeys ? 64 : GROUP_ROUNDS * NW * GPW;
+      // every "did anyone hit" decision is taken with a barrier reduction so that it is uniform across the CTA
+      int any_hit = 0;
+      if (!podkeys) {
+        for (int gr = 0; gr < GROUP_ROUNDS && !any_hit; gr++) {
+          if (gr * NW * GPW >= n) break;  // uniform
+          const int idx = gr * NW * GPW + warp * GPW + (lane / G);
+          const bool live = idx < n;
+          const int c = live ? ord[idx] : 0;
+          const bool tolerated = live ? ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0) : true;
+          uint64_t o_[WPL];
+          const bool fits = group_inflight_nokeys<G, WPL>(kt, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
+                                                          c_mask + (size_t)c * W, tolerated, pd.req, ract, o_);
+          if (live && gl == 0) my_evals += (unsigned long long)c_nopt[c];
+          if (fits) {
+            my_idx0 = idx;
+            my_c0 = c;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) out0[i] = o_[i];
+            if (gl == 0) atomicMin(&S.best[cur], idx);
+          }
+          any_hit = __syncthreads_or(fits ? 1 : 0);
+        }
+      } else {
+        bool hit = false;
+        if (warp < 2 && warp * 32 < n) hit = scan_block(warp * 32);
+        any_hit = __syncthreads_or(hit ? 1 : 0);
+      }
+      if (!any_hit && n > ROUND0) {
         for (int it = 0;; it++) {
           const int b0 = ROUND0 + (it * NW + warp) * 32;
           int best_now = 0;
@@ -430,8 +461,30 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         A.pod_seq[p] = S.seq++;
       }
     } else if (found != INT_MAX) {
-      const int c = S.hit_c[found < 64 ? (found >> 5) : (((found - 64) >> 5) % NW)];  // not ord[found]: warp 2 reorders ord
-      if (warp == 1 && lane < G) {  // NodeClaim.Add (nodeclaim.go:168-180): the full surviving set, by one lane group
+      const int r0sz = podkeys ? 64 : 2 * NW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
+      const bool by_group = !podkeys && found < r0sz;   // found by a lane group that still holds the new instance types
+      if (by_group) {
+        if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
+          const int c = my_c0;
+          int cnt = 0;
+#pragma unroll
+          for (int i = 0; i < WPL; i++) {
+            int w = gl + i * G;
+            if (w < W) c_mask[(size_t)c * W + w] = out0[i];
+            cnt += popc64(out0[i]);
+          }
+          cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
+          for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += pd.req[r];
+          if (gl == 0) {
+            c_nopt[c] = cnt;
+            c_npods[c]++;
+            A.pod_kind[p] = B200S_PLACE_CLAIM;
+            A.pod_index[p] = c;
+            A.pod_seq[p] = S.seq++;
+          }
+        }
+      } else if (warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
+        const int c = S.hit_c[found < r0sz ? (found >> 5) : (((found - r0sz) >> 5) % NW)];  // not ord[found]: warp 2 reorders ord
         StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
                     c_req + (size_t)c * R, 1, 0};
         uint64_t cand[WPL], out[WPL];
@@ -457,16 +510,15 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         if (gl == 0) {
           c_nopt[c] = cnt;
           c_npods[c]++;
+          A.pod_kind[p] = B200S_PLACE_CLAIM;
+          A.pod_index[p] = c;
+          A.pod_seq[p] = S.seq++;
         }
-      } else if (warp == 2) {  // the claim moved one pod up: what sort.Slice will do with that
+      }
+      if (warp == 2) {  // the claim moved one pod up: what sort.Slice will do with that
         if (lane == 0) key[found]++;
         __syncwarp();
         warp_normalise(S, ord, key, g_snap, n, found, false);
-      }
-      if (tid == 0) {
-        A.pod_kind[p] = B200S_PLACE_CLAIM;
-        A.pod_index[p] = c;
-        A.pod_seq[p] = S.seq++;
       }
     } else if (t_new >= 0) {
       // ---- addToNewNodeClaim: the template walk was done for every pod by stage A ----
