@@ -52,6 +52,16 @@ struct KeyTab {
   const uint64_t* price;   // [n_zc*S]
 };
 
+// read-only table loads: through the non-coherent (L1-cached) path on the device
+template <class Tp>
+B2_HD Tp ldg(const Tp* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 B2_HD int ctz64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
   return __ffsll((long long)x) - 1;
@@ -178,7 +188,7 @@ B2_HD int fit_rank(const int64_t* dv, int nd, int64_t x) {
   int lo = 0, hi = nd;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (dv[mid] < x) lo = mid + 1; else hi = mid;
+    if (ldg(dv + mid) < x) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
@@ -201,10 +211,10 @@ struct WordEval {
 B2_HD uint64_t eval_fits_word(const KeyTab& kt, const int32_t* fit_row, int w) {
   const int W = kt.n_words;
   const uint64_t* rows = kt.rows;
-  uint64_t fits = rows[(size_t)kt.row_nonneg * W + w];
+  uint64_t fits = ldg(rows + (size_t)kt.row_nonneg * W + w);
   for (int r = 0; r < kt.n_res; r++) {
     int row = fit_row[r];
-    fits &= row < 0 ? 0ull : rows[(size_t)row * W + w];
+    fits &= row < 0 ? 0ull : ldg(rows + (size_t)row * W + w);
   }
   return fits;
 }
@@ -216,12 +226,12 @@ B2_HD uint64_t eval_key_word(const KeyTab& kt, int k, uint64_t allowed, bool for
   const int W = kt.n_words;
   const uint64_t* rows = kt.rows;
   int row0 = kt.key_row0[k], nv = kt.nvals[k];
-  uint64_t acc = rows[(size_t)(row0 + nv) * W + w];
-  if (forgive) acc |= rows[(size_t)(row0 + nv + 1) * W + w];
+  uint64_t acc = ldg(rows + (size_t)(row0 + nv) * W + w);
+  if (forgive) acc |= ldg(rows + (size_t)(row0 + nv + 1) * W + w);
   while (allowed) {
     int v = ctz64(allowed);
     allowed &= allowed - 1;
-    acc |= rows[(size_t)(row0 + v) * W + w];
+    acc |= ldg(rows + (size_t)(row0 + v) * W + w);
   }
   return acc;
 }
@@ -252,7 +262,7 @@ B2_HD uint64_t eval_off_word(const KeyTab& kt, uint64_t zone_allowed, uint64_t c
     while (ca) {
       int c = ctz64(ca);
       ca &= ca - 1;
-      off |= rows[(size_t)(kt.zc_row0 + z * kt.n_cts + c) * W + w];
+      off |= ldg(rows + (size_t)(kt.zc_row0 + z * kt.n_cts + c) * W + w);
     }
   }
   return off;

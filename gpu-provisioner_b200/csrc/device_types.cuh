@@ -281,7 +281,7 @@ __device__ __forceinline__ bool group_inflight(const KeyTab& kt, const StateRef&
 #pragma unroll
     for (int i = 0; i < WPL; i++) {
       int w = gl + i * G;
-      if (w < W) keep[i] &= kt.rows[(size_t)row * W + w];
+      if (w < W) keep[i] &= ldg(kt.rows + (size_t)row * W + w);
     }
   }
   // keys the pod defines (nodeclaim.go:125-131): Compatible, merge, and the merged key's SKU rows
@@ -336,10 +336,28 @@ __device__ __forceinline__ bool group_inflight(const KeyTab& kt, const StateRef&
 // exits, full-mask shuffles and votes only (sub-warp masks compile to shuffle loops) — with `live` predicating the
 // groups that have no claim to look at.  Lane gl < R of a group owns resource gl, lane w owns SKU word w (+ i*G).
 // Returns whether the pod fits; out[] is the claim's new InstanceTypeOptions when it does.
+// Per-lane constants of the resource a lane owns (lane gl < R owns resource gl for the whole kernel): hoisted
+// once, because indexing the constant bank with a per-lane index serialises into one access per distinct lane.
+struct LaneRes {
+  const int64_t* dv;
+  int32_t nd, p2, row0;
+};
+
+__device__ __forceinline__ LaneRes lane_res(const KeyTab& kt, int r) {
+  LaneRes l{nullptr, 0, 0, 0};
+  if (r < kt.n_res) {
+    l.dv = kt.res_dv + kt.res_dv0[r];
+    l.nd = kt.res_nd[r];
+    l.p2 = kt.res_p2[r];
+    l.row0 = kt.res_row0[r];
+  }
+  return l;
+}
+
 template <int G, int WPL>
-__device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, bool live, const int64_t* creq, const int64_t* chi,
-                                                      const uint64_t* cmask, bool tolerated, const int64_t* preq,
-                                                      uint32_t ract, uint64_t (&out)[WPL]) {
+__device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, const LaneRes& lr, bool live, const int64_t* creq,
+                                                      const int64_t* chi, const uint64_t* cmask, bool tolerated,
+                                                      const int64_t* preq, uint32_t ract, uint64_t (&out)[WPL]) {
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (G - 1), gbase = lane & ~(unsigned)(G - 1);
   const int R = kt.n_res, W = kt.n_words;
@@ -360,15 +378,15 @@ __device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, bool liv
   int row = -1;  // -1: this lane contributes no row
   bool dead = !tolerated;
   if (mine) {
-    const int nd = kt.res_nd[gl];
-    const int64_t* dv = kt.res_dv + kt.res_dv0[gl];
+    const int nd = lr.nd;
+    const int64_t* dv = lr.dv;
     int lo = 0;
-    for (int step = kt.res_p2[gl]; step > 0; step >>= 1) {
+    for (int step = lr.p2; step > 0; step >>= 1) {
       const int mid = lo + step;
-      if (mid <= nd && dv[mid - 1] < x) lo = mid;
+      if (mid <= nd && ldg(dv + mid - 1) < x) lo = mid;
     }
     dead = dead || x > hi || lo >= nd;
-    row = kt.res_row0[gl] + lo;
+    row = lr.row0 + lo;
   }
   const unsigned deadb = __ballot_sync(FULL, dead);
   const bool gdead = ((deadb >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0;
@@ -380,7 +398,7 @@ __device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, bool liv
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
           const int w = (int)gl + i * G;
-          if (w < W) keep[i] &= kt.rows[(size_t)rr * W + w];
+          if (w < W) keep[i] &= ldg(kt.rows + (size_t)rr * W + w);
         }
       }
     }
@@ -462,7 +480,7 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
     for (int r = 0; r < MAXR; r++) {
       if (((ract >> r) & 1u) && step <= kt.res_p2[r]) {
         int mid = lo[r] + step;
-        if (mid <= kt.res_nd[r] && kt.res_dv[kt.res_dv0[r] + mid - 1] < x[r]) lo[r] = mid;
+        if (mid <= kt.res_nd[r] && ldg(kt.res_dv + kt.res_dv0[r] + mid - 1) < x[r]) lo[r] = mid;
       }
     }
   }
@@ -483,7 +501,7 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
       uint64_t m = cmask[w];
 #pragma unroll
       for (int r = 0; r < MAXR; r++)
-        if ((ract >> r) & 1u) m &= kt.rows[rowoff[r] + w];
+        if ((ract >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
       any = any || m != 0;
     }
     return any ? 2 : 1;
@@ -493,7 +511,7 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
     if (m == 0) continue;
 #pragma unroll
     for (int r = 0; r < MAXR; r++)
-      if ((ract >> r) & 1u) m &= kt.rows[rowoff[r] + w];
+      if ((ract >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
     if (m == 0) continue;
     if (nk <= MAX_FAST_KEYS) {
 #pragma unroll

@@ -561,7 +561,8 @@ cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, cons
   if (items == 0) return cudaGetLastError();
   int G, WPL;
   pick_group(kt.n_words, &G, &WPL);
-  int in_smem = class_smem_bytes(kt, G, 1) <= (size_t)smem_limit;
+  (void)smem_limit;
+  int in_smem = 0;  // tables are read through the non-coherent L1 path (ldg), which shared-memory copies cannot use
   size_t bytes = class_smem_bytes(kt, G, in_smem);
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                                      \

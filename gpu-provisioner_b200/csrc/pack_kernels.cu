@@ -18,7 +18,7 @@
 
 namespace b200 {
 
-constexpr int PACK_THREADS = 256;
+constexpr int PACK_THREADS = 512;
 constexpr int ORD_SMEM_CAP = 8192;  // NodeClaims whose order / count-by-position arrays stay in shared memory
 constexpr int MODE_NONE = 0;
 
@@ -32,6 +32,7 @@ struct PackShared {
   uint32_t p_keys[2];  // bit k: the pod's requirements define key k
   uint32_t p_ract[2];  // bit r: the pod requests resource r (non-zero)
   int32_t p_id[2];     // pod index, -1 when the queue is done
+  int32_t pre_pod, pre_sig, pre_rq;  // class ids of the queue's next head, fetched one step ahead
   int64_t zero_b[MAXB];
   int32_t best[2];
   int32_t hit_c[PACK_THREADS / 32];  // claim id behind each warp's first feasible index of the current scan
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   int32_t* s_key = s_ord + ORD_SMEM_CAP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gl = tid & (G - 1);
   const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
+  const LaneRes lres = lane_res(kt, gl);
 
   PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     S.n_claims = 0; S.head = 0; S.len = n_pods; S.seq = 0; S.evals = 0;
     S.ord_global = 0; S.n_pushed = 0; S.mode = MODE_NONE; S.undo_mode = MODE_NONE;
     S.best[0] = INT_MAX; S.best[1] = INT_MAX;
+    S.pre_pod = -1;
   }
   unsigned long long my_evals = 0;
   unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -303,7 +306,24 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     }
     p = __shfl_sync(0xffffffffu, p, 0);
     if (p < 0) return;
-    const int sig = pods.sig_id[p], rq = pods.req_id[p];
+    int sig, rq;
+    if (S.pre_pod == p) {  // ids fetched during the previous step
+      sig = S.pre_sig;
+      rq = S.pre_rq;
+    } else {
+      sig = pods.sig_id[p];
+      rq = pods.req_id[p];
+    }
+    __syncwarp();
+    if (lane == 31) {  // one step ahead: the ids of what is now at the head of the queue (entries ahead of the
+                       // tail never change; with an empty queue there is nothing to fetch)
+      int nxt = S.len > 0 ? queue[S.head] : -1;
+      S.pre_pod = nxt;
+      if (nxt >= 0) {
+        S.pre_sig = pods.sig_id[nxt];
+        S.pre_rq = pods.req_id[nxt];
+      }
+    }
     int64_t myreq = 0;
     if (lane < R) myreq = pods.rq_req[(size_t)lane * pods.NQ + rq];
     const unsigned ract = __ballot_sync(0xffffffffu, myreq != 0);
@@ -399,9 +419,11 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           const bool live = idx < n;
           const int c = live ? ord[idx] : 0;
           const bool tolerated = live ? ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0) : true;
+          if (tid == 0 && tolerated) { long long now_ = clock64(); prof[5] += (unsigned long long)(now_ - tick); tick = now_; }
           uint64_t o_[WPL];
-          const bool fits = group_inflight_nokeys<G, WPL>(kt, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
+          const bool fits = group_inflight_nokeys<G, WPL>(kt, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
                                                           c_mask + (size_t)c * W, tolerated, pd.req, ract, o_);
+          if (tid == 0 && (fits || !fits)) { long long now_ = clock64(); prof[6] += (unsigned long long)(now_ - tick); tick = now_; }
           if (live && gl == 0) my_evals += (unsigned long long)c_nopt[c];
           if (fits) {
             my_idx0 = idx;
@@ -588,8 +610,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     // ---- what is left of the order normalisation: long rotates and the full pdqsort's bookkeeping ----
     if (S.mode != MODE_NONE) {
       const int mode = S.mode, src = S.rot_src, dst = S.rot_dst, orig = S.rot_orig;
-      prof[5] += tid == 0;
-      prof[6] += (tid == 0 && mode == MODE_GENERIC);
+
       if (mode == MODE_ROTATE) cta_rotate(ord, key, src, dst);
       if (tid == 0) {
         S.undo_mode = mode;

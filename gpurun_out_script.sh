@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 300 python tools/profile_target.py solve c2 10000 500 2 > gpurun_out/t_solve_c2.log 2>&1; tail -4 gpurun_out/t_solve_c2.log
-timeout 300 python tools/profile_target.py solve c3 100000 1000 2 > gpurun_out/t_solve_c3.log 2>&1; tail -4 gpurun_out/t_solve_c3.log
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 10 --warmup 3 --large > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-600
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-300
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_r01_v1.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_ncu.log 2>&1
