@@ -91,10 +91,10 @@ class ClockSampler:
 def dense_bytes(enc) -> int:
     """Algorithmic bytes of one dense launch with this repo's layout: every pod row (two class
     ids) read once, every output (SKU mask, first feasible template, per-template codes) written once, every class
-    row (C, O per signature x template; F per request vector x template; status) read once."""
+    row (C&O per signature x template; F per request vector x template; status) read once."""
     pod_row = 4 + 4
     out_row = enc.W * 8 + 4 + enc.T
-    tables = (enc.NS * 2 + enc.NQ) * enc.T * enc.W * 8 + enc.NS * enc.T
+    tables = (enc.NS + enc.NQ) * enc.T * enc.W * 8 + enc.NS * enc.T  # C&O and F rows + status (C, O alone: failures only)
     return enc.P * (pod_row + out_row) + tables
 
 

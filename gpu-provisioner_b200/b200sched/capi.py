@@ -148,6 +148,10 @@ def lib():
     L.b200s_resident_copy_fit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200s_resident_last_launches.argtypes = [C.c_void_p]
     L.b200s_resident_pack_profile.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint64)]
+    i64p, u8p = _P(C.c_int64), _P(C.c_uint8)
+    L.b200s_pod_requests.argtypes = [C.c_int32, C.c_int32, C.c_int32, i64p, u8p, i64p, u8p, C.c_int32, i64p, u8p, i64p, u8p, u8p,
+                                     i64p, i64p]
+    L.b200s_allocatable.argtypes = [C.c_int32, C.c_int32, i64p, u8p, i64p, i64p, i64p, u8p, i64p]
     L.b200s_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
                                       _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]
     _lib = L

@@ -88,6 +88,7 @@ struct b200s_resident {
   uint8_t* sg_status = nullptr;
   uint64_t* sgC = nullptr;
   uint64_t* sgO = nullptr;
+  uint64_t* sgCO = nullptr;
   uint64_t* rqF = nullptr;
   int32_t* tm_count = nullptr;
   // stage A
@@ -326,6 +327,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sg_status = r->dalloc<uint8_t>(NS * T1);
   r->sgC = r->dalloc<uint64_t>(NS * T1 * W);
   r->sgO = r->dalloc<uint64_t>(NS * T1 * W);
+  r->sgCO = r->dalloc<uint64_t>(NS * T1 * W);
   r->rqF = r->dalloc<uint64_t>(NQ * T1 * W);
   r->tm_count = r->dalloc<int32_t>(MAXT);
   r->a_tmpl = r->dalloc<int32_t>(P);
@@ -372,7 +374,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sel_sku = r->dalloc<int32_t>(P);
   r->sel_price = r->dalloc<uint64_t>(P);
   r->sel_nopt = r->dalloc<int32_t>(P);
-  void* must[] = {r->sg_status, r->sgC, r->sgO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
+  void* must[] = {r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
                   A.c_tmpl, A.c_npods, A.c_nopt, A.ord, A.ord_key, A.ord_snap, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
                   A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
                   r->sel_sku, r->sel_price, r->sel_nopt};
@@ -389,9 +391,9 @@ int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, ctx->stream),
            "template_prefilter launch");
   CUDA_TRY(ctx, launch_class_tables(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->sg_status, r->sgC, r->sgO,
-                                    r->rqF, r->tm_count, ctx->n_sm, ctx->smem_limit, ctx->stream),
+                                    r->sgCO, r->rqF, r->tm_count, ctx->n_sm, ctx->smem_limit, ctx->stream),
            "class_tables launch");
-  CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->rqF, r->tm_count, r->a_tmpl,
+  CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl,
                                  r->a_mask, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
            "fit_dense launch");
   *launches += 1 + (r->T > 0 ? 1 : 0) + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);

@@ -652,4 +652,66 @@ int b200s_create_select(const char* name, int32_t n_types, const char* const* in
   return B200S_OK;
 }
 
+int b200s_pod_requests(int32_t R, int32_t res_pods, int32_t n_containers, const int64_t* req, const uint8_t* req_has,
+                       const int64_t* lim, const uint8_t* lim_has, int32_t n_init, const int64_t* init_req,
+                       const uint8_t* init_req_has, const int64_t* init_lim, const uint8_t* init_lim_has,
+                       const uint8_t* init_restart_always, const int64_t* overhead, int64_t* out) {
+  if (R <= 0 || R > B200S_MAX_RES || res_pods < 0 || res_pods >= R || n_containers < 0 || n_init < 0 || !out) return B200S_EINVAL;
+  // all quantities are non-negative, so a dense vector with 0 for "absent" is equivalent to the ResourceList maps
+  // under Merge (sum) and MaxResources (max)
+  int64_t total[B200S_MAX_RES] = {0}, sidecars[B200S_MAX_RES] = {0}, high[B200S_MAX_RES] = {0};
+  auto effective = [&](const int64_t* q, const uint8_t* qh, const int64_t* l, const uint8_t* lh, int i, int r) -> int64_t {
+    if (qh[(size_t)i * R + r]) return q[(size_t)i * R + r];          // MergeResourceLimitsIntoRequests (resources.go:204-217)
+    if (lh && lh[(size_t)i * R + r]) return l[(size_t)i * R + r];
+    return 0;
+  };
+  for (int i = 0; i < n_containers; i++)
+    for (int r = 0; r < R; r++) {
+      int64_t v = effective(req, req_has, lim, lim_has, i, r);
+      if (v < 0) return B200S_ENOTREPRESENTABLE;
+      total[r] += v;
+    }
+  for (int i = 0; i < n_init; i++) {
+    const bool always = init_restart_always && init_restart_always[i];
+    for (int r = 0; r < R; r++) {
+      int64_t v = effective(init_req, init_req_has, init_lim, init_lim_has, i, r);
+      if (v < 0) return B200S_ENOTREPRESENTABLE;
+      if (always) {  // resources.go:125-128
+        total[r] += v;
+        sidecars[r] += v;
+        high[r] = std::max(high[r], sidecars[r]);
+      } else {       // resources.go:129-132
+        high[r] = std::max(high[r], v + sidecars[r]);
+      }
+    }
+  }
+  for (int r = 0; r < R; r++) {
+    out[r] = std::max(total[r], high[r]);  // resources.go:135
+    if (overhead) {
+      if (overhead[r] < 0) return B200S_ENOTREPRESENTABLE;
+      out[r] += overhead[r];               // resources.go:137-139
+    }
+  }
+  out[res_pods] = 1;  // RequestsForPods (resources.go:36)
+  return B200S_OK;
+}
+
+int b200s_allocatable(int32_t R, int32_t res_memory, const int64_t* capacity, const uint8_t* capacity_has,
+                      const int64_t* kube_reserved, const int64_t* system_reserved, const int64_t* eviction_threshold,
+                      const uint8_t* is_hugepages, int64_t* out) {
+  if (R <= 0 || R > B200S_MAX_RES || res_memory < 0 || res_memory >= R || !capacity || !capacity_has || !out) return B200S_EINVAL;
+  for (int r = 0; r < R; r++) {  // resources.Subtract keeps exactly the keys of the left side (resources.go:81-94)
+    int64_t ov = (kube_reserved ? kube_reserved[r] : 0) + (system_reserved ? system_reserved[r] : 0) +
+                 (eviction_threshold ? eviction_threshold[r] : 0);
+    out[r] = capacity_has[r] ? capacity[r] - ov : 0;
+  }
+  if (is_hugepages)
+    for (int r = 0; r < R; r++)
+      if (is_hugepages[r] && capacity_has[r]) {  // types.go:189-198
+        out[res_memory] -= capacity[r];
+        if (out[res_memory] < 0) out[res_memory] = 0;
+      }
+  return B200S_OK;
+}
+
 }  // extern "C"

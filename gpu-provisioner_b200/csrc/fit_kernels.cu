@@ -14,6 +14,9 @@
 // All integer / compare / bitset work: no tensor cores, no floating-point arithmetic (prices are compared
 // as their IEEE-754 bit patterns, which is order-preserving for the non-negative finite prices the
 // encoder admits).  Bit-row tables are staged in shared memory; pods stream through in SoA tiles.
+#include <cstdlib>
+#include <cstring>
+
 #include "device_types.cuh"
 #include "kernels.h"
 
@@ -99,6 +102,7 @@ __global__ void __launch_bounds__(CLS_THREADS) class_tables_kernel(KeyTab kt, co
                                                                    const int32_t* __restrict__ alive_g, PodsDev pods,
                                                                    uint8_t* __restrict__ sg_status,
                                                                    uint64_t* __restrict__ sgC, uint64_t* __restrict__ sgO,
+                                                                   uint64_t* __restrict__ sgCO,
                                                                    uint64_t* __restrict__ rqF, int tables_in_smem) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NG = CLS_THREADS / G;
@@ -139,6 +143,7 @@ __global__ void __launch_bounds__(CLS_THREADS) class_tables_kernel(KeyTab kt, co
         if (w < W) {
           sgC[(size_t)item * W + w] = C[i];
           sgO[(size_t)item * W + w] = O[i];
+          sgCO[(size_t)item * W + w] = C[i] & O[i];
         }
       }
     } else {
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(int P, int T
                                                                     const uint8_t* __restrict__ sg_status,
                                                                     const ulonglong2* __restrict__ sgC,
                                                                     const ulonglong2* __restrict__ sgO,
+                                                                    const ulonglong2* __restrict__ sgCO,
                                                                     const ulonglong2* __restrict__ rqF,
                                                                     const int32_t* __restrict__ tm_count,
                                                                     int32_t* __restrict__ tmpl_out,
@@ -291,17 +297,41 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(int P, int T
   // all lanes of a warp run the same number of iterations (P is rounded up per warp; idle groups are predicated off)
   const int p_first = blockIdx.x * NG + threadIdx.x / LPG;
   const int warp_first = p_first - (int)(lane / LPG);
+  // software pipeline over the pod stream: the class ids are fetched two iterations ahead and the first chunk of
+  // status bytes one iteration ahead, so an iteration starts with its gather addresses already known
+  const int psub = (int)(lane / LPG);
+  unsigned sig_n1 = 0, rq_n1 = 0, sig_n2 = 0, rq_n2 = 0;  // iteration +1, +2
+  uint32_t st_n1 = 0xFFu;
+  {
+    const int p0 = warp_first + psub, p1 = p0 + stride;
+    if (p0 < P) { sig_n1 = (unsigned)sig_id[p0]; rq_n1 = (unsigned)req_id[p0]; }
+    if (p1 < P) { sig_n2 = (unsigned)sig_id[p1]; rq_n2 = (unsigned)req_id[p1]; }
+    st_n1 = sg_status[sig_n1 * (unsigned)T + ((int)gl < T ? gl : 0u)];
+  }
   for (int pw = warp_first; pw < P; pw += stride) {
-    const int p = pw + (int)(lane / LPG);
+    const int p = pw + psub;
     const bool live = p < P;
-    const unsigned sig = live ? (unsigned)sig_id[p] : 0u, rq = live ? (unsigned)req_id[p] : 0u;
+    const unsigned sig = sig_n1, rq = rq_n1;
+    const uint32_t st_first = st_n1;
+    sig_n1 = sig_n2;
+    rq_n1 = rq_n2;
+    {
+      const int p2 = p + 2 * stride;
+      // unconditional loads from clamped addresses (class 0 / template 0 always exist): nothing may consume the
+      // loaded registers before the next iteration, or the scoreboard wait lands here
+      st_n1 = sg_status[sig_n1 * (unsigned)T + ((int)gl < T ? gl : 0u)];
+      const int p2c = p2 < P ? p2 : P - 1;
+      sig_n2 = (unsigned)sig_id[p2c];
+      rq_n2 = (unsigned)req_id[p2c];
+    }
     int chosen = -1;
     ulonglong2 keep[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(0ull, 0ull);
     for (int t0 = 0; t0 < T; t0 += LPG) {
       const int t = t0 + (int)gl;
-      uint32_t code = (live && t < T) ? sg_status[sig * (unsigned)T + (unsigned)t] : 0xFFu;
+      uint32_t code = t0 == 0 ? st_first : ((live && t < T) ? sg_status[sig * (unsigned)T + (unsigned)t] : 0xFFu);
+      if (!live || t >= T) code = 0xFFu;
       const uint32_t status = code;
       unsigned ok = (__ballot_sync(FULL, status == B200S_FIT_NONE) >> gshift) & GLOW;
       for (;;) {  // addToNewNodeClaim walks the templates in order and stops at the first that works
@@ -311,36 +341,41 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(int P, int T
         if (active) ok &= ok - 1;
         const unsigned tt = (unsigned)(t0 + j);
         const unsigned cb = (sig * (unsigned)T + tt) * (unsigned)W2, fb = (rq * (unsigned)T + tt) * (unsigned)W2;
-        ulonglong2 c[VPL], o[VPL], f[VPL];
+        ulonglong2 co[VPL], f[VPL];
         bool nz = false;
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
           const unsigned v = gl + i * LPG;
-          c[i] = o[i] = f[i] = make_ulonglong2(0ull, 0ull);
+          co[i] = f[i] = make_ulonglong2(0ull, 0ull);
           if (active && v < (unsigned)W2) {
-            c[i] = __ldg(sgC + cb + v);
-            o[i] = __ldg(sgO + cb + v);
+            co[i] = __ldg(sgCO + cb + v);
             f[i] = __ldg(rqF + fb + v);
           }
-          nz = nz || ((c[i].x & o[i].x & f[i].x) | (c[i].y & o[i].y & f[i].y)) != 0;
+          nz = nz || ((co[i].x & f[i].x) | (co[i].y & f[i].y)) != 0;
         }
         if (active && gl == 0) my_evals += (unsigned)tm_count[tt];
         const bool fits = ((__ballot_sync(FULL, nz) >> gshift) & GLOW) != 0;
         if (active && fits) {
           chosen = (int)tt;
 #pragma unroll
-          for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(c[i].x & o[i].x & f[i].x, c[i].y & o[i].y & f[i].y);
+          for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(co[i].x & f[i].x, co[i].y & f[i].y);
         }
         if (__any_sync(FULL, active && !fits)) {  // InstanceTypeFilterError: the six flags (nodeclaim.go:409-416)
           bool bC = false, bF = false, bO = false, bCF = false, bCO = false, bFO = false;
 #pragma unroll
           for (int i = 0; i < VPL; i++) {
-            bC = bC || (c[i].x | c[i].y);
+            const unsigned v = gl + i * LPG;
+            ulonglong2 c = make_ulonglong2(0ull, 0ull), o = c;
+            if (active && !fits && v < (unsigned)W2) {  // the separate C and O rows are only read on this path
+              c = __ldg(sgC + cb + v);
+              o = __ldg(sgO + cb + v);
+            }
+            bC = bC || (c.x | c.y);
             bF = bF || (f[i].x | f[i].y);
-            bO = bO || (o[i].x | o[i].y);
-            bCF = bCF || ((c[i].x & f[i].x & ~o[i].x) | (c[i].y & f[i].y & ~o[i].y));
-            bCO = bCO || ((c[i].x & o[i].x & ~f[i].x) | (c[i].y & o[i].y & ~f[i].y));
-            bFO = bFO || ((f[i].x & o[i].x & ~c[i].x) | (f[i].y & o[i].y & ~c[i].y));
+            bO = bO || (o.x | o.y);
+            bCF = bCF || ((c.x & f[i].x & ~o.x) | (c.y & f[i].y & ~o.y));
+            bCO = bCO || ((c.x & o.x & ~f[i].x) | (c.y & o.y & ~f[i].y));
+            bFO = bFO || ((f[i].x & o.x & ~c.x) | (f[i].y & o.y & ~c.y));
           }
           const unsigned vC = (__ballot_sync(FULL, bC) >> gshift) & GLOW, vF = (__ballot_sync(FULL, bF) >> gshift) & GLOW,
                          vO = (__ballot_sync(FULL, bO) >> gshift) & GLOW, vCF = (__ballot_sync(FULL, bCF) >> gshift) & GLOW,
@@ -553,8 +588,8 @@ static size_t class_smem_bytes(const KeyTab& kt, int G, int in_smem) {
 }
 
 cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
-                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* rqF,
-                                int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream) {
+                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* sgCO,
+                                uint64_t* rqF, int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
   if (T > 0) template_count_kernel<<<1, MAXT, 0, stream>>>(T, kt.n_words, tmask, tm_count);
   long long items = ((long long)pods.NS + pods.NQ) * T;
@@ -572,7 +607,7 @@ cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, cons
     if (err != cudaSuccess) return err;                                                                     \
     long long need = (items + (CLS_THREADS / G_) - 1) / (CLS_THREADS / G_);                                 \
     int grid = (int)(need < (long long)n_sm * 4 ? need : (long long)n_sm * 4);                              \
-    kern<<<grid, CLS_THREADS, bytes, stream>>>(kt, tg, tmask, alive, pods, sg_status, sgC, sgO, rqF, in_smem); \
+    kern<<<grid, CLS_THREADS, bytes, stream>>>(kt, tg, tmask, alive, pods, sg_status, sgC, sgO, sgCO, rqF, in_smem); \
   } while (0)
   DISPATCH_GROUP(kt.n_words, CALL);
 #undef CALL
@@ -580,7 +615,8 @@ cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, cons
 }
 
 cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const uint8_t* sg_status, const uint64_t* sgC,
-                             const uint64_t* sgO, const uint64_t* rqF, const int32_t* tm_count, int32_t* tmpl_out,
+                             const uint64_t* sgO, const uint64_t* sgCO, const uint64_t* rqF, const int32_t* tm_count,
+                             int32_t* tmpl_out,
                              uint64_t* mask_out, uint8_t* code_out, unsigned long long* evals, int n_sm,
                              cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
@@ -596,13 +632,21 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
     int grid = (int)(need < (long long)n_sm * 8 ? need : (long long)n_sm * 8);                                   \
     fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(                                          \
         pods.P, T, W2, pods.sig_id, pods.req_id, sg_status, reinterpret_cast<const ulonglong2*>(sgC),           \
-        reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out, \
+        reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(sgCO),                    \
+        reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out,                                            \
         reinterpret_cast<ulonglong2*>(mask_out), code_out, evals);                                               \
   } while (0)
-    if (W2 <= 4) VCALL(4, 1);
-    else if (W2 <= 8) VCALL(8, 1);
-    else if (W2 <= 16) VCALL(16, 1);
-    else if (W2 <= 32) VCALL(32, 1);
+    // few lanes per pod, several 16-byte pieces per lane: the per-iteration instruction overhead of a warp is
+    // shared by 8 (or 4) pods instead of 2
+    const char* cfg = getenv("B200S_DENSE_CFG");  // tuning aid: "LPGxVPL"
+    if (cfg && !strcmp(cfg, "4x4") && W2 <= 16) VCALL(4, 4);
+    else if (cfg && !strcmp(cfg, "16x1") && W2 <= 16) VCALL(16, 1);
+    else if (cfg && !strcmp(cfg, "4x2") && W2 <= 8) VCALL(4, 2);
+    else if (cfg && !strcmp(cfg, "8x1") && W2 <= 8) VCALL(8, 1);
+    else if (W2 <= 4) VCALL(4, 1);
+    else if (W2 <= 8) VCALL(4, 2);
+    else if (W2 <= 16) VCALL(8, 2);   // measured best at 1M x 2k (profiles/README.md)
+    else if (W2 <= 32) VCALL(16, 2);
     else VCALL(32, 2);
 #undef VCALL
     return cudaGetLastError();

@@ -69,10 +69,11 @@ struct ClaimOut {
 cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
                                       int32_t* alive, cudaStream_t stream);
 cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
-                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* rqF,
-                                int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream);
+                                const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* sgCO,
+                                uint64_t* rqF, int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream);
 cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const uint8_t* sg_status, const uint64_t* sgC,
-                             const uint64_t* sgO, const uint64_t* rqF, const int32_t* tm_count, int32_t* tmpl_out,
+                             const uint64_t* sgO, const uint64_t* sgCO, const uint64_t* rqF, const int32_t* tm_count,
+                             int32_t* tmpl_out,
                              uint64_t* mask_out, uint8_t* code_out, unsigned long long* evals, int n_sm,
                              cudaStream_t stream);
 int ffd_padded(int P);

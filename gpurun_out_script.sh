@@ -1,7 +1,4 @@
-set -x
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 --large > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log | cut -c1-600
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log | cut -c1-300
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches_r01_v1.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_ncu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu.py -m gpu -q -x -k "fit or config2 or ragged or fuzz or config3" > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
+echo c5; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fit_dense_vec -c 3 --csv python tools/profile_target.py fit c5 1000000 2000 3 2>/dev/null | grep fit_dense | awk -F'","' '{print substr($5,1,34), $NF}'
+echo c3; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fit_dense_vec -c 3 --csv python tools/profile_target.py fit c3 100000 1000 3 2>/dev/null | grep fit_dense | awk -F'","' '{print substr($5,1,34), $NF}'

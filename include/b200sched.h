@@ -418,6 +418,23 @@ int b200s_create_select(const char* name, int32_t n_types, const char* const* in
                         const double* prices, int64_t storage_bytes, int32_t* chosen, int32_t* disk_gb,
                         int32_t* is_gpu);
 
+/* ---- host helpers for the two per-object computations the model's int64 vectors come from ----
+ * b200s_pod_requests: resources.RequestsForPods for one pod (K/utils/resources/resources.go:30-38, :114-144):
+ *   per container requests, falling back to limits where a request is absent (:204-217); sum over containers;
+ *   max with the init-container high-water mark (restartPolicy Always init containers are sidecars: they add to
+ *   the sum and to every later init container's need); plus pod overhead; then pods is SET to 1.
+ *   Arrays are dense [count * n_res] int64 with a presence byte per entry; absent means "not in the ResourceList".
+ * b200s_allocatable: InstanceType.Allocatable (K/cloudprovider/types.go:181-214): capacity minus
+ *   (kubeReserved + systemReserved + evictionThreshold) for the resources capacity lists, then every hugepages-*
+ *   capacity is taken off memory, clamped at zero. */
+int b200s_pod_requests(int32_t n_res, int32_t res_pods, int32_t n_containers, const int64_t* req, const uint8_t* req_has,
+                       const int64_t* lim, const uint8_t* lim_has, int32_t n_init, const int64_t* init_req,
+                       const uint8_t* init_req_has, const int64_t* init_lim, const uint8_t* init_lim_has,
+                       const uint8_t* init_restart_always, const int64_t* overhead, int64_t* out);
+int b200s_allocatable(int32_t n_res, int32_t res_memory, const int64_t* capacity, const uint8_t* capacity_has,
+                      const int64_t* kube_reserved, const int64_t* system_reserved, const int64_t* eviction_threshold,
+                      const uint8_t* is_hugepages, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

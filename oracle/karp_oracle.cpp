@@ -1144,4 +1144,67 @@ int oracle_create_select(const char* name, int32_t n_types, const char* const* i
   return 0;
 }
 
+// ---- resources.RequestsForPods for one pod, reference-shaped: ResourceLists as name->quantity maps
+// (K/utils/resources/resources.go:30-38 RequestsForPods, :114-144 podRequests, :187-201 MaxResources,
+//  :204-217 MergeResourceLimitsIntoRequests)
+int oracle_pod_requests(int32_t R, int32_t res_pods, int32_t n_containers, const int64_t* req, const uint8_t* req_has,
+                        const int64_t* lim, const uint8_t* lim_has, int32_t n_init, const int64_t* init_req,
+                        const uint8_t* init_req_has, const int64_t* init_lim, const uint8_t* init_lim_has,
+                        const uint8_t* init_restart_always, const int64_t* overhead, int64_t* out) {
+  using RL = std::map<int, int64_t>;
+  auto mergeInto = [](RL& dest, const RL& src) { for (auto& kv : src) dest[kv.first] += kv.second; };
+  auto maxResources = [](const RL& a, const RL& b) {
+    RL r;
+    for (const RL* l : {&a, &b})
+      for (auto& kv : *l) {
+        auto it = r.find(kv.first);
+        if (it == r.end() || kv.second > it->second) r[kv.first] = kv.second;
+      }
+    return r;
+  };
+  auto container = [&](const int64_t* q, const uint8_t* qh, const int64_t* l, const uint8_t* lh, int i) {
+    RL ret;
+    for (int r = 0; r < R; r++) if (qh[(size_t)i * R + r]) ret[r] = q[(size_t)i * R + r];
+    if (lh) for (int r = 0; r < R; r++) if (lh[(size_t)i * R + r] && !qh[(size_t)i * R + r]) ret[r] = l[(size_t)i * R + r];
+    return ret;
+  };
+  RL requests, restartable, maxInit;
+  for (int i = 0; i < n_containers; i++) mergeInto(requests, container(req, req_has, lim, lim_has, i));
+  for (int i = 0; i < n_init; i++) {
+    RL c = container(init_req, init_req_has, init_lim, init_lim_has, i);
+    if (init_restart_always && init_restart_always[i]) {
+      mergeInto(requests, c);
+      mergeInto(restartable, c);
+      maxInit = maxResources(maxInit, restartable);
+    } else {
+      RL sum = c;
+      mergeInto(sum, restartable);
+      maxInit = maxResources(maxInit, sum);
+    }
+  }
+  requests = maxResources(requests, maxInit);
+  if (overhead) { RL ov; for (int r = 0; r < R; r++) if (overhead[r]) ov[r] = overhead[r]; mergeInto(requests, ov); }
+  requests[res_pods] = 1;
+  for (int r = 0; r < R; r++) { auto it = requests.find(r); out[r] = it == requests.end() ? 0 : it->second; }
+  return 0;
+}
+
+// ---- InstanceType.Allocatable (K/cloudprovider/types.go:181-214)
+int oracle_allocatable(int32_t R, int32_t res_memory, const int64_t* capacity, const uint8_t* capacity_has,
+                       const int64_t* kube, const int64_t* system, const int64_t* eviction, const uint8_t* is_hugepages,
+                       int64_t* out) {
+  std::map<int, int64_t> total, alloc;  // Overhead.Total() = Merge(kube, system, eviction) (types.go:343-345)
+  for (int r = 0; r < R; r++) total[r] = (kube ? kube[r] : 0) + (system ? system[r] : 0) + (eviction ? eviction[r] : 0);
+  for (int r = 0; r < R; r++) if (capacity_has[r]) alloc[r] = capacity[r] - total[r];  // resources.Subtract
+  for (int r = 0; r < R; r++)
+    if (capacity_has[r] && is_hugepages && is_hugepages[r]) {
+      int64_t current = alloc.count(res_memory) ? alloc[res_memory] : 0;
+      current -= capacity[r];
+      if (current < 0) current = 0;
+      alloc[res_memory] = current;
+    }
+  for (int r = 0; r < R; r++) out[r] = alloc.count(r) ? alloc[r] : 0;
+  return 0;
+}
+
 }  // extern "C"

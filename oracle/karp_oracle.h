@@ -56,6 +56,14 @@ int oracle_tolerates(const b200s_model_t* model, int32_t taint0, int32_t taint1,
 int oracle_create_select(const char* name, int32_t n_types, const char* const* instance_types, const double* prices,
                          int64_t storage_bytes, int32_t* chosen, int32_t* disk_gb, int32_t* is_gpu);
 
+int oracle_pod_requests(int32_t n_res, int32_t res_pods, int32_t n_containers, const int64_t* req, const uint8_t* req_has,
+                        const int64_t* lim, const uint8_t* lim_has, int32_t n_init, const int64_t* init_req,
+                        const uint8_t* init_req_has, const int64_t* init_lim, const uint8_t* init_lim_has,
+                        const uint8_t* init_restart_always, const int64_t* overhead, int64_t* out);
+int oracle_allocatable(int32_t n_res, int32_t res_memory, const int64_t* capacity, const uint8_t* capacity_has,
+                       const int64_t* kube, const int64_t* system, const int64_t* eviction, const uint8_t* is_hugepages,
+                       int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

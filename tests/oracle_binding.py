@@ -57,6 +57,10 @@ def lib():
         _lib.oracle_req_algebra.restype = C.c_int
         _lib.oracle_tolerates.restype = C.c_int
         _lib.oracle_create_select.restype = C.c_int
+        i64p, u8p = _P(C.c_int64), _P(C.c_uint8)
+        _lib.oracle_pod_requests.argtypes = [C.c_int32, C.c_int32, C.c_int32, i64p, u8p, i64p, u8p, C.c_int32, i64p, u8p, i64p,
+                                             u8p, u8p, i64p, i64p]
+        _lib.oracle_allocatable.argtypes = [C.c_int32, C.c_int32, i64p, u8p, i64p, i64p, i64p, u8p, i64p]
         _lib.oracle_create_select.argtypes = [C.c_char_p, C.c_int32, _P(C.c_char_p), _P(C.c_double), C.c_int64,
                                               _P(C.c_int32), _P(C.c_int32), _P(C.c_int32)]
     return _lib
