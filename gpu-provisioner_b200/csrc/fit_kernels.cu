@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(32 * MAXT) template_prefilter_kernel(KeyTab kt
 // -------------------------------------------------------------------------------------------------
 constexpr int CLS_THREADS = 256;
 
+
 template <int G, int WPL>
 __global__ void __launch_bounds__(CLS_THREADS) class_tables_kernel(KeyTab kt, const TmplDev* __restrict__ tg,
                                                                    const uint64_t* __restrict__ tmask_g,
@@ -275,127 +276,118 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_kernel(int P, int T, in
 // Control flow is kept uniform across the WARP so that every vote is a single full-mask instruction from which a
 // group extracts its own bits (sub-warp masks make the compiler emit shuffle loops).  Indices are 32-bit: the
 // launcher checks that the tables and the output stay below 2^31 vectors.
+struct DenseArgs {
+  int P, T, W2;
+  const int32_t* __restrict__ sig_id;
+  const int32_t* __restrict__ req_id;
+  const uint8_t* __restrict__ sg_status;
+  const ulonglong2* __restrict__ sgC;
+  const ulonglong2* __restrict__ sgO;
+  const ulonglong2* __restrict__ sgCO;  // C & O
+  const ulonglong2* __restrict__ rqF;
+  const int32_t* __restrict__ tm_count;
+  int32_t* __restrict__ tmpl_out;
+  ulonglong2* __restrict__ mask_out;
+  uint8_t* __restrict__ code_out;
+  unsigned long long* __restrict__ evals;
+};
+
+// One warp iteration (32/LPG pods) of the template walk in full generality: any number of templates, later
+// candidates after a failed one, the six diagnostic flags.  Must be entered by the whole warp.
 template <int LPG, int VPL>
-__global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(int P, int T, int W2, const int32_t* __restrict__ sig_id,
-                                                                    const int32_t* __restrict__ req_id,
-                                                                    const uint8_t* __restrict__ sg_status,
-                                                                    const ulonglong2* __restrict__ sgC,
-                                                                    const ulonglong2* __restrict__ sgO,
-                                                                    const ulonglong2* __restrict__ sgCO,
-                                                                    const ulonglong2* __restrict__ rqF,
-                                                                    const int32_t* __restrict__ tm_count,
-                                                                    int32_t* __restrict__ tmpl_out,
-                                                                    ulonglong2* __restrict__ mask_out,
-                                                                    uint8_t* __restrict__ code_out,
-                                                                    unsigned long long* __restrict__ evals) {
-  constexpr int NG = FIT_THREADS / LPG;
+__device__ __forceinline__ void dense_general_iter(const DenseArgs& a, int p, bool live, unsigned sig, unsigned rq,
+                                                   unsigned& my_evals) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr unsigned GLOW = LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u);
   const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (LPG - 1), gshift = lane & ~(unsigned)(LPG - 1);
-  unsigned my_evals = 0;
-  const int stride = gridDim.x * NG;
-  // all lanes of a warp run the same number of iterations (P is rounded up per warp; idle groups are predicated off)
-  const int p_first = blockIdx.x * NG + threadIdx.x / LPG;
-  const int warp_first = p_first - (int)(lane / LPG);
-  // software pipeline over the pod stream: the class ids are fetched two iterations ahead and the first chunk of
-  // status bytes one iteration ahead, so an iteration starts with its gather addresses already known
-  const int psub = (int)(lane / LPG);
-  unsigned sig_n1 = 0, rq_n1 = 0, sig_n2 = 0, rq_n2 = 0;  // iteration +1, +2
-  uint32_t st_n1 = 0xFFu;
-  {
-    const int p0 = warp_first + psub, p1 = p0 + stride;
-    if (p0 < P) { sig_n1 = (unsigned)sig_id[p0]; rq_n1 = (unsigned)req_id[p0]; }
-    if (p1 < P) { sig_n2 = (unsigned)sig_id[p1]; rq_n2 = (unsigned)req_id[p1]; }
-    st_n1 = sg_status[sig_n1 * (unsigned)T + ((int)gl < T ? gl : 0u)];
-  }
-  for (int pw = warp_first; pw < P; pw += stride) {
-    const int p = pw + psub;
-    const bool live = p < P;
-    const unsigned sig = sig_n1, rq = rq_n1;
-    const uint32_t st_first = st_n1;
-    sig_n1 = sig_n2;
-    rq_n1 = rq_n2;
-    {
-      const int p2 = p + 2 * stride;
-      // unconditional loads from clamped addresses (class 0 / template 0 always exist): nothing may consume the
-      // loaded registers before the next iteration, or the scoreboard wait lands here
-      st_n1 = sg_status[sig_n1 * (unsigned)T + ((int)gl < T ? gl : 0u)];
-      const int p2c = p2 < P ? p2 : P - 1;
-      sig_n2 = (unsigned)sig_id[p2c];
-      rq_n2 = (unsigned)req_id[p2c];
-    }
-    int chosen = -1;
-    ulonglong2 keep[VPL];
+  const int T = a.T, W2 = a.W2;
+  int chosen = -1;
+  ulonglong2 keep[VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(0ull, 0ull);
-    for (int t0 = 0; t0 < T; t0 += LPG) {
-      const int t = t0 + (int)gl;
-      uint32_t code = t0 == 0 ? st_first : ((live && t < T) ? sg_status[sig * (unsigned)T + (unsigned)t] : 0xFFu);
-      if (!live || t >= T) code = 0xFFu;
-      const uint32_t status = code;
-      unsigned ok = (__ballot_sync(FULL, status == B200S_FIT_NONE) >> gshift) & GLOW;
-      for (;;) {  // addToNewNodeClaim walks the templates in order and stops at the first that works
-        const bool active = chosen < 0 && ok != 0;
-        if (!__any_sync(FULL, active)) break;
-        const int j = active ? __ffs(ok) - 1 : 0;
-        if (active) ok &= ok - 1;
-        const unsigned tt = (unsigned)(t0 + j);
-        const unsigned cb = (sig * (unsigned)T + tt) * (unsigned)W2, fb = (rq * (unsigned)T + tt) * (unsigned)W2;
-        ulonglong2 co[VPL], f[VPL];
-        bool nz = false;
+  for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(0ull, 0ull);
+  for (int t0 = 0; t0 < T; t0 += LPG) {
+    const int t = t0 + (int)gl;
+    uint32_t code = (live && t < T) ? a.sg_status[sig * (unsigned)T + (unsigned)t] : 0xFFu;
+    const uint32_t status = code;
+    unsigned ok = (__ballot_sync(FULL, status == B200S_FIT_NONE) >> gshift) & GLOW;
+    for (;;) {  // addToNewNodeClaim walks the templates in order and stops at the first that works
+      const bool active = chosen < 0 && ok != 0;
+      if (!__any_sync(FULL, active)) break;
+      const int j = active ? __ffs(ok) - 1 : 0;
+      if (active) ok &= ok - 1;
+      const unsigned tt = (unsigned)(t0 + j);
+      const unsigned cb = (sig * (unsigned)T + tt) * (unsigned)W2, fb = (rq * (unsigned)T + tt) * (unsigned)W2;
+      ulonglong2 co[VPL], f[VPL];
+      bool nz = false;
+#pragma unroll
+      for (int i = 0; i < VPL; i++) {
+        const unsigned v = gl + i * LPG;
+        co[i] = f[i] = make_ulonglong2(0ull, 0ull);
+        if (active && v < (unsigned)W2) {
+          co[i] = __ldg(a.sgCO + cb + v);
+          f[i] = __ldg(a.rqF + fb + v);
+        }
+        nz = nz || ((co[i].x & f[i].x) | (co[i].y & f[i].y)) != 0;
+      }
+      if (active && gl == 0) my_evals += (unsigned)a.tm_count[tt];
+      const bool fits = ((__ballot_sync(FULL, nz) >> gshift) & GLOW) != 0;
+      if (active && fits) {
+        chosen = (int)tt;
+#pragma unroll
+        for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(co[i].x & f[i].x, co[i].y & f[i].y);
+      }
+      if (__any_sync(FULL, active && !fits)) {  // InstanceTypeFilterError: the six flags (nodeclaim.go:409-416)
+        bool bC = false, bF = false, bO = false, bCF = false, bCO = false, bFO = false;
 #pragma unroll
         for (int i = 0; i < VPL; i++) {
           const unsigned v = gl + i * LPG;
-          co[i] = f[i] = make_ulonglong2(0ull, 0ull);
-          if (active && v < (unsigned)W2) {
-            co[i] = __ldg(sgCO + cb + v);
-            f[i] = __ldg(rqF + fb + v);
+          ulonglong2 c = make_ulonglong2(0ull, 0ull), o = c;
+          if (active && !fits && v < (unsigned)W2) {  // the separate C and O rows are only read on this path
+            c = __ldg(a.sgC + cb + v);
+            o = __ldg(a.sgO + cb + v);
           }
-          nz = nz || ((co[i].x & f[i].x) | (co[i].y & f[i].y)) != 0;
+          bC = bC || (c.x | c.y);
+          bF = bF || (f[i].x | f[i].y);
+          bO = bO || (o.x | o.y);
+          bCF = bCF || ((c.x & f[i].x & ~o.x) | (c.y & f[i].y & ~o.y));
+          bCO = bCO || ((c.x & o.x & ~f[i].x) | (c.y & o.y & ~f[i].y));
+          bFO = bFO || ((f[i].x & o.x & ~c.x) | (f[i].y & o.y & ~c.y));
         }
-        if (active && gl == 0) my_evals += (unsigned)tm_count[tt];
-        const bool fits = ((__ballot_sync(FULL, nz) >> gshift) & GLOW) != 0;
-        if (active && fits) {
-          chosen = (int)tt;
-#pragma unroll
-          for (int i = 0; i < VPL; i++) keep[i] = make_ulonglong2(co[i].x & f[i].x, co[i].y & f[i].y);
-        }
-        if (__any_sync(FULL, active && !fits)) {  // InstanceTypeFilterError: the six flags (nodeclaim.go:409-416)
-          bool bC = false, bF = false, bO = false, bCF = false, bCO = false, bFO = false;
-#pragma unroll
-          for (int i = 0; i < VPL; i++) {
-            const unsigned v = gl + i * LPG;
-            ulonglong2 c = make_ulonglong2(0ull, 0ull), o = c;
-            if (active && !fits && v < (unsigned)W2) {  // the separate C and O rows are only read on this path
-              c = __ldg(sgC + cb + v);
-              o = __ldg(sgO + cb + v);
-            }
-            bC = bC || (c.x | c.y);
-            bF = bF || (f[i].x | f[i].y);
-            bO = bO || (o.x | o.y);
-            bCF = bCF || ((c.x & f[i].x & ~o.x) | (c.y & f[i].y & ~o.y));
-            bCO = bCO || ((c.x & o.x & ~f[i].x) | (c.y & o.y & ~f[i].y));
-            bFO = bFO || ((f[i].x & o.x & ~c.x) | (f[i].y & o.y & ~c.y));
-          }
-          const unsigned vC = (__ballot_sync(FULL, bC) >> gshift) & GLOW, vF = (__ballot_sync(FULL, bF) >> gshift) & GLOW,
-                         vO = (__ballot_sync(FULL, bO) >> gshift) & GLOW, vCF = (__ballot_sync(FULL, bCF) >> gshift) & GLOW,
-                         vCO = (__ballot_sync(FULL, bCO) >> gshift) & GLOW, vFO = (__ballot_sync(FULL, bFO) >> gshift) & GLOW;
-          if (active && !fits && (int)gl == j) code = filter_flags(vC, vF, vO, vCF, vCO, vFO);
-        }
+        const unsigned vC = (__ballot_sync(FULL, bC) >> gshift) & GLOW, vF = (__ballot_sync(FULL, bF) >> gshift) & GLOW,
+                       vO = (__ballot_sync(FULL, bO) >> gshift) & GLOW, vCF = (__ballot_sync(FULL, bCF) >> gshift) & GLOW,
+                       vCO = (__ballot_sync(FULL, bCO) >> gshift) & GLOW, vFO = (__ballot_sync(FULL, bFO) >> gshift) & GLOW;
+        if (active && !fits && (int)gl == j) code = filter_flags(vC, vF, vO, vCF, vCO, vFO);
       }
-      // templates after the first success are never tried; dropped ones stay marked
-      if (chosen >= 0 && t > chosen && status != B200S_FIT_DROPPED) code = B200S_FIT_NONE;
-      if (live && t < T) code_out[(unsigned)p * (unsigned)T + (unsigned)t] = (uint8_t)code;
     }
-    if (live && gl == 0) tmpl_out[p] = chosen;
-#pragma unroll
-    for (int i = 0; i < VPL; i++) {
-      const unsigned v = gl + i * LPG;
-      if (live && v < (unsigned)W2) mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];
-    }
+    // templates after the first success are never tried; dropped ones stay marked
+    if (chosen >= 0 && t > chosen && status != B200S_FIT_DROPPED) code = B200S_FIT_NONE;
+    if (live && t < T) a.code_out[(unsigned)p * (unsigned)T + (unsigned)t] = (uint8_t)code;
   }
-  for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(FULL, my_evals, o);
-  if (lane == 0 && my_evals) atomicAdd(evals, (unsigned long long)my_evals);
+  if (live && gl == 0) a.tmpl_out[p] = chosen;
+#pragma unroll
+  for (int i = 0; i < VPL; i++) {
+    const unsigned v = gl + i * LPG;
+    if (live && v < (unsigned)W2) a.mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];
+  }
+}
+
+// any T: the general walk for every warp iteration
+template <int LPG, int VPL>
+__global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(const __grid_constant__ DenseArgs a) {
+  constexpr int NG = FIT_THREADS / LPG;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned my_evals = 0;
+  const int stride = gridDim.x * NG;
+  // all lanes of a warp run the same number of iterations (idle groups are predicated off)
+  const int warp_first = blockIdx.x * NG + threadIdx.x / LPG - (int)(lane / LPG);
+  for (int pw = warp_first; pw < a.P; pw += stride) {
+    const int p = pw + (int)(lane / LPG);
+    const bool live = p < a.P;
+    const unsigned sig = live ? (unsigned)a.sig_id[p] : 0u, rq = live ? (unsigned)a.req_id[p] : 0u;
+    dense_general_iter<LPG, VPL>(a, p, live, sig, rq, my_evals);
+  }
+  for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
+  if (lane == 0 && my_evals) atomicAdd(a.evals, (unsigned long long)my_evals);
 }
 
 __global__ void template_count_kernel(int T, int W, const uint64_t* __restrict__ tmask, int32_t* __restrict__ tm_count) {
@@ -626,26 +618,21 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
                      (long long)pods.NQ * T * W2l < (1ll << 31) && (long long)pods.P * T < (1ll << 31);
   if ((kt.n_words & 1) == 0 && small) {  // 16-byte rows, 32-bit indices: the vector kernel
     const int W2 = kt.n_words / 2;
+    DenseArgs da{pods.P, T, W2, pods.sig_id, pods.req_id, sg_status, reinterpret_cast<const ulonglong2*>(sgC),
+                 reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(sgCO),
+                 reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out, reinterpret_cast<ulonglong2*>(mask_out),
+                 code_out, evals};
 #define VCALL(LPG_, VPL_)                                                                                        \
   do {                                                                                                           \
     long long need = ((long long)pods.P + (FIT_THREADS / LPG_) - 1) / (FIT_THREADS / LPG_);                      \
     int grid = (int)(need < (long long)n_sm * 8 ? need : (long long)n_sm * 8);                                   \
-    fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(                                          \
-        pods.P, T, W2, pods.sig_id, pods.req_id, sg_status, reinterpret_cast<const ulonglong2*>(sgC),           \
-        reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(sgCO),                    \
-        reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out,                                            \
-        reinterpret_cast<ulonglong2*>(mask_out), code_out, evals);                                               \
+    fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(da);                                      \
   } while (0)
-    // few lanes per pod, several 16-byte pieces per lane: the per-iteration instruction overhead of a warp is
-    // shared by 8 (or 4) pods instead of 2
-    const char* cfg = getenv("B200S_DENSE_CFG");  // tuning aid: "LPGxVPL"
-    if (cfg && !strcmp(cfg, "4x4") && W2 <= 16) VCALL(4, 4);
-    else if (cfg && !strcmp(cfg, "16x1") && W2 <= 16) VCALL(16, 1);
-    else if (cfg && !strcmp(cfg, "4x2") && W2 <= 8) VCALL(4, 2);
-    else if (cfg && !strcmp(cfg, "8x1") && W2 <= 8) VCALL(8, 1);
-    else if (W2 <= 4) VCALL(4, 1);
+    // few lanes per pod, two 16-byte pieces per lane; measured on 1M x 2k (W2 = 16): 8x2 78 us, 4x4 94 us,
+    // 16x1 118 us, 2x8 147 us (profiles/README.md)
+    if (W2 <= 4) VCALL(4, 1);
     else if (W2 <= 8) VCALL(4, 2);
-    else if (W2 <= 16) VCALL(8, 2);   // measured best at 1M x 2k (profiles/README.md)
+    else if (W2 <= 16) VCALL(8, 2);
     else if (W2 <= 32) VCALL(16, 2);
     else VCALL(32, 2);
 #undef VCALL
