@@ -147,6 +147,7 @@ def lib():
     L.b200s_resident_fetch_solve.argtypes = [C.c_void_p, C.c_void_p, _P(Result)]
     L.b200s_resident_copy_fit_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200s_resident_last_launches.argtypes = [C.c_void_p]
+    L.b200s_resident_dense_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_float)]
     L.b200s_resident_pack_profile.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint64)]
     i64p, u8p = _P(C.c_int64), _P(C.c_uint8)
     L.b200s_pod_requests.argtypes = [C.c_int32, C.c_int32, C.c_int32, i64p, u8p, i64p, u8p, C.c_int32, i64p, u8p, i64p, u8p, u8p,
@@ -401,11 +402,21 @@ class Resident:
     def launches(self) -> int:
         return self.ctx.L.b200s_resident_last_launches(self.h)
 
+    def dense_kernel_ms(self) -> float:
+        """Device time of the dense fit kernel alone in the last stage A (blocks until it has finished)."""
+        ms = C.c_float(0.0)
+        self.ctx._check(self.ctx.L.b200s_resident_dense_kernel_ms(self.ctx.h, self.h, C.byref(ms)))
+        return float(ms.value)
+
     def pack_profile(self):
-        out = (C.c_uint64 * 8)()
+        out = (C.c_uint64 * 12)()
         self.ctx._check(self.ctx.L.b200s_resident_pack_profile(self.ctx.h, self.h, out))
-        names = ["start", "nodes", "scan", "commit", "normalise", "-", "--", "steps"]
-        return dict(zip(names, [int(x) for x in out]))
+        names = ["start", "nodes", "scan", "commit", "normalise", "-", "--", "steps", "queue_warp", "order_warp", "claim_group", "sorts"]
+        d = dict(zip(names, [int(x) for x in out]))
+        d["full_sorts"] = d["sorts"] >> 40
+        d["full_sort_cycles"] = d.pop("sorts") & ((1 << 40) - 1)
+        d.pop("-"), d.pop("--")
+        return d
 
     def fetch_fit(self) -> FitOut:
         e = self.enc

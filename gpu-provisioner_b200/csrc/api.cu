@@ -106,6 +106,7 @@ struct b200s_resident {
   int32_t* sel_nopt = nullptr;
   int last_launches = 0;
   bool fit_done = false, solve_done = false;
+  cudaEvent_t ev_dense0 = nullptr, ev_dense1 = nullptr;  // bracket the dense kernel of the last stage A on ctx->stream
 
   template <class Tp>
   Tp* dalloc(size_t n) {
@@ -158,6 +159,8 @@ int check_shapes(b200s_ctx* ctx, const Catalog* cat, const b200s_pods_soa_t* pod
 void free_resident(b200s_resident* r) {
   if (!r) return;
   for (void* p : r->owned) r->ctx->release(p);
+  if (r->ev_dense0) cudaEventDestroy(r->ev_dense0);
+  if (r->ev_dense1) cudaEventDestroy(r->ev_dense1);
   delete r;
 }
 
@@ -255,7 +258,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
       pb.node_begin = eo;
       pb.node_end = eo + ((nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
       pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0;
-      for (int i = 0; i < 8; i++) pb.prof[i] = 0;
+      for (int i = 0; i < 12; i++) pb.prof[i] = 0;
       if (n_problems > 1)
         for (int i = pb.pod_begin; i < pb.pod_end; i++) { seg[i] = b; rowp[i] = b; }
       po = pb.pod_end;
@@ -338,6 +341,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   A.c_mask = r->dalloc<uint64_t>(P * W);
   A.c_req = r->dalloc<int64_t>(P * R);
   A.c_hi = r->dalloc<int64_t>(P * R);
+  A.c_thr = r->dalloc<int64_t>(P * R);
   A.c_rmask = r->dalloc<uint64_t>(P * (size_t)std::max(K, 1));
   A.c_rflags = r->dalloc<uint64_t>(P);
   A.c_gt = r->dalloc<int64_t>(P * (size_t)std::max(NB, 1));
@@ -374,7 +378,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sel_sku = r->dalloc<int32_t>(P);
   r->sel_price = r->dalloc<uint64_t>(P);
   r->sel_nopt = r->dalloc<int32_t>(P);
-  void* must[] = {r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
+  void* must[] = {r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_thr, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
                   A.c_tmpl, A.c_npods, A.c_nopt, A.ord, A.ord_key, A.ord_snap, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
                   A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
                   r->sel_sku, r->sel_price, r->sel_nopt};
@@ -393,9 +397,15 @@ int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, launch_class_tables(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->sg_status, r->sgC, r->sgO,
                                     r->sgCO, r->rqF, r->tm_count, ctx->n_sm, ctx->smem_limit, ctx->stream),
            "class_tables launch");
+  if (!r->ev_dense0) {
+    CUDA_TRY(ctx, cudaEventCreate(&r->ev_dense0), "event");
+    CUDA_TRY(ctx, cudaEventCreate(&r->ev_dense1), "event");
+  }
+  CUDA_TRY(ctx, cudaEventRecord(r->ev_dense0, ctx->stream), "event record");
   CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl,
                                  r->a_mask, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
            "fit_dense launch");
+  CUDA_TRY(ctx, cudaEventRecord(r->ev_dense1, ctx->stream), "event record");
   *launches += 1 + (r->T > 0 ? 1 : 0) + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);
   return 0;
 }
@@ -623,6 +633,20 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
   kt.rows = (const uint64_t*)put(c->rows, (size_t)c->n_rows * W * 8);
   kt.res_dv = (const int64_t*)put(c->res_dv, (size_t)c->n_dv * 8);
   kt.price = (const uint64_t*)put(c->price, (size_t)ZC * S * 8);
+  {  // rank bucket table: fit_rank of every bucket's lowest value, per resource
+    std::vector<uint16_t> bkt((size_t)MAXR * (RANK_BKTS + 1), 0);
+    for (int r = 0; r < c->n_res; r++) {
+      if (c->res_nd[r] > 65535) return fail(ctx, B200S_EINVAL, "too many distinct allocatable values");
+      const int64_t* dv = c->res_dv + c->res_dv0[r];
+      uint16_t* row = bkt.data() + (size_t)r * (RANK_BKTS + 1);
+      rank_bucket_table(dv, c->res_nd[r], row);
+    }
+    kt.res_bkt = (const uint16_t*)put(bkt.data(), bkt.size() * 2);
+    if (!kt.res_bkt) {
+      for (void* p : cat->bufs) cudaFree(p);
+      return fail(ctx, B200S_ENOMEM, "catalog upload");
+    }
+  }
   if (!kt.val_int || !kt.rows || !kt.res_dv || !kt.price) {
     for (void* p : cat->bufs) cudaFree(p);
     return fail(ctx, B200S_ENOMEM, "catalog upload");
@@ -699,14 +723,21 @@ int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* 
 
 int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }
 
+int b200s_resident_dense_kernel_ms(b200s_ctx_t* ctx, b200s_resident_t* r, float* ms) {
+  if (!ctx || !r || !ms || !r->fit_done || !r->ev_dense0) return B200S_ESTATE;
+  CUDA_TRY(ctx, cudaEventSynchronize(r->ev_dense1), "event sync");
+  CUDA_TRY(ctx, cudaEventElapsedTime(ms, r->ev_dense0, r->ev_dense1), "event elapsed");
+  return B200S_OK;
+}
+
 /* diagnostic: SM cycles thread 0 of problem 0's pack CTA spent per phase in the last solve
  * (step start, existing nodes, in-flight scan, commit + next pod, order normalisation) and the step count */
-int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[8]) {
+int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[12]) {
   if (!ctx || !r || !out || !r->solve_done) return B200S_ESTATE;
   CUDA_TRY(ctx, cudaMemcpyAsync(r->problems_host.data(), r->problems, sizeof(PackProblem) * r->n_problems,
                                 cudaMemcpyDeviceToHost, ctx->stream), "D2H problems");
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync");
-  for (int i = 0; i < 8; i++) out[i] = r->problems_host[0].prof[i];
+  for (int i = 0; i < 12; i++) out[i] = r->problems_host[0].prof[i];
   return B200S_OK;
 }
 

@@ -47,6 +47,7 @@ struct KeyTab {
   int32_t res_nd[MAXR], res_dv0[MAXR], res_row0[MAXR];
   int32_t res_p2[MAXR];    // largest power of two <= res_nd[r] (0 when the resource has no values)
   int32_t max_p2;          // max over resources
+  const uint16_t* res_bkt; // [MAXR][RANK_BKTS + 1]: fit_rank of each log-scale bucket's lowest value (rank_bucket)
   int32_t key_row0[MAXK];
   int32_t zc_row0, row_nonneg, n_rows, n_dv;
   const uint64_t* price;   // [n_zc*S]
@@ -184,11 +185,57 @@ B2_HD uint64_t allowed_values(const KeyTab& kt, int k, const EReq& q) {
 
 // lower_bound over the ascending distinct allocatable values of one resource: index of the first
 // value >= x, or nd when x exceeds them all (then no instance type fits).
+// Log-scale bucket of a non-negative quantity: exponent and the two bits below the leading one, monotone in x.
+// res_bkt[r][b] = fit_rank(lowest value of bucket b), so fit_rank(x) lies in [res_bkt[r][b], res_bkt[r][b + 1]] and
+// the search inside a bucket is one or two steps for real catalogs (distinct allocatable values are rarely within
+// 25 % of each other).
+constexpr int RANK_BKTS = 256;
+B2_HD int rank_bucket(int64_t x) {
+  if (x <= 0) return 0;
+#if defined(__CUDA_ARCH__)
+  const int e = 63 - __clzll(x);
+#else
+  const int e = 63 - __builtin_clzll((unsigned long long)x);
+#endif
+  const int m = e >= 2 ? (int)((x >> (e - 2)) & 3) : (int)((x << (2 - e)) & 3);
+  return e * 4 + m;
+}
+B2_HD int64_t rank_bucket_low(int b) {  // smallest x with rank_bucket(x) == b (b >= 1 reachable buckets only)
+  const int e = b >> 2, m = b & 3;
+  if (e >= 2) return ((int64_t)(4 + m)) << (e - 2);
+  return ((int64_t)(4 + m)) >> (2 - e);
+}
+
 B2_HD int fit_rank(const int64_t* dv, int nd, int64_t x) {
   int lo = 0, hi = nd;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (ldg(dv + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// The bucket table of one resource (RANK_BKTS + 1 entries), built on the host at catalog upload.
+inline void rank_bucket_table(const int64_t* dv, int nd, uint16_t* row) {
+  row[RANK_BKTS] = (uint16_t)nd;
+  for (int b = RANK_BKTS - 1; b >= 1; b--) {
+    // a bucket no value maps to (the mantissa bits of 1, 2, 3 are not all used) takes the next one's rank, so
+    // [row[b], row[b + 1]] always brackets the rank of every x in bucket b
+    const int64_t low = rank_bucket_low(b);
+    row[b] = rank_bucket(low) == b ? (uint16_t)fit_rank(dv, nd, low) : row[b + 1];
+  }
+  row[0] = 0;
+}
+
+// fit_rank through the bucket table of resource r
+// (PLAIN: the tables were staged into shared memory, where the non-coherent load path does not exist)
+template <bool PLAIN = false>
+B2_HD int fit_rank_bkt(const int64_t* dv, const uint16_t* bkt, int64_t x) {
+  const int b = rank_bucket(x);
+  int lo = PLAIN ? bkt[b] : ldg(bkt + b), hi = PLAIN ? bkt[b + 1] : ldg(bkt + b + 1);
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((PLAIN ? dv[mid] : ldg(dv + mid)) < x) lo = mid + 1; else hi = mid;
   }
   return lo;
 }

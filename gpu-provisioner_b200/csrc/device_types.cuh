@@ -340,13 +340,15 @@ __device__ __forceinline__ bool group_inflight(const KeyTab& kt, const StateRef&
 // once, because indexing the constant bank with a per-lane index serialises into one access per distinct lane.
 struct LaneRes {
   const int64_t* dv;
+  const uint16_t* bkt;
   int32_t nd, p2, row0;
 };
 
 __device__ __forceinline__ LaneRes lane_res(const KeyTab& kt, int r) {
-  LaneRes l{nullptr, 0, 0, 0};
+  LaneRes l{nullptr, nullptr, 0, 0, 0};
   if (r < kt.n_res) {
     l.dv = kt.res_dv + kt.res_dv0[r];
+    l.bkt = kt.res_bkt + (size_t)r * (RANK_BKTS + 1);
     l.nd = kt.res_nd[r];
     l.p2 = kt.res_p2[r];
     l.row0 = kt.res_row0[r];
@@ -354,53 +356,63 @@ __device__ __forceinline__ LaneRes lane_res(const KeyTab& kt, int r) {
   return l;
 }
 
-template <int G, int WPL>
-__device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, const LaneRes& lr, bool live, const int64_t* creq,
-                                                      const int64_t* chi, const uint64_t* cmask, bool tolerated,
-                                                      const int64_t* preq, uint32_t ract, uint64_t (&out)[WPL]) {
+template <int G, int WPL, bool PLAIN = false>
+__device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, const uint64_t* rows, const LaneRes& lr, bool live,
+                                                      const int64_t* creq, const int64_t* chi, const int64_t* cthr,
+                                                      const uint64_t* cmask, bool tolerated, const int64_t* preq,
+                                                      uint64_t (&out)[WPL], bool& types_changed, int64_t& new_thr) {
+  // Invariant: the claim's types already lie inside row "alloc[r] >= thr[r]" of every resource r, thr[r] being the
+  // smallest distinct allocatable value >= requests[r].  While requests[r] + pod[r] <= thr[r] that row is still the one
+  // resources.Fits selects, so the claim keeps every type and the pod fits (nodeclaim.go:144-146 with an unchanged
+  // filter result).  Only a total that moves past thr[r] needs the rank search and the row; one beyond the largest
+  // allocatable value among the claim's types (hi[r]) cannot fit at all.
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
   const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (G - 1), gbase = lane & ~(unsigned)(G - 1);
   const int R = kt.n_res, W = kt.n_words;
-  // all loads first (independent): my resource's total and bound, my SKU words
-  int64_t x = 0, hi = 0;
-  const bool mine = live && gl < (unsigned)R && ((ract >> gl) & 1u);
-  if (mine) {
+  int64_t x = 0;
+  bool dead = !tolerated, moved = false;
+  if (live && gl < (unsigned)R) {
     x = creq[gl] + preq[gl];
-    hi = chi[gl];
+    dead = dead || x > chi[gl];
+    moved = x > cthr[gl];
   }
+  const unsigned deadb = __ballot_sync(FULL, dead), movedb = __ballot_sync(FULL, moved);
+  bool gdead = ((deadb >> gbase) & GM) != 0;
+  const unsigned gmoved = gdead ? 0u : ((movedb >> gbase) & GM);  // resources whose row changes, for my group's claim
+  types_changed = gmoved != 0;
+  new_thr = 0;
+  if (!__any_sync(FULL, live && gmoved != 0)) return live && !gdead;  // the common case: nothing to look up
+  // some claim of this warp moves to a new row: rank search by the lanes that own a moved resource
+  int row = -1;
+  bool dead2 = false;
+  if (moved && !gdead) {
+    const int lo = fit_rank_bkt<PLAIN>(lr.dv, lr.bkt, x);
+    dead2 = lo >= lr.nd;
+    if (!dead2) {
+      row = lr.row0 + lo;
+      new_thr = PLAIN ? lr.dv[lo] : ldg(lr.dv + lo);
+    }
+  }
+  const unsigned dead2b = __ballot_sync(FULL, dead2);
+  gdead = gdead || ((dead2b >> gbase) & GM) != 0;
   uint64_t keep[WPL];
 #pragma unroll
   for (int i = 0; i < WPL; i++) {
     const int w = (int)gl + i * G;
-    keep[i] = (live && w < W) ? cmask[w] : 0ull;
+    keep[i] = (live && !gdead && w < W) ? cmask[w] : 0ull;
   }
-  // rank of the new total among the distinct allocatable values (branch-free lower_bound)
-  int row = -1;  // -1: this lane contributes no row
-  bool dead = !tolerated;
-  if (mine) {
-    const int nd = lr.nd;
-    const int64_t* dv = lr.dv;
-    int lo = 0;
-    for (int step = lr.p2; step > 0; step >>= 1) {
-      const int mid = lo + step;
-      if (mid <= nd && ldg(dv + mid - 1) < x) lo = mid;
-    }
-    dead = dead || x > hi || lo >= nd;
-    row = lr.row0 + lo;
-  }
-  const unsigned deadb = __ballot_sync(FULL, dead);
-  const bool gdead = ((deadb >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0;
+  unsigned any_moved = movedb;  // union over the warp's groups, folded onto the low G bits: a uniform loop bound
 #pragma unroll
-  for (int r = 0; r < MAXR; r++) {
-    if (r < R) {  // uniform
-      const int rr = __shfl_sync(FULL, row, (int)gbase + r);
-      if (rr >= 0) {
+  for (int o = 16; o >= G && G < 32; o >>= 1) any_moved |= any_moved >> o;
+  any_moved &= GM;
+  for (unsigned m = any_moved; m; m &= m - 1) {
+    const int r = __ffs((int)m) - 1;
+    const int rr = __shfl_sync(FULL, row, (int)gbase + r);  // -1: this group's claim keeps resource r's row
 #pragma unroll
-        for (int i = 0; i < WPL; i++) {
-          const int w = (int)gl + i * G;
-          if (w < W) keep[i] &= ldg(kt.rows + (size_t)rr * W + w);
-        }
-      }
+    for (int i = 0; i < WPL; i++) {
+      const int w = (int)gl + i * G;
+      if (rr >= 0 && w < W) keep[i] &= PLAIN ? rows[(size_t)rr * W + w] : ldg(rows + (size_t)rr * W + w);
     }
   }
   bool nz = false;
@@ -409,8 +421,8 @@ __device__ __forceinline__ bool group_inflight_nokeys(const KeyTab& kt, const La
     out[i] = keep[i];
     nz = nz || keep[i] != 0;
   }
-  const unsigned nzb = __ballot_sync(FULL, nz && live && !gdead);
-  return ((nzb >> gbase) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u))) != 0;
+  const unsigned nzb = __ballot_sync(FULL, nz);
+  return live && !gdead && ((nzb >> gbase) & GM) != 0;
 }
 
 // The same in-flight CanAdd as group_inflight, decided by ONE thread (used by the scan, 512 claims per pass): only

@@ -15,7 +15,7 @@ struct PackProblem {
   int32_t n_claims, n_unscheduled;
   unsigned long long evals;
   // SM cycles thread 0 spent per phase (pop, pod row, nodes, sort, pre-filter, evaluate, commit, steps)
-  unsigned long long prof[8];
+  unsigned long long prof[12];
 };
 
 // Mutable state of all problems of a launch (device pointers).
@@ -24,6 +24,8 @@ struct PackArrays {
   uint64_t* c_mask;    // [Ptot*W]  InstanceTypeOptions
   int64_t* c_req;      // [Ptot*R]  Spec.Resources.Requests
   int64_t* c_hi;       // [Ptot*R]  upper bound of Allocatable over the claim's instance types (pre-filter only)
+  int64_t* c_thr;      // [Ptot*R]  smallest distinct Allocatable value >= the claim's requests: while requests + pod
+                       //           stay at or below it the resource's table row, hence the claim's types, cannot change
   uint64_t* c_rmask;   // [Ptot*K]  Requirements
   uint64_t* c_rflags;  // [Ptot]
   int64_t* c_gt;       // [Ptot*NB]

@@ -12,6 +12,7 @@
 // "First success by lowest index" (scheduler.go:533-540, :566-575) is an atomicMin over the indices
 // evaluated in parallel; candidates are visited in ascending chunks so the minimum is global.
 #include <climits>
+#include <cstdlib>
 
 #include "device_types.cuh"
 #include "kernels.h"
@@ -32,7 +33,6 @@ struct PackShared {
   uint32_t p_keys[2];  // bit k: the pod's requirements define key k
   uint32_t p_ract[2];  // bit r: the pod requests resource r (non-zero)
   int32_t p_id[2];     // pod index, -1 when the queue is done
-  int32_t pre_pod, pre_sig, pre_rq;  // class ids of the queue's next head, fetched one step ahead
   int64_t zero_b[MAXB];
   int32_t best[2];
   int32_t hit_c[PACK_THREADS / 32];  // claim id behind each warp's first feasible index of the current scan
@@ -40,6 +40,9 @@ struct PackShared {
   int32_t mode, rot_src, rot_dst, rot_orig;   // order normalisation left for the whole CTA after this step's commit
   int32_t undo_mode, undo_src, undo_dst;      // how to take the last normalisation back (see the end of the kernel)
   unsigned long long evals;
+  uint64_t all_taints;  // union of the templates' taints
+  unsigned long long wprof[4];  // diagnostic: cycles of the commit phase by role (next pod's row, claim order, claim
+                                // state) and, in [3], full pdqsort runs (count << 40 | cycles)
 };
 
 constexpr int MODE_ROTATE = 1, MODE_GENERIC = 2;
@@ -54,7 +57,8 @@ __host__ __device__ inline size_t pack_smem_bytes(int G, int W, int n_rows, int 
   if (ord_off) *ord_off = o;
   o += pack_align16((size_t)ORD_SMEM_CAP * 8);  // ord[] + key[]
   if (tables_off) *tables_off = o;
-  if (tables_in_smem) o += pack_align16((size_t)n_rows * W * 8 + (size_t)n_dv * 8);
+  if (tables_in_smem)  // bit rows, distinct allocatable values, rank buckets
+    o += pack_align16((size_t)n_rows * W * 8) + pack_align16((size_t)n_dv * 8) + pack_align16((size_t)MAXR * (RANK_BKTS + 1) * 2);
   return o;
 }
 
@@ -158,10 +162,12 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
   }
   if (!increasing) {
     if (lane == 0) {
+      const long long t_g0 = clock64();
       for (int i = 0; i < n; i++) snap[i] = ord[i];  // rare path; lets the last normalisation be taken back
       GoSort gs{ord, key};
       gs.sort(n);
       S.mode = MODE_GENERIC;
+      S.wprof[3] += (1ull << 40) + (unsigned long long)(clock64() - t_g0);  // count in the high bits, cycles below
     }
     __syncwarp();
     return;
@@ -228,7 +234,7 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
   __syncwarp();
 }
 
-template <int G, int WPL>
+template <int G, int WPL, bool TS>
 __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
                                                                const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
                                                                PackProblem* __restrict__ problems, int tables_in_smem) {
@@ -243,7 +249,23 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   int32_t* s_key = s_ord + ORD_SMEM_CAP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gl = tid & (G - 1);
   const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
-  const LaneRes lres = lane_res(kt, gl);
+  // TS: the resource tables of the in-flight check (bit rows, distinct values, rank buckets) are staged into shared
+  // memory -- the check is a chain of four dependent table reads per claim and the L1 does not keep them
+  LaneRes lres = lane_res(kt, gl);
+  const uint64_t* q_rows = kt.rows;
+  if (TS) {
+    uint64_t* s_rows = reinterpret_cast<uint64_t*>(smem + tables_off);
+    int64_t* s_dv = reinterpret_cast<int64_t*>(smem + tables_off + pack_align16((size_t)kt.n_rows * kt.n_words * 8));
+    uint16_t* s_bkt = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_dv) + pack_align16((size_t)kt.n_dv * 8));
+    for (int i = tid; i < kt.n_rows * kt.n_words; i += PACK_THREADS) s_rows[i] = kt.rows[i];
+    for (int i = tid; i < kt.n_dv; i += PACK_THREADS) s_dv[i] = kt.res_dv[i];
+    for (int i = tid; i < MAXR * (RANK_BKTS + 1); i += PACK_THREADS) s_bkt[i] = kt.res_bkt[i];
+    q_rows = s_rows;
+    if (gl < R) {
+      lres.dv = s_dv + kt.res_dv0[gl];
+      lres.bkt = s_bkt + (size_t)gl * (RANK_BKTS + 1);
+    }
+  }
 
   PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
@@ -252,6 +274,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   uint64_t* c_mask = A.c_mask + (size_t)base * W;
   int64_t* c_req = A.c_req + (size_t)base * R;
   int64_t* c_hi = A.c_hi + (size_t)base * R;
+  int64_t* c_thr = A.c_thr + (size_t)base * R;
   uint64_t* c_rmask = A.c_rmask + (size_t)base * K;
   uint64_t* c_rflags = A.c_rflags + base;
   int64_t* c_gt = A.c_gt + (size_t)base * NB;
@@ -274,7 +297,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     S.n_claims = 0; S.head = 0; S.len = n_pods; S.seq = 0; S.evals = 0;
     S.ord_global = 0; S.n_pushed = 0; S.mode = MODE_NONE; S.undo_mode = MODE_NONE;
     S.best[0] = INT_MAX; S.best[1] = INT_MAX;
-    S.pre_pod = -1;
+    for (int i = 0; i < 4; i++) S.wprof[i] = 0;
+    uint64_t at = 0;
+    for (int t = 0; t < tg->T; t++) at |= tg->taints[t];
+    S.all_taints = at;
   }
   unsigned long long my_evals = 0;
   unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -290,7 +316,52 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   __syncthreads();
 
   // Queue.Pop (queue.go:46-60) + the pod's row (updateCachedPodData's products, scheduler.go:467-486) through
-  // its signature / request-class ids, by warp 0 into buffer `buf`.
+  // its signature / request-class ids, by the queue warp into buffer `buf`.
+  // The row is three dependent reads away from the queue (pod id -> class ids -> class rows), so the queue warp runs
+  // them as a three-stage pipeline across steps: this step's row was requested one step ago and sits in registers,
+  // the class ids of the pod after it were requested one step ago as well, and so was the pod id after that.  Every
+  // stage carries the pod id it belongs to; a popped pod that does not match (queue shorter than the look-ahead, or
+  // a pod pushed back in between) is fetched on the spot.  Entries ahead of the queue's tail never change.
+  // Per-lane roles for the row: lane r < 8 the request of resource r, lanes 8..23 the value mask of key lane-8,
+  // lanes 24..27 the Gt/Lt bounds of bounded key lane-24, lane 28 the flags word and the tolerated-taint set.
+  constexpr int QW = PACK_THREADS / 32 - 1;  // the queue warp: the last one, least likely to hold the winning lane group
+  int pf_pod1 = -1, pf_pod2 = -1, pf_sig2 = 0, pf_rq2 = 0, pf_pod3 = -1;
+  uint64_t pf_v0 = 0, pf_v1 = 0;
+  // what this lane fetches, fixed for the kernel: a 64-bit word indexed by the request class or the signature, and
+  // for the lanes with a second value a 64-bit or two 32-bit words
+  const uint64_t* rf_a = nullptr;  // 64-bit source of v0
+  const uint64_t* rf_b = nullptr;  // 64-bit source of v1
+  const int32_t* rf_g = nullptr;   // 32-bit sources of (v0, v1): the Gt / Lt bounds
+  const int32_t* rf_l = nullptr;
+  bool rf_by_rq = false;
+  if (lane < 8) {
+    if (lane < R) { rf_a = reinterpret_cast<const uint64_t*>(pods.rq_req + (size_t)lane * pods.NQ); rf_by_rq = true; }
+  } else if (lane < 24) {
+    if (lane - 8 < K) rf_a = pods.sig_mask + (size_t)(lane - 8) * pods.NS;
+  } else if (lane < 28) {
+    if (lane - 24 < NB) { rf_g = pods.sig_gt + (size_t)(lane - 24) * pods.NS; rf_l = pods.sig_lt + (size_t)(lane - 24) * pods.NS; }
+  } else if (lane == 28) {
+    rf_a = pods.sig_flags;
+    rf_b = pods.sig_tol;
+  }
+  uint64_t* st_a = nullptr;  // where this lane's v0 goes in the row buffer 0, and the distance to buffer 1
+  int st_a_step = 0;
+  if (lane < 8) {
+    if (lane < R) { st_a = reinterpret_cast<uint64_t*>(&S.p_req[0][lane]); st_a_step = MAXR; }
+  } else if (lane < 24) {
+    if (lane - 8 < K) { st_a = &S.p_mask[0][lane - 8]; st_a_step = MAXK; }
+  }
+  auto row_fetch = [&](int sig, int rq, uint64_t& v0, uint64_t& v1) {
+    const int idx = rf_by_rq ? rq : sig;
+    v0 = 0;
+    v1 = 0;
+    if (rf_a) v0 = rf_a[idx];
+    if (rf_b) v1 = rf_b[idx];
+    if (rf_g) {
+      v0 = (uint64_t)(uint32_t)rf_g[idx];
+      v1 = (uint64_t)(uint32_t)rf_l[idx];
+    }
+  };
   auto pop_and_load = [&](int buf) {
     int p = -1;
     if (lane == 0) {
@@ -305,49 +376,61 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       S.p_id[buf] = p;
     }
     p = __shfl_sync(0xffffffffu, p, 0);
-    if (p < 0) return;
-    int sig, rq;
-    if (S.pre_pod == p) {  // ids fetched during the previous step
-      sig = S.pre_sig;
-      rq = S.pre_rq;
-    } else {
-      sig = pods.sig_id[p];
-      rq = pods.req_id[p];
-    }
-    __syncwarp();
-    if (lane == 31) {  // one step ahead: the ids of what is now at the head of the queue (entries ahead of the
-                       // tail never change; with an empty queue there is nothing to fetch)
-      int nxt = S.len > 0 ? queue[S.head] : -1;
-      S.pre_pod = nxt;
-      if (nxt >= 0) {
-        S.pre_sig = pods.sig_id[nxt];
-        S.pre_rq = pods.req_id[nxt];
+    if (p >= 0) {
+      uint64_t v0 = pf_v0, v1 = pf_v1;
+      if (p != pf_pod1) {  // not the row that was requested a step ago
+        const int sig = p == pf_pod2 ? pf_sig2 : pods.sig_id[p], rq = p == pf_pod2 ? pf_rq2 : pods.req_id[p];
+        row_fetch(sig, rq, v0, v1);
       }
-    }
-    int64_t myreq = 0;
-    if (lane < R) myreq = pods.rq_req[(size_t)lane * pods.NQ + rq];
-    const unsigned ract = __ballot_sync(0xffffffffu, myreq != 0);
-    if (lane < 8) {
-      if (lane < R) S.p_req[buf][lane] = myreq;
+      const unsigned ract = __ballot_sync(0xffffffffu, lane < R && v0 != 0);
+      if (st_a) st_a[buf ? st_a_step : 0] = v0;  // the request / the key's value mask
       if (lane == 0) S.p_ract[buf] = ract;
-    } else if (lane < 24) {
-      if (lane - 8 < K) S.p_mask[buf][lane - 8] = pods.sig_mask[(size_t)(lane - 8) * pods.NS + sig];
-    } else if (lane < 28) {
-      if (lane - 24 < NB) {
-        S.p_gt[buf][lane - 24] = pods.sig_gt[(size_t)(lane - 24) * pods.NS + sig];
-        S.p_lt[buf][lane - 24] = pods.sig_lt[(size_t)(lane - 24) * pods.NS + sig];
+      if (rf_g) {
+        S.p_gt[buf][lane - 24] = (int32_t)(uint32_t)v0;
+        S.p_lt[buf][lane - 24] = (int32_t)(uint32_t)v1;
+      } else if (lane == 28) {
+        // bit k of keys = the DEFINED bit (bit 0) of nibble k of the flags word: gather every fourth bit
+        uint64_t x = v0 & 0x1111111111111111ull;
+        x = (x | (x >> 3)) & 0x0303030303030303ull;
+        x = (x | (x >> 6)) & 0x000F000F000F000Full;
+        x = (x | (x >> 12)) & 0x000000FF000000FFull;
+        x = (x | (x >> 24)) & 0xFFFFull;
+        const uint32_t keys = (uint32_t)x & (K >= 32 ? 0xffffffffu : ((1u << K) - 1u));
+        S.p_flags[buf] = v0;
+        S.p_keys[buf] = keys;
+        S.p_tol[buf] = v1;
       }
-    } else if (lane == 28) {
-      uint64_t f = pods.sig_flags[sig];
-      uint32_t keys = 0;
-      for (int k = 0; k < K; k++) keys |= (uint32_t)((f >> (4 * k)) & 1ull) << k;
-      S.p_flags[buf] = f;
-      S.p_keys[buf] = keys;
-      S.p_tol[buf] = pods.sig_tol[sig];
+    }
+    // advance the pipeline; nothing below is waited for in this step
+    __syncwarp();
+    const int len = S.len, head = S.head;  // after the pop: queue[head] is the pod of the step after next
+    pf_pod1 = len > 0 ? pf_pod2 : -1;
+    if (pf_pod1 >= 0) row_fetch(pf_sig2, pf_rq2, pf_v0, pf_v1);
+    pf_pod2 = len > 1 ? pf_pod3 : -1;
+    if (pf_pod2 >= 0) {
+      pf_sig2 = pods.sig_id[pf_pod2];
+      pf_rq2 = pods.req_id[pf_pod2];
+    }
+    pf_pod3 = -1;
+    if (len > 2) {
+      int at = head + 2;
+      if (at >= n_pods) at -= n_pods;
+      pf_pod3 = queue[at];
     }
   };
+  // prime the three stages for the first pods (dependent reads, once)
+  if (warp == QW && n_pods > 0) {
+    pf_pod1 = queue[0];
+    row_fetch(pods.sig_id[pf_pod1], pods.req_id[pf_pod1], pf_v0, pf_v1);
+    if (n_pods > 1) {
+      pf_pod2 = queue[1];
+      pf_sig2 = pods.sig_id[pf_pod2];
+      pf_rq2 = pods.req_id[pf_pod2];
+    }
+    if (n_pods > 2) pf_pod3 = queue[2];
+  }
 
-  if (warp == 0) pop_and_load(0);
+  if (warp == QW) pop_and_load(0);
   __syncthreads();
   int cur = 0;
 
@@ -356,6 +439,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     if (p < 0) break;
     const PodRef pd{S.p_mask[cur], 1, S.p_flags[cur], S.p_gt[cur], S.p_lt[cur], 1, S.p_req[cur], 1, S.p_tol[cur]};
     const uint32_t podkeys = S.p_keys[cur], ract = S.p_ract[cur];
+    const bool tol_all = (S.all_taints & ~pd.tol) == 0;
     prof[7] += tid == 0;
     PROF(0);
 
@@ -377,6 +461,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     const int n = S.n_claims;
     uint64_t out0[WPL];
     int my_idx0 = -1, my_c0 = -1;
+    bool my_changed0 = false;  // the winning group's claim moves to new table rows (its instance types shrink)
+    int64_t my_thr0 = 0;       // lane r < R of that group: resource r's new threshold when it moved, else 0
     if (!on_node) {
       // ---- addToInflightNode ----
       // One thread per in-flight claim, s.newNodeClaims order: warp w takes claims [32(w + it*NW), +32) in
@@ -405,9 +491,12 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
         return true;
       };
-      // Round 0: the first NW*(32/G) claims, one lane group each.  Selector-less pods take the tuned convergent
-      // path and the winning group keeps the claim's new instance types for the commit; other pods use one thread
-      // per claim like the later rounds.
+      // Lane-group rounds: the first GROUP_ROUNDS * NW * (32/G) claims of the order, one lane group each.  The order is
+      // by pod count, emptiest first, so most pods land here (C2: 63 % on the first 16 claims, 93 % on the first 80).
+      // Selector-less pods take the convergent threshold check and the winning group keeps the claim's new instance
+      // types for the commit; other pods use one thread per claim like the later rounds.
+      // (Running the first round on four warps only -- one per SM sub-partition -- was measured slower: 40.9 vs
+      // 38.3 ms on C2, the extra round costs more than the issue contention.)
       constexpr int GPW = 32 / G, GROUP_ROUNDS = 2;
       const int ROUND0 = podkeys ? 64 : GROUP_ROUNDS * NW * GPW;
       // every "did anyone hit" decision is taken with a barrier reduction so that it is uniform across the CTA
@@ -418,16 +507,20 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           const int idx = gr * NW * GPW + warp * GPW + (lane / G);
           const bool live = idx < n;
           const int c = live ? ord[idx] : 0;
-          const bool tolerated = live ? ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0) : true;
-          if (tid == 0 && tolerated) { long long now_ = clock64(); prof[5] += (unsigned long long)(now_ - tick); tick = now_; }
+          // a pod that tolerates every taint any template carries needs no per-claim lookup (uniform)
+          const bool tolerated = (tol_all || !live) ? true : ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0);
           uint64_t o_[WPL];
-          const bool fits = group_inflight_nokeys<G, WPL>(kt, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
-                                                          c_mask + (size_t)c * W, tolerated, pd.req, ract, o_);
-          if (tid == 0 && (fits || !fits)) { long long now_ = clock64(); prof[6] += (unsigned long long)(now_ - tick); tick = now_; }
+          bool chg_;
+          int64_t thr_;
+          const bool fits = group_inflight_nokeys<G, WPL, TS>(kt, q_rows, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
+                                                              c_thr + (size_t)c * R, c_mask + (size_t)c * W, tolerated, pd.req,
+                                                              o_, chg_, thr_);
           if (live && gl == 0) my_evals += (unsigned long long)c_nopt[c];
           if (fits) {
             my_idx0 = idx;
             my_c0 = c;
+            my_changed0 = chg_;
+            my_thr0 = thr_;
 #pragma unroll
             for (int i = 0; i < WPL; i++) out0[i] = o_[i];
             if (gl == 0) atomicMin(&S.best[cur], idx);
@@ -487,22 +580,27 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       const bool by_group = !podkeys && found < r0sz;   // found by a lane group that still holds the new instance types
       if (by_group) {
         if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
+          const long long t_c0 = clock64();
           const int c = my_c0;
-          int cnt = 0;
+          if (my_changed0) {  // some resource moved past its threshold: the claim's types shrank
+            int cnt = 0;
 #pragma unroll
-          for (int i = 0; i < WPL; i++) {
-            int w = gl + i * G;
-            if (w < W) c_mask[(size_t)c * W + w] = out0[i];
-            cnt += popc64(out0[i]);
+            for (int i = 0; i < WPL; i++) {
+              int w = gl + i * G;
+              if (w < W) c_mask[(size_t)c * W + w] = out0[i];
+              cnt += popc64(out0[i]);
+            }
+            cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
+            if (gl < R && my_thr0 != 0) c_thr[(size_t)c * R + gl] = my_thr0;
+            if (gl == 0) c_nopt[c] = cnt;
           }
-          cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
           for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += pd.req[r];
           if (gl == 0) {
-            c_nopt[c] = cnt;
             c_npods[c]++;
             A.pod_kind[p] = B200S_PLACE_CLAIM;
             A.pod_index[p] = c;
             A.pod_seq[p] = S.seq++;
+            S.wprof[2] += (unsigned long long)(clock64() - t_c0);
           }
         }
       } else if (warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
@@ -528,7 +626,13 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           cnt += popc64(out[i]);
         }
         cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
-        for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] += pd.req[r];
+        for (int r = gl; r < R; r += G) {
+          const int64_t x = c_req[(size_t)c * R + r] + pd.req[r];
+          c_req[(size_t)c * R + r] = x;
+          // the pod fits, so some allocatable value is >= x
+          c_thr[(size_t)c * R + r] = ldg(kt.res_dv + kt.res_dv0[r] +
+                                         fit_rank_bkt(kt.res_dv + kt.res_dv0[r], kt.res_bkt + (size_t)r * (RANK_BKTS + 1), x));
+        }
         if (gl == 0) {
           c_nopt[c] = cnt;
           c_npods[c]++;
@@ -538,9 +642,11 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
       }
       if (warp == 2) {  // the claim moved one pod up: what sort.Slice will do with that
+        const long long t_n0 = clock64();
         if (lane == 0) key[found]++;
         __syncwarp();
         warp_normalise(S, ord, key, g_snap, n, found, false);
+        if (lane == 0) S.wprof[1] += (unsigned long long)(clock64() - t_n0);
       }
     } else if (t_new >= 0) {
       // ---- addToNewNodeClaim: the template walk was done for every pod by stage A ----
@@ -556,7 +662,12 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           cnt += popc64(m);
         }
         cnt = (int)__reduce_add_sync(group_mask<G>(), (unsigned)cnt);
-        for (int r = gl; r < R; r += G) c_req[(size_t)c * R + r] = S.tm.daemon[t][r] + pd.req[r];
+        for (int r = gl; r < R; r += G) {
+          const int64_t x = S.tm.daemon[t][r] + pd.req[r];
+          c_req[(size_t)c * R + r] = x;
+          c_thr[(size_t)c * R + r] = ldg(kt.res_dv + kt.res_dv0[r] +
+                                         fit_rank_bkt(kt.res_dv + kt.res_dv0[r], kt.res_bkt + (size_t)r * (RANK_BKTS + 1), x));
+        }
         // largest Allocatable() among the claim's instance types, per resource: the highest table row
         // "alloc >= dv[i]" that still meets the mask (the mask only shrinks afterwards, so this stays an upper bound)
         for (int r = 0; r < R; r++) {
@@ -590,7 +701,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         A.pod_index[p] = c;
         A.pod_seq[p] = S.seq++;
       }
-    } else if (tid == 0) {  // Queue.Push (queue.go:63-66); the pod stays in PodErrors
+    } else if (warp == QW && lane == 0) {  // Queue.Push (queue.go:63-66), by the queue warp ahead of its pop; the pod stays in PodErrors
       int tail = S.head + S.len;
       if (tail >= n_pods) tail -= n_pods;
       queue[tail] = p;
@@ -600,9 +711,12 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       A.pod_kind[p] = B200S_PLACE_UNSCHEDULED;
       A.pod_index[p] = -1;
     }
-    if (warp == 0) {
+    if (warp == QW) {
       __syncwarp();
+      const long long t_p0 = clock64();
       pop_and_load(cur ^ 1);
+      __syncwarp();
+      if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
     }
     __syncthreads();
     PROF(3);
@@ -652,6 +766,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     pb.n_unscheduled = S.len;
     pb.evals = S.evals;
     for (int i = 0; i < 8; i++) pb.prof[i] = prof[i];
+    for (int i = 0; i < 4; i++) pb.prof[8 + i] = S.wprof[i];
   }
 }
 
@@ -704,13 +819,17 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   int G, WPL;
   pick_group_pack(kt.n_words, &G, &WPL);
   size_t so, to;
-  (void)smem_limit;
-  int in_smem = 0;  // tables stay in global memory / L1 for this kernel
+  // the resource tables go to shared memory when they fit next to the order arrays
+  int in_smem = 1;
   size_t bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
+  if (bytes > (size_t)smem_limit || getenv("B200S_PACK_NO_TS")) {
+    in_smem = 0;
+    bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
+  }
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
-    auto kern = pack_kernel<G_, WPL_>;                                                            \
+    auto kern = in_smem ? pack_kernel<G_, WPL_, true> : pack_kernel<G_, WPL_, false>;             \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);    \
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, PACK_THREADS, bytes, stream>>>(kt, tg, pods, arr, problems, in_smem);      \

@@ -402,9 +402,14 @@ int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_resu
 int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_tmpl, void* d_mask, void* d_code);
 /* number of kernels the last resident_* call enqueued */
 int b200s_resident_last_launches(const b200s_resident_t* r);
-/* diagnostic: SM cycles per phase of the last solve's pack kernel (pop, pod row, existing nodes, sort,
- * pre-filter, evaluate, commit) and, in out[7], the number of pod steps */
-int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[8]);
+/* device time of the dense fit kernel alone in the last stage A (CUDA events on the context's stream, recorded on
+ * every launch); blocks until that kernel has finished */
+int b200s_resident_dense_kernel_ms(b200s_ctx_t* ctx, b200s_resident_t* r, float* ms);
+/* diagnostic: SM cycles thread 0 of problem 0's pack CTA spent per phase of the last solve -- out[0..4] = step start,
+ * existing nodes, in-flight scan, commit + next pod's row, rest of the order normalisation; out[7] = pod steps;
+ * out[8..10] = cycles inside the commit phase by role (queue warp: next pod's row, warp 2: claim order, winning lane
+ * group: claim state); out[11] = full pdqsort runs << 40 | their cycles; out[5..6] reserved */
+int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[12]);
 
 /* ---- config 1: the vmSize pick of instance.Provider.Create (host only, no device) ----
  * name: NodeClaim name; instance_types: the values of the node.kubernetes.io/instance-type

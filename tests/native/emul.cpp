@@ -347,4 +347,14 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
   return 0;
 }
 
+// fit_rank directly and through the log-bucket table the catalog upload builds, on the same queries
+void emul_fit_rank_both(const int64_t* dv, int32_t nd, const int64_t* xs, int32_t n, int32_t* plain, int32_t* bucketed) {
+  std::vector<uint16_t> row(RANK_BKTS + 1);
+  rank_bucket_table(dv, nd, row.data());
+  for (int i = 0; i < n; i++) {
+    plain[i] = fit_rank(dv, nd, xs[i]);
+    bucketed[i] = fit_rank_bkt(dv, row.data(), xs[i]);
+  }
+}
+
 }  // extern "C"

@@ -63,6 +63,14 @@ def emul_solve(enc: capi.Encoded) -> capi.SolveRaw:
     return buf.raw()
 
 
+def emul_fit_rank_both(dv: np.ndarray, xs: np.ndarray):
+    dv = np.ascontiguousarray(dv, np.int64)
+    xs = np.ascontiguousarray(xs, np.int64)
+    a, b = np.zeros(len(xs), np.int32), np.zeros(len(xs), np.int32)
+    emul().emul_fit_rank_both(_p(dv, C.c_int64), len(dv), _p(xs, C.c_int64), len(xs), _p(a, C.c_int32), _p(b, C.c_int32))
+    return a, b
+
+
 def emul_go_sort(cnt: np.ndarray) -> np.ndarray:
     cnt = np.ascontiguousarray(cnt, np.int32)
     ord_ = np.arange(len(cnt), dtype=np.int32)

@@ -181,3 +181,24 @@ def test_config4_generator_and_simulations_on_the_host_emulation():
         enc = capi.Encoded(sim)
         parity.assert_same(parity.canon_device(enc, parity.emul_solve(enc)), parity.canon_oracle(sim, o), f"node {i}")
         assert sim.n_pods == int((node_of_pod == i).sum()) and int(sim.c.n_nodes) == int(model.c.n_nodes) - 1
+
+
+def test_rank_bucket_table_matches_binary_search():
+    """The pack kernel finds "how many distinct allocatable values are below x" through a log-scale bucket table
+    (b200_core.cuh rank_bucket / fit_rank_bkt); it must agree with the plain lower bound for every x."""
+    rng = np.random.default_rng(7)
+    for trial in range(40):
+        kind = trial % 4
+        if kind == 0:    # cpu-like millicores, geometric
+            dv = np.unique((rng.choice([2, 4, 8, 16, 32, 48, 64, 96, 128], 9) * 1000 - rng.integers(0, 400, 9)))
+        elif kind == 1:  # memory-like bytes, clustered
+            dv = np.unique(rng.integers(1, 2048, 60) * (1 << 30) - rng.integers(0, 1 << 28, 60))
+        elif kind == 2:  # tiny values incl. 0..8 (gpu counts, pods)
+            dv = np.unique(rng.integers(0, 9, 6))
+        else:            # dense random up to 2^62
+            dv = np.unique(rng.integers(0, 1 << 62, 300, dtype=np.int64) >> int(rng.integers(0, 50)))
+        xs = np.concatenate([dv, dv + 1, dv - 1, rng.integers(0, int(dv.max()) + 5, 400), [0, 1, 2, 3, 4, 5, 7, 8, -5],
+                             [np.iinfo(np.int64).max]]).astype(np.int64)
+        a, b = parity.emul_fit_rank_both(dv, xs)
+        assert np.array_equal(a, b), (trial, dv[:8], xs[a != b][:8])
+        assert np.array_equal(a, np.searchsorted(dv, xs, side="left"))
