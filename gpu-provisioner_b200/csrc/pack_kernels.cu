@@ -161,9 +161,10 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
     increasing = __ballot_sync(0xffffffffu, bad) == 0;
   }
   if (!increasing) {
+    for (int i = lane; i < n; i += 32) snap[i] = ord[i];  // rare path; lets the last normalisation be taken back
+    __syncwarp();
     if (lane == 0) {
       const long long t_g0 = clock64();
-      for (int i = 0; i < n; i++) snap[i] = ord[i];  // rare path; lets the last normalisation be taken back
       GoSort gs{ord, key};
       gs.sort(n);
       S.mode = MODE_GENERIC;

@@ -254,7 +254,9 @@ void sort_slice(std::vector<T>& v, Less less, bool stable = false) {
 // ------------------------------------------------------------------------------------------------
 // scheduling.Requirement — K/scheduling/requirement.go
 // ------------------------------------------------------------------------------------------------
-const b200s_model_t* g_model = nullptr;  // value numerics for withinIntPtrs; set per call (oracle is single-threaded per process call)
+thread_local const b200s_model_t* g_model = nullptr;  // value numerics for withinIntPtrs; set per call, per thread (the
+                                                      // bench's reference arm runs oracle_fit_matrix on pod ranges
+                                                      // from several threads)
 
 enum Operator { OpIn, OpNotIn, OpExists, OpDoesNotExist };
 

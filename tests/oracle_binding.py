@@ -161,6 +161,19 @@ def fit_matrix(model, pod_begin: int = 0, pod_end: Optional[int] = None):
     return tmpl, mask.reshape(n, W), code[:n * Tn].reshape(n, Tn), int(evals.value), Tn
 
 
+def fit_matrix_threads(model, threads: int):
+    """The dense pass split into contiguous pod ranges, one per host thread (the rows are independent; ctypes
+    releases the GIL).  Returns the summed evaluation count; used by bench.py's reference arm only."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib()
+    P = model.n_pods
+    threads = max(1, min(threads, P))
+    bounds = [P * i // threads for i in range(threads + 1)]
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(lambda i: fit_matrix(model, bounds[i], bounds[i + 1])[3], range(threads)))
+    return int(sum(parts))
+
+
 def go_sort_perm(keys: np.ndarray) -> np.ndarray:
     keys = np.ascontiguousarray(keys, dtype=np.int64)
     perm = np.zeros(len(keys), np.int32)
