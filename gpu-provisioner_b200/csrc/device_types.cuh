@@ -434,10 +434,26 @@ constexpr int MAX_FAST_KEYS = 4;  // pod-defined keys handled from registers; mo
 // resource with a zero request leaves the claim's total unchanged, and the claim's instance types already fit
 // that total, so its row is skipped (exact by the invariant above).  Written branch-free over resources and
 // words so that the independent table lookups overlap.
-__device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef& st, const int64_t* hi, const uint64_t* cmask,
-                                               const PodRef& pd, uint32_t podkeys, uint32_t ract) {
+__device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef& st, const int64_t* hi, const int64_t* thr,
+                                               const uint64_t* cmask, const PodRef& pd, uint32_t podkeys, uint32_t ract) {
   const int W = kt.n_words;
   if (st.taints & ~pd.tol) return 0;
+  // New totals first: a claim whose largest allocatable value cannot hold the pod is rejected for a few loads -- on a
+  // long scan most claims are full -- and a total that stays at or below the claim's threshold (device_types.cuh,
+  // group_inflight_nokeys) keeps the resource's row, so only the resources in `mv` need a rank and a row at all.
+  int64_t x[MAXR];
+  uint32_t mv = 0;
+  bool dead = false;
+#pragma unroll
+  for (int r = 0; r < MAXR; r++) {
+    x[r] = 0;
+    if ((ract >> r) & 1u) {
+      x[r] = st.req[(size_t)r * st.rs] + pd.req[(size_t)r * pd.rs];
+      dead = dead || x[r] > hi[r];
+      if (x[r] > thr[r]) mv |= 1u << r;
+    }
+  }
+  if (dead) return 1;
   // keys the pod defines: Compatible + merged admitted values (nodeclaim.go:125-131)
   int kk[MAX_FAST_KEYS];
   uint64_t ka[MAX_FAST_KEYS];
@@ -473,36 +489,15 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
       }
     }
   }
-  // new totals, headroom, and the rank of each requested resource (interleaved branch-free lower_bound)
-  int64_t x[MAXR];
-  int lo[MAXR];
-  bool dead = false;
-#pragma unroll
-  for (int r = 0; r < MAXR; r++) {
-    x[r] = 0;
-    lo[r] = 0;
-    if ((ract >> r) & 1u) {
-      x[r] = st.req[(size_t)r * st.rs] + pd.req[(size_t)r * pd.rs];
-      dead = dead || x[r] > hi[r];
-    }
-  }
-  if (dead) return 1;
-  for (int step = kt.max_p2; step > 0; step >>= 1) {
-#pragma unroll
-    for (int r = 0; r < MAXR; r++) {
-      if (((ract >> r) & 1u) && step <= kt.res_p2[r]) {
-        int mid = lo[r] + step;
-        if (mid <= kt.res_nd[r] && ldg(kt.res_dv + kt.res_dv0[r] + mid - 1) < x[r]) lo[r] = mid;
-      }
-    }
-  }
+  if (!podkeys && !mv) return 2;  // nothing can change the claim's (non-empty) instance types
   int rowoff[MAXR];
 #pragma unroll
   for (int r = 0; r < MAXR; r++) {
     rowoff[r] = 0;
-    if ((ract >> r) & 1u) {
-      dead = dead || lo[r] >= kt.res_nd[r];
-      rowoff[r] = (kt.res_row0[r] + lo[r]) * W;
+    if ((mv >> r) & 1u) {
+      const int lo = fit_rank_bkt(kt.res_dv + kt.res_dv0[r], kt.res_bkt + (size_t)r * (RANK_BKTS + 1), x[r]);
+      dead = dead || lo >= kt.res_nd[r];
+      rowoff[r] = (kt.res_row0[r] + lo) * W;
     }
   }
   if (dead) return 1;
@@ -513,7 +508,7 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
       uint64_t m = cmask[w];
 #pragma unroll
       for (int r = 0; r < MAXR; r++)
-        if ((ract >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
+        if ((mv >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
       any = any || m != 0;
     }
     return any ? 2 : 1;
@@ -523,7 +518,7 @@ __device__ __forceinline__ int thread_inflight(const KeyTab& kt, const StateRef&
     if (m == 0) continue;
 #pragma unroll
     for (int r = 0; r < MAXR; r++)
-      if ((ract >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
+      if ((mv >> r) & 1u) m &= ldg(kt.rows + rowoff[r] + w);
     if (m == 0) continue;
     if (nk <= MAX_FAST_KEYS) {
 #pragma unroll

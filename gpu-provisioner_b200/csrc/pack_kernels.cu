@@ -161,7 +161,8 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
     increasing = __ballot_sync(0xffffffffu, bad) == 0;
   }
   if (!increasing) {
-    for (int i = lane; i < n; i += 32) snap[i] = ord[i];  // rare path; lets the last normalisation be taken back
+    // rare path (measured: one packed word per element instead of two arrays made this sort slower, not faster)
+    for (int i = lane; i < n; i += 32) snap[i] = ord[i];  // lets the last normalisation be taken back
     __syncwarp();
     if (lane == 0) {
       const long long t_g0 = clock64();
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           c = ord[idx];
           StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
                       c_req + (size_t)c * R, 1, S.tm.taints[c_tmpl[c]]};
-          code = thread_inflight(kt, st, c_hi + (size_t)c * R, c_mask + (size_t)c * W, pd, podkeys, ract);
+          code = thread_inflight(kt, st, c_hi + (size_t)c * R, c_thr + (size_t)c * R, c_mask + (size_t)c * W, pd, podkeys, ract);
           if (code) my_evals += (unsigned long long)c_nopt[c];
         }
         const unsigned hit = __ballot_sync(0xffffffffu, code == 2);
@@ -669,24 +670,27 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           c_thr[(size_t)c * R + r] = ldg(kt.res_dv + kt.res_dv0[r] +
                                          fit_rank_bkt(kt.res_dv + kt.res_dv0[r], kt.res_bkt + (size_t)r * (RANK_BKTS + 1), x));
         }
+        if (gl == 0) {
+          c_tmpl[c] = t;
+          c_npods[c] = 1;
+          c_nopt[c] = cnt;
+        }
+      } else if (warp >= 3 && warp < QW) {
         // largest Allocatable() among the claim's instance types, per resource: the highest table row
-        // "alloc >= dv[i]" that still meets the mask (the mask only shrinks afterwards, so this stays an upper bound)
-        for (int r = 0; r < R; r++) {
+        // "alloc >= dv[i]" that still meets the mask (the mask only shrinks afterwards, so this stays an upper
+        // bound).  One lane group per resource, beside the group that builds the claim.
+        const int r = ((warp - 3) * 32 + lane) / G;
+        if (r < R) {
           int lo = 0, hi = kt.res_nd[r] - 1;  // row 0 always meets a non-empty mask
           while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
             unsigned hit = 0;
             for (int w = gl; w < W; w += G)
-              hit |= (A.a_mask[(size_t)p * W + w] & kt.rows[(size_t)(kt.res_row0[r] + mid) * W + w]) ? 1u : 0u;
+              hit |= (A.a_mask[(size_t)p * W + w] & ldg(kt.rows + (size_t)(kt.res_row0[r] + mid) * W + w)) ? 1u : 0u;
             hit = __reduce_or_sync(group_mask<G>(), hit);
             if (hit) lo = mid; else hi = mid - 1;
           }
-          if (gl == 0) c_hi[(size_t)c * R + r] = kt.res_dv[kt.res_dv0[r] + lo];
-        }
-        if (gl == 0) {
-          c_tmpl[c] = t;
-          c_npods[c] = 1;
-          c_nopt[c] = cnt;
+          if (gl == 0) c_hi[(size_t)c * R + r] = ldg(kt.res_dv + kt.res_dv0[r] + lo);
         }
       } else if (warp == 2) {
         if (lane == 0) {
