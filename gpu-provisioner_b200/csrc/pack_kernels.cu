@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   // a pod pushed back in between) is fetched on the spot.  Entries ahead of the queue's tail never change.
   // Per-lane roles for the row: lane r < 8 the request of resource r, lanes 8..23 the value mask of key lane-8,
   // lanes 24..27 the Gt/Lt bounds of bounded key lane-24, lane 28 the flags word and the tolerated-taint set.
-  constexpr int QW = PACK_THREADS / 32 - 1;  // the queue warp: the last one, least likely to hold the winning lane group
+  constexpr int QW = NW - 1;  // the queue warp: the last one; it takes no part in the claim scan
   int pf_pod1 = -1, pf_pod2 = -1, pf_sig2 = 0, pf_rq2 = 0, pf_pod3 = -1;
   uint64_t pf_v0 = 0, pf_v1 = 0;
   // what this lane fetches, fixed for the kernel: a 64-bit word indexed by the request class or the signature, and
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       v1 = (uint64_t)(uint32_t)rf_l[idx];
     }
   };
-  auto pop_and_load = [&](int buf) {
+  auto pop_and_load = [&](int buf) -> int {
     int p = -1;
     if (lane == 0) {
       if (S.len > 0) {
@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       if (at >= n_pods) at -= n_pods;
       pf_pod3 = queue[at];
     }
+    return p;
   };
   // prime the three stages for the first pods (dependent reads, once)
   if (warp == QW && n_pods > 0) {
@@ -442,6 +443,17 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     const PodRef pd{S.p_mask[cur], 1, S.p_flags[cur], S.p_gt[cur], S.p_lt[cur], 1, S.p_req[cur], 1, S.p_tol[cur]};
     const uint32_t podkeys = S.p_keys[cur], ract = S.p_ract[cur];
     const bool tol_all = (S.all_taints & ~pd.tol) == 0;
+    // While no pod has ever been pushed back, Queue.Pop does not depend on this pod's outcome (the lastLen rule only
+    // looks at pods that were pushed, queue.go:46-60): the queue warp pops the next pod and stores its row NOW, beside
+    // the scan it takes no part in, instead of in the commit phase where it was the longest role.
+    const bool fast = S.n_pushed == 0;
+    bool spec_popped = false;
+    if (warp == QW && fast) {
+      const long long t_p0 = clock64();
+      spec_popped = pop_and_load(cur ^ 1) >= 0;
+      __syncwarp();
+      if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
+    }
     prof[7] += tid == 0;
     PROF(0);
 
@@ -499,14 +511,18 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       // types for the commit; other pods use one thread per claim like the later rounds.
       // (Running the first round on four warps only -- one per SM sub-partition -- was measured slower: 40.9 vs
       // 38.3 ms on C2, the extra round costs more than the issue contention.)
-      constexpr int GPW = 32 / G, GROUP_ROUNDS = 2;
-      const int ROUND0 = podkeys ? 64 : GROUP_ROUNDS * NW * GPW;
+      constexpr int GPW = 32 / G, GROUP_ROUNDS = 2, SW = QW;  // SW scanning warps: all but the queue warp
+      const int ROUND0 = podkeys ? 64 : GROUP_ROUNDS * SW * GPW;
       // every "did anyone hit" decision is taken with a barrier reduction so that it is uniform across the CTA
       int any_hit = 0;
       if (!podkeys) {
         for (int gr = 0; gr < GROUP_ROUNDS && !any_hit; gr++) {
-          if (gr * NW * GPW >= n) break;  // uniform
-          const int idx = gr * NW * GPW + warp * GPW + (lane / G);
+          if (gr * SW * GPW >= n) break;  // uniform
+          if (warp == QW) {  // the queue warp only keeps the barrier count
+            any_hit = __syncthreads_or(0);
+            continue;
+          }
+          const int idx = gr * SW * GPW + warp * GPW + (lane / G);
           const bool live = idx < n;
           const int c = live ? ord[idx] : 0;
           // a pod that tolerates every taint any template carries needs no per-claim lookup (uniform)
@@ -517,7 +533,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           const bool fits = group_inflight_nokeys<G, WPL, TS>(kt, q_rows, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
                                                               c_thr + (size_t)c * R, c_mask + (size_t)c * W, tolerated, pd.req,
                                                               o_, chg_, thr_);
-          if (live && gl == 0) my_evals += (unsigned long long)c_nopt[c];
+          if (live && gl == 0 && chg_) my_evals += (unsigned long long)c_nopt[c];  // types actually re-filtered
           if (fits) {
             my_idx0 = idx;
             my_c0 = c;
@@ -535,8 +551,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         any_hit = __syncthreads_or(hit ? 1 : 0);
       }
       if (!any_hit && n > ROUND0) {
-        for (int it = 0;; it++) {
-          const int b0 = ROUND0 + (it * NW + warp) * 32;
+        for (int it = 0; warp != QW; it++) {
+          const int b0 = ROUND0 + (it * SW + warp) * 32;
           int best_now = 0;
           if (lane == 0) best_now = *(volatile int32_t*)&S.best[cur];
           best_now = __shfl_sync(0xffffffffu, best_now, 0);  // one read per warp keeps the loop exit uniform
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         A.pod_seq[p] = S.seq++;
       }
     } else if (found != INT_MAX) {
-      const int r0sz = podkeys ? 64 : 2 * NW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
+      const int r0sz = podkeys ? 64 : 2 * QW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
       const bool by_group = !podkeys && found < r0sz;   // found by a lane group that still holds the new instance types
       if (by_group) {
         if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
@@ -606,7 +622,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           }
         }
       } else if (warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
-        const int c = S.hit_c[found < r0sz ? (found >> 5) : (((found - r0sz) >> 5) % NW)];  // not ord[found]: warp 2 reorders ord
+        const int c = S.hit_c[found < r0sz ? (found >> 5) : (((found - r0sz) >> 5) % QW)];  // not ord[found]: warp 2 reorders ord
         StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
                     c_req + (size_t)c * R, 1, 0};
         uint64_t cand[WPL], out[WPL];
@@ -712,16 +728,23 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       queue[tail] = p;
       S.len++;
       S.n_pushed++;
-      A.lastlen[p] = S.len;
+      // lastLen = the queue's length right after the append (queue.go:63-66); a next pod popped ahead of time is
+      // still in the reference's queue at that moment
+      A.lastlen[p] = S.len + (spec_popped ? 1 : 0);
       A.pod_kind[p] = B200S_PLACE_UNSCHEDULED;
       A.pod_index[p] = -1;
     }
     if (warp == QW) {
+      // pop here when pods have been pushed back before (the lastLen rule needs this pod's outcome first), or when
+      // the early pop found the queue empty and this pod has just been appended to it
+      const bool pushed_now = !on_node && found == INT_MAX && t_new < 0;
       __syncwarp();
-      const long long t_p0 = clock64();
-      pop_and_load(cur ^ 1);
-      __syncwarp();
-      if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
+      if (!fast || (pushed_now && !spec_popped)) {
+        const long long t_p0 = clock64();
+        pop_and_load(cur ^ 1);
+        __syncwarp();
+        if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
+      }
     }
     __syncthreads();
     PROF(3);

@@ -299,7 +299,8 @@ typedef struct b200s_result {
   /* counts, set by the library */
   int32_t n_claims;          /* len(Results.NewNodeClaims) */
   int32_t n_unscheduled;     /* len(Results.PodErrors) */
-  int64_t fit_evals;         /* instance types passed through the filter loop by the device path */
+  int64_t fit_evals;         /* instance types the device path actually re-filtered (informational: claims that keep
+                              * their types under the threshold rule are decided without touching them) */
   /* per pod [P] */
   int32_t* pod_place_kind;   /* B200S_PLACE_* */
   int32_t* pod_place_index;
