@@ -36,7 +36,8 @@ struct PackShared {
   int64_t zero_b[MAXB];
   int32_t best[2];
   int32_t hit_c[PACK_THREADS / 32];  // claim id behind each warp's first feasible index of the current scan
-  int32_t n_claims, head, len, seq, n_pushed, ord_global;
+  int32_t n_claims, seq, ord_global, _pad0;
+  int32_t head, len, n_pushed, _pad1;  // the queue warp's own words, kept apart from what the other warps read
   int32_t mode, rot_src, rot_dst, rot_orig;   // order normalisation left for the whole CTA after this step's commit
   int32_t undo_mode, undo_src, undo_dst;      // how to take the last normalisation back (see the end of the kernel)
   unsigned long long evals;
@@ -447,6 +448,9 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     // looks at pods that were pushed, queue.go:46-60): the queue warp pops the next pod and stores its row NOW, beside
     // the scan it takes no part in, instead of in the commit phase where it was the longest role.
     const bool fast = S.n_pushed == 0;
+    // read before the queue warp goes off on its own: a step without a barrier in its scan (no claims yet, or the pod
+    // lands on an existing node) lets the other warps reach the commit, where warp 2 may add a claim
+    const int n = S.n_claims;
     bool spec_popped = false;
     if (warp == QW && fast) {
       const long long t_p0 = clock64();
@@ -472,7 +476,6 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
 
     int32_t* ord = S.ord_global ? g_ord : s_ord;
     int32_t* key = S.ord_global ? g_key : s_key;
-    const int n = S.n_claims;
     uint64_t out0[WPL];
     int my_idx0 = -1, my_c0 = -1;
     bool my_changed0 = false;  // the winning group's claim moves to new table rows (its instance types shrink)
@@ -518,30 +521,29 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       if (!podkeys) {
         for (int gr = 0; gr < GROUP_ROUNDS && !any_hit; gr++) {
           if (gr * SW * GPW >= n) break;  // uniform
-          if (warp == QW) {  // the queue warp only keeps the barrier count
-            any_hit = __syncthreads_or(0);
-            continue;
-          }
-          const int idx = gr * SW * GPW + warp * GPW + (lane / G);
-          const bool live = idx < n;
-          const int c = live ? ord[idx] : 0;
-          // a pod that tolerates every taint any template carries needs no per-claim lookup (uniform)
-          const bool tolerated = (tol_all || !live) ? true : ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0);
-          uint64_t o_[WPL];
-          bool chg_;
-          int64_t thr_;
-          const bool fits = group_inflight_nokeys<G, WPL, TS>(kt, q_rows, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
-                                                              c_thr + (size_t)c * R, c_mask + (size_t)c * W, tolerated, pd.req,
-                                                              o_, chg_, thr_);
-          if (live && gl == 0 && chg_) my_evals += (unsigned long long)c_nopt[c];  // types actually re-filtered
-          if (fits) {
-            my_idx0 = idx;
-            my_c0 = c;
-            my_changed0 = chg_;
-            my_thr0 = thr_;
+          bool fits = false;
+          if (warp != QW) {  // the queue warp has no claims to look at; it meets the others at the same barrier below
+            const int idx = gr * SW * GPW + warp * GPW + (lane / G);
+            const bool live = idx < n;
+            const int c = live ? ord[idx] : 0;
+            // a pod that tolerates every taint any template carries needs no per-claim lookup (uniform)
+            const bool tolerated = (tol_all || !live) ? true : ((S.tm.taints[c_tmpl[c]] & ~pd.tol) == 0);
+            uint64_t o_[WPL];
+            bool chg_;
+            int64_t thr_;
+            fits = group_inflight_nokeys<G, WPL, TS>(kt, q_rows, lres, live, c_req + (size_t)c * R, c_hi + (size_t)c * R,
+                                                     c_thr + (size_t)c * R, c_mask + (size_t)c * W, tolerated, pd.req, o_,
+                                                     chg_, thr_);
+            if (live && gl == 0 && chg_) my_evals += (unsigned long long)c_nopt[c];  // types actually re-filtered
+            if (fits) {
+              my_idx0 = idx;
+              my_c0 = c;
+              my_changed0 = chg_;
+              my_thr0 = thr_;
 #pragma unroll
-            for (int i = 0; i < WPL; i++) out0[i] = o_[i];
-            if (gl == 0) atomicMin(&S.best[cur], idx);
+              for (int i = 0; i < WPL; i++) out0[i] = o_[i];
+              if (gl == 0) atomicMin(&S.best[cur], idx);
+            }
           }
           any_hit = __syncthreads_or(fits ? 1 : 0);
         }
@@ -564,6 +566,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       found = S.best[cur];
     }
     PROF(2);
+
+    // a step whose scan had no barrier (existing node, or no claim yet) still has to order the queue warp's early
+    // reads of this step against the commit's writes
+    if (on_node || (!podkeys && n == 0)) __syncthreads();
 
     // ---- commit: exactly one of (node, in-flight claim, new claim, push back).  Warp 0 handles the queue and the
     // next pod's row, the first lane group of warp 1 the claim state, warp 2 the claim order. ----
@@ -750,10 +756,12 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     PROF(3);
 
     // ---- what is left of the order normalisation: long rotates and the full pdqsort's bookkeeping ----
-    if (S.mode != MODE_NONE) {
-      const int mode = S.mode, src = S.rot_src, dst = S.rot_dst, orig = S.rot_orig;
-
+    const int mode = S.mode;  // written by warp 2 before the barrier above; nobody writes it before the next one
+    if (mode != MODE_NONE) {  // uniform
+      const int src = S.rot_src, dst = S.rot_dst, orig = S.rot_orig;
       if (mode == MODE_ROTATE) cta_rotate(ord, key, src, dst);
+      __syncthreads();  // every thread has read S.mode: only now may it be reset (a late warp that saw MODE_NONE
+                        // would skip this block and fall one barrier behind)
       if (tid == 0) {
         S.undo_mode = mode;
         S.undo_src = dst;

@@ -205,3 +205,24 @@ def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
                            "multi-node re-pack")
     finally:
         gpu_ctx.release_catalog(cid)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tool,ok", [("memcheck", "ERROR SUMMARY: 0 errors"), ("racecheck", "RACECHECK SUMMARY: 0 hazards")])
+def test_solve_is_sanitizer_clean(tool, ok):
+    """The pack kernel is one CTA of sixteen warps in different roles that meet at CTA barriers: a warp that takes a
+    different number of barriers than the others (a flag read after another thread already reset it, a scan without
+    a barrier) is undefined behaviour that plain runs do not show.  compute-sanitizer does."""
+    import shutil
+    import subprocess
+    import sys
+    exe = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(exe):
+        pytest.skip("compute-sanitizer not installed")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for kind, pods, skus in (("c2", 700, 300), ("c3", 700, 200)):
+        out = subprocess.run([exe, "--tool", tool, "--print-limit", "3", sys.executable,
+                              os.path.join(root, "tools", "profile_target.py"), "solve", kind, str(pods), str(skus), "1"],
+                             capture_output=True, text=True, timeout=900)
+        text = out.stdout + out.stderr
+        assert ok in text, (kind, text[-3000:])
