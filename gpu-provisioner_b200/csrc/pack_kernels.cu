@@ -552,6 +552,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         if (warp < 2 && warp * 32 < n) hit = scan_block(warp * 32);
         any_hit = __syncthreads_or(hit ? 1 : 0);
       }
+      // (Measured and dropped for the long scans of config[2]-like inputs: a per-claim "refuses this signature" memo
+      // -- no gain, the pass is bound by its dependent loads, not by the requirement algebra -- and four blocks per
+      // warp iteration with their loads issued together -- the four inlined copies of the check made the whole kernel
+      // slower, 1.9 -> 2.4 s on 100k x 1k and 33 -> 36 ms on config[1].)
       if (!any_hit && n > ROUND0) {
         for (int it = 0; warp != QW; it++) {
           const int b0 = ROUND0 + (it * SW + warp) * 32;
@@ -701,8 +705,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         // largest Allocatable() among the claim's instance types, per resource: the highest table row
         // "alloc >= dv[i]" that still meets the mask (the mask only shrinks afterwards, so this stays an upper
         // bound).  One lane group per resource, beside the group that builds the claim.
-        const int r = ((warp - 3) * 32 + lane) / G;
-        if (r < R) {
+        constexpr int HI_GROUPS = (QW - 3) * 32 / G;
+        for (int r = ((warp - 3) * 32 + lane) / G; r < R; r += HI_GROUPS) {
           int lo = 0, hi = kt.res_nd[r] - 1;  // row 0 always meets a non-empty mask
           while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;

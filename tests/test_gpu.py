@@ -1,6 +1,8 @@
 """GPU parity tests (run with -m gpu on a B200).  Everything goes through the C-ABI of libb200sched.so and is
 compared bit for bit with the CPU oracle; at BASELINE.json's full sizes, where the reference-shaped oracle would
 take minutes, size-independent properties are checked instead."""
+import os
+
 import numpy as np
 import pytest
 
