@@ -178,16 +178,34 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def dense_leg(ctx, capi, synth, kind, P, S, steps, warmup, peak):
+def as_deployments(model, replicas: int, seed: int = 7):
+    """The same pod population as Deployments: P/replicas pods drawn at random, each listed `replicas` times in a row
+    (replicas of one Deployment share spec and arrive consecutively in a real pod list).  Only the dense stage is
+    measured on it: UIDs repeat, which the fit matrix does not look at."""
+    import numpy as _np
+    from b200sched import model as M
+    P = model.n_pods
+    rng = _np.random.default_rng(seed)
+    base = rng.integers(0, P, size=(P + replicas - 1) // replicas)
+    perm = _np.repeat(base, replicas)[:P]
+    return M.subset(model, perm, _np.zeros(0, _np.int64))
+
+
+def dense_leg(ctx, capi, synth, kind, P, S, steps, warmup, peak, run=0):
     """The dense stage alone on a larger config: the whole stage (template pre-filter, class tables, dense kernel)
     timed by events around the call, the dense kernel by the library's own event pair around that one launch."""
     model = synth.config(kind, P, S)
     enc = capi.Encoded(model)
+    if run:
+        model = as_deployments(model, run)
+        enc = capi.Encoded(model)
     cid = ctx.upload_catalog(enc)
     res = ctx.resident(cid, enc)
     ms, ms_k = time_device(ctx, res.fit_matrix, steps, warmup, inner=res.dense_kernel_ms)
     ab = dense_bytes(enc)
-    out = {"workload": f"{P} pods x {S} SKUs ({'4 tainted NodePools, selectors' if kind == 'c3' else '1 NodePool'}), one GPU",
+    out = {"workload": f"{P} pods x {S} SKUs ({'4 tainted NodePools, selectors' if kind == 'c3' else '1 NodePool'}), one GPU"
+                       + (f"; the pod list is {P // run} Deployments of {run} replicas each, replicas consecutive" if run else
+                          "; every pod's class drawn independently (worst case for the class-row gathers)"),
            "signatures": enc.NS, "request_classes": enc.NQ, "algorithmic_bytes": ab,
            "kernel": "fit_dense_vec_kernel", "kernel_ms": ms_k, "achieved": ab / (ms_k * 1e-3) / 1e9,
            "frac": ab / (ms_k * 1e-3) / 1e9 / peak, "evals_per_s_kernel": P * S / (ms_k * 1e-3),
@@ -495,7 +513,8 @@ def main():
         traffic = json.load(open(tr)).get("dram_bytes_per_launch") if os.path.exists(tr) else None
         line["roofline_at_scale"] = {"bound": "hbm", "achieved": big["achieved"], "peak": peak, "unit": "GB/s",
                                      "frac": big["frac"], "traffic": traffic, **big}
-        line["roofline_large"] = {"c3": dense_leg(ctx, capi, synth, "c3", 100_000, 1_000, 10, 3, peak), "c5": big}
+        line["roofline_large"] = {"c3": dense_leg(ctx, capi, synth, "c3", 100_000, 1_000, 10, 3, peak), "c5": big,
+                                  "c5_deployments_of_32": dense_leg(ctx, capi, synth, "c3", 1_000_000, 2_000, 10, 3, peak, run=32)}
     ctx.close()
     if rank == 0:
         print(json.dumps(line))

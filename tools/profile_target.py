@@ -16,6 +16,9 @@ P = int(sys.argv[3]) if len(sys.argv) > 3 else defaults[kind][0]
 S = int(sys.argv[4]) if len(sys.argv) > 4 else defaults[kind][1]
 iters = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 model = synth.config("c2" if kind == "c2" else "c3", P, S)
+if os.environ.get("B200S_DEPLOY"):  # the pod list as Deployments of N consecutive replicas (bench.as_deployments)
+    import bench
+    model = bench.as_deployments(model, int(os.environ["B200S_DEPLOY"]))
 enc = capi.Encoded(model)
 ctx = capi.Context(0)
 cid = ctx.upload_catalog(enc)
