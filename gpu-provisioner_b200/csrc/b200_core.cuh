@@ -347,14 +347,76 @@ B2_HD EReq make_ereq(uint64_t mask, uint64_t flags_word, int k, int64_t gt, int6
 struct GoSort {
   int32_t* ord;
   int32_t* key;
+  // coop (device only): ALL 32 lanes of a warp run the algorithm with identical control flow on arrays in shared or
+  // global memory; lane 0 alone writes, and the long linear scans of partition / partialInsertionSort -- where a
+  // nearly sorted input spends its time -- test 32 elements per step.
+  bool coop = false;
   B2_HD bool less(int i, int j) const { return key[i] < key[j]; }
   B2_HD void swap(int i, int j) const {
+#if defined(__CUDA_ARCH__)
+    if (coop) {
+      if ((threadIdx.x & 31) == 0) swap1(i, j);
+      __syncwarp();
+      return;
+    }
+#endif
+    swap1(i, j);
+  }
+  B2_HD void swap1(int i, int j) const {
     int32_t t = ord[i];
     ord[i] = ord[j];
     ord[j] = t;
     t = key[i];
     key[i] = key[j];
     key[j] = t;
+  }
+  // for (; i <= j && P(key[i], kv); i++);  P = "<" (le false) or "<=" (le true)
+  B2_HD int fwd_while(int i, int j, int32_t kv, bool le) const {
+#if defined(__CUDA_ARCH__)
+    if (coop) {
+      const int lane = threadIdx.x & 31;
+      for (;; i += 32) {
+        const int x = i + lane;
+        const bool stop = x > j || !(le ? key[x] <= kv : key[x] < kv);
+        const unsigned sb = __ballot_sync(0xffffffffu, stop);
+        if (sb) return i + __ffs((int)sb) - 1;
+      }
+    }
+#endif
+    while (i <= j && (le ? key[i] <= kv : key[i] < kv)) i++;
+    return i;
+  }
+  // for (; i <= j && P(key[j], kv); j--);  P = ">=" (gt false) or ">" (gt true)
+  B2_HD int bwd_while(int i, int j, int32_t kv, bool gt) const {
+#if defined(__CUDA_ARCH__)
+    if (coop) {
+      const int lane = threadIdx.x & 31;
+      for (;; j -= 32) {
+        const int x = j - lane;
+        const bool stop = x < i || !(gt ? key[x] > kv : key[x] >= kv);
+        const unsigned sb = __ballot_sync(0xffffffffu, stop);
+        if (sb) return j - (__ffs((int)sb) - 1);
+      }
+    }
+#endif
+    while (i <= j && (gt ? key[j] > kv : key[j] >= kv)) j--;
+    return j;
+  }
+  // for (; i < b && !(key[i] < key[i-1]); i++);
+  B2_HD int fwd_while_nondecreasing(int i, int b) const {
+#if defined(__CUDA_ARCH__)
+    if (coop) {
+      const int lane = threadIdx.x & 31;
+      for (;; i += 32) {
+        const int x = i + lane;
+        const bool stop = x >= b || key[x] < key[x - 1];
+        const unsigned sb = __ballot_sync(0xffffffffu, stop);
+        if (sb) return i + __ffs((int)sb) - 1;
+      }
+    }
+#endif
+    while (i < b && !less(i, i - 1)) i++;
+    return i;
   }
 
   B2_HD void insertion(int a, int b) const {
@@ -414,7 +476,7 @@ struct GoSort {
   B2_HD bool partial_insertion(int a, int b) const {
     int i = a + 1;
     for (int s = 0; s < 5; s++) {
-      while (i < b && !less(i, i - 1)) i++;
+      i = fwd_while_nondecreasing(i, b);
       if (i == b) return true;
       if (b - a < 50) return false;
       swap(i, i - 1);
@@ -453,8 +515,9 @@ struct GoSort {
     swap(a, pivot);
     int i = a + 1, j = b - 1;
     for (;;) {
-      while (i <= j && !less(a, i)) i++;
-      while (i <= j && less(a, j)) j--;
+      const int32_t kv = key[a];
+      i = fwd_while(i, j, kv, true);   // while (i <= j && !less(a, i)) i++
+      j = bwd_while(i, j, kv, true);   // while (i <= j && less(a, j)) j--
       if (i > j) break;
       swap(i, j);
       i++; j--;
@@ -464,8 +527,9 @@ struct GoSort {
   B2_HD int partition(int a, int b, int pivot, bool* already) const {
     swap(a, pivot);
     int i = a + 1, j = b - 1;
-    while (i <= j && less(i, a)) i++;
-    while (i <= j && !less(j, a)) j--;
+    const int32_t kv = key[a];  // data[a] holds the pivot until the final swap
+    i = fwd_while(i, j, kv, false);  // while (i <= j && less(i, a)) i++
+    j = bwd_while(i, j, kv, false);  // while (i <= j && !less(j, a)) j--
     if (i > j) {
       swap(j, a);
       *already = true;
@@ -474,8 +538,8 @@ struct GoSort {
     swap(i, j);
     i++; j--;
     for (;;) {
-      while (i <= j && less(i, a)) i++;
-      while (i <= j && !less(j, a)) j--;
+      i = fwd_while(i, j, kv, false);
+      j = bwd_while(i, j, kv, false);
       if (i > j) break;
       swap(i, j);
       i++; j--;

@@ -165,12 +165,15 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
     // rare path (measured: one packed word per element instead of two arrays made this sort slower, not faster)
     for (int i = lane; i < n; i += 32) snap[i] = ord[i];  // lets the last normalisation be taken back
     __syncwarp();
-    if (lane == 0) {
+    {
       const long long t_g0 = clock64();
-      GoSort gs{ord, key};
+      GoSort gs{ord, key, true};  // the whole warp: lane 0 writes, the linear scans go 32 elements per step
       gs.sort(n);
-      S.mode = MODE_GENERIC;
-      S.wprof[3] += (1ull << 40) + (unsigned long long)(clock64() - t_g0);  // count in the high bits, cycles below
+      __syncwarp();
+      if (lane == 0) {
+        S.mode = MODE_GENERIC;
+        S.wprof[3] += (1ull << 40) + (unsigned long long)(clock64() - t_g0);  // count in the high bits, cycles below
+      }
     }
     __syncwarp();
     return;
