@@ -228,3 +228,22 @@ def test_solve_is_sanitizer_clean(tool, ok):
                              capture_output=True, text=True, timeout=900)
         text = out.stdout + out.stderr
         assert ok in text, (kind, text[-3000:])
+
+
+def test_more_claims_than_the_shared_memory_order_holds(gpu_ctx):
+    """9 000 pods that each need a NodeClaim of their own push the claim order past the 8 192 entries kept in shared
+    memory (it spills to global memory), and 2 500 small pods then land on the first claim of the order one after the
+    other, each sending that claim to the far end: rotates of thousands of slots, done by the whole CTA, with the
+    undo bookkeeping of the last one.  Bit for bit against the oracle."""
+    model = synth.config("c2", 11_500, 500)
+    req = model.arrays["pod_requests"].copy()  # [P, R]: cpu (millicores), memory, ephemeral-storage, gpu, pods
+    big = np.arange(model.n_pods) < 9_000
+    req[big, 0] = 70_000           # 70 cores: one per node even on the largest SKU
+    req[big, 1] = 1 << 30
+    req[~big, 0] = 1_000           # 1 core: fits beside a big pod
+    req[~big, 1] = 1 << 28
+    req[:, 2] = 0
+    req[:, 3] = 0
+    model.arrays["pod_requests"] = np.ascontiguousarray(req)
+    model.finalize()
+    _solve_parity(gpu_ctx, model, "spill: 9000 single-pod claims + 2500 riders")
