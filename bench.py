@@ -384,6 +384,8 @@ def run_c4(args, rank, world, local):
 
 
 def main():
+    # stdout carries exactly one JSON line: whatever NCCL has to say (its version banner, NCCL_DEBUG=INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
