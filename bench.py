@@ -513,8 +513,17 @@ def main():
         big = dense_leg(ctx, capi, synth, "c3", 1_000_000, 2_000, 10, 3, peak)
         tr = os.path.join(ROOT, "profiles", "dense_traffic.json")  # dram bytes of one launch from the ncu --set full capture
         traffic = json.load(open(tr)).get("dram_bytes_per_launch") if os.path.exists(tr) else None
-        line["roofline_at_scale"] = {"bound": "hbm", "achieved": big["achieved"], "peak": peak, "unit": "GB/s",
-                                     "frac": big["frac"], "traffic": traffic, **big}
+        at_scale = {"bound": "hbm", "achieved": big["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": big["frac"], "traffic": traffic, **big, "peak_source": peak_src}
+        # SURVEY section 8(d), caveat H3: config[1] fits in L2 and moves 0.8 MB per launch, the fraction is claimed where
+        # the kernel is HBM-relevant.  `roofline` is therefore the dense kernel at configs[4]'s size on this GPU, measured
+        # in this run; the same kernel inside the config[1] step stays visible as `roofline_config1`.
+        line["roofline_config1"] = line["roofline"]
+        line["roofline"] = dict(at_scale, note="fit_dense_vec_kernel on 1M pods x 2k SKUs (configs[4]'s size, one GPU), "
+                                "timed by the library's event pair around that launch in this run; config[1] itself moves "
+                                "0.8 MB per launch (roofline_config1) and its step time is the sequential pack "
+                                "(step_breakdown)")
+        line["roofline_at_scale"] = at_scale
         line["roofline_large"] = {"c3": dense_leg(ctx, capi, synth, "c3", 100_000, 1_000, 10, 3, peak), "c5": big,
                                   "c5_deployments_of_32": dense_leg(ctx, capi, synth, "c3", 1_000_000, 2_000, 10, 3, peak, run=32)}
     ctx.close()
