@@ -212,7 +212,7 @@ def dense_leg(ctx, capi, synth, kind, P, S, steps, warmup, peak, run=0):
            "stage_ms": ms, "evals_per_s_stage": P * S / (ms * 1e-3), "achieved_gbs_stage": ab / (ms * 1e-3) / 1e9,
            "frac_stage": ab / (ms * 1e-3) / 1e9 / peak,
            "note": "kernel = the dense kernel alone (library event pair on its stream); stage = template pre-filter + "
-                   "class tables + dense kernel (4 launches)"}
+                   "class tables + dense kernel (3 launches)"}
     res.close()
     ctx.release_catalog(cid)
     return out

@@ -392,7 +392,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
 // stage A: template pre-filter, class tables, dense fit matrix
 int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, cudaMemsetAsync(r->a_evals, 0, sizeof(unsigned long long), ctx->stream), "memset");
-  CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, ctx->stream),
+  CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, r->tm_count, ctx->stream),
            "template_prefilter launch");
   CUDA_TRY(ctx, launch_class_tables(r->cat->kt, r->tmpl, r->T, r->tmask, r->alive, r->pods, r->sg_status, r->sgC, r->sgO,
                                     r->sgCO, r->rqF, r->tm_count, ctx->n_sm, ctx->smem_limit, ctx->stream),
@@ -406,7 +406,7 @@ int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
                                  r->a_mask, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
            "fit_dense launch");
   CUDA_TRY(ctx, cudaEventRecord(r->ev_dense1, ctx->stream), "event record");
-  *launches += 1 + (r->T > 0 ? 1 : 0) + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);
+  *launches += 1 + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);
   return 0;
 }
 

@@ -53,7 +53,8 @@ template <int G, int WPL>
 __global__ void __launch_bounds__(32 * MAXT) template_prefilter_kernel(KeyTab kt, const TmplDev* __restrict__ tg,
                                                                        const uint64_t* __restrict__ type_admit,
                                                                        uint64_t* __restrict__ tmask,
-                                                                       int32_t* __restrict__ alive) {
+                                                                       int32_t* __restrict__ alive,
+                                                                       int32_t* __restrict__ tm_count) {
   __shared__ EvalScratch sc[MAXT];
   __shared__ int64_t zero_req[MAXR];
   __shared__ uint64_t zero_mask[MAXK];
@@ -77,18 +78,21 @@ __global__ void __launch_bounds__(32 * MAXT) template_prefilter_kernel(KeyTab kt
   uint8_t code = 0;
   int visited;
   int stt = group_can_add<G, WPL>(kt, &sc[t], st, pd, false, cand, out, &code, &visited);
-  unsigned any = 0;
+  unsigned cnt = 0;  // the template's instance types after the pre-filter: what one fresh-claim evaluation visits
 #pragma unroll
   for (int i = 0; i < WPL; i++) {
     int w = gl + i * G;
     if (w < kt.n_words) {
       uint64_t v = stt == ST_OK ? out[i] : 0ull;
       tmask[(size_t)t * kt.n_words + w] = v;
-      any |= v ? 1u : 0u;
+      cnt += (unsigned)popc64(v);
     }
   }
-  any = __reduce_or_sync(group_mask<G>(), any);
-  if (gl == 0) alive[t] = any ? 1 : 0;
+  cnt = __reduce_add_sync(group_mask<G>(), cnt);
+  if (gl == 0) {
+    alive[t] = cnt ? 1 : 0;
+    tm_count[t] = (int32_t)cnt;
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -390,14 +394,6 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(const __grid
   if (lane == 0 && my_evals) atomicAdd(a.evals, (unsigned long long)my_evals);
 }
 
-__global__ void template_count_kernel(int T, int W, const uint64_t* __restrict__ tmask, int32_t* __restrict__ tm_count) {
-  int t = threadIdx.x;
-  if (t >= T) return;
-  int n = 0;
-  for (int w = 0; w < W; w++) n += __popcll(tmask[(size_t)t * W + w]);
-  tm_count[t] = n;
-}
-
 // -------------------------------------------------------------------------------------------------
 // FFD order: bitonic sort of pod indices.  less(a,b) is queue.go:72-108; indices >= P are +infinity.
 // `seg` (may be null) is a leading ascending key: the problem a pod belongs to in a batched solve.
@@ -565,9 +561,9 @@ static void pick_group(int W, int* G, int* WPL) {
   } while (0)
 
 cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
-                                      int32_t* alive, cudaStream_t stream) {
+                                      int32_t* alive, int32_t* tm_count, cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
-#define CALL(G, WPL) template_prefilter_kernel<G, WPL><<<1, 32 * MAXT, 0, stream>>>(kt, tg, type_admit, tmask, alive)
+#define CALL(G, WPL) template_prefilter_kernel<G, WPL><<<1, 32 * MAXT, 0, stream>>>(kt, tg, type_admit, tmask, alive, tm_count)
   DISPATCH_GROUP(kt.n_words, CALL);
 #undef CALL
   return cudaGetLastError();
@@ -583,7 +579,8 @@ cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, cons
                                 const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* sgCO,
                                 uint64_t* rqF, int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream) {
   if (kt.n_words > 128) return cudaErrorInvalidValue;
-  if (T > 0) template_count_kernel<<<1, MAXT, 0, stream>>>(T, kt.n_words, tmask, tm_count);
+  (void)tmask;
+  (void)tm_count;  // filled by the template pre-filter
   long long items = ((long long)pods.NS + pods.NQ) * T;
   if (items == 0) return cudaGetLastError();
   int G, WPL;

@@ -69,7 +69,7 @@ struct ClaimOut {
 };
 
 cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
-                                      int32_t* alive, cudaStream_t stream);
+                                      int32_t* alive, int32_t* tm_count, cudaStream_t stream);
 cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,
                                 const PodsDev& pods, uint8_t* sg_status, uint64_t* sgC, uint64_t* sgO, uint64_t* sgCO,
                                 uint64_t* rqF, int32_t* tm_count, int n_sm, int smem_limit, cudaStream_t stream);
