@@ -71,6 +71,7 @@ struct b200s_resident {
   b200s_ctx* ctx = nullptr;
   Catalog* cat = nullptr;
   int P = 0, Ppad = 0, E = 0, T = 0, n_problems = 0;
+  bool plain = true;  // no pod defines a requirement key (selects the pack kernel's form together with E == 0)
   std::vector<void*> owned;
   PodsDev pods{};
   int32_t* seg = nullptr;          // problem of each pod (batch only)
@@ -236,6 +237,8 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
         if (!rc) rc = upload(ctx, d_slt + (size_t)x * NStot + soff, ps->sig_lt + (size_t)x * ns, ns);
       }
       if (!rc) rc = upload(ctx, d_sflags + soff, ps->sig_flags, ns);
+      for (size_t i = 0; i < ns; i++)
+        if (ps->sig_flags[i] & 0x1111111111111111ull) r->plain = false;  // a DEFINED bit in some key's nibble
       if (!rc) rc = upload(ctx, d_stol + soff, ps->sig_tolerated, ns);
       for (int x = 0; x < R && !rc; x++) rc = upload(ctx, d_rq_req + (size_t)x * NQtot + qoff, ps->rq_requests + (size_t)x * nq, nq);
       if (rc) return rc;
@@ -429,7 +432,8 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   int nl = 0;
   CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
   *launches += nl;
-  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, ctx->smem_limit, ctx->stream),
+  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0,
+                            ctx->smem_limit, ctx->stream),
            "pack launch");
   CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),
            "pack_finalize launch");

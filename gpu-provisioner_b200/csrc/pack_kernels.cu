@@ -240,7 +240,11 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
   __syncwarp();
 }
 
-template <int G, int WPL, bool TS>
+// KEYS: some pod of the batch defines a requirement key; NODES: there are existing nodes.  Without them the compiler
+// drops the requirement algebra / the node paths from the step loop (16.3 k -> 8.2 k SASS instructions without both),
+// and this kernel's speed follows its size: one CTA, every warp in a different region of ~250 KB of code
+// (config[1]: 30.4 -> 25.8 ms).
+template <int G, int WPL, bool TS, bool KEYS, bool NODES>
 __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
                                                                const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
                                                                PackProblem* __restrict__ problems, int tables_in_smem) {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
 
   PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
-  const int E0 = pb.node_begin, E = pb.node_end - pb.node_begin;
+  const int E0 = pb.node_begin, E = NODES ? pb.node_end - pb.node_begin : 0;
   // this problem's slices
   uint64_t* c_mask = A.c_mask + (size_t)base * W;
   int64_t* c_req = A.c_req + (size_t)base * R;
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     const int p = S.p_id[cur];
     if (p < 0) break;
     const PodRef pd{S.p_mask[cur], 1, S.p_flags[cur], S.p_gt[cur], S.p_lt[cur], 1, S.p_req[cur], 1, S.p_tol[cur]};
-    const uint32_t podkeys = S.p_keys[cur], ract = S.p_ract[cur];
+    const uint32_t podkeys = KEYS ? S.p_keys[cur] : 0u, ract = S.p_ract[cur];
     const bool tol_all = (S.all_taints & ~pd.tol) == 0;
     // While no pod has ever been pushed back, Queue.Pop does not depend on this pod's outcome (the lastLen rule only
     // looks at pods that were pushed, queue.go:46-60): the queue warp pops the next pod and stores its row NOW, beside
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       // (Running the first round on four warps only -- one per SM sub-partition -- was measured slower: 40.9 vs
       // 38.3 ms on C2, the extra round costs more than the issue contention.)
       constexpr int GPW = 32 / G, GROUP_ROUNDS = 2, SW = QW;  // SW scanning warps: all but the queue warp
-      const int ROUND0 = podkeys ? 64 : GROUP_ROUNDS * SW * GPW;
+      const int ROUND0 = podkeys ? 0 : GROUP_ROUNDS * SW * GPW;  // pods with selectors go straight to one thread per claim
       // every "did anyone hit" decision is taken with a barrier reduction so that it is uniform across the CTA
       int any_hit = 0;
       if (!podkeys) {
@@ -550,10 +554,6 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
           }
           any_hit = __syncthreads_or(fits ? 1 : 0);
         }
-      } else {
-        bool hit = false;
-        if (warp < 2 && warp * 32 < n) hit = scan_block(warp * 32);
-        any_hit = __syncthreads_or(hit ? 1 : 0);
       }
       // (Measured and dropped for the long scans of config[2]-like inputs: a per-claim "refuses this signature" memo
       // -- no gain, the pass is bound by its dependent loads, not by the requirement algebra -- and four blocks per
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
 
     // a step whose scan had no barrier (existing node, or no claim yet) still has to order the queue warp's early
     // reads of this step against the commit's writes
-    if (on_node || (!podkeys && n == 0)) __syncthreads();
+    if (on_node || n == 0) __syncthreads();
 
     // ---- commit: exactly one of (node, in-flight claim, new claim, push back).  Warp 0 handles the queue and the
     // next pod's row, the first lane group of warp 1 the claim state, warp 2 the claim order. ----
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         A.pod_seq[p] = S.seq++;
       }
     } else if (found != INT_MAX) {
-      const int r0sz = podkeys ? 64 : 2 * QW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
+      const int r0sz = podkeys ? 0 : 2 * QW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
       const bool by_group = !podkeys && found < r0sz;   // found by a lane group that still holds the new instance types
       if (by_group) {
         if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
@@ -855,7 +855,8 @@ static void pick_group_pack(int W, int* G, int* WPL) {
 }
 
 cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
-                        PackProblem* problems, int n_problems, int smem_limit, cudaStream_t stream) {
+                        PackProblem* problems, int n_problems, bool keys, bool nodes, int smem_limit,
+                        cudaStream_t stream) {
   (void)T;
   if (kt.n_words > 128) return cudaErrorInvalidValue;
   if (n_problems == 0) return cudaSuccess;
@@ -872,7 +873,10 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
-    auto kern = in_smem ? pack_kernel<G_, WPL_, true> : pack_kernel<G_, WPL_, false>;             \
+    auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true>                              \
+                : nodes  ? pack_kernel<G_, WPL_, true, true, true>                               \
+                : keys   ? pack_kernel<G_, WPL_, true, true, false>                              \
+                         : pack_kernel<G_, WPL_, true, false, false>;                            \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);    \
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, PACK_THREADS, bytes, stream>>>(kt, tg, pods, arr, problems, in_smem);      \
