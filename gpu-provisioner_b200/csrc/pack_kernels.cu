@@ -684,8 +684,21 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       const int t = t_new, c = n;
       if (warp == 1 && lane < G) {  // NewNodeClaim + Add (nodeclaim.go:83-109, :168-180)
         StateRef st{S.tm.rmask[t], 1, S.tm.rflags[t], S.tm.gt[t], S.tm.lt[t], 1, S.tm.daemon[t], 1, 0};
-        group_store_merged<G>(kt, st, pd, c_rmask + (size_t)c * K, 1, &c_rflags[c], c_gt + (size_t)c * NB,
-                              c_lt + (size_t)c * NB, 1);
+        if constexpr (KEYS) {
+          group_store_merged<G>(kt, st, pd, c_rmask + (size_t)c * K, 1, &c_rflags[c], c_gt + (size_t)c * NB,
+                                c_lt + (size_t)c * NB, 1);
+        } else {  // the pod defines no key: Requirements.Add leaves the template's requirements as they are
+          for (int k = gl; k < K; k += G) {
+            c_rmask[(size_t)c * K + k] = S.tm.rmask[t][k];
+            const int b = kt.bslot[k];
+            if (b >= 0) {
+              const uint32_t nib = (uint32_t)((S.tm.rflags[t] >> (4 * k)) & 0xFu);
+              c_gt[(size_t)c * NB + b] = (nib & RF_GT) ? S.tm.gt[t][b] : 0;
+              c_lt[(size_t)c * NB + b] = (nib & RF_LT) ? S.tm.lt[t][b] : 0;
+            }
+          }
+          if (gl == 0) c_rflags[c] = S.tm.rflags[t];
+        }
         int cnt = 0;
         for (int w = gl; w < W; w += G) {
           uint64_t m = A.a_mask[(size_t)p * W + w];
