@@ -429,10 +429,12 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_seq, 0xFF, P * 4, ctx->stream), "memset");
   CUDA_TRY(ctx, cudaMemcpyAsync(r->problems, r->problems_host.data(), sizeof(PackProblem) * r->n_problems,
                                 cudaMemcpyHostToDevice, ctx->stream), "H2D problems");
+  int max_pods = 0;  // the largest problem of the batch
+  for (const PackProblem& pb : r->problems_host) max_pods = std::max(max_pods, pb.pod_end - pb.pod_begin);
   int nl = 0;
   CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
   *launches += nl;
-  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0,
+  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0, max_pods,
                             ctx->smem_limit, ctx->stream),
            "pack launch");
   CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),

@@ -355,6 +355,7 @@ struct GoSort {
   B2_HD void swap(int i, int j) const {
 #if defined(__CUDA_ARCH__)
     if (coop) {
+      __syncwarp();  // every lane has finished the reads that led here
       if ((threadIdx.x & 31) == 0) swap1(i, j);
       __syncwarp();
       return;

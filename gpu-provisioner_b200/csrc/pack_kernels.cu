@@ -20,7 +20,9 @@
 namespace b200 {
 
 constexpr int PACK_THREADS = 512;
-constexpr int ORD_SMEM_CAP = 8192;  // NodeClaims whose order / count-by-position arrays stay in shared memory
+constexpr int ORD_SMEM_CAP = 8192;    // NodeClaims whose order / count-by-position arrays stay in shared memory
+constexpr int ORD_SMALL_CAP = 12288;  // the same for the SMALL form: no problem has more pods than this, so the order
+                                      // never leaves shared memory and the spill code is compiled out
 constexpr int MODE_NONE = 0;
 
 struct PackShared {
@@ -51,12 +53,12 @@ constexpr int MODE_ROTATE = 1, MODE_GENERIC = 2;
 __host__ __device__ inline size_t pack_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t pack_smem_bytes(int G, int W, int n_rows, int n_dv, int tables_in_smem, size_t* scratch_off,
-                                                  size_t* tables_off, size_t* ord_off = nullptr) {
+                                                  size_t* tables_off, size_t* ord_off = nullptr, int ord_cap = ORD_SMEM_CAP) {
   (void)G;
   size_t o = pack_align16(sizeof(PackShared));
   if (scratch_off) *scratch_off = o;
   if (ord_off) *ord_off = o;
-  o += pack_align16((size_t)ORD_SMEM_CAP * 8);  // ord[] + key[]
+  o += pack_align16((size_t)ord_cap * 8);  // ord[] + key[]
   if (tables_off) *tables_off = o;
   if (tables_in_smem)  // bit rows, distinct allocatable values, rank buckets
     o += pack_align16((size_t)n_rows * W * 8) + pack_align16((size_t)n_dv * 8) + pack_align16((size_t)MAXR * (RANK_BKTS + 1) * 2);
@@ -244,7 +246,7 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
 // drops the requirement algebra / the node paths from the step loop (16.3 k -> 8.2 k SASS instructions without both),
 // and this kernel's speed follows its size: one CTA, every warp in a different region of ~250 KB of code
 // (config[1]: 30.4 -> 25.8 ms).
-template <int G, int WPL, bool TS, bool KEYS, bool NODES>
+template <int G, int WPL, bool TS, bool KEYS, bool NODES, bool SMALL>
 __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
                                                                const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
                                                                PackProblem* __restrict__ problems, int tables_in_smem) {
@@ -254,9 +256,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   constexpr int NW = PACK_THREADS / 32;
   PackShared& S = *reinterpret_cast<PackShared*>(smem);
   size_t scratch_off, tables_off, ord_off;
-  pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, tables_in_smem, &scratch_off, &tables_off, &ord_off);
+  constexpr int ORD_CAP = SMALL ? ORD_SMALL_CAP : ORD_SMEM_CAP;
+  pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, tables_in_smem, &scratch_off, &tables_off, &ord_off, ORD_CAP);
   int32_t* s_ord = reinterpret_cast<int32_t*>(smem + ord_off);
-  int32_t* s_key = s_ord + ORD_SMEM_CAP;
+  int32_t* s_key = s_ord + ORD_CAP;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gl = tid & (G - 1);
   const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
   // TS: the resource tables of the in-flight check (bit rows, distinct values, rank buckets) are staged into shared
@@ -481,8 +484,9 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     const bool on_node = found != INT_MAX;
     PROF(1);
 
-    int32_t* ord = S.ord_global ? g_ord : s_ord;
-    int32_t* key = S.ord_global ? g_key : s_key;
+    const bool og = SMALL ? false : (S.ord_global != 0);
+    int32_t* ord = og ? g_ord : s_ord;
+    int32_t* key = og ? g_key : s_key;
     uint64_t out0[WPL];
     int my_idx0 = -1, my_c0 = -1;
     bool my_changed0 = false;  // the winning group's claim moves to new table rows (its instance types shrink)
@@ -790,7 +794,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       }
       __syncthreads();
     }
-    if (!S.ord_global && S.n_claims >= ORD_SMEM_CAP) {  // spill the order arrays to global memory
+    if (!SMALL && !S.ord_global && S.n_claims >= ORD_SMEM_CAP) {  // spill the order arrays to global memory
       for (int i = tid; i < S.n_claims; i += PACK_THREADS) { g_ord[i] = s_ord[i]; g_key[i] = s_key[i]; }
       __syncthreads();
       if (tid == 0) S.ord_global = 1;
@@ -803,15 +807,16 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   // Results.NewNodeClaims is the order after the LAST sort the reference ran plus the modification that followed it:
   // if no later add() reached the sort, the eager normalisation of that last modification has to be taken back.
   {
-    int32_t* ord = S.ord_global ? g_ord : s_ord;
-    int32_t* key = S.ord_global ? g_key : s_key;
+    const bool og = SMALL ? false : (S.ord_global != 0);
+    int32_t* ord = og ? g_ord : s_ord;
+    int32_t* key = og ? g_key : s_key;
     const int um = S.undo_mode, n = S.n_claims;
     __syncthreads();
     if (um == MODE_ROTATE) cta_rotate(ord, key, S.undo_src, S.undo_dst);
     else if (um == MODE_GENERIC)
       for (int i = tid; i < n; i += PACK_THREADS) ord[i] = g_snap[i];
     __syncthreads();
-    if (!S.ord_global)
+    if (!og)
       for (int i = tid; i < n; i += PACK_THREADS) g_ord[i] = s_ord[i];
   }
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
@@ -868,7 +873,7 @@ static void pick_group_pack(int W, int* G, int* WPL) {
 }
 
 cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
-                        PackProblem* problems, int n_problems, bool keys, bool nodes, int smem_limit,
+                        PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, int smem_limit,
                         cudaStream_t stream) {
   (void)T;
   if (kt.n_words > 128) return cudaErrorInvalidValue;
@@ -876,20 +881,28 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   int G, WPL;
   pick_group_pack(kt.n_words, &G, &WPL);
   size_t so, to;
-  // the resource tables go to shared memory when they fit next to the order arrays
+  // the resource tables go to shared memory when they fit next to the order arrays; a batch whose problems all have
+  // few pods keeps a larger order array there and never spills it
   int in_smem = 1;
-  size_t bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
+  bool small = max_pods <= ORD_SMALL_CAP && !keys && !nodes;
+  size_t bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to, nullptr, small ? ORD_SMALL_CAP : ORD_SMEM_CAP);
+  if (small && bytes > (size_t)smem_limit) {
+    small = false;
+    bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
+  }
   if (bytes > (size_t)smem_limit || getenv("B200S_PACK_NO_TS")) {
     in_smem = 0;
+    small = false;
     bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
   }
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
-    auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true>                              \
-                : nodes  ? pack_kernel<G_, WPL_, true, true, true>                               \
-                : keys   ? pack_kernel<G_, WPL_, true, true, false>                              \
-                         : pack_kernel<G_, WPL_, true, false, false>;                            \
+    auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true, false>                       \
+                : nodes  ? pack_kernel<G_, WPL_, true, true, true, false>                        \
+                : keys   ? pack_kernel<G_, WPL_, true, true, false, false>                       \
+                : small  ? pack_kernel<G_, WPL_, true, false, false, true>                       \
+                         : pack_kernel<G_, WPL_, true, false, false, false>;                     \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);    \
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, PACK_THREADS, bytes, stream>>>(kt, tg, pods, arr, problems, in_smem);      \
