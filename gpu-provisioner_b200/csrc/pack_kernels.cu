@@ -67,6 +67,7 @@ __host__ __device__ inline size_t pack_smem_bytes(int G, int W, int n_rows, int 
 
 // ExistingNode.CanAdd (existingnode.go:70-107) for one node by one thread: taints, Fits(pod, remaining),
 // Compatible(node labels, pod requirements) with no allow-set.
+template <bool KEYS>
 __device__ __forceinline__ bool node_can_add(const KeyTab& kt, const PackArrays& A, int row, const PodRef& pd,
                                              const int64_t* zero_b) {
   if (A.n_taints[row] & ~pd.tol) return false;
@@ -74,9 +75,11 @@ __device__ __forceinline__ bool node_can_add(const KeyTab& kt, const PackArrays&
     int64_t avail = A.n_avail[(size_t)r * A.Etot + row];
     if (avail < 0 || pd.req[r] > avail) return false;  // resources.go:234-243
   }
-  StateRef st{A.n_rmask + row, (size_t)A.Etot, A.n_rflags[row], zero_b, zero_b, 1, nullptr, 0, 0};
-  for (int k = 0; k < kt.n_keys; k++)
-    if (!compatible_key(kt, k, state_req(kt, st, k), pod_req(kt, pd, k), false)) return false;
+  if constexpr (KEYS) {  // a pod without requirements is compatible with any label set
+    StateRef st{A.n_rmask + row, (size_t)A.Etot, A.n_rflags[row], zero_b, zero_b, 1, nullptr, 0, 0};
+    for (int k = 0; k < kt.n_keys; k++)
+      if (!compatible_key(kt, k, state_req(kt, st, k), pod_req(kt, pd, k), false)) return false;
+  }
   return true;
 }
 
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     int found = INT_MAX;
     for (int eb = 0; eb < E; eb += PACK_THREADS) {
       int e = eb + tid;
-      if (e < E && node_can_add(kt, A, E0 + e, pd, S.zero_b)) atomicMin(&S.best[cur], e);
+      if (e < E && node_can_add<KEYS>(kt, A, E0 + e, pd, S.zero_b)) atomicMin(&S.best[cur], e);
       __syncthreads();
       found = S.best[cur];
       __syncthreads();
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       const int row = E0 + found;  // ExistingNode.Add (existingnode.go:111-119)
       if (warp == 1) {
         if (lane < R) A.n_avail[(size_t)lane * A.Etot + row] -= pd.req[lane];
-      } else if (warp == 2) {
+      } else if (KEYS && warp == 2) {  // Requirements.Add of a pod without requirements leaves the node's labels alone
         const int k = lane;
         uint32_t nib_lo = 0, nib_hi = 0;
         if (k < K) {
@@ -899,7 +902,8 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
     auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true, false>                       \
-                : nodes  ? pack_kernel<G_, WPL_, true, true, true, false>                        \
+                : nodes  ? (keys ? pack_kernel<G_, WPL_, true, true, true, false>                \
+                                 : pack_kernel<G_, WPL_, true, false, true, false>)              \
                 : keys   ? pack_kernel<G_, WPL_, true, true, false, false>                       \
                 : small  ? pack_kernel<G_, WPL_, true, false, false, true>                       \
                          : pack_kernel<G_, WPL_, true, false, false, false>;                     \
