@@ -41,6 +41,19 @@ METRIC = "pod x SKU fit evaluations/s"
 WORKLOAD = "config[1]: 10k pending pods x 500 Azure SKUs, 1 NodePool; dense fit matrix + FFD pack + cheapest SKU (one Solve)"
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """The run's one JSON line, on the process's original stdout."""
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -163,7 +176,7 @@ def run_reference(args, rank):
         nclaims = o.n_claims
     ms = 1e3 * sum(times) / len(times)
     value = credited / (ms / 1e3)
-    print(json.dumps({
+    emit({
         "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64/u64",
         "data": "synthetic", "impl": "reference",
@@ -175,7 +188,7 @@ def run_reference(args, rank):
                                    "one dense pass split over all host threads",
                          "solve_ms": 1e3 * solve_s / max(len(times), 1), "dense_ms": 1e3 * fit_s / max(len(times), 1),
                          "host_cores": os.cpu_count()},
-        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def as_deployments(model, replicas: int, seed: int = 7):
@@ -304,7 +317,7 @@ def run_c5(args, rank, world, local):
     res.close()
     ctx.close()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -380,12 +393,16 @@ def run_c4(args, rank, world, local):
             "e2e": {"value": B / (ms * 1e-3), "unit": "simulations/s"},
             "clocks": clk.summary(), "parity": "32 simulations + the multi-node re-pack bit-identical to the CPU oracle"}
     ctx.close()
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
-    # stdout carries exactly one JSON line: whatever NCCL has to say (its version banner, NCCL_DEBUG=INFO) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line.  Native libraries write to file descriptor 1 on their own (NCCL prints its
+    # version banner there), so fd 1 is pointed at stderr for the whole run and the line goes out through a saved copy.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -528,7 +545,7 @@ def main():
                                   "c5_deployments_of_32": dense_leg(ctx, capi, synth, "c3", 1_000_000, 2_000, 10, 3, peak, run=32)}
     ctx.close()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
