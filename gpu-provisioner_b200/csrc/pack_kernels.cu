@@ -528,8 +528,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       // types for the commit; other pods use one thread per claim like the later rounds.
       // (Running the first round on four warps only -- one per SM sub-partition -- was measured slower: 40.9 vs
       // 38.3 ms on C2, the extra round costs more than the issue contention.)
-      constexpr int GPW = 32 / G, GROUP_ROUNDS = 2, SW = QW;  // SW scanning warps: all but the queue warp
-      const int ROUND0 = podkeys ? 0 : GROUP_ROUNDS * SW * GPW;  // pods with selectors go straight to one thread per claim
+      // SMALL (selector-less pods, few of them): lane-group rounds all the way -- the one-thread-per-claim code and the
+      // claim recomputation that goes with it are compiled out, and for this kernel less code is more speed
+      constexpr int GPW = 32 / G, GROUP_ROUNDS = SMALL ? (1 << 20) : 2, SW = QW;  // SW scanning warps: all but the queue warp
+      const int ROUND0 = podkeys ? 0 : 2 * SW * GPW;  // pods with selectors go straight to one thread per claim
       // every "did anyone hit" decision is taken with a barrier reduction so that it is uniform across the CTA
       int any_hit = 0;
       if (!podkeys) {
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       // -- no gain, the pass is bound by its dependent loads, not by the requirement algebra -- and four blocks per
       // warp iteration with their loads issued together -- the four inlined copies of the check made the whole kernel
       // slower, 1.9 -> 2.4 s on 100k x 1k and 33 -> 36 ms on config[1].)
-      if (!any_hit && n > ROUND0) {
+      if (!SMALL && !any_hit && n > ROUND0) {
         for (int it = 0; warp != QW; it++) {
           const int b0 = ROUND0 + (it * SW + warp) * 32;
           int best_now = 0;
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       }
     } else if (found != INT_MAX) {
       const int r0sz = podkeys ? 0 : 2 * QW * (32 / G);  // claims covered by the lane-group rounds (ROUND0 of the scan)
-      const bool by_group = !podkeys && found < r0sz;   // found by a lane group that still holds the new instance types
+      const bool by_group = SMALL || (!podkeys && found < r0sz);  // found by a lane group that still holds the new instance types
       if (by_group) {
         if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
           const long long t_c0 = clock64();
@@ -641,7 +643,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
             S.wprof[2] += (unsigned long long)(clock64() - t_c0);
           }
         }
-      } else if (warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
+      } else if (!SMALL && warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
         const int c = S.hit_c[found < r0sz ? (found >> 5) : (((found - r0sz) >> 5) % QW)];  // not ord[found]: warp 2 reorders ord
         StateRef st{c_rmask + (size_t)c * K, 1, podkeys ? c_rflags[c] : 0ull, c_gt + (size_t)c * NB, c_lt + (size_t)c * NB, 1,
                     c_req + (size_t)c * R, 1, 0};
