@@ -149,6 +149,7 @@ def lib():
     L.b200s_resident_last_launches.argtypes = [C.c_void_p]
     L.b200s_resident_dense_kernel_ms.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_float)]
     L.b200s_resident_pack_profile.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint64)]
+    L.b200s_resident_set_pack_profile.argtypes = [C.c_void_p, C.c_int]
     i64p, u8p = _P(C.c_int64), _P(C.c_uint8)
     L.b200s_pod_requests.argtypes = [C.c_int32, C.c_int32, C.c_int32, i64p, u8p, i64p, u8p, C.c_int32, i64p, u8p, i64p, u8p, u8p,
                                      i64p, i64p]
@@ -407,6 +408,10 @@ class Resident:
         ms = C.c_float(0.0)
         self.ctx._check(self.ctx.L.b200s_resident_dense_kernel_ms(self.ctx.h, self.h, C.byref(ms)))
         return float(ms.value)
+
+    def set_pack_profile(self, on: bool) -> None:
+        """Run the next solves with the pack kernel's cycle counters (small selector-less batches run without)."""
+        self.ctx._check(self.ctx.L.b200s_resident_set_pack_profile(self.h, 1 if on else 0))
 
     def pack_profile(self):
         out = (C.c_uint64 * 12)()

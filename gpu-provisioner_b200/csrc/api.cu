@@ -71,6 +71,7 @@ struct b200s_resident {
   b200s_ctx* ctx = nullptr;
   Catalog* cat = nullptr;
   int P = 0, Ppad = 0, E = 0, T = 0, n_problems = 0;
+  bool profile_pack = false;  // b200s_resident_set_pack_profile
   bool plain = true;  // no pod defines a requirement key (selects the pack kernel's form together with E == 0)
   std::vector<void*> owned;
   PodsDev pods{};
@@ -435,7 +436,7 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
   *launches += nl;
   CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0, max_pods,
-                            ctx->smem_limit, ctx->stream),
+                            r->profile_pack, ctx->smem_limit, ctx->stream),
            "pack launch");
   CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),
            "pack_finalize launch");
@@ -728,6 +729,12 @@ int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* 
 }
 
 int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }
+
+int b200s_resident_set_pack_profile(b200s_resident_t* r, int on) {
+  if (!r) return B200S_EINVAL;
+  r->profile_pack = on != 0;
+  return B200S_OK;
+}
 
 int b200s_resident_dense_kernel_ms(b200s_ctx_t* ctx, b200s_resident_t* r, float* ms) {
   if (!ctx || !r || !ms || !r->fit_done || !r->ev_dense0) return B200S_ESTATE;

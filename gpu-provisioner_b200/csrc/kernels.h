@@ -85,8 +85,8 @@ cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* mask
                                    size_t bks, int32_t* sku_out, uint64_t* price_out, int32_t* nopt_out,
                                    const PackProblem* problems, const int32_t* row_problem, cudaStream_t stream);
 cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
-                        PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, int smem_limit,
-                        cudaStream_t stream);
+                        PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, bool profile,
+                        int smem_limit, cudaStream_t stream);
 cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
                                  int n_problems, ClaimOut out, cudaStream_t stream);
 

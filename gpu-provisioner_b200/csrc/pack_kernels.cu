@@ -249,7 +249,9 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
 // drops the requirement algebra / the node paths from the step loop (16.3 k -> 8.2 k SASS instructions without both),
 // and this kernel's speed follows its size: one CTA, every warp in a different region of ~250 KB of code
 // (config[1]: 30.4 -> 25.8 ms).
-template <int G, int WPL, bool TS, bool KEYS, bool NODES, bool SMALL>
+// PROFILE: the per-phase / per-role cycle counters of b200s_resident_pack_profile (clock reads on the step's critical
+// path, ~3 % of it); the SMALL form is also built without them and runs that way unless profiling was asked for.
+template <int G, int WPL, bool TS, bool KEYS, bool NODES, bool SMALL, bool PROFILE>
 __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
                                                                const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
                                                                PackProblem* __restrict__ problems, int tables_in_smem) {
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   long long tick = clock64();
 #define PROF(i)                                       \
   do {                                                \
-    if (tid == 0) {                                   \
+    if (PROFILE && tid == 0) {                        \
       long long now_ = clock64();                     \
       prof[i] += (unsigned long long)(now_ - tick);   \
       tick = now_;                                    \
@@ -466,10 +468,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     const int n = S.n_claims;
     bool spec_popped = false;
     if (warp == QW && fast) {
-      const long long t_p0 = clock64();
+      const long long t_p0 = PROFILE ? clock64() : 0;
       spec_popped = pop_and_load(cur ^ 1) >= 0;
       __syncwarp();
-      if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
+      if (PROFILE && lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
     }
     prof[7] += tid == 0;
     PROF(0);
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       const bool by_group = SMALL || (!podkeys && found < r0sz);  // found by a lane group that still holds the new instance types
       if (by_group) {
         if (my_idx0 == found) {  // NodeClaim.Add (nodeclaim.go:168-180) by the group that evaluated the claim
-          const long long t_c0 = clock64();
+          const long long t_c0 = PROFILE ? clock64() : 0;
           const int c = my_c0;
           if (my_changed0) {  // some resource moved past its threshold: the claim's types shrank
             int cnt = 0;
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
             A.pod_kind[p] = B200S_PLACE_CLAIM;
             A.pod_index[p] = c;
             A.pod_seq[p] = S.seq++;
-            S.wprof[2] += (unsigned long long)(clock64() - t_c0);
+            if (PROFILE) S.wprof[2] += (unsigned long long)(clock64() - t_c0);
           }
         }
       } else if (!SMALL && warp == 1 && lane < G) {  // found by the one-thread-per-claim scan: one lane group redoes the claim in full
@@ -682,11 +684,11 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
       }
       if (warp == 2) {  // the claim moved one pod up: what sort.Slice will do with that
-        const long long t_n0 = clock64();
+        const long long t_n0 = PROFILE ? clock64() : 0;
         if (lane == 0) key[found]++;
         __syncwarp();
         warp_normalise(S, ord, key, g_snap, n, found, false);
-        if (lane == 0) S.wprof[1] += (unsigned long long)(clock64() - t_n0);
+        if (PROFILE && lane == 0) S.wprof[1] += (unsigned long long)(clock64() - t_n0);
       }
     } else if (t_new >= 0) {
       // ---- addToNewNodeClaim: the template walk was done for every pod by stage A ----
@@ -775,10 +777,10 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
       const bool pushed_now = !on_node && found == INT_MAX && t_new < 0;
       __syncwarp();
       if (!fast || (pushed_now && !spec_popped)) {
-        const long long t_p0 = clock64();
+        const long long t_p0 = PROFILE ? clock64() : 0;
         pop_and_load(cur ^ 1);
         __syncwarp();
-        if (lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
+        if (PROFILE && lane == 0) S.wprof[0] += (unsigned long long)(clock64() - t_p0);
       }
     }
     __syncthreads();
@@ -878,8 +880,8 @@ static void pick_group_pack(int W, int* G, int* WPL) {
 }
 
 cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
-                        PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, int smem_limit,
-                        cudaStream_t stream) {
+                        PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, bool profile,
+                        int smem_limit, cudaStream_t stream) {
   (void)T;
   if (kt.n_words > 128) return cudaErrorInvalidValue;
   if (n_problems == 0) return cudaSuccess;
@@ -903,12 +905,13 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   cudaError_t err = cudaSuccess;
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
-    auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true, false>                       \
-                : nodes  ? (keys ? pack_kernel<G_, WPL_, true, true, true, false>                \
-                                 : pack_kernel<G_, WPL_, true, false, true, false>)              \
-                : keys   ? pack_kernel<G_, WPL_, true, true, false, false>                       \
-                : small  ? pack_kernel<G_, WPL_, true, false, false, true>                       \
-                         : pack_kernel<G_, WPL_, true, false, false, false>;                     \
+    auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true, false, true>                 \
+                : nodes  ? (keys ? pack_kernel<G_, WPL_, true, true, true, false, true>          \
+                                 : pack_kernel<G_, WPL_, true, false, true, false, true>)        \
+                : keys   ? pack_kernel<G_, WPL_, true, true, false, false, true>                 \
+                : small  ? (profile ? pack_kernel<G_, WPL_, true, false, false, true, true>      \
+                                    : pack_kernel<G_, WPL_, true, false, false, true, false>)    \
+                         : pack_kernel<G_, WPL_, true, false, false, false, true>;               \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);    \
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, PACK_THREADS, bytes, stream>>>(kt, tg, pods, arr, problems, in_smem);      \

@@ -24,6 +24,8 @@ ctx = capi.Context(0)
 cid = ctx.upload_catalog(enc)
 res = ctx.resident(cid, enc)
 ev0, ev1 = ctx.event(), ctx.event()
+if mode == "solve" and not os.environ.get("B200S_NO_PROFILE"):
+    res.set_pack_profile(True)
 for i in range(iters):
     ctx.flush_l2()
     ctx.record(ev0)
