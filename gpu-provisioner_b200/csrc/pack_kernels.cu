@@ -250,7 +250,8 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
 // and this kernel's speed follows its size: one CTA, every warp in a different region of ~250 KB of code
 // (config[1]: 30.4 -> 25.8 ms).
 // PROFILE: the per-phase / per-role cycle counters of b200s_resident_pack_profile (clock reads on the step's critical
-// path, ~3 % of it); the SMALL form is also built without them and runs that way unless profiling was asked for.
+// path, 3-4 % of it); every shared-memory-table form is also built without them and runs that way unless profiling
+// was asked for (b200s_resident_set_pack_profile).
 template <int G, int WPL, bool TS, bool KEYS, bool NODES, bool SMALL, bool PROFILE>
 __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_constant__ KeyTab kt,
                                                                const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
@@ -903,15 +904,15 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
     bytes = pack_smem_bytes(G, kt.n_words, kt.n_rows, kt.n_dv, in_smem, &so, &to);
   }
   cudaError_t err = cudaSuccess;
+#define PICK(G_, WPL_, K_, N_, S_) \
+  (profile ? pack_kernel<G_, WPL_, true, K_, N_, S_, true> : pack_kernel<G_, WPL_, true, K_, N_, S_, false>)
 #define CALL(G_, WPL_)                                                                            \
   do {                                                                                            \
     auto kern = !in_smem ? pack_kernel<G_, WPL_, false, true, true, false, true>                 \
-                : nodes  ? (keys ? pack_kernel<G_, WPL_, true, true, true, false, true>          \
-                                 : pack_kernel<G_, WPL_, true, false, true, false, true>)        \
-                : keys   ? pack_kernel<G_, WPL_, true, true, false, false, true>                 \
-                : small  ? (profile ? pack_kernel<G_, WPL_, true, false, false, true, true>      \
-                                    : pack_kernel<G_, WPL_, true, false, false, true, false>)    \
-                         : pack_kernel<G_, WPL_, true, false, false, false, true>;               \
+                : nodes  ? (keys ? PICK(G_, WPL_, true, true, false) : PICK(G_, WPL_, false, true, false)) \
+                : keys   ? PICK(G_, WPL_, true, false, false)                                    \
+                : small  ? PICK(G_, WPL_, false, false, true)                                    \
+                         : PICK(G_, WPL_, false, false, false);                                  \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);    \
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, PACK_THREADS, bytes, stream>>>(kt, tg, pods, arr, problems, in_smem);      \
@@ -922,6 +923,7 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
   else if (WPL == 2) CALL(32, 2);
   else CALL(32, 4);
 #undef CALL
+#undef PICK
   return cudaGetLastError();
 }
 

@@ -411,8 +411,8 @@ int b200s_resident_dense_kernel_ms(b200s_ctx_t* ctx, b200s_resident_t* r, float*
  * out[8..10] = cycles inside the commit phase by role (queue warp: next pod's row, warp 2: claim order, winning lane
  * group: claim state); out[11] = full pdqsort runs << 40 | their cycles; out[5..6] reserved */
 int b200s_resident_pack_profile(b200s_ctx_t* ctx, b200s_resident_t* r, uint64_t out[12]);
-/* The cycle counters cost ~3 % of a step; the pack kernel's form for small selector-less batches runs without them
- * unless they are switched on here before the solve (then only out[7], the step count, and out[11] are filled). */
+/* The cycle counters cost 3-4 % of a step: solves run without them unless they are switched on here beforehand
+ * (without them only out[7], the step count, and out[11] are filled). */
 int b200s_resident_set_pack_profile(b200s_resident_t* r, int on);
 
 /* ---- config 1: the vmSize pick of instance.Provider.Create (host only, no device) ----
