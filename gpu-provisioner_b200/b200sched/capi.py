@@ -21,6 +21,9 @@ MAX_KEYS, MAX_RES, MAX_TEMPLATES, MAX_BOUNDED = 16, 8, 16, 4
 PRICE_NONE = 0x7FEFFFFFFFFFFFFF
 FIT_NONE, FIT_TAINT, FIT_INCOMPATIBLE, FIT_LIMITS, FIT_DROPPED, FIT_FILTER = 0x00, 0x01, 0x02, 0x03, 0x7F, 0x80
 PLACE_UNSCHEDULED, PLACE_NODE, PLACE_CLAIM = -1, 0, 1
+CMD_NONE, CMD_DELETE, CMD_REPLACE = 0, 1, 2
+WHY_OK, WHY_UNSCHEDULABLE, WHY_MANY_CLAIMS, WHY_NOT_CHEAPER, WHY_S2S_DISABLED, WHY_S2S_TOO_FEW = 0, 1, 2, 3, 4, 5
+S2S_MIN_TYPES = 15
 OK, EINVAL, ENODEVICE, ECUDA, ENOTREPRESENTABLE, ECAPACITY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 CREATE_EBADNAME, CREATE_ENOTYPE, CREATE_ENOSTORAGE = -20, -21, -22
 
@@ -38,6 +41,25 @@ class CatalogSoA(C.Structure):
         ("res_nd", C.c_int32 * MAX_RES), ("res_dv0", C.c_int32 * MAX_RES), ("res_row0", C.c_int32 * MAX_RES),
         ("res_dv", _P(C.c_int64)), ("n_dv", C.c_int32), ("key_row0", C.c_int32 * MAX_KEYS), ("zc_row0", C.c_int32),
         ("price", _P(C.c_uint64)), ("alloc", _P(C.c_int64)), ("capacity", _P(C.c_int64)),
+        ("price_max", _P(C.c_uint64)),
+    ]
+
+
+class ConsolidationSims(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("spot_to_spot", C.c_int32), ("ct_spot", C.c_int32), ("ct_on_demand", C.c_int32),
+        ("ct_reserved", C.c_int32),
+        ("n_unscheduled", _P(C.c_int32)), ("n_claims", _P(C.c_int32)), ("n_candidates", _P(C.c_int32)),
+        ("all_spot", _P(C.c_uint8)), ("candidate_price", _P(C.c_double)),
+        ("claim_mask", _P(C.c_uint64)), ("claim_req_mask", _P(C.c_uint64)), ("claim_req_flags", _P(C.c_uint64)),
+        ("claim_req_gt", _P(C.c_int64)), ("claim_req_lt", _P(C.c_int64)),
+    ]
+
+
+class ConsolidationCmds(C.Structure):
+    _fields_ = [
+        ("decision", _P(C.c_int32)), ("reason", _P(C.c_int32)), ("n_options", _P(C.c_int32)), ("mask", _P(C.c_uint64)),
+        ("spot_required", _P(C.c_uint8)), ("head", _P(C.c_int32)), ("price_tie", _P(C.c_uint8)),
     ]
 
 
@@ -132,6 +154,7 @@ def lib():
                                    _P(C.c_uint8), _P(C.c_int64)]
     L.b200s_select_cheapest.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(C.c_uint64), _P(C.c_uint64),
                                         _P(C.c_uint64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int32), _P(C.c_uint64)]
+    L.b200s_consolidation_commands.argtypes = [C.c_void_p, C.c_uint64, _P(ConsolidationSims), _P(ConsolidationCmds)]
     L.b200s_solve.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates), _P(SolveOpts),
                               _P(Result)]
     L.b200s_solve_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(_P(PodsSoA)), _P(_P(NodesSoA)),
@@ -202,6 +225,17 @@ class Encoded:
         self.key_model = [L.b200s_encoded_key_model_id(h, k) for k in range(self.K)]
         self.bounded_key = [c.bounded_key[b] for b in range(self.NB)]
         self.pool_index = [self.templates.contents.pool_index[t] for t in range(self.T)]
+
+    def value_bit(self, model_key: int, model_value: int) -> int:
+        """device bit of a model value inside its key's word, -1 when the encoding does not carry it"""
+        if model_key not in self.key_model:
+            return -1
+        k = self.key_model.index(model_key)
+        L = lib()
+        for b in range(self.catalog.contents.key_nvals[k]):
+            if L.b200s_encoded_value_model_id(self.handle, k, b) == model_value:
+                return b
+        return -1
 
     def close(self):
         if self.handle:
@@ -358,6 +392,46 @@ class Context:
                                                  _p(req_flags, C.c_uint64), _p(req_gt, C.c_int64), _p(req_lt, C.c_int64),
                                                  _p(sku, C.c_int32), _p(price, C.c_uint64)))
         return sku[:n], price[:n]
+
+    def consolidation_commands(self, cid: int, enc: Encoded, sims: Sequence[SolveRaw], candidate_price: Sequence[float],
+                               all_spot: Sequence[bool], n_candidates: Sequence[int], ct_spot: int, ct_on_demand: int,
+                               ct_reserved: int = -1, spot_to_spot: bool = False, n_unscheduled=None) -> dict:
+        """computeConsolidation (consolidation.go:133-307) over finished simulations (b200s_solve_batch results)."""
+        n = len(sims)
+        W, K, NB = enc.W, max(enc.K, 1), max(enc.NB, 1)
+        cm = np.zeros((max(n, 1), W), np.uint64)
+        rm = np.zeros((max(n, 1), K), np.uint64)
+        rf = np.zeros(max(n, 1), np.uint64)
+        gt = np.zeros((max(n, 1), NB), np.int64)
+        lt = np.zeros((max(n, 1), NB), np.int64)
+        for i, r in enumerate(sims):
+            if r.n_claims == 1:
+                cm[i] = r.claim_mask[0]
+                rm[i, :enc.K] = r.claim_req_mask[0]
+                rf[i] = r.claim_req_flags[0]
+                gt[i, :enc.NB] = r.claim_req_gt[0]
+                lt[i, :enc.NB] = r.claim_req_lt[0]
+        un = np.asarray([r.n_unscheduled for r in sims] if n_unscheduled is None else n_unscheduled, np.int32)
+        nc = np.asarray([r.n_claims for r in sims], np.int32)
+        cand = np.asarray(n_candidates, np.int32)
+        spot = np.asarray(all_spot, np.uint8)
+        price = np.asarray(candidate_price, np.float64)
+        s = ConsolidationSims()
+        s.n, s.spot_to_spot, s.ct_spot, s.ct_on_demand, s.ct_reserved = n, int(spot_to_spot), ct_spot, ct_on_demand, ct_reserved
+        s.n_unscheduled, s.n_claims, s.n_candidates = _p(un, C.c_int32), _p(nc, C.c_int32), _p(cand, C.c_int32)
+        s.all_spot, s.candidate_price = _p(spot, C.c_uint8), _p(price, C.c_double)
+        s.claim_mask, s.claim_req_mask, s.claim_req_flags = _p(cm, C.c_uint64), _p(rm, C.c_uint64), _p(rf, C.c_uint64)
+        s.claim_req_gt, s.claim_req_lt = _p(gt, C.c_int64), _p(lt, C.c_int64)
+        n1 = max(n, 1)
+        out = dict(decision=np.zeros(n1, np.int32), reason=np.zeros(n1, np.int32), n_options=np.zeros(n1, np.int32),
+                   mask=np.zeros((n1, W), np.uint64), spot_required=np.zeros(n1, np.uint8),
+                   head=np.zeros((n1, S2S_MIN_TYPES), np.int32), price_tie=np.zeros(n1, np.uint8))
+        c = ConsolidationCmds()
+        c.decision, c.reason, c.n_options = _p(out["decision"], C.c_int32), _p(out["reason"], C.c_int32), _p(out["n_options"], C.c_int32)
+        c.mask, c.spot_required = _p(out["mask"], C.c_uint64), _p(out["spot_required"], C.c_uint8)
+        c.head, c.price_tie = _p(out["head"], C.c_int32), _p(out["price_tie"], C.c_uint8)
+        self._check(self.L.b200s_consolidation_commands(self.h, cid, C.byref(s), C.byref(c)))
+        return {k: v[:n] for k, v in out.items()}
 
     # ---- resident (device-timed) path ----
     def resident(self, cid: int, enc: Encoded) -> "Resident":

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -640,6 +641,7 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
   kt.rows = (const uint64_t*)put(c->rows, (size_t)c->n_rows * W * 8);
   kt.res_dv = (const int64_t*)put(c->res_dv, (size_t)c->n_dv * 8);
   kt.price = (const uint64_t*)put(c->price, (size_t)ZC * S * 8);
+  kt.price_max = c->price_max ? (const uint64_t*)put(c->price_max, (size_t)ZC * S * 8) : nullptr;
   {  // rank bucket table: fit_rank of every bucket's lowest value, per resource
     std::vector<uint16_t> bkt((size_t)MAXR * (RANK_BKTS + 1), 0);
     for (int r = 0; r < c->n_res; r++) {
@@ -802,6 +804,90 @@ int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, cons
   }
   if (!rc && cudaMemcpyAsync(sku_out, d_sku, N * 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
   if (!rc && cudaMemcpyAsync(price_out, d_price, N * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, B200S_ECUDA, "sync");
+  cleanup();
+  return rc;
+}
+
+int b200s_consolidation_commands(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_consolidation_sims_t* sims,
+                                 b200s_consolidation_cmds_t* out) {
+  if (!ctx || !sims || !out || sims->n < 0) return B200S_EINVAL;
+  if (!out->decision || !out->reason || !out->n_options || !out->mask || !out->spot_required || !out->head || !out->price_tie)
+    return fail(ctx, B200S_EINVAL, "consolidation: null output array");
+  cudaSetDevice(ctx->device);
+  auto it = ctx->catalogs.find(catalog_id);
+  if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
+  Catalog* cat = it->second.get();
+  const KeyTab& kt = cat->kt;
+  if (!kt.price_max) return fail(ctx, B200S_EINVAL, "consolidation: the catalog was uploaded without price_max");
+  // Has(spot) / Has(on-demand) are evaluated on the catalog's value universe: both values must be in it
+  if (kt.key_ct < 0 || sims->ct_spot < 0 || sims->ct_spot >= kt.n_cts || sims->ct_on_demand < 0 ||
+      sims->ct_on_demand >= kt.n_cts || sims->ct_reserved >= kt.n_cts || sims->ct_spot == sims->ct_on_demand)
+    return fail(ctx, B200S_ENOTREPRESENTABLE, "consolidation: spot / on-demand are not values of the catalog's capacity-type key");
+  if (sims->n == 0) return B200S_OK;
+  const size_t N = (size_t)sims->n, K = (size_t)cat->K, NB = (size_t)cat->NB, W = (size_t)cat->W;
+  std::vector<uint64_t> limit(N);
+  for (size_t i = 0; i < N; i++) {
+    const double p = sims->candidate_price[i];
+    if (!(p >= 0.0) || !std::isfinite(p)) return fail(ctx, B200S_EINVAL, "consolidation: candidate price must be finite and non-negative");
+    std::memcpy(&limit[i], &p, 8);
+  }
+  std::vector<void*> held;
+  auto dev = [&](size_t bytes) -> void* {
+    void* p = ctx->alloc(bytes);
+    if (p) held.push_back(p);
+    return p;
+  };
+  auto cleanup = [&]() {
+    for (void* p : held) ctx->release(p);
+  };
+  ConsolidationArgs a;
+  a.n = sims->n; a.spot_to_spot = sims->spot_to_spot != 0;
+  a.ct_spot = sims->ct_spot; a.ct_on_demand = sims->ct_on_demand; a.ct_reserved = sims->ct_reserved;
+  int32_t* d_unsched = (int32_t*)dev(N * 4);
+  int32_t* d_claims = (int32_t*)dev(N * 4);
+  int32_t* d_cand = (int32_t*)dev(N * 4);
+  uint8_t* d_spot = (uint8_t*)dev(N);
+  uint64_t* d_limit = (uint64_t*)dev(N * 8);
+  uint64_t* d_cmask = (uint64_t*)dev(N * W * 8);
+  uint64_t* d_rmask = (uint64_t*)dev(N * std::max<size_t>(K, 1) * 8);
+  uint64_t* d_rflags = (uint64_t*)dev(N * 8);
+  int64_t* d_gt = (int64_t*)dev(N * std::max<size_t>(NB, 1) * 8);
+  int64_t* d_lt = (int64_t*)dev(N * std::max<size_t>(NB, 1) * 8);
+  a.decision = (int32_t*)dev(N * 4);
+  a.reason = (int32_t*)dev(N * 4);
+  a.n_options = (int32_t*)dev(N * 4);
+  a.head = (int32_t*)dev(N * B200S_S2S_MIN_TYPES * 4);
+  a.mask = (uint64_t*)dev(N * W * 8);
+  a.spot_required = (uint8_t*)dev(N);
+  a.price_tie = (uint8_t*)dev(N);
+  if (held.size() != 17) { cleanup(); return fail(ctx, B200S_ENOMEM, "device allocation"); }
+  a.n_unscheduled = d_unsched; a.n_claims = d_claims; a.n_candidates = d_cand; a.all_spot = d_spot;
+  a.candidate_price = d_limit; a.claim_mask = d_cmask; a.rmask = d_rmask; a.rflags = d_rflags; a.rgt = d_gt; a.rlt = d_lt;
+  int rc = upload(ctx, d_unsched, sims->n_unscheduled, N);
+  if (!rc) rc = upload(ctx, d_claims, sims->n_claims, N);
+  if (!rc) rc = upload(ctx, d_cand, sims->n_candidates, N);
+  if (!rc) rc = upload(ctx, d_spot, sims->all_spot, N);
+  if (!rc) rc = upload(ctx, d_limit, (const uint64_t*)limit.data(), N);
+  if (!rc) rc = upload(ctx, d_cmask, sims->claim_mask, N * W);
+  if (!rc) rc = upload(ctx, d_rmask, sims->claim_req_mask, N * K);
+  if (!rc) rc = upload(ctx, d_rflags, sims->claim_req_flags, N);
+  if (!rc && NB) rc = upload(ctx, d_gt, sims->claim_req_gt, N * NB);
+  if (!rc && NB) rc = upload(ctx, d_lt, sims->claim_req_lt, N * NB);
+  if (!rc) {
+    cudaError_t e = launch_consolidation(kt, a, ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "consolidation launch", e);
+  }
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    if (!rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
+  };
+  down(out->decision, a.decision, N * 4);
+  down(out->reason, a.reason, N * 4);
+  down(out->n_options, a.n_options, N * 4);
+  down(out->head, a.head, N * B200S_S2S_MIN_TYPES * 4);
+  down(out->mask, a.mask, N * W * 8);
+  down(out->spot_required, a.spot_required, N);
+  down(out->price_tie, a.price_tie, N);
   if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, B200S_ECUDA, "sync");
   cleanup();
   return rc;

@@ -51,6 +51,7 @@ struct KeyTab {
   int32_t key_row0[MAXK];
   int32_t zc_row0, row_nonneg, n_rows, n_dv;
   const uint64_t* price;   // [n_zc*S]
+  const uint64_t* price_max;  // [n_zc*S] most expensive available offering, B200S_PRICE_ABSENT if none (may be null)
 };
 
 // read-only table loads: through the non-coherent (L1-cached) path on the device

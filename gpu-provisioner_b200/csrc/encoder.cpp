@@ -37,7 +37,7 @@ struct b200s_encoded {
   b200s_nodes_soa_t nodes{};
   // owned storage
   std::vector<int64_t> val_int, res_dv, alloc_rm, cap_rm, rq_requests, pod_ts, node_available;
-  std::vector<uint64_t> val_isint, rows, price, type_admit, sig_mask, sig_flags, sig_tolerated, pod_uid_hi, pod_uid_lo,
+  std::vector<uint64_t> val_isint, rows, price, price_max, type_admit, sig_mask, sig_flags, sig_tolerated, pod_uid_hi, pod_uid_lo,
       node_req_mask, node_req_flags, node_taints;
   std::vector<int32_t> sig_gt, sig_lt, pod_sig, pod_reqcls, node_index;
   // decode maps
@@ -307,6 +307,7 @@ void do_encode(Ctx& c) {
   }
   // offerings (types.go:355-362): exactly zone In{z} and capacity-type In{c}
   E->price.assign((size_t)std::max(ZC, 1) * S, B200S_PRICE_NONE);
+  E->price_max.assign((size_t)std::max(ZC, 1) * S, B200S_PRICE_ABSENT);
   for (int s = 0; s < S; s++) {
     for (int o = M->sku_off_off[s]; o < M->sku_off_off[s + 1]; o++) {
       int z = -1, ct = -1;
@@ -328,6 +329,8 @@ void do_encode(Ctx& c) {
       std::memcpy(&bits, &p, 8);
       uint64_t& slot = E->price[(size_t)zc * S + s];
       if (bits < slot) slot = bits;
+      uint64_t& top = E->price_max[(size_t)zc * S + s];  // lo.MaxBy keeps the first of equals: same price either way
+      if (top == B200S_PRICE_ABSENT || bits > top) top = bits;
     }
   }
 
@@ -346,6 +349,7 @@ void do_encode(Ctx& c) {
   cat.res_dv = E->res_dv.data();
   cat.n_dv = (int)E->res_dv.size();
   cat.price = E->price.data();
+  cat.price_max = E->price_max.data();
   cat.alloc = E->alloc_rm.data();
   cat.capacity = E->cap_rm.data();
 

@@ -539,6 +539,152 @@ __global__ void __launch_bounds__(256) select_cheapest_kernel(KeyTab kt, int n, 
 }
 
 // -------------------------------------------------------------------------------------------------
+// consolidation commands: computeConsolidation (K/controllers/disruption/consolidation.go:133-307) on
+// finished simulations, one warp per simulation.  Prices are compared as IEEE-754 bit patterns (all
+// non-negative and finite, so the integer order is the float order).
+// -------------------------------------------------------------------------------------------------
+// OrderByPrice's key (types.go:221-240): cheapest available offering the requirements admit, MaxFloat64 if none
+__device__ __forceinline__ uint64_t cheapest_price(const KeyTab& kt, uint64_t za, uint64_t ca, int s) {
+  uint64_t p = B200S_PRICE_NONE;
+  for (uint64_t z = za; z; z &= z - 1) {
+    const int zi = ctz64(z);
+    for (uint64_t c = ca; c; c &= c - 1) {
+      uint64_t q = kt.price[(size_t)(zi * kt.n_cts + ctz64(c)) * kt.n_skus + s];
+      p = q < p ? q : p;
+    }
+  }
+  return p;
+}
+
+// Offerings.Available().WorstLaunchPrice(reqs) (types.go:460-474): the most expensive compatible offering of the
+// first capacity type, in the order reserved, spot, on-demand, that has one
+__device__ __forceinline__ uint64_t worst_launch_price(const KeyTab& kt, uint64_t za, uint64_t ca, int ct0, int ct1, int ct2,
+                                                       int s) {
+  const int order[3] = {ct0, ct1, ct2};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int c = order[i];
+    if (c < 0 || !((ca >> c) & 1ull)) continue;
+    uint64_t top = 0;
+    bool any = false;
+    for (uint64_t z = za; z; z &= z - 1) {
+      uint64_t q = kt.price_max[(size_t)(ctz64(z) * kt.n_cts + c) * kt.n_skus + s];
+      if (q != B200S_PRICE_ABSENT) { any = true; top = q > top ? q : top; }
+    }
+    if (any) return top;
+  }
+  return B200S_PRICE_NONE;
+}
+
+__global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, ConsolidationArgs a) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= a.n) return;
+  const int W = kt.n_words, K = kt.n_keys, NB = kt.n_bounded;
+  uint64_t* out_mask = a.mask + (size_t)row * W;
+  for (int w = lane; w < W; w += 32) out_mask[w] = 0;
+  if (lane < B200S_S2S_MIN_TYPES) a.head[(size_t)row * B200S_S2S_MIN_TYPES + lane] = -1;
+  int decision = B200S_CMD_NONE, why = B200S_WHY_OK, n_options = 0;
+  bool spot_required = false, tie = false;
+  if (a.n_unscheduled[row] > 0) {
+    why = B200S_WHY_UNSCHEDULABLE;
+  } else if (a.n_claims[row] == 0) {
+    decision = B200S_CMD_DELETE;
+  } else if (a.n_claims[row] != 1) {
+    why = B200S_WHY_MANY_CLAIMS;
+  } else {
+    // zones / capacity types the replacement NodeClaim's requirements admit
+    const uint64_t flags = a.rflags[row];
+    auto allowed_of = [&](int k) -> uint64_t {
+      const int b = kt.bslot[k];
+      EReq q = make_ereq(a.rmask[(size_t)row * K + k], flags, k, b >= 0 ? a.rgt[(size_t)row * NB + b] : 0,
+                         b >= 0 ? a.rlt[(size_t)row * NB + b] : 0);
+      return (q.f & RF_DEF) ? allowed_values(kt, k, q) : ~0ull;
+    };
+    uint64_t za = kt.key_zone >= 0 ? allowed_of(kt.key_zone) : ~0ull;
+    uint64_t ca = allowed_of(kt.key_ct);
+    za &= kt.n_zones >= 64 ? ~0ull : ((1ull << kt.n_zones) - 1ull);
+    ca &= kt.n_cts >= 64 ? ~0ull : ((1ull << kt.n_cts) - 1ull);
+    const bool has_spot = (ca >> a.ct_spot) & 1ull, has_od = (ca >> a.ct_on_demand) & 1ull;
+    const bool s2s = a.all_spot[row] && has_spot;  // consolidation.go:189-192
+    if (s2s && !a.spot_to_spot) {
+      why = B200S_WHY_S2S_DISABLED;
+    } else {
+      // spot-to-spot first narrows the requirements to In{spot} (:240); InstanceTypes.Compatible (:242) is implied by
+      // the price filter, whose MaxFloat64 for "no compatible offering" is never below a finite candidate price
+      const uint64_t cf = s2s ? (1ull << a.ct_spot) : ca;
+      const uint64_t limit = a.candidate_price[row];
+      int count = 0;
+      for (int w = lane; w < W; w += 32) {
+        uint64_t keep = 0;
+        for (uint64_t m = a.claim_mask[(size_t)row * W + w]; m; m &= m - 1) {
+          const int b = ctz64(m);
+          if (worst_launch_price(kt, za, cf, a.ct_reserved, a.ct_spot, a.ct_on_demand, (w << 6) + b) < limit) keep |= 1ull << b;
+        }
+        out_mask[w] = keep;
+        count += popc64(keep);
+      }
+      for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+      if (count == 0) {
+        why = B200S_WHY_NOT_CHEAPER;
+      } else if (s2s && a.n_candidates[row] == 1) {
+        if (count < B200S_S2S_MIN_TYPES) {
+          why = B200S_WHY_S2S_TOO_FEW;
+          for (int w = lane; w < W; w += 32) out_mask[w] = 0;
+        } else {
+          // keep the 15 cheapest in OrderByPrice order, which was taken under the requirements BEFORE the narrowing
+          // (:187): 16 rounds of "smallest (price, index) above the previous pick"; lane i remembers pick i
+          uint64_t last_p = 0, my_p = 0;
+          int last_s = -1, my_s = -1;
+          const int rounds = count > B200S_S2S_MIN_TYPES ? B200S_S2S_MIN_TYPES + 1 : B200S_S2S_MIN_TYPES;
+          for (int rd = 0; rd < rounds; rd++) {
+            uint64_t best_p = ~0ull;
+            int best_s = -1;
+            for (int w = lane; w < W; w += 32)
+              for (uint64_t m = out_mask[w]; m; m &= m - 1) {
+                const int s = (w << 6) + ctz64(m);
+                const uint64_t p = cheapest_price(kt, za, ca, s);
+                const bool above = rd == 0 || p > last_p || (p == last_p && s > last_s);
+                if (above && (p < best_p || (p == best_p && s < best_s))) { best_p = p; best_s = s; }
+              }
+            for (int o = 16; o > 0; o >>= 1) {
+              uint64_t op = __shfl_xor_sync(0xffffffffu, best_p, o);
+              int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+              if (os >= 0 && (best_s < 0 || op < best_p || (op == best_p && os < best_s))) { best_p = op; best_s = os; }
+            }
+            last_p = best_p; last_s = best_s;
+            if (lane == rd) { my_p = best_p; my_s = best_s; }
+          }
+          const uint64_t next_p = __shfl_down_sync(0xffffffffu, my_p, 1);
+          tie = __ballot_sync(0xffffffffu, lane + 1 < rounds && my_p == next_p) != 0;
+          __syncwarp();
+          for (int w = lane; w < W; w += 32) out_mask[w] = 0;
+          __syncwarp();
+          if (lane < B200S_S2S_MIN_TYPES) {
+            atomicOr((unsigned long long*)&out_mask[my_s >> 6], 1ull << (my_s & 63));
+            a.head[(size_t)row * B200S_S2S_MIN_TYPES + lane] = my_s;
+          }
+          decision = B200S_CMD_REPLACE;
+          n_options = B200S_S2S_MIN_TYPES;
+        }
+      } else {
+        decision = B200S_CMD_REPLACE;
+        n_options = count;
+      }
+      // OD -> [OD, spot]: the filter assumed the spot price, so the launch must not fall back to on-demand (:218-221)
+      spot_required = decision == B200S_CMD_REPLACE && (s2s || (has_spot && has_od));
+    }
+  }
+  if (lane == 0) {
+    a.decision[row] = decision;
+    a.reason[row] = why;
+    a.n_options[row] = n_options;
+    a.spot_required[row] = spot_required ? 1 : 0;
+    a.price_tie[row] = tie ? 1 : 0;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
 static void pick_group(int W, int* G, int* WPL) {
@@ -684,6 +830,13 @@ cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* mask
   int blocks = (int)(((long long)n * 32 + 255) / 256);
   select_cheapest_kernel<<<blocks, 256, 0, stream>>>(kt, n, masks, rmask, rms, rks, rflags, rgt, rlt, bms, bks, sku_out,
                                                      price_out, nopt_out, problems, row_problem);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, cudaStream_t stream) {
+  if (a.n <= 0) return cudaSuccess;
+  const int blocks = (a.n * 32 + 255) / 256;
+  consolidation_kernel<<<blocks, 256, 0, stream>>>(kt, a);
   return cudaGetLastError();
 }
 

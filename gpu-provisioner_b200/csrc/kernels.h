@@ -68,6 +68,20 @@ struct ClaimOut {
   int32_t* pos_of_claim;  // [Ptot] position in Results.NewNodeClaims of local claim id
 };
 
+// consolidation_kernel's arguments: DEVICE pointers, row i = simulation i (b200s_consolidation_sims_t / _cmds_t)
+struct ConsolidationArgs {
+  int n, spot_to_spot, ct_spot, ct_on_demand, ct_reserved;
+  const int32_t *n_unscheduled, *n_claims, *n_candidates;
+  const uint8_t* all_spot;
+  const uint64_t* candidate_price;  // float64 bits
+  const uint64_t *claim_mask, *rmask, *rflags;
+  const int64_t *rgt, *rlt;
+  int32_t *decision, *reason, *n_options, *head;
+  uint64_t* mask;
+  uint8_t *spot_required, *price_tie;
+};
+cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, cudaStream_t stream);
+
 cudaError_t launch_template_prefilter(const KeyTab& kt, const TmplDev* tg, const uint64_t* type_admit, uint64_t* tmask,
                                       int32_t* alive, int32_t* tm_count, cudaStream_t stream);
 cudaError_t launch_class_tables(const KeyTab& kt, const TmplDev* tg, int T, const uint64_t* tmask, const int32_t* alive,

@@ -217,9 +217,12 @@ typedef struct b200s_catalog_soa {
   const uint64_t* price;     /* [n_zones*n_cts*S] cheapest available offering price (float64 bits) per (zone,ct,SKU), B200S_PRICE_NONE if none */
   const int64_t* alloc;      /* [R*S] raw allocatable, resource-major                        */
   const int64_t* capacity;   /* [R*S] raw capacity, resource-major                           */
+  const uint64_t* price_max; /* [n_zones*n_cts*S] MOST expensive available offering per (zone,ct,SKU), B200S_PRICE_ABSENT if
+                                none: Offerings.MostExpensive for WorstLaunchPrice (types.go:454-474) */
 } b200s_catalog_soa_t;
 
 #define B200S_PRICE_NONE 0x7FEFFFFFFFFFFFFFull /* math.MaxFloat64 (types.go:224-225) */
+#define B200S_PRICE_ABSENT 0xFFFFFFFFFFFFFFFFull /* price_max cell without an available offering */
 
 typedef struct b200s_templates {
   int32_t n_templates;       /* T, already in OrderByWeight order */
@@ -384,6 +387,57 @@ int b200s_solve_batch(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems,
                       const b200s_pods_soa_t* const* pods, const b200s_nodes_soa_t* const* existing,
                       const b200s_templates_t* templates, const b200s_solve_opts_t* opts,
                       b200s_result_t* const* out);
+
+/* ---- consolidation commands over a batch of simulations (SURVEY section 8f N2, config 4's consumer) ----
+ * computeConsolidation (K/controllers/disruption/consolidation.go:133-307) applied to n finished simulations at
+ * once, one warp per simulation: the decision on the counts of the Solve result, OrderByPrice, the price filter
+ * RemoveInstanceTypeOptionsByPriceAndMinValues (nodeclaim.go:270-279; minValues is nil in this scope) with
+ * Offerings.WorstLaunchPrice (types.go:460-474), the spot-to-spot rules (:230-307) and the capacity-type
+ * requirement the command adds.  Inputs are HOST arrays, row i = simulation i; the claim_* rows are
+ * Results.NewNodeClaims[0] as b200s_solve / b200s_solve_batch returned it and are read only when n_claims[i] == 1. */
+typedef struct b200s_consolidation_sims {
+  int32_t n;
+  int32_t spot_to_spot;            /* the SpotToSpotConsolidation feature gate (consolidation.go:233) */
+  int32_t ct_spot, ct_on_demand, ct_reserved; /* DEVICE value bits of "spot" / "on-demand" / "reserved" inside the
+                                      capacity-type key (b200s_encoded_value_model_id maps bits to model values);
+                                      ct_reserved may be -1 when no offering and no requirement names it */
+  const int32_t* n_unscheduled;    /* [n] PodErrors left after OmitBy(IsProvisionable) (scheduler.go:326-330) */
+  const int32_t* n_claims;         /* [n] len(Results.NewNodeClaims) */
+  const int32_t* n_candidates;     /* [n] nodes the command would remove */
+  const uint8_t* all_spot;         /* [n] every candidate is a spot node (consolidation.go:178-183) */
+  const double* candidate_price;   /* [n] getCandidatePrices (consolidation.go:310-328): finite, >= 0 */
+  const uint64_t* claim_mask;      /* [n*W] InstanceTypeOptions */
+  const uint64_t* claim_req_mask;  /* [n*K] */
+  const uint64_t* claim_req_flags; /* [n] */
+  const int64_t* claim_req_gt;     /* [n*NB] */
+  const int64_t* claim_req_lt;     /* [n*NB] */
+} b200s_consolidation_sims_t;
+
+#define B200S_CMD_NONE 0     /* Command{}: leave the candidates alone */
+#define B200S_CMD_DELETE 1   /* the pods fit on what is already there (consolidation.go:155-160) */
+#define B200S_CMD_REPLACE 2  /* one cheaper replacement NodeClaim */
+#define B200S_WHY_OK 0
+#define B200S_WHY_UNSCHEDULABLE 1    /* !AllNonPendingPodsScheduled (:147)                  */
+#define B200S_WHY_MANY_CLAIMS 2      /* len(NewNodeClaims) != 1 (:163)                      */
+#define B200S_WHY_NOT_CHEAPER 3      /* nothing left after the price filter (:205, :258)    */
+#define B200S_WHY_S2S_DISABLED 4     /* spot-to-spot with the gate off (:233)               */
+#define B200S_WHY_S2S_TOO_FEW 5      /* fewer than 15 cheaper spot types, one candidate (:279) */
+#define B200S_S2S_MIN_TYPES 15       /* MinInstanceTypesForSpotToSpotConsolidation (consolidation.go:49) */
+
+typedef struct b200s_consolidation_cmds {   /* caller-allocated HOST arrays */
+  int32_t* decision;      /* [n] B200S_CMD_*  */
+  int32_t* reason;        /* [n] B200S_WHY_*  */
+  int32_t* n_options;     /* [n] len(Replacements[0].InstanceTypeOptions), 0 unless REPLACE */
+  uint64_t* mask;         /* [n*W] those instance types as a set (zeros unless REPLACE) */
+  uint8_t* spot_required; /* [n] 1: the command narrowed the NodeClaim's capacity-type requirement to In{spot}
+                             (consolidation.go:218-221, :240) */
+  int32_t* head;          /* [n*B200S_S2S_MIN_TYPES] the options in OrderByPrice order when the command truncated them to
+                             the 15 cheapest (single-candidate spot-to-spot, :303), else filled with -1 */
+  uint8_t* price_tie;     /* [n] 1: two of the 16 cheapest share a price, so `head` depends on Go's unstable sort */
+} b200s_consolidation_cmds_t;
+
+int b200s_consolidation_commands(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_consolidation_sims_t* sims,
+                                 b200s_consolidation_cmds_t* out);
 
 /* ---- resident (device-pointer) variants used for device-timed measurement ---- */
 typedef struct b200s_resident b200s_resident_t;

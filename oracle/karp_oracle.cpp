@@ -559,6 +559,50 @@ const InstanceType* OrderByPriceHead(std::vector<const InstanceType*> its, const
   return keyed[0].second;
 }
 
+// types.go:221-240, the whole list (sort.Slice: Go's pdqsort, so equal prices land in its order)
+std::vector<const InstanceType*> OrderByPrice(const std::vector<const InstanceType*>& its, const Requirements& reqs,
+                                              bool stable, std::vector<double>* keysOut) {
+  std::vector<std::pair<double, const InstanceType*>> keyed;
+  keyed.reserve(its.size());
+  for (auto* it : its) {
+    double p = 1.7976931348623157e308;
+    for (const Offering& of : it->offerings)
+      if (of.available && Compatible(reqs, of.requirements, true) && of.price < p) p = of.price;
+    keyed.emplace_back(p, it);
+  }
+  sort_slice(keyed, [](const std::pair<double, const InstanceType*>& a, const std::pair<double, const InstanceType*>& b) {
+    return a.first < b.first;
+  }, stable);
+  std::vector<const InstanceType*> out;
+  for (auto& kv : keyed) {
+    out.push_back(kv.second);
+    if (keysOut) keysOut->push_back(kv.first);
+  }
+  return out;
+}
+
+// requirement.go:252-257
+bool RequirementHas(const Requirement& r, int valueId) {
+  bool in = r.has(valueId);
+  return (r.complement ? !in : in) && withinIntPtrs(valueId, r.hasGt, r.gt, r.hasLt, r.lt);
+}
+
+// Offerings.Available().WorstLaunchPrice(reqs) — types.go:460-474; ctReqs = Reserved, Spot, OnDemand (types.go:45-47)
+double WorstLaunchPrice(const InstanceType* it, const Requirements& reqs, const std::vector<Requirements>& ctReqs) {
+  for (const Requirements& ct : ctReqs) {
+    bool any = false;
+    double top = 0;
+    for (const Offering& of : it->offerings) {
+      if (!of.available) continue;
+      if (!Compatible(reqs, of.requirements, true) || !Compatible(ct, of.requirements, true)) continue;
+      if (!any || of.price > top) top = of.price;  // MostExpensive, types.go:454-458
+      any = true;
+    }
+    if (any) return top;
+  }
+  return 1.7976931348623157e308;
+}
+
 // ------------------------------------------------------------------------------------------------
 // NodeClaimTemplate / NodeClaim / ExistingNode — K/controllers/provisioning/scheduling
 // ------------------------------------------------------------------------------------------------
@@ -820,7 +864,11 @@ extern "C" {
 
 int oracle_version(void) { return 100; }
 
-int oracle_solve(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out) {
+static void computeConsolidation(Scheduler& S, int nUnscheduled, const oracle_consolidation_in_t* in,
+                                 oracle_consolidation_out_t* o);
+
+static int solve_then(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out,
+                      const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout) {
   g_model = M;
   Scheduler S;
   S.M = M;
@@ -1008,8 +1056,98 @@ int oracle_solve(const b200s_model_t* M, const oracle_opts_t* opts, oracle_resul
   out->price_ties = S.C.price_ties;
   out->newclaim_evals = S.C.newclaim_evals;
   out->value_overflow = overflow;
+  if (cin && cout) computeConsolidation(S, out->n_unscheduled, cin, cout);
   g_model = nullptr;
   return 0;
+}
+
+int oracle_solve(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out) {
+  return solve_then(M, opts, out, nullptr, nullptr);
+}
+
+/* SimulateScheduling's Solve followed by computeConsolidation (K/controllers/disruption/consolidation.go:133-307).
+ * Every pod of the model counts as a non-pending pod of the candidates (AllNonPendingPodsScheduled, scheduler.go:326). */
+int oracle_consolidate(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out,
+                       const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout) {
+  if (!cin || !cout || cin->val_spot < 0 || cin->val_on_demand < 0 || M->key_capacity_type < 0) return B200S_EINVAL;
+  return solve_then(M, opts, out, cin, cout);
+}
+
+static void computeConsolidation(Scheduler& S, int nUnscheduled, const oracle_consolidation_in_t* in,
+                                 oracle_consolidation_out_t* o) {
+  const b200s_model_t* M = S.M;
+  const int W = (M->n_skus + 63) / 64, ctKey = M->key_capacity_type;
+  o->decision = B200S_CMD_NONE;
+  o->reason = B200S_WHY_OK;
+  o->n_options = 0;
+  o->spot_required = 0;
+  o->price_tie = 0;
+  for (int i = 0; i < B200S_S2S_MIN_TYPES; i++) o->head[i] = -1;
+  for (int w = 0; w < W; w++) o->mask[w] = 0;
+  auto finish = [&](const std::vector<const InstanceType*>& its) {
+    o->decision = B200S_CMD_REPLACE;
+    o->n_options = (int)its.size();
+    for (size_t i = 0; i < its.size(); i++) {
+      o->mask[its[i]->index / 64] |= 1ull << (its[i]->index % 64);
+      if (o->order) o->order[i] = its[i]->index;
+    }
+  };
+  if (nUnscheduled > 0) { o->reason = B200S_WHY_UNSCHEDULABLE; return; }          // :147
+  if (S.newNodeClaims.empty()) { o->decision = B200S_CMD_DELETE; return; }         // :155
+  if (S.newNodeClaims.size() != 1) { o->reason = B200S_WHY_MANY_CLAIMS; return; }  // :163
+  NodeClaim* n = S.newNodeClaims[0];
+  auto single = [&](int v) {
+    Requirements r;
+    int32_t vv = v;
+    r.Add(NewRequirement(ctKey, B200S_OP_IN, &vv, 1, 0));
+    return r;
+  };
+  std::vector<Requirements> ctReqs;  // reserved, spot, on-demand (types.go:464-468)
+  if (in->val_reserved >= 0) ctReqs.push_back(single(in->val_reserved));
+  ctReqs.push_back(single(in->val_spot));
+  ctReqs.push_back(single(in->val_on_demand));
+  std::vector<double> keys;
+  std::vector<const InstanceType*> its = OrderByPrice(n->instanceTypeOptions, n->requirements, S.stableSort, &keys);  // :187
+  std::unordered_map<const InstanceType*, double> keyOf;
+  for (size_t i = 0; i < its.size(); i++) keyOf[its[i]] = keys[i];
+  auto byPrice = [&](const std::vector<const InstanceType*>& in_, const Requirements& reqs) {  // nodeclaim.go:270-274
+    std::vector<const InstanceType*> keep;
+    for (auto* it : in_)
+      if (WorstLaunchPrice(it, reqs, ctReqs) < in->candidate_price) keep.push_back(it);
+    return keep;
+  };
+  if (in->all_spot && RequirementHas(n->requirements.Get(ctKey), in->val_spot)) {  // :189-192 -> :230-307
+    if (!in->spot_to_spot) { o->reason = B200S_WHY_S2S_DISABLED; return; }
+    int32_t spot = in->val_spot;
+    n->requirements.Add(NewRequirement(ctKey, B200S_OP_IN, &spot, 1, 0));  // :240
+    std::vector<const InstanceType*> compat;                              // :242, types.go:243-251
+    for (auto* it : its) {
+      bool has = false;
+      for (const Offering& of : it->offerings)
+        if (of.available && Compatible(n->requirements, of.requirements, true)) { has = true; break; }
+      if (has) compat.push_back(it);
+    }
+    std::vector<const InstanceType*> cheaper = byPrice(compat, n->requirements);  // :246
+    if (cheaper.empty()) { o->reason = B200S_WHY_NOT_CHEAPER; return; }          // :253
+    if (in->n_candidates > 1) { o->spot_required = 1; finish(cheaper); return; }  // :262
+    if ((int)cheaper.size() < B200S_S2S_MIN_TYPES) { o->reason = B200S_WHY_S2S_TOO_FEW; return; }  // :279
+    for (size_t i = 0; i + 1 < cheaper.size() && i < (size_t)B200S_S2S_MIN_TYPES; i++)
+      if (keyOf[cheaper[i]] == keyOf[cheaper[i + 1]]) o->price_tie = 1;
+    cheaper.resize(B200S_S2S_MIN_TYPES);  // :303 (no minValues)
+    for (int i = 0; i < B200S_S2S_MIN_TYPES; i++) o->head[i] = cheaper[i]->index;
+    o->spot_required = 1;
+    finish(cheaper);
+    return;
+  }
+  std::vector<const InstanceType*> cheaper = byPrice(its, n->requirements);  // :198
+  if (cheaper.empty()) { o->reason = B200S_WHY_NOT_CHEAPER; return; }       // :205
+  Requirement ctReq = n->requirements.Get(ctKey);                          // :218-221
+  if (RequirementHas(ctReq, in->val_spot) && RequirementHas(ctReq, in->val_on_demand)) {
+    int32_t spot = in->val_spot;
+    n->requirements.Add(NewRequirement(ctKey, B200S_OP_IN, &spot, 1, 0));
+    o->spot_required = 1;
+  }
+  finish(cheaper);
 }
 
 // Dense stage A on the CPU, reference-shaped: for every pod run addToNewNodeClaim's template walk

@@ -44,8 +44,25 @@ typedef struct oracle_result {
   uint64_t* claim_price;
 } oracle_result_t;
 
+/* computeConsolidation over one simulation (K/controllers/disruption/consolidation.go:133-307); value ids are MODEL
+ * value ids of the capacity-type key */
+typedef struct oracle_consolidation_in {
+  int32_t n_candidates, all_spot, spot_to_spot;
+  int32_t val_spot, val_on_demand, val_reserved; /* val_reserved may be -1 */
+  double candidate_price;
+} oracle_consolidation_in_t;
+
+typedef struct oracle_consolidation_out {
+  int32_t decision, reason, n_options, spot_required, price_tie; /* B200S_CMD_*, B200S_WHY_* */
+  int32_t head[B200S_S2S_MIN_TYPES];
+  uint64_t* mask;  /* [W] */
+  int32_t* order;  /* [n_skus] the replacement's InstanceTypeOptions in their final order (may be NULL) */
+} oracle_consolidation_out_t;
+
 int oracle_version(void);
 int oracle_solve(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out);
+int oracle_consolidate(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out,
+                       const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout);
 int oracle_fit_matrix(const b200s_model_t* model, int32_t pod_begin, int32_t pod_end, int32_t* tmpl_out,
                       uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out, int32_t* n_templates_out);
 int oracle_go_sort_perm(const int64_t* keys, int32_t n, int32_t* perm_out);

@@ -52,6 +52,7 @@ def lib():
         build()
         _lib = C.CDLL(LIB)
         _lib.oracle_solve.restype = C.c_int
+        _lib.oracle_consolidate.restype = C.c_int
         _lib.oracle_fit_matrix.restype = C.c_int
         _lib.oracle_go_sort_perm.restype = C.c_int
         _lib.oracle_req_algebra.restype = C.c_int
@@ -98,7 +99,34 @@ class SolveOut:
     counters: Dict[str, int]
 
 
-def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None) -> SolveOut:
+class ConsolidationIn(C.Structure):
+    _fields_ = [("n_candidates", C.c_int32), ("all_spot", C.c_int32), ("spot_to_spot", C.c_int32),
+                ("val_spot", C.c_int32), ("val_on_demand", C.c_int32), ("val_reserved", C.c_int32),
+                ("candidate_price", C.c_double)]
+
+
+class ConsolidationOut(C.Structure):
+    _fields_ = [("decision", C.c_int32), ("reason", C.c_int32), ("n_options", C.c_int32), ("spot_required", C.c_int32),
+                ("price_tie", C.c_int32), ("head", C.c_int32 * 15), ("mask", _P(C.c_uint64)), ("order", _P(C.c_int32))]
+
+
+def consolidate(model, candidate_price: float, all_spot: bool, n_candidates: int, val_spot: int, val_on_demand: int,
+                val_reserved: int = -1, spot_to_spot: bool = False):
+    """Solve + computeConsolidation (consolidation.go:133-307) on one simulation; returns (SolveOut, command dict)."""
+    cin = ConsolidationIn(n_candidates, int(all_spot), int(spot_to_spot), val_spot, val_on_demand, val_reserved,
+                          float(candidate_price))
+    mask = np.zeros(model.n_words, np.uint64)
+    order = np.full(max(model.n_skus, 1), -1, np.int32)
+    cout = ConsolidationOut()
+    cout.mask, cout.order = _p(mask, C.c_uint64), _p(order, C.c_int32)
+    out = solve(model, _consolidation=(cin, cout))
+    cmd = dict(decision=cout.decision, reason=cout.reason, n_options=cout.n_options, spot_required=cout.spot_required,
+               price_tie=cout.price_tie, head=np.array(cout.head[:], np.int32), mask=mask,
+               order=order[:cout.n_options].copy())
+    return out, cmd
+
+
+def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None, _consolidation=None) -> SolveOut:
     L = lib()
     P, R, W, K, E = model.n_pods, model.n_res, model.n_words, len(model.key_names), int(model.c.n_nodes)
     cap = cap_claims if cap_claims is not None else max(P, 1)
@@ -121,7 +149,11 @@ def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None) ->
         setattr(res, k, _p(a, ctypes_of[a.dtype]))
     opts = OracleOpts()
     opts.stable_sort = 1 if stable_sort else 0
-    rc = L.oracle_solve(C.byref(model.c), C.byref(opts), C.byref(res))
+    if _consolidation is None:
+        rc = L.oracle_solve(C.byref(model.c), C.byref(opts), C.byref(res))
+    else:
+        rc = L.oracle_consolidate(C.byref(model.c), C.byref(opts), C.byref(res), C.byref(_consolidation[0]),
+                                  C.byref(_consolidation[1]))
     if rc != 0:
         raise RuntimeError(f"oracle_solve failed: {rc}")
     N, Tn = res.n_claims, res.n_templates

@@ -169,3 +169,29 @@ def assert_same(a: Dict[str, np.ndarray], b: Dict[str, np.ndarray], what: str = 
             i = tuple(bad[0])
             raise AssertionError(f"{what}: field {f} differs at {i}: {x[i]} vs {y[i]} ({len(bad)} mismatches of {x.size})")
     assert digest(a) == digest(b)
+
+
+def mask_bits(mask: np.ndarray):
+    """indices of the set bits of a little-endian u64 word array"""
+    out = []
+    for w, word in enumerate(np.asarray(mask, np.uint64).tolist()):
+        while word:
+            b = (word & -word).bit_length() - 1
+            out.append(w * 64 + b)
+            word &= word - 1
+    return out
+
+
+def capacity_type_values(model):
+    """(model key id of karpenter.sh/capacity-type, value ids of spot, on-demand, reserved; -1 when not interned)"""
+    from b200sched import model as M
+    key = model.key_names.index(M.KEY_CAPACITY_TYPE)
+    ids = {model.val_names[v]: v for v, k in enumerate(model.arrays["val_key"]) if int(k) == key}
+    return key, ids.get("spot", -1), ids.get("on-demand", -1), ids.get("reserved", -1)
+
+
+def device_commands_as_oracle(enc: capi.Encoded, cmds: Dict[str, np.ndarray], i: int) -> Dict[str, object]:
+    """row i of b200s_consolidation_commands in the shape oracle_binding.consolidate reports"""
+    return dict(decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]), n_options=int(cmds["n_options"][i]),
+                spot_required=int(cmds["spot_required"][i]), price_tie=int(cmds["price_tie"][i]),
+                head=cmds["head"][i].tolist(), mask=cmds["mask"][i].tolist())

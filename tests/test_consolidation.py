@@ -1,0 +1,188 @@
+"""computeConsolidation (K/controllers/disruption/consolidation.go:133-307) in the oracle, on cases small enough to
+decide by hand from the Go text, plus an independent numpy restatement of the price rules on the synthetic catalog.
+The device side of the same rows is in test_gpu.py."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import parity
+from b200sched import capi
+from b200sched import model as M
+from b200sched import synth
+
+RES = ["cpu", "memory", "pods"]
+GiB = 1 << 30
+
+
+def _offerings(spot, od, spot_ok=True, od_ok=True, zones=("z1",)):
+    out = []
+    for i, z in enumerate(zones):
+        out.append(([(M.KEY_ZONE, M.OP_IN, [z]), (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot"])], spot * (1 + i), spot_ok))
+        out.append(([(M.KEY_ZONE, M.OP_IN, [z]), (M.KEY_CAPACITY_TYPE, M.OP_IN, ["on-demand"])], od * (1 + i), od_ok))
+    return out
+
+
+def _builder(pool_reqs=(), a_spot_ok=True, zones=("z1",)):
+    b = M.ModelBuilder(RES)
+    for name, cpu, spot, od, ok in [("a", 4000, 0.1, 0.3, a_spot_ok), ("b", 8000, 0.2, 0.6, True), ("c", 16000, 0.4, 1.2, True)]:
+        b.add_sku(name, [(M.KEY_ARCH, M.OP_IN, ["amd64"]), (M.KEY_ZONE, M.OP_IN, list(zones)),
+                         (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot", "on-demand"])],
+                  [cpu, 64 * GiB, 100], [cpu, 64 * GiB, 100], _offerings(spot, od, spot_ok=ok, zones=zones))
+    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])] + list(pool_reqs))
+    return b
+
+
+def _run(model, price, all_spot=False, n_candidates=1, gate=False):
+    _, spot, od, res = parity.capacity_type_values(model)
+    return ob.consolidate(model, price, all_spot, n_candidates, spot, od, res, gate)
+
+
+def _names(model, cmd):
+    return sorted(model.sku_names[s] for s in parity.mask_bits(cmd["mask"]))
+
+
+def test_on_demand_candidate_is_replaced_by_types_whose_spot_price_is_lower():
+    b = _builder()
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    out, cmd = _run(m, 0.25)
+    assert out.n_claims == 1 and out.n_unscheduled == 0
+    # WorstLaunchPrice takes spot before on-demand (types.go:464-468): a 0.1, b 0.2, c 0.4 against 0.25
+    assert (cmd["decision"], cmd["reason"], cmd["n_options"]) == (capi.CMD_REPLACE, capi.WHY_OK, 2)
+    assert _names(m, cmd) == ["a", "b"]
+    assert cmd["order"].tolist() == [m.sku_names.index("a"), m.sku_names.index("b")]  # OrderByPrice order survives
+    # the requirements allowed both capacity types, so the command pins spot (consolidation.go:218-221)
+    assert cmd["spot_required"] == 1
+
+
+def test_unavailable_spot_offering_falls_back_to_the_on_demand_price():
+    b = _builder(a_spot_ok=False)
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    _, cmd = _run(m, 0.25)
+    assert _names(m, cmd) == ["b"]  # a: no available spot offering -> on-demand 0.3 >= 0.25
+
+
+def test_worst_launch_price_is_the_most_expensive_zone():
+    b = _builder(zones=("z1", "z2"))  # z2 costs twice z1
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    _, cmd = _run(m, 0.25)
+    assert _names(m, cmd) == ["a"]  # a: max(0.1, 0.2) < 0.25; b: max(0.2, 0.4) is not
+    b = _builder(zones=("z1", "z2"))
+    b.add_pod([(M.KEY_ZONE, M.OP_IN, ["z1"])], [2000, GiB, 1])  # the claim is pinned to z1: z2's price no longer counts
+    m = b.build()
+    _, cmd = _run(m, 0.25)
+    assert _names(m, cmd) == ["a", "b"]
+
+
+def test_on_demand_only_pool_compares_on_demand_prices_and_adds_no_requirement():
+    b = _builder(pool_reqs=[(M.KEY_CAPACITY_TYPE, M.OP_IN, ["on-demand"])])
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    _, cmd = _run(m, 0.7)
+    assert _names(m, cmd) == ["a", "b"] and cmd["spot_required"] == 0
+    _, cmd = _run(m, 0.3)  # strictly cheaper only (nodeclaim.go:273)
+    assert (cmd["decision"], cmd["reason"]) == (capi.CMD_NONE, capi.WHY_NOT_CHEAPER)
+
+
+def test_counts_decide_before_prices():
+    b = _builder()
+    b.add_pod([], [64000, GiB, 1])  # fits nothing
+    _, cmd = _run(b.build(), 10.0)
+    assert (cmd["decision"], cmd["reason"]) == (capi.CMD_NONE, capi.WHY_UNSCHEDULABLE)
+    b = _builder()
+    b.add_pod([], [9000, GiB, 1])
+    b.add_pod([], [9000, GiB, 1])  # 18 cpu: two NodeClaims
+    out, cmd = _run(b.build(), 10.0)
+    assert out.n_claims == 2 and (cmd["decision"], cmd["reason"]) == (capi.CMD_NONE, capi.WHY_MANY_CLAIMS)
+    b = _builder()
+    b.add_pod([], [2000, GiB, 1])
+    b.add_node("n1", {M.KEY_ZONE: "z1", M.KEY_CAPACITY_TYPE: "on-demand", M.KEY_NODEPOOL: "p", M.KEY_ARCH: "amd64"},
+               [4000, 8 * GiB, 10])
+    out, cmd = _run(b.build(), 10.0)
+    assert out.n_claims == 0 and (cmd["decision"], cmd["n_options"]) == (capi.CMD_DELETE, 0)
+
+
+def test_spot_to_spot_rules():
+    b = _builder()
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    _, cmd = _run(m, 0.25, all_spot=True, gate=False)
+    assert (cmd["decision"], cmd["reason"]) == (capi.CMD_NONE, capi.WHY_S2S_DISABLED)
+    _, cmd = _run(m, 0.25, all_spot=True, gate=True)  # one candidate needs 15 cheaper types
+    assert (cmd["decision"], cmd["reason"]) == (capi.CMD_NONE, capi.WHY_S2S_TOO_FEW)
+    _, cmd = _run(m, 0.25, all_spot=True, gate=True, n_candidates=2)
+    assert cmd["decision"] == capi.CMD_REPLACE and _names(m, cmd) == ["a", "b"] and cmd["spot_required"] == 1
+    # a spot candidate whose replacement may only be on-demand is an ordinary consolidation
+    b = _builder(pool_reqs=[(M.KEY_CAPACITY_TYPE, M.OP_IN, ["on-demand"])])
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    _, cmd = _run(m, 0.7, all_spot=True, gate=False)
+    assert cmd["decision"] == capi.CMD_REPLACE and cmd["spot_required"] == 0
+
+
+def _price_tables(model):
+    """cheapest / most expensive AVAILABLE offering per (zone value, capacity-type value, SKU), straight from the model"""
+    a = model.arrays
+    kz, kc = model.key_names.index(M.KEY_ZONE), model.key_names.index(M.KEY_CAPACITY_TYPE)
+    lo, hi = {}, {}
+    for s in range(model.n_skus):
+        for o in range(a["sku_off_off"][s], a["sku_off_off"][s + 1]):
+            if not a["off_available"][o]:
+                continue
+            z = c = None
+            for i in range(a["off_req_off"][o], a["off_req_off"][o + 1]):
+                key, v = int(a["reqs"][i]["key"]), int(a["req_values"][a["reqs"][i]["val_off"]])
+                if key == kz:
+                    z = v
+                elif key == kc:
+                    c = v
+            p = float(a["off_price"][o])
+            lo[(z, c, s)] = min(lo.get((z, c, s), np.inf), p)
+            hi[(z, c, s)] = max(hi.get((z, c, s), -np.inf), p)
+    return lo, hi
+
+
+def test_single_candidate_spot_to_spot_keeps_the_fifteen_cheapest_in_price_order():
+    b = synth.new_builder()
+    synth.add_catalog(b, 80)
+    synth.add_pools(b, "c2")
+    b.add_pod([], [500, GiB, 0, 0, 1])
+    m = b.build()
+    _, spot, od, res = parity.capacity_type_values(m)
+    out, cmd = ob.consolidate(m, 1.0, True, 1, spot, od, res, True)
+    assert out.n_claims == 1 and cmd["decision"] == capi.CMD_REPLACE and cmd["n_options"] == 15 and cmd["spot_required"] == 1
+    assert cmd["price_tie"] == 0
+    # independent restatement: order by the cheapest offering (any capacity type the claim allowed), keep the types
+    # whose dearest SPOT offering is below the candidate price, take 15
+    lo, hi = _price_tables(m)
+    options = parity.mask_bits(out.claim_mask[0])
+    zones = {z for (z, _, _) in lo}
+    cheapest = {s: min(lo.get((z, c, s), np.inf) for z in zones for c in (spot, od)) for s in options}
+    dearest_spot = {s: max(hi.get((z, spot, s), -np.inf) for z in zones) for s in options}
+    want = [s for s in sorted(options, key=lambda s: cheapest[s]) if 0 <= dearest_spot[s] < 1.0][:15]
+    assert cmd["head"].tolist() == want and cmd["order"].tolist() == want
+    assert sorted(parity.mask_bits(cmd["mask"])) == sorted(want)
+
+
+def test_the_encoder_carries_the_most_expensive_offering_per_cell():
+    """price_max feeds WorstLaunchPrice on the device (types.go:454-474): check the table against the model."""
+    b = synth.new_builder()
+    synth.add_catalog(b, 70)
+    synth.add_pools(b, "c2")
+    b.add_pod([], [500, GiB, 0, 0, 1])
+    m = b.build()
+    enc = capi.Encoded(m)
+    c = enc.catalog.contents
+    S, ZC = c.n_skus, c.n_zones * c.n_cts
+    top = np.ctypeslib.as_array(c.price_max, shape=(ZC * S,)).reshape(ZC, S)
+    low = np.ctypeslib.as_array(c.price, shape=(ZC * S,)).reshape(ZC, S)
+    lo, hi = _price_tables(m)
+    kz, kc = m.key_names.index(M.KEY_ZONE), m.key_names.index(M.KEY_CAPACITY_TYPE)
+    seen = 0
+    for (z, ct, s), p in hi.items():
+        cell = enc.value_bit(kz, z) * c.n_cts + enc.value_bit(kc, ct)
+        assert top[cell, s] == np.float64(p).view(np.uint64) and low[cell, s] == np.float64(lo[(z, ct, s)]).view(np.uint64)
+        seen += 1
+    assert (top != np.uint64(0xFFFFFFFFFFFFFFFF)).sum() == seen

@@ -209,6 +209,83 @@ def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
         gpu_ctx.release_catalog(cid)
 
 
+def _consolidation_cases():
+    """(model, [(candidate price or factor of the replacement's cheapest price, all_spot, n_candidates)]) per
+    simulation: the hand-decided catalogs of test_consolidation.py and consolidation simulations of config 4."""
+    import test_consolidation as tc
+    from b200sched import model as M
+    GiB = tc.GiB
+    groups = []
+    tiny = []
+    every = [(0.25, False, 1), (0.25, True, 1), (0.25, True, 2), (0.7, False, 1), (0.3, False, 1), (10.0, True, 1)]
+    for kw, pods, nodes in [
+            (dict(), [([], [2000, GiB, 1])], False), (dict(a_spot_ok=False), [([], [2000, GiB, 1])], False),
+            (dict(zones=("z1", "z2")), [([], [2000, GiB, 1])], False),
+            (dict(zones=("z1", "z2")), [([(M.KEY_ZONE, M.OP_IN, ["z1"])], [2000, GiB, 1])], False),
+            (dict(pool_reqs=[(M.KEY_CAPACITY_TYPE, M.OP_IN, ["on-demand"])]), [([], [2000, GiB, 1])], False),
+            (dict(pool_reqs=[(M.KEY_CAPACITY_TYPE, M.OP_NOTIN, ["on-demand"])]), [([], [2000, GiB, 1])], False),
+            (dict(), [([], [64000, GiB, 1])], False), (dict(), [([], [9000, GiB, 1]), ([], [9000, GiB, 1])], False),
+            (dict(), [([], [2000, GiB, 1])], True)]:
+        b = tc._builder(**kw)
+        for reqs, requests in pods:
+            b.add_pod(reqs, requests)
+        if nodes:
+            b.add_node("n1", {M.KEY_ZONE: "z1", M.KEY_CAPACITY_TYPE: "on-demand", M.KEY_NODEPOOL: "p", M.KEY_ARCH: "amd64"},
+                       [4000, 8 * GiB, 10])
+        tiny.append((b.build(), [(p, s, c, False) for p, s, c in every]))
+    groups.extend([[t] for t in tiny])  # each tiny model has its own catalog
+    # config 4: the candidates' pods with and without the other nodes to land on, and small samples with many options
+    model, node_of_pod, util = synth.c4(4000, 300, solve=ob.solve)
+    sims = synth.c4_simulations(model, node_of_pod, util, 12)
+    none = np.array([], np.int64)
+    c4 = [m for _, m in sims[:4]] + [M.subset(model, np.nonzero(node_of_pod == i)[0], none) for i, _ in sims]
+    rng = np.random.default_rng(11)
+    c4 += [M.subset(model, np.sort(rng.choice(model.n_pods, 3, replace=False)), none) for _ in range(8)]
+    rel = [(0.5, False, 1), (1.0001, False, 1), (1.5, False, 1), (3.0, True, 2), (1e3, True, 1), (1e3, False, 1), (2.0, True, 1)]
+    groups.append([(m, [(f, s, c, True) for f, s, c in rel]) for m in c4])
+    return groups
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gate", [False, True])
+def test_consolidation_commands_match_the_oracle(gpu_ctx, gate):
+    """computeConsolidation over a batch of finished simulations, one warp each, against the
+    oracle's restatement -- decision, reason, surviving instance types, the added spot requirement and the 15 cheapest
+    in price order."""
+    seen = set()
+    for group in _consolidation_cases():
+        models = [m for m, _ in group]
+        encs = [capi.Encoded(m) for m in models]
+        cid = gpu_ctx.upload_catalog(encs[0])
+        try:
+            raws = gpu_ctx.solve_batch(cid, encs)
+            key, spot, od, res = parity.capacity_type_values(models[0])
+            bits = [encs[0].value_bit(key, v) if v >= 0 else -1 for v in (spot, od, res)]
+            rows, prices, spots, cands, want = [], [], [], [], []
+            for (m, variants), raw in zip(group, raws):
+                base = float(raw.claim_price[:1].view(np.float64)[0]) if raw.n_claims == 1 else 1.0
+                for price, all_spot, n_cand, relative in variants:
+                    p = price * base if relative else price
+                    rows.append(raw); prices.append(p); spots.append(all_spot); cands.append(n_cand)
+                    want.append(ob.consolidate(m, p, all_spot, n_cand, spot, od, res, gate)[1])
+            got = gpu_ctx.consolidation_commands(cid, encs[0], rows, prices, spots, cands, bits[0], bits[1], bits[2], gate)
+            for i, w in enumerate(want):
+                g = parity.device_commands_as_oracle(encs[0], got, i)
+                for f in ("decision", "reason", "n_options", "spot_required", "price_tie"):
+                    assert g[f] == w[f], (i, f, g, w)
+                assert g["mask"] == w["mask"].tolist() and g["head"] == w["head"].tolist(), (i, g, w)
+                seen.add((w["decision"], w["reason"], w["n_options"] == capi.S2S_MIN_TYPES and w["head"][0] >= 0))
+        finally:
+            gpu_ctx.release_catalog(cid)
+    # every branch of computeConsolidation was exercised
+    reasons = {r for d, r, _ in seen if d == capi.CMD_NONE}
+    want_reasons = {capi.WHY_UNSCHEDULABLE, capi.WHY_MANY_CLAIMS, capi.WHY_NOT_CHEAPER}
+    want_reasons |= {capi.WHY_S2S_TOO_FEW} if gate else {capi.WHY_S2S_DISABLED}
+    assert want_reasons <= reasons, seen
+    assert any(d == capi.CMD_DELETE for d, _, _ in seen) and any(d == capi.CMD_REPLACE for d, _, _ in seen)
+    assert (not gate) or any(t for _, _, t in seen), "no simulation reached the 15-type truncation"
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("tool,ok", [("memcheck", "ERROR SUMMARY: 0 errors"), ("racecheck", "RACECHECK SUMMARY: 0 hazards")])
 def test_solve_is_sanitizer_clean(tool, ok):
