@@ -353,21 +353,41 @@ def run_c4(args, rank, world, local):
     E = int(model.c.n_nodes)
     sims = synth.c4_simulations(model, node_of_pod, util, B)
     encs = [capi.Encoded(m) for _, m in sims]
+    sample = list(range(0, B, max(B // 32, 1)))[:32]  # every 8th simulation: parity check and the CPU arm's timing
     t_build = time.perf_counter() - t0
     cid = ctx.upload_catalog(encs[0])
     # parity of a sample of simulations against the oracle, and the reference arm's time on the same sample
     t0 = time.perf_counter()
-    oracle_out = [ob.solve(m) for _, m in sims[:32]]
+    oracle_out = [ob.solve(sims[j][1]) for j in sample]
     t_cpu = (time.perf_counter() - t0) / len(oracle_out)
-    for _ in range(args.warmup):
+    # what computeConsolidation needs besides the Solve results: the candidates' price and capacity type
+    cand_price, cand_spot = synth.candidate_prices(model, [i for i, _ in sims])
+    ct_key, v_spot, v_od, v_res = parity.capacity_type_values(model)
+    ct_bits = [encs[0].value_bit(ct_key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res)]
+
+    def step():
         outs = ctx.solve_batch(cid, encs)
+        cmds = ctx.consolidation_commands(cid, encs[0], outs, cand_price, cand_spot, [1] * B, ct_bits[0], ct_bits[1],
+                                          ct_bits[2], spot_to_spot=True)
+        return outs, cmds
+
+    for _ in range(args.warmup):
+        outs, cmds = step()
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            outs = ctx.solve_batch(cid, encs)
+            outs, cmds = step()
         ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    for (i, m), e, r, o in zip(sims[:32], encs[:32], outs[:32], oracle_out):
-        parity.assert_same(parity.canon_device(e, r), parity.canon_oracle(m, o), f"c4 simulation of node {i}")
+    for j in sample:
+        i, m = sims[j]
+        want = ob.consolidate(m, cand_price[j], cand_spot[j], 1, v_spot, v_od, v_res, True)[1]
+        got = parity.device_commands_as_oracle(encs[0], cmds, j)
+        for f in ("decision", "reason", "n_options", "spot_required", "price_tie"):
+            assert got[f] == want[f], (f"c4 command of node {i}", f, got, want)
+        assert got["mask"] == want["mask"].tolist() and got["head"] == want["head"].tolist(), f"c4 command of node {i}"
+    for j, o in zip(sample, oracle_out):
+        parity.assert_same(parity.canon_device(encs[j], outs[j]), parity.canon_oracle(sims[j][1], o),
+                           f"c4 simulation of node {sims[j][0]}")
     removable = sum(1 for r in outs if r.n_claims == 0 and r.n_unscheduled == 0)
     # multi-node re-pack: every pod of the candidates at once against the remaining nodes
     cand = np.array([i for i, _ in sims])
@@ -383,15 +403,19 @@ def run_c4(args, rank, world, local):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
             "config": {"workload": f"config[3]: {P} running pods on {E} loosely packed nodes ({S} SKUs); {B} single-node "
-                                   "consolidation simulations per step through b200s_solve_batch (host buffers in and out), "
-                                   "plus one multi-node re-pack", "build_s": t_build},
+                                   "consolidation simulations per step (lowest utilisation first) through b200s_solve_batch and their commands through "
+                                   "b200s_consolidation_commands (host buffers in and out); plus one multi-node re-pack "
+                                   "outside the timed region", "build_s": t_build},
+            "commands": {"delete": int((cmds["decision"] == capi.CMD_DELETE).sum()),
+                         "replace": int((cmds["decision"] == capi.CMD_REPLACE).sum()),
+                         "none": int((cmds["decision"] == capi.CMD_NONE).sum())},
             "nodes_before": E, "single_node_removable": int(removable), "batch": B,
             "multi_node_repack": {"pods": int(len(pods)), "candidates": int(len(cand)), "new_nodeclaims": int(rm.n_claims),
                                   "unschedulable": int(rm.n_unscheduled), "nodes_after": int(E - len(cand) + rm.n_claims)},
             "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "simulations/s", "cores": 1, "kind": "port",
-                             "sample": "32 of the same simulations on one host core", "evals_per_simulation": evals_cpu},
+                             "sample": "32 of the same simulations (every 8th) on one host core", "evals_per_simulation": evals_cpu},
             "e2e": {"value": B / (ms * 1e-3), "unit": "simulations/s"},
-            "clocks": clk.summary(), "parity": "32 simulations + the multi-node re-pack bit-identical to the CPU oracle"}
+            "clocks": clk.summary(), "parity": "32 simulations, their consolidation commands and the multi-node re-pack identical to the CPU oracle"}
     ctx.close()
     emit(line)
 

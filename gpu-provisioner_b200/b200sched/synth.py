@@ -380,14 +380,45 @@ def c4(n_pods: int = 50_000, n_skus: int = 500, cap: float = 0.6, solve=None):
     return model, node_of_pod, util
 
 
-def c4_simulations(model: M.Model, node_of_pod: np.ndarray, util: np.ndarray, n_candidates: int):
+def c4_simulations(model: M.Model, node_of_pod: np.ndarray, util: np.ndarray, n_candidates: int, spread: bool = False):
     """Single-node consolidation candidates, lowest utilisation first (singlenodeconsolidation.go:68-101): one
-    simulation per candidate = its pods against every other node."""
+    simulation per candidate = its pods against every other node.  `spread` takes the candidates evenly across the
+    whole utilisation order instead of its head, so that a batch holds nodes that can be deleted, nodes that need a
+    replacement and nodes that are best left alone."""
     E = int(model.c.n_nodes)
-    order = np.argsort(util, kind="stable")[:n_candidates]
+    order = np.argsort(util, kind="stable")
+    order = order[np.linspace(0, E - 1, n_candidates).astype(np.int64)] if spread else order[:n_candidates]
     all_nodes = np.arange(E)
     sims = []
     for i in order:
         pods = np.nonzero(node_of_pod == i)[0]
         sims.append((int(i), M.subset(model, pods, all_nodes[all_nodes != i])))
     return sims
+
+
+def candidate_prices(model: M.Model, nodes: Sequence[int]):
+    """getCandidatePrices for single-node candidates (K/controllers/disruption/consolidation.go:310-328): the cheapest
+    offering of the node's instance type that its zone / capacity-type labels admit (availability is NOT looked at
+    there), and whether the node is a spot node.  Returns (prices, is_spot) per node."""
+    a = model.arrays
+    k_it, k_z, k_ct = (model.key_names.index(k) for k in (M.KEY_INSTANCE_TYPE, M.KEY_ZONE, M.KEY_CAPACITY_TYPE))
+    sku_of = {n: i for i, n in enumerate(model.sku_names)}
+    prices, spot = [], []
+    for e in nodes:
+        lab = {}
+        for i in range(a["node_req_off"][e], a["node_req_off"][e + 1]):
+            lab[int(a["reqs"][i]["key"])] = int(a["req_values"][a["reqs"][i]["val_off"]])
+        s = sku_of[model.val_names[lab[k_it]]]
+        best = None
+        for o in range(a["sku_off_off"][s], a["sku_off_off"][s + 1]):
+            ok = True
+            for i in range(a["off_req_off"][o], a["off_req_off"][o + 1]):
+                key, v = int(a["reqs"][i]["key"]), int(a["req_values"][a["reqs"][i]["val_off"]])
+                ok = ok and (key not in lab or lab[key] == v)
+            if ok and (best is None or a["off_price"][o] < best):
+                best = float(a["off_price"][o])
+        if best is None:
+            raise ValueError(f"node {e}: unable to determine offering")
+        prices.append(best)
+        spot.append(model.val_names[lab[k_ct]] == "spot")
+    return prices, spot

@@ -186,3 +186,20 @@ def test_the_encoder_carries_the_most_expensive_offering_per_cell():
         assert top[cell, s] == np.float64(p).view(np.uint64) and low[cell, s] == np.float64(lo[(z, ct, s)]).view(np.uint64)
         seen += 1
     assert (top != np.uint64(0xFFFFFFFFFFFFFFFF)).sum() == seen
+
+
+def test_candidate_prices_read_the_offering_the_node_labels_name():
+    """the synthetic feed's getCandidatePrices (consolidation.go:310-328): zone and capacity type of the node pick the
+    offering of its instance type, available or not"""
+    model, node_of_pod, util = synth.c4(600, 60, solve=ob.solve)
+    E = int(model.c.n_nodes)
+    prices, spot = synth.candidate_prices(model, range(E))
+    a = model.arrays
+    kz, kc, ki = (model.key_names.index(k) for k in (M.KEY_ZONE, M.KEY_CAPACITY_TYPE, M.KEY_INSTANCE_TYPE))
+    for e in range(E):
+        lab = {int(a["reqs"][i]["key"]): model.val_names[int(a["req_values"][a["reqs"][i]["val_off"]])]
+               for i in range(a["node_req_off"][e], a["node_req_off"][e + 1])}
+        s = model.sku_names.index(lab[ki])
+        o = a["sku_off_off"][s] + synth.ZONES.index(lab[kz]) * 2 + synth.CAPACITY_TYPES.index(lab[kc])  # add_catalog's order
+        assert prices[e] == float(a["off_price"][o]) and spot[e] == (lab[kc] == "spot")
+    assert any(spot) and not all(spot)
