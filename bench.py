@@ -398,6 +398,22 @@ def run_c4(args, rank, world, local):
     rm = ctx.solve(cid, em)
     om = ob.solve(multi)
     parity.assert_same(parity.canon_device(em, rm), parity.canon_oracle(multi, om), "c4 multi-node re-pack")
+    # firstNConsolidationOption over the 100 cheapest-to-disrupt candidates: every prefix in one batch on the device,
+    # against the reference's sequential binary search on the CPU oracle (outside the timed region; wall clock)
+    import consolidation_ref as cref
+    from b200sched import consolidation as cons
+    ctv = (ct_key, v_spot, v_od, v_res)
+    cand100 = [int(i) for i in np.argsort(util, kind="stable")[:100]]
+    t0 = time.perf_counter()
+    got = cons.first_n_consolidation_option(ctx, cid, model, node_of_pod, cand100, ctv)
+    t_search_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    want_mid, probed = cref.first_n_consolidation_option(model, node_of_pod, cand100, ctv)
+    t_search_cpu = time.perf_counter() - t0
+    assert (got.mid if got is not None else None) == want_mid, "multi-node search ends on a different prefix"
+    if got is not None:
+        w = probed[want_mid][1]
+        assert (got.decision, got.n_options, got.mask.tolist()) == (w["decision"], w["n_options"], w["mask"].tolist())
     evals_cpu = sum(o.counters["fit_evals"] for o in oracle_out) / len(oracle_out)
     line = {"metric": "consolidation simulations/s", "value": B / (ms * 1e-3), "unit": "simulations/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -412,6 +428,11 @@ def run_c4(args, rank, world, local):
             "nodes_before": E, "single_node_removable": int(removable), "batch": B,
             "multi_node_repack": {"pods": int(len(pods)), "candidates": int(len(cand)), "new_nodeclaims": int(rm.n_claims),
                                   "unschedulable": int(rm.n_unscheduled), "nodes_after": int(E - len(cand) + rm.n_claims)},
+            "multi_node_search": {"candidates": len(cand100), "prefixes_in_one_batch": len(cand100) - 1,
+                                  "removes_first": None if got is None else got.mid + 1,
+                                  "decision": None if got is None else ["none", "delete", "replace"][got.decision],
+                                  "device_wall_s_incl_host_encode": t_search_dev,
+                                  "cpu_sequential_search_s": t_search_cpu, "cpu_probes": len(probed)},
             "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "simulations/s", "cores": 1, "kind": "port",
                              "sample": "32 of the same simulations (every 8th) on one host core", "evals_per_simulation": evals_cpu},
             "e2e": {"value": B / (ms * 1e-3), "unit": "simulations/s"},

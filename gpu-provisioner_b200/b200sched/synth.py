@@ -400,25 +400,9 @@ def candidate_prices(model: M.Model, nodes: Sequence[int]):
     """getCandidatePrices for single-node candidates (K/controllers/disruption/consolidation.go:310-328): the cheapest
     offering of the node's instance type that its zone / capacity-type labels admit (availability is NOT looked at
     there), and whether the node is a spot node.  Returns (prices, is_spot) per node."""
-    a = model.arrays
-    k_it, k_z, k_ct = (model.key_names.index(k) for k in (M.KEY_INSTANCE_TYPE, M.KEY_ZONE, M.KEY_CAPACITY_TYPE))
-    sku_of = {n: i for i, n in enumerate(model.sku_names)}
-    prices, spot = [], []
-    for e in nodes:
-        lab = {}
-        for i in range(a["node_req_off"][e], a["node_req_off"][e + 1]):
-            lab[int(a["reqs"][i]["key"])] = int(a["req_values"][a["reqs"][i]["val_off"]])
-        s = sku_of[model.val_names[lab[k_it]]]
-        best = None
-        for o in range(a["sku_off_off"][s], a["sku_off_off"][s + 1]):
-            ok = True
-            for i in range(a["off_req_off"][o], a["off_req_off"][o + 1]):
-                key, v = int(a["reqs"][i]["key"]), int(a["req_values"][a["reqs"][i]["val_off"]])
-                ok = ok and (key not in lab or lab[key] == v)
-            if ok and (best is None or a["off_price"][o] < best):
-                best = float(a["off_price"][o])
-        if best is None:
+    from .consolidation import node_facts
+    facts = node_facts(model, nodes)
+    for e, (_, p, _) in zip(nodes, facts):
+        if p < 0:
             raise ValueError(f"node {e}: unable to determine offering")
-        prices.append(best)
-        spot.append(model.val_names[lab[k_ct]] == "spot")
-    return prices, spot
+    return [p for _, p, _ in facts], [sp for _, _, sp in facts]

@@ -1084,16 +1084,46 @@ static void computeConsolidation(Scheduler& S, int nUnscheduled, const oracle_co
   o->price_tie = 0;
   for (int i = 0; i < B200S_S2S_MIN_TYPES; i++) o->head[i] = -1;
   for (int w = 0; w < W; w++) o->mask[w] = 0;
-  auto finish = [&](const std::vector<const InstanceType*>& its) {
-    o->decision = B200S_CMD_REPLACE;
+  o->valid = 0;
+  std::vector<Requirements> ctReqs;  // reserved, spot, on-demand (types.go:464-468)
+  auto report = [&](const std::vector<const InstanceType*>& its) {
     o->n_options = (int)its.size();
+    for (int w = 0; w < W; w++) o->mask[w] = 0;
     for (size_t i = 0; i < its.size(); i++) {
       o->mask[its[i]->index / 64] |= 1ull << (its[i]->index % 64);
       if (o->order) o->order[i] = its[i]->index;
     }
   };
+  auto finish = [&](std::vector<const InstanceType*> its) {
+    o->decision = B200S_CMD_REPLACE;
+    if (in->filter_same_type) {
+      // filterOutSameInstanceType (multinodeconsolidation.go:172-224): a replacement of one of the removed types must be
+      // cheaper than the cheapest removed node of that type, or the command is just a deletion in disguise
+      std::unordered_map<int, double> priceByType;
+      std::unordered_map<int, bool> existing;
+      for (int i = 0; i < in->n_cand_rows; i++) {
+        existing[in->cand_sku[i]] = true;
+        if (in->cand_price[i] < 0) continue;  // no compatible offering (:185-187)
+        auto f = priceByType.find(in->cand_sku[i]);
+        double have = f == priceByType.end() ? 1.7976931348623157e308 : f->second;
+        if (in->cand_price[i] < have) priceByType[in->cand_sku[i]] = in->cand_price[i];
+      }
+      double maxPrice = 1.7976931348623157e308;
+      for (auto* it : its)
+        if (existing.count(it->index)) {
+          double p = priceByType.count(it->index) ? priceByType[it->index] : 0.0;  // Go map zero value
+          if (p < maxPrice) maxPrice = p;
+        }
+      std::vector<const InstanceType*> keep;
+      for (auto* it : its)
+        if (WorstLaunchPrice(it, S.newNodeClaims[0]->requirements, ctReqs) < maxPrice) keep.push_back(it);
+      its = std::move(keep);
+      o->valid = !its.empty();  // multinodeconsolidation.go:145-148
+    }
+    report(its);
+  };
   if (nUnscheduled > 0) { o->reason = B200S_WHY_UNSCHEDULABLE; return; }          // :147
-  if (S.newNodeClaims.empty()) { o->decision = B200S_CMD_DELETE; return; }         // :155
+  if (S.newNodeClaims.empty()) { o->decision = B200S_CMD_DELETE; o->valid = 1; return; }  // :155
   if (S.newNodeClaims.size() != 1) { o->reason = B200S_WHY_MANY_CLAIMS; return; }  // :163
   NodeClaim* n = S.newNodeClaims[0];
   auto single = [&](int v) {
@@ -1102,7 +1132,6 @@ static void computeConsolidation(Scheduler& S, int nUnscheduled, const oracle_co
     r.Add(NewRequirement(ctKey, B200S_OP_IN, &vv, 1, 0));
     return r;
   };
-  std::vector<Requirements> ctReqs;  // reserved, spot, on-demand (types.go:464-468)
   if (in->val_reserved >= 0) ctReqs.push_back(single(in->val_reserved));
   ctReqs.push_back(single(in->val_spot));
   ctReqs.push_back(single(in->val_on_demand));

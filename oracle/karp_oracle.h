@@ -50,10 +50,17 @@ typedef struct oracle_consolidation_in {
   int32_t n_candidates, all_spot, spot_to_spot;
   int32_t val_spot, val_on_demand, val_reserved; /* val_reserved may be -1 */
   double candidate_price;
+  /* multi-node probes only (multinodeconsolidation.go:139-150): apply filterOutSameInstanceType (:172-224) to a
+   * replacement and report validDecision.  One row per candidate: its instance type and the cheapest offering its
+   * labels admit, < 0 when there is none. */
+  int32_t filter_same_type, n_cand_rows;
+  const int32_t* cand_sku;
+  const double* cand_price;
 } oracle_consolidation_in_t;
 
 typedef struct oracle_consolidation_out {
   int32_t decision, reason, n_options, spot_required, price_tie; /* B200S_CMD_*, B200S_WHY_* */
+  int32_t valid; /* validDecision of firstNConsolidationOption, set when filter_same_type */
   int32_t head[B200S_S2S_MIN_TYPES];
   uint64_t* mask;  /* [W] */
   int32_t* order;  /* [n_skus] the replacement's InstanceTypeOptions in their final order (may be NULL) */

@@ -102,26 +102,35 @@ class SolveOut:
 class ConsolidationIn(C.Structure):
     _fields_ = [("n_candidates", C.c_int32), ("all_spot", C.c_int32), ("spot_to_spot", C.c_int32),
                 ("val_spot", C.c_int32), ("val_on_demand", C.c_int32), ("val_reserved", C.c_int32),
-                ("candidate_price", C.c_double)]
+                ("candidate_price", C.c_double), ("filter_same_type", C.c_int32), ("n_cand_rows", C.c_int32),
+                ("cand_sku", _P(C.c_int32)), ("cand_price", _P(C.c_double))]
 
 
 class ConsolidationOut(C.Structure):
     _fields_ = [("decision", C.c_int32), ("reason", C.c_int32), ("n_options", C.c_int32), ("spot_required", C.c_int32),
-                ("price_tie", C.c_int32), ("head", C.c_int32 * 15), ("mask", _P(C.c_uint64)), ("order", _P(C.c_int32))]
+                ("price_tie", C.c_int32), ("valid", C.c_int32), ("head", C.c_int32 * 15), ("mask", _P(C.c_uint64)),
+                ("order", _P(C.c_int32))]
 
 
 def consolidate(model, candidate_price: float, all_spot: bool, n_candidates: int, val_spot: int, val_on_demand: int,
-                val_reserved: int = -1, spot_to_spot: bool = False):
-    """Solve + computeConsolidation (consolidation.go:133-307) on one simulation; returns (SolveOut, command dict)."""
+                val_reserved: int = -1, spot_to_spot: bool = False, same_type_rows=None):
+    """Solve + computeConsolidation (consolidation.go:133-307) on one simulation; returns (SolveOut, command dict).
+    same_type_rows = [(instance type index, price or -1)] per candidate switches on the multi-node probe's
+    filterOutSameInstanceType and validDecision (multinodeconsolidation.go:139-150, :172-224)."""
     cin = ConsolidationIn(n_candidates, int(all_spot), int(spot_to_spot), val_spot, val_on_demand, val_reserved,
                           float(candidate_price))
+    if same_type_rows is not None:
+        sku = np.asarray([r[0] for r in same_type_rows], np.int32)
+        prc = np.asarray([r[1] for r in same_type_rows], np.float64)
+        cin.filter_same_type, cin.n_cand_rows = 1, len(sku)
+        cin.cand_sku, cin.cand_price = _p(sku, C.c_int32), _p(prc, C.c_double)
     mask = np.zeros(model.n_words, np.uint64)
     order = np.full(max(model.n_skus, 1), -1, np.int32)
     cout = ConsolidationOut()
     cout.mask, cout.order = _p(mask, C.c_uint64), _p(order, C.c_int32)
     out = solve(model, _consolidation=(cin, cout))
     cmd = dict(decision=cout.decision, reason=cout.reason, n_options=cout.n_options, spot_required=cout.spot_required,
-               price_tie=cout.price_tie, head=np.array(cout.head[:], np.int32), mask=mask,
+               price_tie=cout.price_tie, valid=cout.valid, head=np.array(cout.head[:], np.int32), mask=mask,
                order=order[:cout.n_options].copy())
     return out, cmd
 

@@ -287,6 +287,45 @@ def test_consolidation_commands_match_the_oracle(gpu_ctx, gate):
 
 
 @pytest.mark.gpu
+def test_multi_node_consolidation_search_as_one_batch(gpu_ctx):
+    """firstNConsolidationOption (multinodeconsolidation.go:116-170): every prefix the binary search could probe is
+    simulated in one batch and the search replayed on the answers; the reference's sequential search over oracle
+    simulations must end on the same prefix with the same command, and every prefix must agree, not only the probed ones."""
+    import consolidation_ref as ref
+    from b200sched import consolidation as cons
+    model, node_of_pod, util = synth.c4(1500, 120, solve=ob.solve)
+    order = np.argsort(util, kind="stable")
+    filtered = invalid_replace = 0
+    for take, off in ((24, 0), (40, 0), (30, 40), (36, 80), (20, 100), (2, 0), (1, 0)):
+        sub, nop = ref.sub_cluster(model, node_of_pod, order[off:off + take])
+        cand = list(range(take))  # sub_cluster keeps the utilisation order
+        ctv = parity.capacity_type_values(sub)
+        want_mid, _ = ref.first_n_consolidation_option(sub, nop, cand, ctv)
+        enc = capi.Encoded(sub)
+        cid = gpu_ctx.upload_catalog(enc)
+        try:
+            got = cons.first_n_consolidation_option(gpu_ctx, cid, sub, nop, cand, ctv)
+            assert (got.mid if got is not None else None) == want_mid, (take, off)
+            if take < 2:
+                continue
+            lo, hi = cons.search_bounds(take, take)
+            facts = cons.node_facts(sub, cand)
+            probes = cons.multi_node_probes(gpu_ctx, cid, sub, nop, cand, range(lo, hi + 1), ctv)
+            for p in probes:
+                out, cmd = ref.probe(sub, nop, cand, facts, p.mid, ctv, False)
+                assert (p.decision, p.reason, p.valid, p.n_options) == (cmd["decision"], cmd["reason"], bool(cmd["valid"]),
+                                                                        cmd["n_options"]), (take, off, p.mid)
+                assert p.mask.tolist() == cmd["mask"].tolist() and p.spot_required == bool(cmd["spot_required"])
+                assert (p.result.n_claims, p.result.n_unscheduled) == (out.n_claims, out.n_unscheduled)
+                if p.decision == capi.CMD_REPLACE:
+                    invalid_replace += not p.valid
+                    filtered += p.n_options < int(p.result.claim_n_options[0])
+        finally:
+            gpu_ctx.release_catalog(cid)
+    assert filtered > 0 and invalid_replace > 0, "filterOutSameInstanceType was not exercised"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("tool,ok", [("memcheck", "ERROR SUMMARY: 0 errors"), ("racecheck", "RACECHECK SUMMARY: 0 hazards")])
 def test_solve_is_sanitizer_clean(tool, ok):
     """The pack kernel is one CTA of sixteen warps in different roles that meet at CTA barriers: a warp that takes a
