@@ -21,6 +21,7 @@ MAX_KEYS, MAX_RES, MAX_TEMPLATES, MAX_BOUNDED = 16, 8, 16, 4
 PRICE_NONE = 0x7FEFFFFFFFFFFFFF
 FIT_NONE, FIT_TAINT, FIT_INCOMPATIBLE, FIT_LIMITS, FIT_DROPPED, FIT_FILTER = 0x00, 0x01, 0x02, 0x03, 0x7F, 0x80
 PLACE_UNSCHEDULED, PLACE_NODE, PLACE_CLAIM = -1, 0, 1
+RF_DEFINED, RF_COMPLEMENT, RF_HASGT, RF_HASLT = 1, 2, 4, 8  # per-key nibble of a requirement flags word
 CMD_NONE, CMD_DELETE, CMD_REPLACE = 0, 1, 2
 WHY_OK, WHY_UNSCHEDULABLE, WHY_MANY_CLAIMS, WHY_NOT_CHEAPER, WHY_S2S_DISABLED, WHY_S2S_TOO_FEW = 0, 1, 2, 3, 4, 5
 S2S_MIN_TYPES = 15

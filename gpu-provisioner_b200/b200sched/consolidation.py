@@ -82,14 +82,20 @@ class Probe:
 
 
 def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: np.ndarray, candidates: Sequence[int],
-                      mids: Sequence[int], ct_values: Tuple[int, int, int, int], spot_to_spot: bool = False) -> List[Probe]:
+                      mids: Sequence[int], ct_values: Tuple[int, int, int, int], spot_to_spot: bool = False,
+                      timing: Optional[dict] = None) -> List[Probe]:
     """computeConsolidation + filterOutSameInstanceType for the prefixes `mids`, as one batch.
-    ct_values = (model key of the capacity type, model value ids of spot, on-demand, reserved or -1)."""
+    ct_values = (model key of the capacity type, model value ids of spot, on-demand, reserved or -1).
+    timing, when given, receives the wall seconds of the host flattening ("encode_s") and of the library calls
+    ("device_calls_s": host buffers in, results out)."""
+    import time
     mids = list(mids)
     if not mids:
         return []
+    t0 = time.perf_counter()
     facts = node_facts(model, candidates)
     encs = [capi.Encoded(prefix_simulation(model, node_of_pod, candidates, mid)) for mid in mids]
+    t1 = time.perf_counter()
     enc0 = encs[0]
     key, v_spot, v_od, v_res = ct_values
     bit_spot, bit_od, bit_res = (enc0.value_bit(key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res))
@@ -134,6 +140,9 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
         for j, i in enumerate(again):
             valid[i] = second["decision"][j] == capi.CMD_REPLACE  # something is left (:146)
             masks[i], n_opts[i] = second["mask"][j], second["n_options"][j]
+    if timing is not None:
+        timing["encode_s"] = t1 - t0
+        timing["device_calls_s"] = time.perf_counter() - t1
     return [Probe(mid=mids[i], decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]), valid=bool(valid[i]),
                   n_options=int(n_opts[i]), mask=masks[i], spot_required=bool(cmds["spot_required"][i]), result=raws[i])
             for i in range(len(mids))]
@@ -162,12 +171,13 @@ def replay_search(lo: int, hi: int, valid_of) -> Optional[int]:
 
 def first_n_consolidation_option(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: np.ndarray,
                                  candidates: Sequence[int], ct_values: Tuple[int, int, int, int],
-                                 max_parallel: int = MAX_PARALLEL, spot_to_spot: bool = False) -> Optional[Probe]:
+                                 max_parallel: int = MAX_PARALLEL, spot_to_spot: bool = False,
+                                 timing: Optional[dict] = None) -> Optional[Probe]:
     """firstNConsolidationOption: candidates are already in disruption-cost order and capped by the budgets."""
     if len(candidates) < 2:
         return None
     lo, hi = search_bounds(len(candidates), min(max_parallel, len(candidates)))
-    probes = multi_node_probes(ctx, cid, model, node_of_pod, candidates, range(lo, hi + 1), ct_values, spot_to_spot)
+    probes = multi_node_probes(ctx, cid, model, node_of_pod, candidates, range(lo, hi + 1), ct_values, spot_to_spot, timing)
     by_mid = {p.mid: p for p in probes}
     best = replay_search(lo, hi, lambda mid: by_mid[mid].valid)
     return None if best is None else by_mid[best]
