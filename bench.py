@@ -431,7 +431,8 @@ def run_c4(args, rank, world, local):
             "multi_node_search": {"candidates": len(cand100), "prefixes_in_one_batch": len(cand100) - 1,
                                   "removes_first": None if got is None else got.mid + 1,
                                   "decision": None if got is None else ["none", "delete", "replace"][got.decision],
-                                  "host_flatten_s": search_t.get("encode_s"),
+                                  "prefix_models_numpy_s": search_t.get("models_s"),
+                                  "b200s_encode_s": search_t.get("encode_s"),
                                   "library_calls_s": search_t.get("device_calls_s"),
                                   "cpu_sequential_search_s": t_search_cpu, "cpu_probes": len(probed)},
             "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "simulations/s", "cores": 1, "kind": "port",

@@ -86,15 +86,17 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
                       timing: Optional[dict] = None) -> List[Probe]:
     """computeConsolidation + filterOutSameInstanceType for the prefixes `mids`, as one batch.
     ct_values = (model key of the capacity type, model value ids of spot, on-demand, reserved or -1).
-    timing, when given, receives the wall seconds of the host flattening ("encode_s") and of the library calls
-    ("device_calls_s": host buffers in, results out)."""
+    timing, when given, receives the wall seconds of building the prefix models ("models_s"), of b200s_encode
+    ("encode_s") and of the device calls ("device_calls_s": host buffers in, results out)."""
     import time
     mids = list(mids)
     if not mids:
         return []
     t0 = time.perf_counter()
     facts = node_facts(model, candidates)
-    encs = [capi.Encoded(prefix_simulation(model, node_of_pod, candidates, mid)) for mid in mids]
+    sims = [prefix_simulation(model, node_of_pod, candidates, mid) for mid in mids]
+    t_sims = time.perf_counter()
+    encs = [capi.Encoded(m) for m in sims]
     t1 = time.perf_counter()
     enc0 = encs[0]
     key, v_spot, v_od, v_res = ct_values
@@ -141,7 +143,8 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
             valid[i] = second["decision"][j] == capi.CMD_REPLACE  # something is left (:146)
             masks[i], n_opts[i] = second["mask"][j], second["n_options"][j]
     if timing is not None:
-        timing["encode_s"] = t1 - t0
+        timing["models_s"] = t_sims - t0   # numpy row selection of the synthetic model (the cluster-state feed's job)
+        timing["encode_s"] = t1 - t_sims   # b200s_encode of every prefix
         timing["device_calls_s"] = time.perf_counter() - t1
     return [Probe(mid=mids[i], decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]), valid=bool(valid[i]),
                   n_options=int(n_opts[i]), mask=masks[i], spot_required=bool(cmds["spot_required"][i]), result=raws[i])
