@@ -338,12 +338,14 @@ def test_solve_is_sanitizer_clean(tool, ok):
     if not os.path.exists(exe):
         pytest.skip("compute-sanitizer not installed")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for kind, pods, skus in (("c2", 700, 300), ("c3", 700, 200)):
+    for mode, kind, pods, skus in (("solve", "c2", 700, 300), ("solve", "c3", 700, 200), ("consolidate", "c2", 0, 150)):
         out = subprocess.run([exe, "--tool", tool, "--print-limit", "3", sys.executable,
-                              os.path.join(root, "tools", "profile_target.py"), "solve", kind, str(pods), str(skus), "1"],
+                              os.path.join(root, "tools", "profile_target.py"), mode, kind, str(pods), str(skus), "1"],
                              capture_output=True, text=True, timeout=900)
         text = out.stdout + out.stderr
-        assert ok in text, (kind, text[-3000:])
+        assert ok in text, (mode, kind, text[-3000:])
+        if mode == "consolidate":  # the run must have reached the warp-cooperative 15-cheapest selection
+            assert "truncated 0" not in text.split("gate True")[-1], text[-2000:]
 
 
 def test_more_claims_than_the_shared_memory_order_holds(gpu_ctx):

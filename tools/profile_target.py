@@ -1,4 +1,6 @@
-"""Small driver for ncu captures: python tools/profile_target.py {fit|solve} {c2|c3|c5} [pods] [skus] [iters]"""
+"""Small driver for ncu / compute-sanitizer captures:
+  python tools/profile_target.py {fit|solve} {c2|c3|c5} [pods] [skus] [iters]
+  python tools/profile_target.py consolidate c2 [unused] [skus]"""
 import os
 import sys
 
@@ -11,6 +13,36 @@ g.build()
 from b200sched import capi, synth  # noqa: E402
 
 mode, kind = sys.argv[1], sys.argv[2]
+if mode == "consolidate":
+    # a few consolidation simulations on a small catalog and every branch of the command kernel (sanitizer runs)
+    import numpy as np
+    from b200sched import model as M
+    S = int(sys.argv[4]) if len(sys.argv) > 4 else 150
+    b = synth.new_builder()
+    synth.add_catalog(b, S)
+    synth.add_pools(b, "c2")
+    pods = synth.bulk_pods(b, 64, "c2")
+    base = synth.build_model(b, pods)
+    none = np.array([], np.int64)
+    sims = [M.subset(base, np.arange(i, i + n), none) for i, n in ((0, 1), (1, 2), (3, 3), (6, 8), (14, 20), (34, 30))]
+    encs = [capi.Encoded(m) for m in sims]
+    ctx = capi.Context(0)
+    cid = ctx.upload_catalog(encs[0])
+    raws = ctx.solve_batch(cid, encs)
+    key = base.key_names.index(M.KEY_CAPACITY_TYPE)
+    ids = {base.val_names[v]: v for v, k in enumerate(base.arrays["val_key"]) if int(k) == key}
+    spot, od = encs[0].value_bit(key, ids["spot"]), encs[0].value_bit(key, ids["on-demand"])
+    rows, prices, spots, cands = [], [], [], []
+    for r in raws:
+        for price, all_spot, n_cand in ((1e3, True, 1), (1e3, True, 2), (1e3, False, 1), (1e-6, False, 1), (0.4, True, 1)):
+            rows.append(r); prices.append(price); spots.append(all_spot); cands.append(n_cand)
+    for gate in (False, True):
+        c = ctx.consolidation_commands(cid, encs[0], rows, prices, spots, cands, spot, od, -1, gate)
+        print("gate", gate, "decisions", np.bincount(c["decision"], minlength=3).tolist(), "reasons",
+              np.bincount(c["reason"], minlength=6).tolist(), "truncated", int((c["head"][:, 0] >= 0).sum()), flush=True)
+    ctx.release_catalog(cid)
+    ctx.close()
+    sys.exit(0)
 defaults = {"c2": (10_000, 500), "c3": (100_000, 1_000), "c5": (1_000_000, 2_000)}
 P = int(sys.argv[3]) if len(sys.argv) > 3 else defaults[kind][0]
 S = int(sys.argv[4]) if len(sys.argv) > 4 else defaults[kind][1]
