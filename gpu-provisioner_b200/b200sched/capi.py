@@ -25,6 +25,7 @@ RF_DEFINED, RF_COMPLEMENT, RF_HASGT, RF_HASLT = 1, 2, 4, 8  # per-key nibble of 
 CMD_NONE, CMD_DELETE, CMD_REPLACE = 0, 1, 2
 WHY_OK, WHY_UNSCHEDULABLE, WHY_MANY_CLAIMS, WHY_NOT_CHEAPER, WHY_S2S_DISABLED, WHY_S2S_TOO_FEW = 0, 1, 2, 3, 4, 5
 S2S_MIN_TYPES = 15
+MAX_INSTANCE_TYPES = 600  # nodeclaimtemplate.go:41
 OK, EINVAL, ENODEVICE, ECUDA, ENOTREPRESENTABLE, ECAPACITY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
 CREATE_EBADNAME, CREATE_ENOTYPE, CREATE_ENOSTORAGE = -20, -21, -22
 
@@ -155,6 +156,8 @@ def lib():
                                    _P(C.c_uint8), _P(C.c_int64)]
     L.b200s_select_cheapest.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(C.c_uint64), _P(C.c_uint64),
                                         _P(C.c_uint64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int32), _P(C.c_uint64)]
+    L.b200s_order_by_price.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(C.c_uint64), _P(C.c_uint64), _P(C.c_uint64),
+                                       _P(C.c_int64), _P(C.c_int64), C.c_int32, _P(C.c_int32), _P(C.c_int32), _P(C.c_uint8)]
     L.b200s_consolidation_commands.argtypes = [C.c_void_p, C.c_uint64, _P(ConsolidationSims), _P(ConsolidationCmds)]
     L.b200s_solve.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates), _P(SolveOpts),
                               _P(Result)]
@@ -393,6 +396,25 @@ class Context:
                                                  _p(req_flags, C.c_uint64), _p(req_gt, C.c_int64), _p(req_lt, C.c_int64),
                                                  _p(sku, C.c_int32), _p(price, C.c_uint64)))
         return sku[:n], price[:n]
+
+    def order_by_price(self, cid: int, enc: Encoded, raw: SolveRaw, max_types: int = MAX_INSTANCE_TYPES):
+        """ToNodeClaim's instance-type list (nodeclaimtemplate.go:77-82) for every NodeClaim of a Solve result:
+        (order [N, max_types] in price order, -1 padded; count [N]; tie [N])."""
+        n = raw.n_claims
+        n1, K, NB = max(n, 1), max(enc.K, 1), max(enc.NB, 1)
+        masks = np.ascontiguousarray(raw.claim_mask, np.uint64)
+        rm = np.zeros((n1, K), np.uint64)
+        gt = np.zeros((n1, NB), np.int64)
+        lt = np.zeros((n1, NB), np.int64)
+        rm[:n, :enc.K], gt[:n, :enc.NB], lt[:n, :enc.NB] = raw.claim_req_mask, raw.claim_req_gt, raw.claim_req_lt
+        rf = np.ascontiguousarray(raw.claim_req_flags, np.uint64)
+        order = np.full((n1, max_types), -1, np.int32)
+        count = np.zeros(n1, np.int32)
+        tie = np.zeros(n1, np.uint8)
+        self._check(self.L.b200s_order_by_price(self.h, cid, n, _p(masks, C.c_uint64), _p(rm, C.c_uint64), _p(rf, C.c_uint64),
+                                                _p(gt, C.c_int64), _p(lt, C.c_int64), max_types, _p(order, C.c_int32),
+                                                _p(count, C.c_int32), _p(tie, C.c_uint8)))
+        return order[:n], count[:n], tie[:n]
 
     def consolidation_commands(self, cid: int, enc: Encoded, sims: Sequence[SolveRaw], candidate_price: Sequence[float],
                                all_spot: Sequence[bool], n_candidates: Sequence[int], ct_spot: int, ct_on_demand: int,

@@ -809,6 +809,56 @@ int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, cons
   return rc;
 }
 
+int b200s_order_by_price(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, const uint64_t* masks, const uint64_t* req_mask,
+                         const uint64_t* req_flags, const int64_t* req_gt, const int64_t* req_lt, int32_t max_types,
+                         int32_t* order_out, int32_t* count_out, uint8_t* tie_out) {
+  if (!ctx || n < 0 || max_types < 1 || !order_out || !count_out || !tie_out) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  auto it = ctx->catalogs.find(catalog_id);
+  if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
+  Catalog* cat = it->second.get();
+  if (n == 0) return B200S_OK;
+  const size_t N = (size_t)n, K = (size_t)cat->K, NB = (size_t)cat->NB, W = (size_t)cat->W, M = (size_t)max_types;
+  std::vector<void*> held;
+  auto dev = [&](size_t bytes) -> void* {
+    void* p = ctx->alloc(bytes);
+    if (p) held.push_back(p);
+    return p;
+  };
+  auto cleanup = [&]() {
+    for (void* p : held) ctx->release(p);
+  };
+  uint64_t* d_masks = (uint64_t*)dev(N * W * 8);
+  uint64_t* d_rmask = (uint64_t*)dev(N * std::max<size_t>(K, 1) * 8);
+  uint64_t* d_rflags = (uint64_t*)dev(N * 8);
+  int64_t* d_gt = (int64_t*)dev(N * std::max<size_t>(NB, 1) * 8);
+  int64_t* d_lt = (int64_t*)dev(N * std::max<size_t>(NB, 1) * 8);
+  int32_t* d_order = (int32_t*)dev(N * M * 4);
+  int32_t* d_count = (int32_t*)dev(N * 4);
+  uint8_t* d_tie = (uint8_t*)dev(N);
+  if (held.size() != 8) { cleanup(); return fail(ctx, B200S_ENOMEM, "device allocation"); }
+  int rc = upload(ctx, d_masks, masks, N * W);
+  if (!rc && K) rc = upload(ctx, d_rmask, req_mask, N * K);
+  if (!rc) rc = upload(ctx, d_rflags, req_flags, N);
+  if (!rc && NB) rc = upload(ctx, d_gt, req_gt, N * NB);
+  if (!rc && NB) rc = upload(ctx, d_lt, req_lt, N * NB);
+  if (!rc) {
+    cudaError_t e = launch_order_by_price(cat->kt, n, max_types, d_masks, d_rmask, d_rflags, d_gt, d_lt, d_order, d_count,
+                                          d_tie, ctx->smem_limit, ctx->stream);
+    if (e == cudaErrorInvalidConfiguration) rc = fail(ctx, B200S_ENOTREPRESENTABLE, "order_by_price: catalog too large for one CTA's shared memory");
+    else if (e != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "order_by_price launch", e);
+  }
+  auto down = [&](void* dst, const void* src, size_t bytes) {
+    if (!rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "D2H");
+  };
+  down(order_out, d_order, N * M * 4);
+  down(count_out, d_count, N * 4);
+  down(tie_out, d_tie, N);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = fail(ctx, B200S_ECUDA, "sync");
+  cleanup();
+  return rc;
+}
+
 int b200s_consolidation_commands(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_consolidation_sims_t* sims,
                                  b200s_consolidation_cmds_t* out) {
   if (!ctx || !sims || !out || sims->n < 0) return B200S_EINVAL;

@@ -685,6 +685,88 @@ __global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, Consolida
 }
 
 // -------------------------------------------------------------------------------------------------
+// NodeClaimTemplate.ToNodeClaim's instance-type list (nodeclaimtemplate.go:77-82): the whole OrderByPrice(reqs)
+// order of a set, cut at max_types.  One CTA per set: compact the set bits, one key per type, bitonic sort of
+// (price bits, SKU index) pairs in shared memory.
+// -------------------------------------------------------------------------------------------------
+constexpr int ORDER_THREADS = 256;
+
+__global__ void __launch_bounds__(ORDER_THREADS) order_by_price_kernel(KeyTab kt, int n, int n_pad, int max_types,
+                                                                       const uint64_t* __restrict__ masks,
+                                                                       const uint64_t* __restrict__ rmask,
+                                                                       const uint64_t* __restrict__ rflags,
+                                                                       const int64_t* __restrict__ rgt,
+                                                                       const int64_t* __restrict__ rlt,
+                                                                       int32_t* __restrict__ order_out,
+                                                                       int32_t* __restrict__ count_out,
+                                                                       uint8_t* __restrict__ tie_out) {
+  extern __shared__ __align__(16) unsigned char order_smem[];
+  uint64_t* key = (uint64_t*)order_smem;        // [n_pad]
+  int32_t* sku = (int32_t*)(key + n_pad);        // [n_pad]
+  __shared__ int word_off[65];                   // exclusive prefix of the words' popcounts, per 64-word chunk
+  __shared__ int s_count, s_tie;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int W = kt.n_words, K = kt.n_keys, NB = kt.n_bounded;
+  const uint64_t flags = rflags[row];
+  auto allowed_of = [&](int k) -> uint64_t {
+    const int b = kt.bslot[k];
+    EReq q = make_ereq(rmask[(size_t)row * K + k], flags, k, b >= 0 ? rgt[(size_t)row * NB + b] : 0,
+                       b >= 0 ? rlt[(size_t)row * NB + b] : 0);
+    return (q.f & RF_DEF) ? allowed_values(kt, k, q) : ~0ull;
+  };
+  uint64_t za = kt.key_zone >= 0 ? allowed_of(kt.key_zone) : ~0ull;
+  uint64_t ca = kt.key_ct >= 0 ? allowed_of(kt.key_ct) : ~0ull;
+  za &= kt.n_zones >= 64 ? ~0ull : ((1ull << kt.n_zones) - 1ull);
+  ca &= kt.n_cts >= 64 ? ~0ull : ((1ull << kt.n_cts) - 1ull);
+  if (tid == 0) { s_count = 0; s_tie = 0; }
+  for (int i = tid; i < n_pad; i += ORDER_THREADS) { key[i] = ~0ull; sku[i] = 0x7fffffff; }
+  __syncthreads();
+  // compaction, 64 words at a time: thread w of the chunk owns one word
+  for (int w0 = 0; w0 < W; w0 += 64) {
+    const int w = w0 + tid;
+    const uint64_t m = (tid < 64 && w < W) ? masks[(size_t)row * W + w] : 0;
+    if (tid < 64) word_off[tid + 1] = popc64(m);
+    __syncthreads();
+    if (tid == 0) {
+      word_off[0] = s_count;
+      for (int i = 0; i < 64; i++) word_off[i + 1] += word_off[i];
+      s_count = word_off[64];
+    }
+    __syncthreads();
+    if (tid < 64) {
+      int at = word_off[tid];
+      for (uint64_t mm = m; mm; mm &= mm - 1) sku[at++] = (w << 6) + ctz64(mm);
+    }
+    __syncthreads();
+  }
+  const int count = s_count;
+  for (int i = tid; i < count; i += ORDER_THREADS) key[i] = cheapest_price(kt, za, ca, sku[i]);
+  __syncthreads();
+  // bitonic sort, ascending by (price, index); the padding sorts last
+  for (int k = 2; k <= n_pad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < n_pad / 2; t += ORDER_THREADS) {
+        const int i = ((t / j) * 2 * j) + (t % j), l = i + j;
+        const bool up = (i & k) == 0;
+        const uint64_t ka = key[i], kb = key[l];
+        const int sa = sku[i], sb = sku[l];
+        const bool a_gt_b = ka > kb || (ka == kb && sa > sb);
+        if (a_gt_b == up) { key[i] = kb; key[l] = ka; sku[i] = sb; sku[l] = sa; }
+      }
+      __syncthreads();
+    }
+  const int listed = count < max_types ? count : max_types;
+  bool tie = false;
+  for (int i = tid; i < max_types; i += ORDER_THREADS) {
+    order_out[(size_t)row * max_types + i] = i < listed ? sku[i] : -1;
+    if (i < listed && i + 1 < count && key[i] == key[i + 1]) tie = true;  // sort.Slice is not stable: Go's order is its own
+  }
+  if (tie) s_tie = 1;
+  __syncthreads();
+  if (tid == 0) { count_out[row] = listed; tie_out[row] = (uint8_t)s_tie; }
+}
+
+// -------------------------------------------------------------------------------------------------
 // host launchers
 // -------------------------------------------------------------------------------------------------
 static void pick_group(int W, int* G, int* WPL) {
@@ -830,6 +912,26 @@ cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* mask
   int blocks = (int)(((long long)n * 32 + 255) / 256);
   select_cheapest_kernel<<<blocks, 256, 0, stream>>>(kt, n, masks, rmask, rms, rks, rflags, rgt, rlt, bms, bks, sku_out,
                                                      price_out, nopt_out, problems, row_problem);
+  return cudaGetLastError();
+}
+
+int order_by_price_padded(int S) {
+  int p = 2;
+  while (p < S) p <<= 1;
+  return p;
+}
+
+cudaError_t launch_order_by_price(const KeyTab& kt, int n, int max_types, const uint64_t* masks, const uint64_t* rmask,
+                                  const uint64_t* rflags, const int64_t* rgt, const int64_t* rlt, int32_t* order_out,
+                                  int32_t* count_out, uint8_t* tie_out, int smem_limit, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int n_pad = order_by_price_padded(kt.n_skus);
+  const size_t bytes = (size_t)n_pad * 12;
+  if ((long long)bytes > smem_limit - 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e = cudaFuncSetAttribute(order_by_price_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  order_by_price_kernel<<<n, ORDER_THREADS, bytes, stream>>>(kt, n, n_pad, max_types, masks, rmask, rflags, rgt, rlt, order_out,
+                                                             count_out, tie_out);
   return cudaGetLastError();
 }
 

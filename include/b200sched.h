@@ -376,6 +376,19 @@ int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, cons
                           const uint64_t* req_mask, const uint64_t* req_flags, const int64_t* req_gt,
                           const int64_t* req_lt, int32_t* sku_out, uint64_t* price_out);
 
+/* The instance-type list NodeClaimTemplate.ToNodeClaim writes into a NodeClaim
+ * (K/controllers/provisioning/scheduling/nodeclaimtemplate.go:77-82): InstanceTypeOptions.OrderByPrice(reqs)
+ * (types.go:221-240) of each of n SKU sets, cut at max_types (MaxInstanceTypes = 600, nodeclaimtemplate.go:41).
+ * Rows are claim-major as in b200s_result_t: masks [n*W], req_mask [n*K], req_flags [n], req_gt / req_lt [n*NB].
+ * order_out [n*max_types] SKU indices in price order, -1 after count_out[i] entries; tie_out[i] = 1 when two listed
+ * neighbours (or the last listed and the first one cut) share a price -- Go's sort is unstable there, this library
+ * orders equal prices by SKU index. */
+#define B200S_MAX_INSTANCE_TYPES 600
+int b200s_order_by_price(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, const uint64_t* masks,
+                         const uint64_t* req_mask, const uint64_t* req_flags, const int64_t* req_gt,
+                         const int64_t* req_lt, int32_t max_types, int32_t* order_out, int32_t* count_out,
+                         uint8_t* tie_out);
+
 /* Full Solve: stage A, FFD order, pack, finalize, cheapest SKU per NodeClaim. */
 int b200s_solve(b200s_ctx_t* ctx, uint64_t catalog_id, const b200s_pods_soa_t* pods,
                 const b200s_nodes_soa_t* existing, const b200s_templates_t* templates,

@@ -867,8 +867,16 @@ int oracle_version(void) { return 100; }
 static void computeConsolidation(Scheduler& S, int nUnscheduled, const oracle_consolidation_in_t* in,
                                  oracle_consolidation_out_t* o);
 
+struct OrderedOut {
+  int32_t max_types;
+  int32_t* order;
+  int32_t* count;
+  uint8_t* tie;
+};
+
 static int solve_then(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out,
-                      const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout) {
+                      const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout,
+                      const OrderedOut* ordered = nullptr) {
   g_model = M;
   Scheduler S;
   S.M = M;
@@ -1056,6 +1064,20 @@ static int solve_then(const b200s_model_t* M, const oracle_opts_t* opts, oracle_
   out->price_ties = S.C.price_ties;
   out->newclaim_evals = S.C.newclaim_evals;
   out->value_overflow = overflow;
+  if (ordered) {  // ToNodeClaim (nodeclaimtemplate.go:77-82)
+    for (int c = 0; c < nClaims; c++) {
+      NodeClaim* n = S.newNodeClaims[c];
+      std::vector<double> keys;
+      std::vector<const InstanceType*> its = OrderByPrice(n->instanceTypeOptions, n->requirements, S.stableSort, &keys);
+      const int listed = std::min<int>((int)its.size(), ordered->max_types);
+      ordered->count[c] = listed;
+      ordered->tie[c] = 0;
+      for (int i = 0; i < ordered->max_types; i++)
+        ordered->order[(size_t)c * ordered->max_types + i] = i < listed ? its[i]->index : -1;
+      for (int i = 0; i < listed && i + 1 < (int)its.size(); i++)
+        if (keys[i] == keys[i + 1]) ordered->tie[c] = 1;
+    }
+  }
   if (cin && cout) computeConsolidation(S, out->n_unscheduled, cin, cout);
   g_model = nullptr;
   return 0;
@@ -1063,6 +1085,13 @@ static int solve_then(const b200s_model_t* M, const oracle_opts_t* opts, oracle_
 
 int oracle_solve(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out) {
   return solve_then(M, opts, out, nullptr, nullptr);
+}
+
+int oracle_solve_ordered(const b200s_model_t* M, const oracle_opts_t* opts, oracle_result_t* out, int32_t max_types,
+                         int32_t* order_out, int32_t* count_out, uint8_t* tie_out) {
+  if (max_types < 1 || !order_out || !count_out || !tie_out) return B200S_EINVAL;
+  OrderedOut oo{max_types, order_out, count_out, tie_out};
+  return solve_then(M, opts, out, nullptr, nullptr, &oo);
 }
 
 /* SimulateScheduling's Solve followed by computeConsolidation (K/controllers/disruption/consolidation.go:133-307).

@@ -68,6 +68,12 @@ typedef struct oracle_consolidation_out {
 
 int oracle_version(void);
 int oracle_solve(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out);
+/* Solve, then NodeClaimTemplate.ToNodeClaim's instance-type list for every new NodeClaim
+ * (nodeclaimtemplate.go:77-82): OrderByPrice(requirements) cut at max_types.  order_out [cap_claims*max_types]
+ * (-1 padded), count_out / tie_out [cap_claims]; tie = two listed neighbours, or the last listed and the first cut,
+ * have the same price (Go's unstable sort decides their order). */
+int oracle_solve_ordered(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out, int32_t max_types,
+                         int32_t* order_out, int32_t* count_out, uint8_t* tie_out);
 int oracle_consolidate(const b200s_model_t* model, const oracle_opts_t* opts, oracle_result_t* out,
                        const oracle_consolidation_in_t* cin, oracle_consolidation_out_t* cout);
 int oracle_fit_matrix(const b200s_model_t* model, int32_t pod_begin, int32_t pod_end, int32_t* tmpl_out,

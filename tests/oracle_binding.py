@@ -53,6 +53,7 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.oracle_solve.restype = C.c_int
         _lib.oracle_consolidate.restype = C.c_int
+        _lib.oracle_solve_ordered.restype = C.c_int
         _lib.oracle_fit_matrix.restype = C.c_int
         _lib.oracle_go_sort_perm.restype = C.c_int
         _lib.oracle_req_algebra.restype = C.c_int
@@ -135,7 +136,19 @@ def consolidate(model, candidate_price: float, all_spot: bool, n_candidates: int
     return out, cmd
 
 
-def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None, _consolidation=None) -> SolveOut:
+def solve_ordered(model, max_types: int = 600):
+    """Solve + ToNodeClaim's price-ordered instance-type list per new NodeClaim (nodeclaimtemplate.go:77-82);
+    returns (SolveOut, order [N, max_types], count [N], tie [N])."""
+    cap = max(model.n_pods, 1)
+    order = np.full(cap * max_types, -1, np.int32)
+    count = np.zeros(cap, np.int32)
+    tie = np.zeros(cap, np.uint8)
+    out = solve(model, _ordered=(max_types, order, count, tie))
+    N = out.n_claims
+    return out, order.reshape(cap, max_types)[:N], count[:N], tie[:N]
+
+
+def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None, _consolidation=None, _ordered=None) -> SolveOut:
     L = lib()
     P, R, W, K, E = model.n_pods, model.n_res, model.n_words, len(model.key_names), int(model.c.n_nodes)
     cap = cap_claims if cap_claims is not None else max(P, 1)
@@ -158,7 +171,10 @@ def solve(model, stable_sort: bool = False, cap_claims: Optional[int] = None, _c
         setattr(res, k, _p(a, ctypes_of[a.dtype]))
     opts = OracleOpts()
     opts.stable_sort = 1 if stable_sort else 0
-    if _consolidation is None:
+    if _ordered is not None:
+        rc = L.oracle_solve_ordered(C.byref(model.c), C.byref(opts), C.byref(res), C.c_int32(_ordered[0]),
+                                    _p(_ordered[1], C.c_int32), _p(_ordered[2], C.c_int32), _p(_ordered[3], C.c_uint8))
+    elif _consolidation is None:
         rc = L.oracle_solve(C.byref(model.c), C.byref(opts), C.byref(res))
     else:
         rc = L.oracle_consolidate(C.byref(model.c), C.byref(opts), C.byref(res), C.byref(_consolidation[0]),

@@ -203,3 +203,30 @@ def test_candidate_prices_read_the_offering_the_node_labels_name():
         o = a["sku_off_off"][s] + synth.ZONES.index(lab[kz]) * 2 + synth.CAPACITY_TYPES.index(lab[kc])  # add_catalog's order
         assert prices[e] == float(a["off_price"][o]) and spot[e] == (lab[kc] == "spot")
     assert any(spot) and not all(spot)
+
+
+def test_to_nodeclaim_lists_every_claims_types_in_price_order():
+    """ToNodeClaim (nodeclaimtemplate.go:77-82): OrderByPrice(requirements) of each NodeClaim, cut at max_types; the
+    oracle's order against a numpy restatement of the price key on the synthetic catalog."""
+    m = synth.config("c3", 400, 90)
+    out, order, count, tie = ob.solve_ordered(m, 25)
+    assert out.n_claims > 3 and not tie.any()
+    lo, _ = _price_tables(m)
+    kz, kc = m.key_names.index(M.KEY_ZONE), m.key_names.index(M.KEY_CAPACITY_TYPE)
+    bits = m.key_value_bits()
+    zones = {z for (z, _, _) in lo}
+    cts = {c for (_, c, _) in lo}
+    for c in range(out.n_claims):
+        # values of zone / capacity type the claim's merged requirements admit (In sets in this workload, or undefined)
+        def admitted(key, universe):
+            f = int(out.claim_req_flags[c, key])
+            if not f & capi.RF_DEFINED:
+                return set(universe)
+            inside = {v for i, v in enumerate(bits[key]) if (int(out.claim_req_mask[c, key]) >> i) & 1}
+            return (set(universe) - inside) if f & capi.RF_COMPLEMENT else (set(universe) & inside)
+        za, ca = admitted(kz, zones), admitted(kc, cts)
+        options = parity.mask_bits(out.claim_mask[c])
+        price = {s: min([lo.get((z, ct, s), np.inf) for z in za for ct in ca] + [np.inf]) for s in options}
+        want = sorted(options, key=lambda s: (price[s], s))[:25]
+        assert count[c] == len(want) and order[c, :count[c]].tolist() == want
+        assert (order[c, count[c]:] == -1).all()

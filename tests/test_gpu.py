@@ -209,6 +209,29 @@ def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
         gpu_ctx.release_catalog(cid)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,pods,skus", [("c2", 2000, 300), ("c3", 3000, 700), ("c2", 300, 2000)])
+def test_to_nodeclaim_instance_type_lists_match_the_oracle(gpu_ctx, kind, pods, skus):
+    """ToNodeClaim (nodeclaimtemplate.go:77-82): every new NodeClaim's instance types in OrderByPrice order, cut at
+    MaxInstanceTypes and at a small limit -- one CTA per NodeClaim against the oracle's sort.Slice."""
+    model = synth.config(kind, pods, skus)
+    enc = capi.Encoded(model)
+    cid = gpu_ctx.upload_catalog(enc)
+    try:
+        raw = gpu_ctx.solve(cid, enc)
+        for max_types in (capi.MAX_INSTANCE_TYPES, 7):
+            out, order, count, tie = ob.solve_ordered(model, max_types)
+            assert out.n_claims == raw.n_claims and not tie.any()
+            g_order, g_count, g_tie = gpu_ctx.order_by_price(cid, enc, raw, max_types)
+            assert g_count.tolist() == count.tolist() and g_tie.tolist() == tie.tolist()
+            assert (g_order == order).all()
+            assert (g_order[:, 0] == raw.claim_sku).all()  # the head is what Solve already reported
+        g_order, g_count, _ = gpu_ctx.order_by_price(cid, enc, raw, 3)
+        assert g_count.max() <= 3 and (g_order[:, :3] == order[:, :3]).all()
+    finally:
+        gpu_ctx.release_catalog(cid)
+
+
 def _consolidation_cases():
     """(model, [(candidate price or factor of the replacement's cheapest price, all_spot, n_candidates)]) per
     simulation: the hand-decided catalogs of test_consolidation.py and consolidation simulations of config 4."""
