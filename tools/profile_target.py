@@ -40,6 +40,10 @@ if mode == "consolidate":
         c = ctx.consolidation_commands(cid, encs[0], rows, prices, spots, cands, spot, od, -1, gate)
         print("gate", gate, "decisions", np.bincount(c["decision"], minlength=3).tolist(), "reasons",
               np.bincount(c["reason"], minlength=6).tolist(), "truncated", int((c["head"][:, 0] >= 0).sum()), flush=True)
+    for r, e in zip(raws, encs):  # ToNodeClaim's price-ordered lists, cut short and at MaxInstanceTypes
+        for cut in (5, capi.MAX_INSTANCE_TYPES):
+            order, count, tie = ctx.order_by_price(cid, e, r, cut)
+            print("order_by_price", r.n_claims, "claims, cut", cut, "listed", count.tolist(), "ties", int(tie.sum()), flush=True)
     ctx.release_catalog(cid)
     ctx.close()
     sys.exit(0)
