@@ -536,6 +536,13 @@ def main():
     h2d = enc.P * (4 + 4 + 8 + 16) + enc.NS * (enc.K * 8 + 16 + enc.NB * 8) + enc.NQ * enc.R * 8
     d2h = enc.P * (12 + enc.T) + raw.n_claims * (8 + enc.R * 8 + enc.W * 8 + enc.K * 8 + 8 + enc.NB * 16 + 16)
     cpu_ms = 1e3 * (t_solve_mt + t_fit_mt)
+    flat_ms = None
+    if rank == 0:  # the device algorithm itself (class tables, bit rows, threshold rule) on one host thread
+        parity.emul_solve(enc)
+        t0 = time.perf_counter()
+        flat = parity.emul_solve(enc)
+        flat_ms = 1e3 * (time.perf_counter() - t0)
+        assert flat.n_claims == raw.n_claims
     steps_total = (args.steps + args.warmup)
     line = {
         "metric": METRIC, "value": world * credited / (ms_solve * 1e-3), "unit": "evals/s", "n_gpus": world,
@@ -564,6 +571,10 @@ def main():
                                    "host threads", "ms": cpu_ms,
                          "solve_ms": 1e3 * t_solve_mt, "dense_ms": 1e3 * t_fit_mt, "dense_ms_one_thread": 1e3 * t_fit_cpu,
                          "nodeclaims_per_s_solve_only": o.n_claims / t_solve_mt,
+                         "flat_port_ms": flat_ms,
+                         "flat_port_note": "flat_port_ms is the whole step (dense stage + pack) of this library's own "
+                                           "algorithm compiled for the host (tests/native/emul.cpp, g++ -O2, one "
+                                           "thread): the best-effort CPU form, not the reference's shape",
                          "note": "solve_ms is the reference-shaped Solve alone (fresh-claim rows evaluated lazily, "
                                  "as scheduler.go does); the metric also credits the full dense pass, which the "
                                  "reference never runs", "host_cores": os.cpu_count()},
