@@ -232,6 +232,44 @@ def test_to_nodeclaim_instance_type_lists_match_the_oracle(gpu_ctx, kind, pods, 
         gpu_ctx.release_catalog(cid)
 
 
+@pytest.mark.gpu
+def test_consolidation_and_order_entry_points_reject_what_they_cannot_decide(gpu_ctx):
+    """Error behaviour of the two widened entry points: a code, never a guess."""
+    import test_consolidation as tc
+    b = tc._builder()
+    b.add_pod([], [2000, tc.GiB, 1])
+    m = b.build()
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    try:
+        raw = gpu_ctx.solve(cid, enc)
+        key, spot, od, _ = parity.capacity_type_values(m)
+        bs, bo = enc.value_bit(key, spot), enc.value_bit(key, od)
+        ok = gpu_ctx.consolidation_commands(cid, enc, [raw], [0.25], [False], [1], bs, bo)
+        assert ok["decision"].tolist() == [capi.CMD_REPLACE]
+        assert gpu_ctx.consolidation_commands(cid, enc, [], [], [], [], bs, bo)["decision"].shape == (0,)
+        for kwargs, code in ((dict(price=[-1.0]), capi.EINVAL), (dict(price=[float("nan")]), capi.EINVAL),
+                             (dict(price=[float("inf")]), capi.EINVAL), (dict(spot=-1), capi.ENOTREPRESENTABLE),
+                             (dict(spot=bo), capi.ENOTREPRESENTABLE), (dict(od=7), capi.ENOTREPRESENTABLE)):
+            with pytest.raises(capi.B200SError) as e:
+                gpu_ctx.consolidation_commands(cid, enc, [raw], kwargs.get("price", [0.25]), [False], [1],
+                                               kwargs.get("spot", bs), kwargs.get("od", bo))
+            assert e.value.code == code, kwargs
+        # a candidate price of exactly MaxFloat64 is finite: every type with a compatible offering is "cheaper"
+        top = gpu_ctx.consolidation_commands(cid, enc, [raw], [1.7976931348623157e308], [False], [1], bs, bo)
+        assert top["n_options"].tolist() == [3]
+        with pytest.raises(capi.B200SError) as e:
+            gpu_ctx.order_by_price(cid, enc, raw, 0)
+        assert e.value.code == capi.EINVAL
+        order, count, tie = gpu_ctx.order_by_price(cid, enc, raw, 2)
+        assert order.tolist() == [[m.sku_names.index("a"), m.sku_names.index("b")]] and count.tolist() == [2]
+        with pytest.raises(capi.B200SError) as e:
+            gpu_ctx.consolidation_commands(cid + 99, enc, [raw], [0.25], [False], [1], bs, bo)
+        assert e.value.code == capi.ESTATE
+    finally:
+        gpu_ctx.release_catalog(cid)
+
+
 def _consolidation_cases():
     """(model, [(candidate price or factor of the replacement's cheapest price, all_spot, n_candidates)]) per
     simulation: the hand-decided catalogs of test_consolidation.py and consolidation simulations of config 4."""
