@@ -329,9 +329,12 @@ def run_c4(args, rank, world, local):
     g.build()
     import oracle_binding as ob
     import parity
-    from b200sched import capi, model as M, synth
-    if rank != 0:
-        return
+    from b200sched import capi, model as M, sharding, synth
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:  # simulations are independent: dealt round-robin to the ranks, five words per simulation all-gathered
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P, S, B = args.pods or 50_000, args.skus or 500, args.batch
     ctx = capi.Context(local)
     t0 = time.perf_counter()
@@ -351,33 +354,67 @@ def run_c4(args, rank, world, local):
 
     model, node_of_pod, util = synth.c4(P, S, solve=device_solve)
     E = int(model.c.n_nodes)
-    sims = synth.c4_simulations(model, node_of_pod, util, B)
+    all_sims = synth.c4_simulations(model, node_of_pod, util, B)
+    mine = sharding.deal(B, rank, world)            # every rank builds the same cluster and takes its share
+    sims = [all_sims[int(j)] for j in mine]
+    Bm = len(sims)
     encs = [capi.Encoded(m) for _, m in sims]
-    sample = list(range(0, B, max(B // 32, 1)))[:32]  # every 8th simulation: parity check and the CPU arm's timing
+    sample = list(range(0, Bm, max(Bm // 32, 1)))[:32]  # a spread of this rank's simulations: parity check, CPU timing
     t_build = time.perf_counter() - t0
     cid = ctx.upload_catalog(encs[0])
     # parity of a sample of simulations against the oracle, and the reference arm's time on the same sample
-    t0 = time.perf_counter()
-    oracle_out = [ob.solve(sims[j][1]) for j in sample]
-    t_cpu = (time.perf_counter() - t0) / len(oracle_out)
+    oracle_out, t_cpu = [], 0.0
+    if rank == 0:
+        t0 = time.perf_counter()
+        oracle_out = [ob.solve(sims[j][1]) for j in sample]
+        t_cpu = (time.perf_counter() - t0) / len(oracle_out)
     # what computeConsolidation needs besides the Solve results: the candidates' price and capacity type
     cand_price, cand_spot = synth.candidate_prices(model, [i for i, _ in sims])
     ct_key, v_spot, v_od, v_res = parity.capacity_type_values(model)
     ct_bits = [encs[0].value_bit(ct_key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res)]
 
+    rows = sharding.dealt_rows(B, world)
+    d_mine = torch.zeros((rows, 5), dtype=torch.int32, device="cuda")
+    d_all = torch.zeros((world * rows, 5), dtype=torch.int32, device="cuda")
+
     def step():
         outs = ctx.solve_batch(cid, encs)
-        cmds = ctx.consolidation_commands(cid, encs[0], outs, cand_price, cand_spot, [1] * B, ct_bits[0], ct_bits[1],
+        cmds = ctx.consolidation_commands(cid, encs[0], outs, cand_price, cand_spot, [1] * Bm, ct_bits[0], ct_bits[1],
                                           ct_bits[2], spot_to_spot=True)
-        return outs, cmds
+        table = None
+        if world > 1:  # decision, reason, options, new NodeClaims, unschedulable pods of every simulation, to every rank
+            mine_rows = np.stack([cmds["decision"], cmds["reason"], cmds["n_options"],
+                                  np.array([r.n_claims for r in outs], np.int32),
+                                  np.array([r.n_unscheduled for r in outs], np.int32)], axis=1).astype(np.int32)
+            d_mine[:Bm].copy_(torch.from_numpy(mine_rows), non_blocking=False)
+            dist.all_gather_into_tensor(d_all, d_mine)
+            table = sharding.undeal(d_all.cpu().numpy().reshape(world, rows, 5), B, world)
+        return outs, cmds, table
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        outs, cmds = step()
+        outs, cmds, table = step()
+    barrier()
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            outs, cmds = step()
+            outs, cmds, table = step()
+        barrier()
         ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            ctx.close()
+            return
+        deleted_all = int((table[:, 0] == capi.CMD_DELETE).sum())
     for j in sample:
         i, m = sims[j]
         want = ob.consolidate(m, cand_price[j], cand_spot[j], 1, v_spot, v_od, v_res, True)[1]
@@ -388,9 +425,10 @@ def run_c4(args, rank, world, local):
     for j, o in zip(sample, oracle_out):
         parity.assert_same(parity.canon_device(encs[j], outs[j]), parity.canon_oracle(sims[j][1], o),
                            f"c4 simulation of node {sims[j][0]}")
-    removable = sum(1 for r in outs if r.n_claims == 0 and r.n_unscheduled == 0)
+    removable = (int(((table[:, 3] == 0) & (table[:, 4] == 0)).sum()) if world > 1 else
+                 sum(1 for r in outs if r.n_claims == 0 and r.n_unscheduled == 0))
     # multi-node re-pack: every pod of the candidates at once against the remaining nodes
-    cand = np.array([i for i, _ in sims])
+    cand = np.array([i for i, _ in all_sims])
     keep_nodes = np.setdiff1d(np.arange(E), cand)
     pods = np.nonzero(np.isin(node_of_pod, cand))[0]
     multi = M.subset(model, pods, keep_nodes)
@@ -415,13 +453,18 @@ def run_c4(args, rank, world, local):
         w = probed[want_mid][1]
         assert (got.decision, got.n_options, got.mask.tolist()) == (w["decision"], w["n_options"], w["mask"].tolist())
     evals_cpu = sum(o.counters["fit_evals"] for o in oracle_out) / len(oracle_out)
-    line = {"metric": "consolidation simulations/s", "value": B / (ms * 1e-3), "unit": "simulations/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": "consolidation simulations/s", "value": B / (ms * 1e-3), "unit": "simulations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
             "config": {"workload": f"config[3]: {P} running pods on {E} loosely packed nodes ({S} SKUs); {B} single-node "
                                    "consolidation simulations per step (lowest utilisation first) through b200s_solve_batch and their commands through "
                                    "b200s_consolidation_commands (host buffers in and out); plus one multi-node re-pack "
-                                   "outside the timed region", "build_s": t_build},
+                                   "outside the timed region", "build_s": t_build,
+                       "multi_gpu": "one process per GPU; the simulations are dealt round-robin to the ranks and the five "
+                                    "result words per simulation all-gathered (NCCL) inside the step; wall time, max over "
+                                    "ranks" if world > 1 else "single GPU"},
+            "commands_all_ranks": {"delete": deleted_all} if world > 1 else None,
             "commands": {"delete": int((cmds["decision"] == capi.CMD_DELETE).sum()),
                          "replace": int((cmds["decision"] == capi.CMD_REPLACE).sum()),
                          "none": int((cmds["decision"] == capi.CMD_NONE).sum())},

@@ -3,7 +3,8 @@
 The pod x SKU matrix shards by pod rows: rows are independent, the catalog tables are replicated, and the only
 collective is ONE all-gather of the result rows (first feasible template, SKU mask, attempt codes) when a single
 pack has to see them all.  The pack itself does not shard (each placement depends on every earlier one): across
-GPUs it scales over independent Solves only ("replicas only").
+GPUs it scales over independent Solves only ("replicas only") -- e.g. the consolidation simulations of config 4,
+dealt round-robin to the ranks, their few result words per simulation all-gathered (`deal`, `undeal`).
 """
 from __future__ import annotations
 
@@ -34,3 +35,23 @@ def unpad_gathered(g: np.ndarray, n_rows: int, world: int) -> np.ndarray:
         lo, hi = row_shard(n_rows, rank, world)
         parts.append(g[rank, :hi - lo])
     return np.concatenate(parts, axis=0)
+
+
+def deal(n_items: int, rank: int, world: int) -> np.ndarray:
+    """Round-robin share of rank: items rank, rank + world, ... (simulations are ordered cheapest first, so dealing
+    keeps every rank's share representative)."""
+    return np.arange(rank, n_items, world, dtype=np.int64)
+
+
+def dealt_rows(n_items: int, world: int) -> int:
+    """rows every rank pads its share to for an equal-sized all-gather"""
+    return (n_items + world - 1) // world
+
+
+def undeal(g: np.ndarray, n_items: int, world: int) -> np.ndarray:
+    """g: [world, dealt_rows, ...] gathered shares -> [n_items, ...] in item order."""
+    out = np.zeros((n_items,) + g.shape[2:], g.dtype)
+    for rank in range(world):
+        idx = deal(n_items, rank, world)
+        out[idx] = g[rank, :len(idx)]
+    return out

@@ -62,3 +62,60 @@ def test_sharded_dense_stage_with_gloo_allgather(tmp_path):
     s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(os.path.join(str(tmp_path), "ok")).read() == "1"
+
+
+def _worker_deal(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "gpu-provisioner_b200"))
+    import oracle_binding as ob
+    import parity
+    from b200sched import sharding, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model, node_of_pod, util = synth.c4(1200, 100, solve=ob.solve)
+    sims = synth.c4_simulations(model, node_of_pod, util, 11)      # odd count: unequal shares
+    prices, spot = synth.candidate_prices(model, [i for i, _ in sims])
+    _, v_spot, v_od, v_res = parity.capacity_type_values(model)
+
+    def command(j):  # the CPU oracle stands in for solve_batch + consolidation_commands
+        out, cmd = ob.consolidate(sims[j][1], prices[j], spot[j], 1, v_spot, v_od, v_res, True)
+        return [cmd["decision"], cmd["reason"], cmd["n_options"], out.n_claims, out.n_unscheduled]
+
+    mine = sharding.deal(len(sims), rank, world)
+    rows = sharding.dealt_rows(len(sims), world)
+    t = torch.from_numpy(sharding.pad_rows(np.array([command(int(j)) for j in mine], np.int64).reshape(-1, 5), rows))
+    g = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    got = sharding.undeal(torch.stack(g).numpy(), len(sims), world)
+    if rank == 0:
+        want = np.array([command(j) for j in range(len(sims))], np.int64)
+        open(os.path.join(out_dir, "ok"), "w").write("1" if np.array_equal(got, want) else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_deal_is_a_partition():
+    from b200sched import sharding
+    for n in (0, 1, 2, 7, 256, 257):
+        for world in (1, 2, 3, 8):
+            shares = [sharding.deal(n, r, world) for r in range(world)]
+            assert sorted(np.concatenate(shares).tolist()) == list(range(n))
+            assert max(len(s) for s in shares) <= sharding.dealt_rows(n, world) if n else True
+            g = np.zeros((world, max(sharding.dealt_rows(n, world), 1), 2), np.int64)
+            for r, idx in enumerate(shares):
+                g[r, :len(idx), 0] = idx
+                g[r, :len(idx), 1] = idx * 3
+            back = sharding.undeal(g, n, world)
+            assert back[:, 0].tolist() == list(range(n)) and back[:, 1].tolist() == [3 * i for i in range(n)]
+
+
+def test_consolidation_simulations_dealt_across_ranks_with_gloo(tmp_path):
+    """config 4 at N > 1: simulations are independent, so ranks take them round-robin and all-gather five words per
+    simulation.  bench.py --workload c4 --gpus N is the same flow with the device path per rank and NCCL."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_deal, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(os.path.join(str(tmp_path), "ok")).read() == "1"
