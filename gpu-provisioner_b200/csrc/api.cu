@@ -925,7 +925,7 @@ int b200s_consolidation_commands(b200s_ctx_t* ctx, uint64_t catalog_id, const b2
   if (!rc && NB) rc = upload(ctx, d_gt, sims->claim_req_gt, N * NB);
   if (!rc && NB) rc = upload(ctx, d_lt, sims->claim_req_lt, N * NB);
   if (!rc) {
-    cudaError_t e = launch_consolidation(kt, a, ctx->stream);
+    cudaError_t e = launch_consolidation(kt, a, ctx->smem_limit, ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "consolidation launch", e);
   }
   auto down = [&](void* dst, const void* src, size_t bytes) {

@@ -576,7 +576,8 @@ __device__ __forceinline__ uint64_t worst_launch_price(const KeyTab& kt, uint64_
   return B200S_PRICE_NONE;
 }
 
-__global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, ConsolidationArgs a) {
+__global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, ConsolidationArgs a, int key_cap) {
+  extern __shared__ __align__(16) unsigned char cons_smem[];  // key_cap price keys per warp, indexed by SKU (0: none)
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= a.n) return;
@@ -637,13 +638,23 @@ __global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, Consolida
           uint64_t last_p = 0, my_p = 0;
           int last_s = -1, my_s = -1;
           const int rounds = count > B200S_S2S_MIN_TYPES ? B200S_S2S_MIN_TYPES + 1 : B200S_S2S_MIN_TYPES;
+          // every round looks at every survivor's key: computed once into this warp's slice of shared memory when the
+          // catalog fits (a lane only ever reads the keys of its own words, so no warp synchronisation is involved)
+          uint64_t* keys = (uint64_t*)cons_smem + (size_t)(threadIdx.x >> 5) * key_cap;
+          const bool cached = key_cap >= W * 64;
+          if (cached)
+            for (int w = lane; w < W; w += 32)
+              for (uint64_t m = out_mask[w]; m; m &= m - 1) {
+                const int s = (w << 6) + ctz64(m);
+                keys[s] = cheapest_price(kt, za, ca, s);
+              }
           for (int rd = 0; rd < rounds; rd++) {
             uint64_t best_p = ~0ull;
             int best_s = -1;
             for (int w = lane; w < W; w += 32)
               for (uint64_t m = out_mask[w]; m; m &= m - 1) {
                 const int s = (w << 6) + ctz64(m);
-                const uint64_t p = cheapest_price(kt, za, ca, s);
+                const uint64_t p = cached ? keys[s] : cheapest_price(kt, za, ca, s);
                 const bool above = rd == 0 || p > last_p || (p == last_p && s > last_s);
                 if (above && (p < best_p || (p == best_p && s < best_s))) { best_p = p; best_s = s; }
               }
@@ -935,10 +946,15 @@ cudaError_t launch_order_by_price(const KeyTab& kt, int n, int max_types, const 
   return cudaGetLastError();
 }
 
-cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, cudaStream_t stream) {
+cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, int smem_limit, cudaStream_t stream) {
   if (a.n <= 0) return cudaSuccess;
   const int blocks = (a.n * 32 + 255) / 256;
-  consolidation_kernel<<<blocks, 256, 0, stream>>>(kt, a);
+  int key_cap = kt.n_words * 64;  // per warp; 8 warps per CTA
+  size_t bytes = (size_t)key_cap * 8 * 8;
+  if ((long long)bytes > smem_limit - 2048) { key_cap = 0; bytes = 0; }  // large catalog: keys recomputed per round
+  cudaError_t e = cudaFuncSetAttribute(consolidation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  consolidation_kernel<<<blocks, 256, bytes, stream>>>(kt, a, key_cap);
   return cudaGetLastError();
 }
 

@@ -80,7 +80,7 @@ struct ConsolidationArgs {
   uint64_t* mask;
   uint8_t *spot_required, *price_tie;
 };
-cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, cudaStream_t stream);
+cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, int smem_limit, cudaStream_t stream);
 // whole OrderByPrice order per set, claim-major rows (rmask [n*K], rgt/rlt [n*NB]); order_out [n*max_types]
 cudaError_t launch_order_by_price(const KeyTab& kt, int n, int max_types, const uint64_t* masks, const uint64_t* rmask,
                                   const uint64_t* rflags, const int64_t* rgt, const int64_t* rlt, int32_t* order_out,
