@@ -230,3 +230,103 @@ def test_to_nodeclaim_lists_every_claims_types_in_price_order():
         want = sorted(options, key=lambda s: (price[s], s))[:25]
         assert count[c] == len(want) and order[c, :count[c]].tolist() == want
         assert (order[c, count[c]:] == -1).all()
+
+
+# ---- a second, independent restatement of computeConsolidation in plain Python, for fuzzing the oracle ----------
+def _admitted(model, out, c, key, universe):
+    bits = model.key_value_bits()
+    f = int(out.claim_req_flags[c, key])
+    if not f & capi.RF_DEFINED:
+        return set(universe)
+    inside = {v for i, v in enumerate(bits[key]) if (int(out.claim_req_mask[c, key]) >> i) & 1}
+    return (set(universe) - inside) if f & capi.RF_COMPLEMENT else (set(universe) & inside)
+
+
+def _py_consolidate(model, out, price, all_spot, n_cand, gate):
+    """consolidation.go:133-307 on an oracle Solve result, written from the Go text without looking at the C++"""
+    _, spot, od, _ = parity.capacity_type_values(model)
+    if out.n_unscheduled:
+        return ("none", "unschedulable", [])
+    if out.n_claims == 0:
+        return ("delete", "", [])
+    if out.n_claims != 1:
+        return ("none", "many", [])
+    lo, hi = _price_tables(model)
+    kz, kc = model.key_names.index(M.KEY_ZONE), model.key_names.index(M.KEY_CAPACITY_TYPE)
+    zones = {v for v, k in enumerate(model.arrays["val_key"]) if int(k) == kz}
+    cts = {v for v, k in enumerate(model.arrays["val_key"]) if int(k) == kc}
+    za, ca = _admitted(model, out, 0, kz, zones), _admitted(model, out, 0, kc, cts)
+    options = parity.mask_bits(out.claim_mask[0])
+    order_key = {s: min([lo.get((z, c, s), np.inf) for z in za for c in ca] + [np.inf]) for s in options}
+    options = sorted(options, key=lambda s: (order_key[s], s))
+
+    def worst(s, allowed_cts):
+        for ct in (spot, od):  # reserved does not exist in these catalogs: spot comes before on-demand
+            if ct in allowed_cts:
+                ps = [hi[(z, ct, s)] for z in za if (z, ct, s) in hi]
+                if ps:
+                    return max(ps)
+        return np.inf
+
+    s2s = all_spot and spot in ca
+    if s2s and not gate:
+        return ("none", "s2s-disabled", [])
+    allowed = {spot} if s2s else ca
+    keep = [s for s in options if worst(s, allowed) < price]
+    if not keep:
+        return ("none", "not-cheaper", [])
+    if s2s and n_cand == 1:
+        if len(keep) < 15:
+            return ("none", "s2s-too-few", [])
+        keep = keep[:15]
+    return ("replace", "spot" if (s2s or (spot in ca and od in ca)) else "", keep)
+
+
+def test_fuzzed_catalogs_agree_with_the_python_restatement():
+    rng = np.random.default_rng(2024)
+    names = {capi.CMD_NONE: "none", capi.CMD_DELETE: "delete", capi.CMD_REPLACE: "replace"}
+    why = {capi.WHY_UNSCHEDULABLE: "unschedulable", capi.WHY_MANY_CLAIMS: "many", capi.WHY_NOT_CHEAPER: "not-cheaper",
+           capi.WHY_S2S_DISABLED: "s2s-disabled", capi.WHY_S2S_TOO_FEW: "s2s-too-few", capi.WHY_OK: ""}
+    seen = set()
+    for trial in range(160):
+        n_sku = int(rng.integers(3, 40))
+        zones = ["z1", "z2", "z3"][:int(rng.integers(1, 4))]
+        b = M.ModelBuilder(RES)
+        prices = rng.permutation(n_sku * len(zones) * 2) + 1  # distinct prices: no sort ties
+        pi = 0
+        for s in range(n_sku):
+            offs = []
+            for z in zones:
+                for ct in ("spot", "on-demand"):
+                    if rng.random() < 0.85:
+                        offs.append(([(M.KEY_ZONE, M.OP_IN, [z]), (M.KEY_CAPACITY_TYPE, M.OP_IN, [ct])],
+                                     float(prices[pi]) / 100.0, bool(rng.random() < 0.8)))  # all distinct
+                    pi += 1
+            cpu = int(rng.choice([2000, 4000, 8000, 16000]))
+            b.add_sku(f"s{s:02d}", [(M.KEY_ARCH, M.OP_IN, ["amd64"]), (M.KEY_ZONE, M.OP_IN, zones),
+                                    (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot", "on-demand"])],
+                      [cpu, 64 * GiB, 100], [cpu, 64 * GiB, 100], offs)
+        pool = [[], [(M.KEY_CAPACITY_TYPE, M.OP_IN, ["on-demand"])], [(M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot"])],
+                [(M.KEY_CAPACITY_TYPE, M.OP_NOTIN, ["spot"])], [(M.KEY_CAPACITY_TYPE, M.OP_EXISTS, [])],
+                [(M.KEY_ZONE, M.OP_NOTIN, [zones[0]])]][int(rng.integers(0, 6))]
+        b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])] + pool)
+        for _ in range(int(rng.integers(1, 4))):
+            reqs = [(M.KEY_ZONE, M.OP_IN, [str(rng.choice(zones))])] if rng.random() < 0.3 else []
+            b.add_pod(reqs, [int(rng.choice([500, 1500, 3000, 9000, 20000])), GiB, 1])
+        if rng.random() < 0.2:  # a node with room: some simulations need no new NodeClaim at all
+            b.add_node("n1", {M.KEY_ZONE: zones[0], M.KEY_CAPACITY_TYPE: "on-demand", M.KEY_NODEPOOL: "p",
+                              M.KEY_ARCH: "amd64"}, [int(rng.choice([4000, 64000])), 64 * GiB, 50])
+        m = b.build()
+        _, spot, od, res = parity.capacity_type_values(m)
+        if spot < 0 or od < 0:
+            continue
+        for price, all_spot, n_cand, gate in ((float(rng.choice([0.01, 0.5, 2.0, 50.0])), bool(rng.random() < 0.5),
+                                               int(rng.integers(1, 3)), bool(rng.random() < 0.6)) for _ in range(3)):
+            out, cmd = ob.consolidate(m, price, all_spot, n_cand, spot, od, res, gate)
+            want = _py_consolidate(m, out, price, all_spot, n_cand, gate)
+            got = (names[cmd["decision"]], why[cmd["reason"]] if cmd["decision"] == capi.CMD_NONE else
+                   ("spot" if cmd["spot_required"] else ""), cmd["order"].tolist() if cmd["decision"] == capi.CMD_REPLACE else [])
+            assert got == want, (trial, price, all_spot, n_cand, gate, got, want)
+            seen.add(want[:2])
+    assert {("delete", ""), ("replace", "spot"), ("replace", ""), ("none", "many"), ("none", "not-cheaper"),
+            ("none", "s2s-disabled"), ("none", "unschedulable")} <= seen, seen
