@@ -279,7 +279,21 @@ def _py_consolidate(model, out, price, all_spot, n_cand, gate):
         if len(keep) < 15:
             return ("none", "s2s-too-few", [])
         keep = keep[:15]
-    return ("replace", "spot" if (s2s or (spot in ca and od in ca)) else "", keep)
+    narrowed = s2s or (spot in ca and od in ca)
+    if _py_consolidate.rows is not None:  # filterOutSameInstanceType, multinodeconsolidation.go:172-224
+        cheapest = {}
+        for s, p in _py_consolidate.rows:
+            if p >= 0:
+                cheapest[s] = min(cheapest.get(s, np.inf), p)
+            else:
+                cheapest.setdefault(s, None)
+        limit = min([np.inf] + [(cheapest[s] if cheapest[s] is not None else 0.0) for s in keep if s in cheapest])
+        final_cts = {spot} if narrowed else ca
+        keep = [s for s in keep if worst(s, final_cts) < limit]
+    return ("replace", "spot" if narrowed else "", keep)
+
+
+_py_consolidate.rows = None
 
 
 def test_fuzzed_catalogs_agree_with_the_python_restatement():
@@ -288,6 +302,7 @@ def test_fuzzed_catalogs_agree_with_the_python_restatement():
     why = {capi.WHY_UNSCHEDULABLE: "unschedulable", capi.WHY_MANY_CLAIMS: "many", capi.WHY_NOT_CHEAPER: "not-cheaper",
            capi.WHY_S2S_DISABLED: "s2s-disabled", capi.WHY_S2S_TOO_FEW: "s2s-too-few", capi.WHY_OK: ""}
     seen = set()
+    filtered = emptied = 0
     for trial in range(160):
         n_sku = int(rng.integers(3, 40))
         zones = ["z1", "z2", "z3"][:int(rng.integers(1, 4))]
@@ -322,11 +337,21 @@ def test_fuzzed_catalogs_agree_with_the_python_restatement():
             continue
         for price, all_spot, n_cand, gate in ((float(rng.choice([0.01, 0.5, 2.0, 50.0])), bool(rng.random() < 0.5),
                                                int(rng.integers(1, 3)), bool(rng.random() < 0.6)) for _ in range(3)):
-            out, cmd = ob.consolidate(m, price, all_spot, n_cand, spot, od, res, gate)
+            rows = None
+            if n_cand == 2 and rng.random() < 0.7:  # a multi-node probe: the candidates' types and prices
+                rows = [(int(rng.integers(0, n_sku)), float(rng.choice([-1.0, 0.02, 0.2, 1.0, 5.0]))) for _ in range(2)]
+            out, cmd = ob.consolidate(m, price, all_spot, n_cand, spot, od, res, gate, same_type_rows=rows)
+            _py_consolidate.rows = rows
             want = _py_consolidate(m, out, price, all_spot, n_cand, gate)
+            _py_consolidate.rows = None
             got = (names[cmd["decision"]], why[cmd["reason"]] if cmd["decision"] == capi.CMD_NONE else
                    ("spot" if cmd["spot_required"] else ""), cmd["order"].tolist() if cmd["decision"] == capi.CMD_REPLACE else [])
-            assert got == want, (trial, price, all_spot, n_cand, gate, got, want)
+            assert got == want, (trial, price, all_spot, n_cand, gate, rows, got, want)
+            if rows is not None:  # validDecision (multinodeconsolidation.go:139-150)
+                assert bool(cmd["valid"]) == (want[0] == "delete" or (want[0] == "replace" and len(want[2]) > 0))
+                filtered += want[0] == "replace" and len(want[2]) < len(_py_consolidate(m, out, price, all_spot, n_cand, gate)[2])
+                emptied += want[0] == "replace" and not want[2]
             seen.add(want[:2])
     assert {("delete", ""), ("replace", "spot"), ("replace", ""), ("none", "many"), ("none", "not-cheaper"),
             ("none", "s2s-disabled"), ("none", "unschedulable")} <= seen, seen
+    assert filtered > 3 and emptied > 0, (filtered, emptied)
