@@ -341,6 +341,40 @@ B2_HD EReq make_ereq(uint64_t mask, uint64_t flags_word, int k, int64_t gt, int6
   return q;
 }
 
+// ---- offering prices under a requirement set's admitted zones / capacity types (za, ca: value bit sets) ----------
+// OrderByPrice's key (types.go:221-240): cheapest available offering the requirements admit, MaxFloat64 if none
+B2_HD uint64_t cheapest_price(const KeyTab& kt, uint64_t za, uint64_t ca, int s) {
+  uint64_t p = B200S_PRICE_NONE;
+  for (uint64_t z = za; z; z &= z - 1) {
+    const int zi = ctz64(z);
+    for (uint64_t c = ca; c; c &= c - 1) {
+      uint64_t q = kt.price[(size_t)(zi * kt.n_cts + ctz64(c)) * kt.n_skus + s];
+      p = q < p ? q : p;
+    }
+  }
+  return p;
+}
+
+// Offerings.Available().WorstLaunchPrice(reqs) (types.go:460-474): the most expensive compatible offering of the
+// first capacity type, in the order reserved, spot, on-demand, that has one
+B2_HD uint64_t worst_launch_price(const KeyTab& kt, uint64_t za, uint64_t ca, int ct0, int ct1, int ct2,
+                                                       int s) {
+  const int order[3] = {ct0, ct1, ct2};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int c = order[i];
+    if (c < 0 || !((ca >> c) & 1ull)) continue;
+    uint64_t top = 0;
+    bool any = false;
+    for (uint64_t z = za; z; z &= z - 1) {
+      uint64_t q = kt.price_max[(size_t)(ctz64(z) * kt.n_cts + c) * kt.n_skus + s];
+      if (q != B200S_PRICE_ABSENT) { any = true; top = q > top ? q : top; }
+    }
+    if (any) return top;
+  }
+  return B200S_PRICE_NONE;
+}
+
 // ---- Go sort.Slice on the in-flight NodeClaim order (scheduler.go:499) ---------------------------
 // ord[i] = claim id at position i of s.newNodeClaims, key[i] = len(Pods) of that claim (kept by
 // position so a comparison is two adjacent-array reads).  Exact restatement of pdqsort_func

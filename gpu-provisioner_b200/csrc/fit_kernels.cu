@@ -543,39 +543,6 @@ __global__ void __launch_bounds__(256) select_cheapest_kernel(KeyTab kt, int n, 
 // finished simulations, one warp per simulation.  Prices are compared as IEEE-754 bit patterns (all
 // non-negative and finite, so the integer order is the float order).
 // -------------------------------------------------------------------------------------------------
-// OrderByPrice's key (types.go:221-240): cheapest available offering the requirements admit, MaxFloat64 if none
-__device__ __forceinline__ uint64_t cheapest_price(const KeyTab& kt, uint64_t za, uint64_t ca, int s) {
-  uint64_t p = B200S_PRICE_NONE;
-  for (uint64_t z = za; z; z &= z - 1) {
-    const int zi = ctz64(z);
-    for (uint64_t c = ca; c; c &= c - 1) {
-      uint64_t q = kt.price[(size_t)(zi * kt.n_cts + ctz64(c)) * kt.n_skus + s];
-      p = q < p ? q : p;
-    }
-  }
-  return p;
-}
-
-// Offerings.Available().WorstLaunchPrice(reqs) (types.go:460-474): the most expensive compatible offering of the
-// first capacity type, in the order reserved, spot, on-demand, that has one
-__device__ __forceinline__ uint64_t worst_launch_price(const KeyTab& kt, uint64_t za, uint64_t ca, int ct0, int ct1, int ct2,
-                                                       int s) {
-  const int order[3] = {ct0, ct1, ct2};
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int c = order[i];
-    if (c < 0 || !((ca >> c) & 1ull)) continue;
-    uint64_t top = 0;
-    bool any = false;
-    for (uint64_t z = za; z; z &= z - 1) {
-      uint64_t q = kt.price_max[(size_t)(ctz64(z) * kt.n_cts + c) * kt.n_skus + s];
-      if (q != B200S_PRICE_ABSENT) { any = true; top = q > top ? q : top; }
-    }
-    if (any) return top;
-  }
-  return B200S_PRICE_NONE;
-}
-
 __global__ void __launch_bounds__(256) consolidation_kernel(KeyTab kt, ConsolidationArgs a, int key_cap) {
   extern __shared__ __align__(16) unsigned char cons_smem[];  // key_cap price keys per warp, indexed by SKU (0: none)
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -26,6 +26,7 @@ KeyTab keytab_from(const b200s_catalog_soa_t* c) {
   for (int b = 0; b < c->n_bounded; b++) kt.bslot[c->bounded_key[b]] = (int8_t)b;
   for (int r = 0; r < c->n_res; r++) { kt.res_nd[r] = c->res_nd[r]; kt.res_dv0[r] = c->res_dv0[r]; kt.res_row0[r] = c->res_row0[r]; }
   kt.val_int = c->val_int; kt.rows = c->rows; kt.res_dv = c->res_dv; kt.price = c->price;
+  kt.price_max = c->price_max;
   kt.zc_row0 = c->zc_row0; kt.row_nonneg = c->row_nonneg; kt.n_rows = c->n_rows; kt.n_dv = c->n_dv;
   return kt;
 }
@@ -348,6 +349,16 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
 }
 
 // fit_rank directly and through the log-bucket table the catalog upload builds, on the same queries
+// the two price keys the consolidation and price-order kernels compute per instance type (b200_core.cuh), for every SKU
+void emul_price_keys(const b200s_catalog_soa_t* cat, uint64_t za, uint64_t ca, int32_t ct_reserved, int32_t ct_spot,
+                     int32_t ct_on_demand, uint64_t* cheapest, uint64_t* worst) {
+  KeyTab kt = keytab_from(cat);
+  for (int s = 0; s < kt.n_skus; s++) {
+    cheapest[s] = cheapest_price(kt, za, ca, s);
+    worst[s] = worst_launch_price(kt, za, ca, ct_reserved, ct_spot, ct_on_demand, s);
+  }
+}
+
 void emul_fit_rank_both(const int64_t* dv, int32_t nd, const int64_t* xs, int32_t n, int32_t* plain, int32_t* bucketed) {
   std::vector<uint16_t> row(RANK_BKTS + 1);
   rank_bucket_table(dv, nd, row.data());

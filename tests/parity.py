@@ -71,6 +71,18 @@ def emul_fit_rank_both(dv: np.ndarray, xs: np.ndarray):
     return a, b
 
 
+def emul_price_keys(enc: capi.Encoded, za: int, ca: int, ct_reserved: int, ct_spot: int, ct_on_demand: int):
+    """(cheapest, worst-launch) price bits per SKU under the admitted zone / capacity-type bit sets, from the device
+    header's own functions compiled for the host"""
+    cheapest = np.zeros(enc.S, np.uint64)
+    worst = np.zeros(enc.S, np.uint64)
+    f = emul().emul_price_keys
+    f.restype = None
+    f(enc.catalog, C.c_uint64(za), C.c_uint64(ca), C.c_int32(ct_reserved), C.c_int32(ct_spot), C.c_int32(ct_on_demand),
+      _p(cheapest, C.c_uint64), _p(worst, C.c_uint64))
+    return cheapest, worst
+
+
 def emul_go_sort(cnt: np.ndarray) -> np.ndarray:
     cnt = np.ascontiguousarray(cnt, np.int32)
     ord_ = np.arange(len(cnt), dtype=np.int32)

@@ -355,3 +355,38 @@ def test_fuzzed_catalogs_agree_with_the_python_restatement():
     assert {("delete", ""), ("replace", "spot"), ("replace", ""), ("none", "many"), ("none", "not-cheaper"),
             ("none", "s2s-disabled"), ("none", "unschedulable")} <= seen, seen
     assert filtered > 3 and emptied > 0, (filtered, emptied)
+
+
+def test_device_price_keys_match_the_model():
+    """cheapest_price / worst_launch_price of b200_core.cuh (what the consolidation and price-order kernels evaluate
+    per instance type), compiled for the host, against the offerings of the model for every subset of zones and
+    capacity types."""
+    b = synth.new_builder()
+    synth.add_catalog(b, 90)
+    synth.add_pools(b, "c2")
+    b.add_pod([], [500, GiB, 0, 0, 1])
+    m = b.build()
+    enc = capi.Encoded(m)
+    lo, hi = _price_tables(m)
+    key, spot, od, _ = parity.capacity_type_values(m)
+    kz = m.key_names.index(M.KEY_ZONE)
+    zones = sorted({z for (z, _, _) in lo})
+    zbit = {z: enc.value_bit(kz, z) for z in zones}
+    cbit = {c: enc.value_bit(key, c) for c in (spot, od)}
+    none = np.float64(1.7976931348623157e308).view(np.uint64)
+    for zmask in range(1, 1 << len(zones)):
+        zs = [z for i, z in enumerate(zones) if (zmask >> i) & 1]
+        za = sum(1 << zbit[z] for z in zs)
+        for cs in ([spot], [od], [spot, od]):
+            ca = sum(1 << cbit[c] for c in cs)
+            cheapest, worst = parity.emul_price_keys(enc, za, ca, -1, cbit[spot], cbit[od])
+            for s in range(m.n_skus):
+                want_lo = min([lo[(z, c, s)] for z in zs for c in cs if (z, c, s) in lo] + [np.inf])
+                assert cheapest[s] == (np.float64(want_lo).view(np.uint64) if np.isfinite(want_lo) else none)
+                want_hi = np.inf
+                for c in (spot, od):  # reserved, spot, on-demand: the first capacity type with an offering decides
+                    ps = [hi[(z, c, s)] for z in zs if c in cs and (z, c, s) in hi]
+                    if ps:
+                        want_hi = max(ps)
+                        break
+                assert worst[s] == (np.float64(want_hi).view(np.uint64) if np.isfinite(want_hi) else none), (zs, cs, s)
