@@ -122,7 +122,6 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
                 else:
                     cheapest.setdefault(s, None)
             limit = MAX_FLOAT64
-            W = masks.shape[1]
             for s in cheapest:
                 if (int(masks[i, s // 64]) >> (s % 64)) & 1:
                     p = cheapest[s] if cheapest[s] is not None else 0.0  # Go's map zero value (:203)

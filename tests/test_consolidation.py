@@ -2,7 +2,6 @@
 decide by hand from the Go text, plus an independent numpy restatement of the price rules on the synthetic catalog.
 The device side of the same rows is in test_gpu.py."""
 import numpy as np
-import pytest
 
 import oracle_binding as ob
 import parity
