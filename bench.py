@@ -539,7 +539,9 @@ def main():
     o, of, credited, t_solve_cpu, t_fit_cpu = oracle_counts(model)      # full outputs: the parity gate needs them
     dense_evals = of[3]
     nthreads = host_threads()
-    _, _, _, t_solve_mt, t_fit_mt = oracle_counts(model, nthreads)      # the timed baseline: dense pass on all host threads
+    t_solve_mt = t_fit_mt = 0.0
+    if rank == 0:  # the timed baseline runs alone (the other ranks wait at the barrier below): dense pass on all host threads
+        _, _, _, t_solve_mt, t_fit_mt = oracle_counts(model, nthreads)
 
     # parity gate before any timing
     res.solve()
@@ -578,6 +580,8 @@ def main():
     ab = dense_bytes(enc)
     h2d = enc.P * (4 + 4 + 8 + 16) + enc.NS * (enc.K * 8 + 16 + enc.NB * 8) + enc.NQ * enc.R * 8
     d2h = enc.P * (12 + enc.T) + raw.n_claims * (8 + enc.R * 8 + enc.W * 8 + enc.K * 8 + 8 + enc.NB * 16 + 16)
+    if rank != 0:
+        t_solve_mt = t_fit_mt = float("nan")  # only rank 0 times (and reports) the CPU baseline
     cpu_ms = 1e3 * (t_solve_mt + t_fit_mt)
     flat_ms = None
     if rank == 0:  # the device algorithm itself (class tables, bit rows, threshold rule) on one host thread
