@@ -389,3 +389,33 @@ def test_device_price_keys_match_the_model():
                         want_hi = max(ps)
                         break
                 assert worst[s] == (np.float64(want_hi).view(np.uint64) if np.isfinite(want_hi) else none), (zs, cs, s)
+
+
+def test_several_offerings_in_one_zone_and_capacity_type():
+    """Nothing forbids two offerings with the same zone and capacity type: the cheapest available one prices the type
+    (OrderByPrice), the dearest available one is its worst launch price; unavailable ones count for neither."""
+    b = M.ModelBuilder(RES)
+    cell = lambda ct, price, ok: ([(M.KEY_ZONE, M.OP_IN, ["z1"]), (M.KEY_CAPACITY_TYPE, M.OP_IN, [ct])], price, ok)  # noqa: E731
+    b.add_sku("a", [(M.KEY_ARCH, M.OP_IN, ["amd64"]), (M.KEY_ZONE, M.OP_IN, ["z1"]),
+                    (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot", "on-demand"])], [4000, 64 * GiB, 100], [4000, 64 * GiB, 100],
+              [cell("spot", 0.30, True), cell("spot", 0.10, True), cell("spot", 0.90, False), cell("on-demand", 0.50, True)])
+    b.add_sku("b", [(M.KEY_ARCH, M.OP_IN, ["amd64"]), (M.KEY_ZONE, M.OP_IN, ["z1"]),
+                    (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot", "on-demand"])], [8000, 64 * GiB, 100], [8000, 64 * GiB, 100],
+              [cell("spot", 0.20, True), cell("on-demand", 0.60, True)])
+    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])])
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    # the oracle: a's worst spot launch price is 0.30 (not 0.10, not the unavailable 0.90)
+    _, cmd = _run(m, 0.25)
+    assert _names(m, cmd) == ["b"]
+    _, cmd = _run(m, 0.31)
+    assert _names(m, cmd) == ["a", "b"] and cmd["order"].tolist() == [0, 1]  # ordered by the cheapest: a 0.10, b 0.20
+    # the encoding the device reads
+    enc = capi.Encoded(m)
+    key, spot, od, _ = parity.capacity_type_values(m)
+    bs, bo = enc.value_bit(key, spot), enc.value_bit(key, od)
+    cheapest, worst = parity.emul_price_keys(enc, 1, (1 << bs) | (1 << bo), -1, bs, bo)
+    f = lambda x: np.float64(x).view(np.uint64)  # noqa: E731
+    assert cheapest.tolist() == [f(0.10), f(0.20)] and worst.tolist() == [f(0.30), f(0.20)]
+    cheapest, worst = parity.emul_price_keys(enc, 1, 1 << bo, -1, bs, bo)
+    assert cheapest.tolist() == [f(0.50), f(0.60)] and worst.tolist() == [f(0.50), f(0.60)]
