@@ -419,3 +419,39 @@ def test_several_offerings_in_one_zone_and_capacity_type():
     assert cheapest.tolist() == [f(0.10), f(0.20)] and worst.tolist() == [f(0.30), f(0.20)]
     cheapest, worst = parity.emul_price_keys(enc, 1, 1 << bo, -1, bs, bo)
     assert cheapest.tolist() == [f(0.50), f(0.60)] and worst.tolist() == [f(0.50), f(0.60)]
+
+
+def test_golden_digests_of_the_widened_rows():
+    """tests/golden/widened_digests.json (written by tests/golden/make_golden.py from OUR oracle: a drift guard, not a
+    reference output): ToNodeClaim lists on a config-3-shaped Solve and every probe of a multi-node search."""
+    import hashlib
+    import json
+    import os
+
+    import consolidation_ref as ref
+    from b200sched import consolidation as cons
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "widened_digests.json")))
+
+    def sha(*arrays):
+        h = hashlib.sha256()
+        for a in arrays:
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+
+    g = gold["to_nodeclaim_c3_1500x150"]
+    o, order, count, tie = ob.solve_ordered(synth.config("c3", 1500, 150), 600)
+    assert (int(o.n_claims), int(count.sum()), int(tie.sum())) == (g["n_claims"], g["listed"], g["ties"])
+    assert sha(order.astype(np.int32), count.astype(np.int32)) == g["digest"]
+
+    g = gold["multi_node_search_c4_1500x120_first40"]
+    model, node_of_pod, util = synth.c4(1500, 120, solve=ob.solve)
+    sub, nop = ref.sub_cluster(model, node_of_pod, np.argsort(util, kind="stable")[:40])
+    cand = list(range(40))
+    ctv = parity.capacity_type_values(sub)
+    facts = cons.node_facts(sub, cand)
+    best, _ = ref.first_n_consolidation_option(sub, nop, cand, ctv)
+    assert (None if best is None else best + 1) == g["removes_first"]
+    for mid, decision, reason, valid, n_options, digest in g["probes"]:
+        _, cmd = ref.probe(sub, nop, cand, facts, mid, ctv, False)
+        assert [int(cmd["decision"]), int(cmd["reason"]), int(cmd["valid"]), int(cmd["n_options"]),
+                sha(cmd["mask"].astype(np.uint64))[:16]] == [decision, reason, valid, n_options, digest], mid
