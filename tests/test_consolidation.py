@@ -455,3 +455,33 @@ def test_golden_digests_of_the_widened_rows():
         _, cmd = ref.probe(sub, nop, cand, facts, mid, ctv, False)
         assert [int(cmd["decision"]), int(cmd["reason"]), int(cmd["valid"]), int(cmd["n_options"]),
                 sha(cmd["mask"].astype(np.uint64))[:16]] == [decision, reason, valid, n_options, digest], mid
+
+
+def test_reserved_offerings_come_first_in_the_worst_launch_price():
+    """types.go:464-468: reserved, then spot, then on-demand.  A type with a compatible reserved offering is priced by
+    it alone, however cheap its spot offering is."""
+    b = M.ModelBuilder(RES)
+    off = lambda ct, price: ([(M.KEY_ZONE, M.OP_IN, ["z1"]), (M.KEY_CAPACITY_TYPE, M.OP_IN, [ct])], price, True)  # noqa: E731
+    for name, cpu, offerings in (("a", 4000, [off("spot", 0.10), off("on-demand", 0.30)]),
+                                 ("b", 8000, [off("reserved", 0.40), off("spot", 0.05), off("on-demand", 0.60)]),
+                                 ("c", 16000, [off("reserved", 0.01), off("on-demand", 1.20)])):
+        b.add_sku(name, [(M.KEY_ARCH, M.OP_IN, ["amd64"]), (M.KEY_ZONE, M.OP_IN, ["z1"]),
+                         (M.KEY_CAPACITY_TYPE, M.OP_IN, ["spot", "on-demand", "reserved"])],
+                  [cpu, 64 * GiB, 100], [cpu, 64 * GiB, 100], offerings)
+    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])])
+    b.add_pod([], [2000, GiB, 1])
+    m = b.build()
+    key, spot, od, res = parity.capacity_type_values(m)
+    assert res >= 0
+    out, cmd = ob.consolidate(m, 0.25, False, 1, spot, od, res, False)
+    assert _names(m, cmd) == ["a", "c"]  # b: reserved 0.40 decides, its 0.05 spot offering does not
+    # without telling the oracle which value is "reserved" the precedence is gone: b is then priced by spot
+    _, cmd = ob.consolidate(m, 0.25, False, 1, spot, od, -1, False)
+    assert _names(m, cmd) == ["a", "b"]  # and c has neither spot nor a cheap on-demand offering
+    enc = capi.Encoded(m)
+    bs, bo, br = (enc.value_bit(key, v) for v in (spot, od, res))
+    f = lambda x: np.float64(x).view(np.uint64)  # noqa: E731
+    _, worst = parity.emul_price_keys(enc, 1, (1 << bs) | (1 << bo) | (1 << br), br, bs, bo)
+    assert worst.tolist() == [f(0.10), f(0.40), f(0.01)]
+    _, worst = parity.emul_price_keys(enc, 1, (1 << bs) | (1 << bo), br, bs, bo)  # requirements exclude reserved
+    assert worst.tolist() == [f(0.10), f(0.05), f(1.20)]
