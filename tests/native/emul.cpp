@@ -359,6 +359,14 @@ void emul_price_keys(const b200s_catalog_soa_t* cat, uint64_t za, uint64_t ca, i
   }
 }
 
+// values of key k a requirement row admits, as the kernels compute them (undefined keys admit everything)
+uint64_t emul_allowed_values(const b200s_catalog_soa_t* cat, int32_t k, uint64_t mask, uint64_t flags_word, int64_t gt,
+                             int64_t lt) {
+  KeyTab kt = keytab_from(cat);
+  EReq q = make_ereq(mask, flags_word, k, gt, lt);
+  return (q.f & RF_DEF) ? allowed_values(kt, k, q) : ~0ull;
+}
+
 void emul_fit_rank_both(const int64_t* dv, int32_t nd, const int64_t* xs, int32_t n, int32_t* plain, int32_t* bucketed) {
   std::vector<uint16_t> row(RANK_BKTS + 1);
   rank_bucket_table(dv, nd, row.data());

@@ -485,3 +485,34 @@ def test_reserved_offerings_come_first_in_the_worst_launch_price():
     assert worst.tolist() == [f(0.10), f(0.40), f(0.01)]
     _, worst = parity.emul_price_keys(enc, 1, (1 << bs) | (1 << bo), br, bs, bo)  # requirements exclude reserved
     assert worst.tolist() == [f(0.10), f(0.05), f(1.20)]
+
+
+def test_multi_node_search_driver_on_the_host_stand_in():
+    """b200sched/consolidation.py (all prefixes as one batch, filterOutSameInstanceType as a second command pass, the
+    binary search replayed) driven through tests/fake_device.py -- the device algorithm compiled for the host -- must
+    end where the reference's sequential search over oracle simulations ends, with the same command for every prefix.
+    The same check against the real kernels is tests/test_gpu.py::test_multi_node_consolidation_search_as_one_batch."""
+    import consolidation_ref as ref
+    import fake_device
+    from b200sched import consolidation as cons
+    model, node_of_pod, util = synth.c4(1500, 120, solve=ob.solve)
+    order = np.argsort(util, kind="stable")
+    ctx = fake_device.FakeContext()
+    replaced = 0
+    for take, off in ((24, 0), (30, 40), (2, 0), (1, 0)):
+        sub, nop = ref.sub_cluster(model, node_of_pod, order[off:off + take])
+        cand = list(range(take))
+        ctv = parity.capacity_type_values(sub)
+        want_mid, _ = ref.first_n_consolidation_option(sub, nop, cand, ctv)
+        got = cons.first_n_consolidation_option(ctx, 0, sub, nop, cand, ctv)
+        assert (got.mid if got is not None else None) == want_mid
+        if take < 2:
+            continue
+        lo_, hi_ = cons.search_bounds(take, take)
+        facts = cons.node_facts(sub, cand)
+        for p in cons.multi_node_probes(ctx, 0, sub, nop, cand, range(lo_, hi_ + 1), ctv):
+            _, cmd = ref.probe(sub, nop, cand, facts, p.mid, ctv, False)
+            assert (p.decision, p.reason, p.valid, p.n_options, p.mask.tolist()) == (
+                cmd["decision"], cmd["reason"], bool(cmd["valid"]), cmd["n_options"], cmd["mask"].tolist()), (take, off, p.mid)
+            replaced += p.decision == capi.CMD_REPLACE
+    assert replaced >= 3
