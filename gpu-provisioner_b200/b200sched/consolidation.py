@@ -115,17 +115,15 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
         k_ct = enc0.key_model.index(key)
         rows, limits = [], []
         for i in again:
-            cheapest = {}
+            existing, cheapest = set(), {}
             for s, p, _ in facts[:mids[i] + 1]:
-                if p >= 0:
+                existing.add(s)
+                if p >= 0:  # candidates without a compatible offering name a type but price nothing (:185-187)
                     cheapest[s] = min(cheapest.get(s, MAX_FLOAT64), p)
-                else:
-                    cheapest.setdefault(s, None)
             limit = MAX_FLOAT64
-            for s in cheapest:
+            for s in existing:
                 if (int(masks[i, s // 64]) >> (s % 64)) & 1:
-                    p = cheapest[s] if cheapest[s] is not None else 0.0  # Go's map zero value (:203)
-                    limit = min(limit, p)
+                    limit = min(limit, cheapest.get(s, 0.0))  # Go's map zero value for an unpriced type (:203)
             r = raws[i]
             req_mask, req_flags = r.claim_req_mask[:1].copy(), r.claim_req_flags[:1].copy()
             if cmds["spot_required"][i]:  # Requirements.Add(capacity-type In [spot]) happened before (:218-221, :240)
