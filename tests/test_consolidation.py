@@ -516,3 +516,32 @@ def test_multi_node_search_driver_on_the_host_stand_in():
                 cmd["decision"], cmd["reason"], bool(cmd["valid"]), cmd["n_options"], cmd["mask"].tolist()), (take, off, p.mid)
             replaced += p.decision == capi.CMD_REPLACE
     assert replaced >= 3
+
+
+def test_to_nodeclaim_lists_on_fuzzed_models():
+    """The oracle's ToNodeClaim lists on 100 random models (NotIn / Exists / DoesNotExist zone and capacity-type
+    requirements on pools and pods, unavailable offerings, existing nodes) against the numpy price key."""
+    import fuzz_models
+    checked = 0
+    for seed in range(100):
+        m = fuzz_models.random_model(1000 + seed)
+        out, order, count, tie = ob.solve_ordered(m, 9)
+        if out.n_claims == 0:
+            continue
+        lo, _ = _price_tables(m)
+        kz, kc = m.key_names.index(M.KEY_ZONE), m.key_names.index(M.KEY_CAPACITY_TYPE)
+        zones = {v for v, k in enumerate(m.arrays["val_key"]) if int(k) == kz}
+        cts = {v for v, k in enumerate(m.arrays["val_key"]) if int(k) == kc}
+        for c in range(out.n_claims):
+            za, ca = _admitted(m, out, c, kz, zones), _admitted(m, out, c, kc, cts)
+            options = parity.mask_bits(out.claim_mask[c])
+            price = {s: min([lo.get((z, ct, s), np.inf) for z in za for ct in ca] + [np.inf]) for s in options}
+            ranked = sorted(options, key=lambda s: (price[s], s))
+            cut = ranked[:9]
+            has_tie = any(price[a] == price[b] for a, b in zip(cut, ranked[1:10]))
+            assert bool(tie[c]) == has_tie, (seed, c)
+            if not has_tie:
+                assert order[c, :count[c]].tolist() == cut, (seed, c)
+                assert int(out.claim_sku[c]) == cut[0]
+            checked += 1
+    assert checked > 100
