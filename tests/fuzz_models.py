@@ -28,7 +28,7 @@ def _rand_req(rng, key, allow_bounds=True):
     return (key, op, None)
 
 
-def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40) -> M.Model:
+def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40, keyless: bool = False) -> M.Model:
     rng = np.random.default_rng(seed)
     b = M.ModelBuilder(RES)
     for k in [M.KEY_INSTANCE_TYPE, M.KEY_ZONE, M.KEY_CAPACITY_TYPE] + WK + CUSTOM + [M.KEY_NODEPOOL]:
@@ -101,7 +101,7 @@ def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40) -> M.Mo
     for p in range(P):
         reqs = []
         for key in WK + CUSTOM + [M.KEY_ZONE, M.KEY_CAPACITY_TYPE]:
-            if rng.random() < 0.22:
+            if rng.random() < 0.22 and not keyless:  # keyless: pods without nodeSelector / affinity (the common case)
                 if key in (M.KEY_ZONE, M.KEY_CAPACITY_TYPE):
                     pool = ZONES if key == M.KEY_ZONE else CTS
                     reqs.append((key, M.OP_IN if rng.random() < 0.7 else M.OP_NOTIN,

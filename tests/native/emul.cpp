@@ -377,3 +377,290 @@ void emul_fit_rank_both(const int64_t* dv, int32_t nd, const int64_t* xs, int32_
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Serial twin of pack_reg_kernel (pack_reg_kernels.cu): the register-resident form of the pack for batches
+// without pod selectors and without existing nodes.  What differs from emul_solve, and is therefore checked here
+// against the oracle on the CPU: (1) the claim order is never read by the scan -- every claim carries a priority
+// (len(Pods), tie-break) such that "first feasible claim in s.newNodeClaims order" == "feasible claim of least
+// priority", updated locally on a win (front of the next bucket) or a new claim (back of bucket 1) and re-derived
+// from the explicit order only after a full pdqsort; (2) the in-flight check is the threshold / upper-bound /
+// row-AND form with the claim's types recomputed only when a resource moves to a new table row.
+namespace {
+
+struct OrderEmu {  // the order warp's arrays and its eager normalisation with undo (pack_kernels.cu warp_normalise)
+  std::vector<int32_t> ord, key, pos_of, snap;
+  int undo_mode = 0, undo_src = 0, undo_dst = 0;  // 0 none, 1 rotate, 2 generic
+  bool generic = false;
+  void move(int src, int dst) {
+    int x = ord[src], kx = key[src];
+    if (src < dst) for (int i = src; i < dst; i++) { ord[i] = ord[i + 1]; key[i] = key[i + 1]; pos_of[ord[i]] = i; }
+    else for (int i = src; i > dst; i--) { ord[i] = ord[i - 1]; key[i] = key[i - 1]; pos_of[ord[i]] = i; }
+    ord[dst] = x; key[dst] = kx; pos_of[x] = dst;
+  }
+  void normalise(int pos, bool appended) {
+    const int n = (int)ord.size();
+    generic = false;
+    undo_mode = 0;
+    if (n <= 1) return;
+    const bool sorted = appended ? !(key[n - 1] < key[n - 2]) : (pos == n - 1 || !(key[pos + 1] < key[pos]));
+    if (sorted) return;
+    bool increasing = false;
+    if (n >= 50) {
+      const int q = n / 4;
+      int v[9];
+      for (int l = 0; l < 9; l++) v[l] = key[q * (l / 3 + 1) + (l % 3) - 1];
+      bool bad = false;
+      for (int l = 0; l < 9; l++) {
+        if ((l % 3) != 2 && v[l + 1] < v[l]) bad = true;
+        if ((l == 1 || l == 4) && v[l + 3] < v[l]) bad = true;
+      }
+      increasing = !bad;
+    }
+    if (!increasing) {
+      snap = ord;
+      GoSort gs{ord.data(), key.data()};
+      gs.sort(n);
+      for (int i = 0; i < n; i++) pos_of[ord[i]] = i;
+      generic = true;
+      undo_mode = 2;
+      return;
+    }
+    const int kx = key[pos];
+    int dst = pos;
+    if (!appended) { while (dst + 1 < n && key[dst + 1] < kx) dst++; }
+    else { while (dst - 1 >= 0 && kx < key[dst - 1]) dst--; }
+    move(pos, dst);
+    undo_mode = dst != pos ? 1 : 0;
+    undo_src = dst;
+    undo_dst = pos;
+  }
+  void undo() {
+    if (undo_mode == 1) move(undo_src, undo_dst);
+    else if (undo_mode == 2) { ord = snap; }
+  }
+};
+
+}  // namespace
+
+extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, const b200s_pods_soa_t* pods,
+                              b200s_result_t* out, int64_t* stats) {
+  KeyTab kt = keytab_from(cat);
+  const int W = kt.n_words, T = tm->n_templates, P = pods->n_pods, R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded;
+  for (int s = 0; s < pods->n_sigs; s++)
+    if (pods->sig_flags[s] & 0x1111111111111111ull) return B200S_EINVAL;  // a pod defines a requirement key
+  std::vector<int32_t> a_tmpl(std::max(P, 1));
+  std::vector<uint64_t> a_mask((size_t)std::max(P, 1) * W);
+  std::vector<uint8_t> a_code((size_t)std::max(P, 1) * std::max(T, 1));
+  int64_t evals = 0;
+  emul_fit_matrix(cat, tm, pods, a_tmpl.data(), a_mask.data(), a_code.data(), &evals);
+  std::vector<int> q(P);
+  for (int i = 0; i < P; i++) q[i] = i;
+  auto req = [&](int r, int p) { return pod_request(pods, r, p); };
+  std::sort(q.begin(), q.end(), [&](int a, int b) {
+    if (req(pods->res_cpu, a) != req(pods->res_cpu, b)) return req(pods->res_cpu, a) > req(pods->res_cpu, b);
+    if (req(pods->res_memory, a) != req(pods->res_memory, b)) return req(pods->res_memory, a) > req(pods->res_memory, b);
+    if (pods->ts[a] != pods->ts[b]) return pods->ts[a] < pods->ts[b];
+    if (pods->uid_hi[a] != pods->uid_hi[b]) return pods->uid_hi[a] < pods->uid_hi[b];
+    if (pods->uid_lo[a] != pods->uid_lo[b]) return pods->uid_lo[a] < pods->uid_lo[b];
+    return a < b;
+  });
+  // feasibility table per template (pack_reg_kernels.cu feas_table_kernel): bit [i_0, .., i_{R-1}] = some instance
+  // type of the template's pre-filtered set has Allocatable()[r] >= dv_r[i_r] for every r.  A claim of selector-less
+  // pods keeps exactly the template's types that fit its requests, so CanAdd's filter result is non-empty iff the
+  // cell of the new total's ranks is set (nodeclaim.go:144-146, :392-423).
+  std::vector<uint64_t> tmask;
+  std::vector<int> alive;
+  prefilter(kt, tm, &tmask, &alive);
+  int64_t stride[MAXR], cells = 1;
+  for (int r = 0; r < R; r++) { stride[r] = cells; cells *= std::max(kt.res_nd[r], 1); }
+  std::vector<std::vector<uint8_t>> table(std::max(T, 1), std::vector<uint8_t>((size_t)cells, 0));
+  for (int t = 0; t < T; t++)
+    for (int64_t cell = 0; cell < cells; cell++) {
+      bool any = false;
+      for (int w = 0; w < W && !any; w++) {
+        uint64_t m = tmask[(size_t)t * W + w] & kt.rows[(size_t)kt.row_nonneg * W + w];
+        for (int r = 0; r < R; r++) {
+          int i = (int)((cell / stride[r]) % std::max(kt.res_nd[r], 1));
+          m &= kt.rows[(size_t)(kt.res_row0[r] + i) * W + w];
+        }
+        any = m != 0;
+      }
+      table[t][(size_t)cell] = any;
+    }
+  struct Claim { std::vector<int64_t> req, thr; std::vector<int> rk; int tmpl; int64_t prio; int npods; int first; };
+  std::vector<Claim> claims;
+  OrderEmu oe;
+  const int TB = 24;
+  const int64_t OFF = 1ll << 23;
+  int64_t front = OFF - 1, back = OFF;
+  std::vector<int> lastlen(P, 0), pod_claim(P, -1);
+  size_t head = 0;
+  int seq = 0;
+  std::vector<int64_t> preq(R), x(R);
+  int64_t n_generic = 0, n_resolve = 0, n_steps = 0;
+  for (int p = 0; p < P; p++) { out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED; out->pod_place_index[p] = -1; out->pod_seq[p] = -1; }
+  auto reset_prios = [&]() {
+    const int n = (int)claims.size();
+    for (int c = 0; c < n; c++) claims[c].prio = ((int64_t)claims[c].npods << TB) | (OFF + oe.pos_of[c]);
+    front = OFF - 1;
+    back = OFF + n;
+  };
+  auto check_order = [&]() -> bool {  // the priorities order the claims exactly as the explicit array does
+    for (size_t i = 1; i < oe.ord.size(); i++)
+      if (!(claims[oe.ord[i - 1]].prio < claims[oe.ord[i]].prio)) return false;
+    return true;
+  };
+  for (;;) {
+    size_t len = q.size() - head;
+    if (len == 0) break;
+    int p = q[head];
+    if (lastlen[p] == (int)len) break;
+    head++;
+    n_steps++;
+    oe.undo_mode = 0;  // the reference sorts at the start of this add() too: the last normalisation stands
+    const uint64_t tol = pod_tolerated(pods, p);
+    for (int r = 0; r < R; r++) preq[r] = req(r, p);
+    // in-flight: every claim classified independently, least priority among the feasible ones wins
+    int win = -1;
+    std::vector<int> win_rk, nrk(R);
+    bool win_moved = false;
+    for (int c = 0; c < (int)claims.size(); c++) {
+      Claim& cl = claims[c];
+      if (tm->taints[cl.tmpl] & ~tol) continue;
+      bool moved = false;
+      for (int r = 0; r < R; r++) {
+        x[r] = cl.req[r] + preq[r];
+        if (preq[r] != 0 && x[r] > cl.thr[r]) moved = true;  // a resource the pod does not request keeps its row
+      }
+      if (moved) {
+        n_resolve++;
+        bool ok = true;
+        int64_t cell = 0;
+        for (int r = 0; r < R && ok; r++) {
+          int i = cl.rk[r];
+          if (preq[r] != 0 && x[r] > cl.thr[r]) {
+            const int64_t* dv = kt.res_dv + kt.res_dv0[r];
+            i++;
+            while (i < kt.res_nd[r] && dv[i] < x[r]) i++;
+            if (i >= kt.res_nd[r]) { ok = false; break; }
+          }
+          nrk[r] = i;
+          cell += (int64_t)i * stride[r];
+        }
+        if (!ok || !table[cl.tmpl][(size_t)cell]) continue;
+      }
+      if (win < 0 || cl.prio < claims[win].prio) {
+        win = c;
+        win_moved = moved;
+        if (moved) win_rk = nrk;
+      }
+    }
+    if (win >= 0) {
+      Claim& cl = claims[win];
+      if (win_moved) {
+        cl.rk = win_rk;
+        for (int r = 0; r < R; r++) cl.thr[r] = kt.res_dv[kt.res_dv0[r] + cl.rk[r]];
+      }
+      for (int r = 0; r < R; r++) cl.req[r] += preq[r];
+      cl.npods++;
+      cl.prio = ((int64_t)cl.npods << TB) | front;
+      front--;
+      pod_claim[p] = win;
+      out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
+      const int a = oe.pos_of[win];
+      oe.key[a]++;
+      oe.normalise(a, false);
+      if (oe.generic) { n_generic++; reset_prios(); }
+      if (!check_order()) return -1000 - (int)n_steps % 1000;
+      continue;
+    }
+    int t = a_tmpl[p];
+    if (t >= 0) {
+      Claim c;
+      c.req.resize(R); c.thr.resize(R); c.rk.resize(R);
+      for (int r = 0; r < R; r++) {
+        c.req[r] = tm->daemon[t][r] + preq[r];
+        c.rk[r] = fit_rank(kt.res_dv + kt.res_dv0[r], kt.res_nd[r], c.req[r]);
+        c.thr[r] = kt.res_dv[kt.res_dv0[r] + c.rk[r]];
+      }
+      c.first = p;
+      c.tmpl = t;
+      c.npods = 1;
+      c.prio = ((int64_t)1 << TB) | back;
+      back++;
+      claims.push_back(c);
+      const int cid = (int)claims.size() - 1;
+      oe.ord.push_back(cid); oe.key.push_back(1); oe.pos_of.push_back(cid);
+      oe.pos_of[cid] = (int)oe.ord.size() - 1;
+      oe.normalise((int)oe.ord.size() - 1, true);
+      if (oe.generic) { n_generic++; reset_prios(); }
+      if (!check_order()) return -2000;
+      pod_claim[p] = cid;
+      out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
+    } else {
+      q.push_back(p);
+      lastlen[p] = (int)(q.size() - head);
+      out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED;
+    }
+  }
+  oe.undo();
+  if (stats) { stats[0] = n_steps; stats[1] = n_generic; stats[2] = n_resolve; }
+  const int n = (int)claims.size();
+  if (n > out->cap_claims) return B200S_ECAPACITY;
+  out->n_claims = n;
+  out->n_unscheduled = (int)(q.size() - head);
+  out->fit_evals = evals;
+  std::vector<int> pos(n);
+  for (int i = 0; i < n; i++) pos[oe.ord[i]] = i;
+  for (int p = 0; p < P; p++) {
+    if (out->pod_place_kind[p] == B200S_PLACE_CLAIM) out->pod_place_index[p] = pos[pod_claim[p]];
+    for (int t = 0; t < T; t++) {
+      uint8_t c = a_code[(size_t)p * T + t];
+      out->pod_fit_code[(size_t)p * T + t] = (out->pod_place_kind[p] == B200S_PLACE_UNSCHEDULED || c == B200S_FIT_DROPPED) ? c : (uint8_t)B200S_FIT_NONE;
+    }
+  }
+  const int ZC = kt.n_zones * kt.n_cts;
+  for (int i = 0; i < n; i++) {
+    const Claim& c = claims[oe.ord[i]];
+    // InstanceTypeOptions: the first pod's stage-A row inside the rows of the final totals (the rows are nested, so
+    // the AND of every row the claim ever moved to is the last one)
+    std::vector<uint64_t> cmask(W);
+    for (int w = 0; w < W; w++) {
+      uint64_t m = a_mask[(size_t)c.first * W + w];
+      for (int r = 0; r < R; r++) m &= kt.rows[(size_t)(kt.res_row0[r] + c.rk[r]) * W + w];
+      cmask[w] = m;
+    }
+    out->claim_template[i] = c.tmpl;
+    out->claim_npods[i] = c.npods;
+    for (int r = 0; r < R; r++) out->claim_requests[(size_t)i * R + r] = c.req[r];
+    if (out->claim_mask) for (int w = 0; w < W; w++) out->claim_mask[(size_t)i * W + w] = cmask[w];
+    for (int k = 0; k < K; k++) out->claim_req_mask[(size_t)i * K + k] = tm->req_mask[c.tmpl][k];
+    out->claim_req_flags[i] = tm->req_flags[c.tmpl];
+    for (int b = 0; b < NB; b++) {
+      const uint32_t nib = (uint32_t)((tm->req_flags[c.tmpl] >> (4 * cat->bounded_key[b])) & 0xFu);
+      out->claim_req_gt[(size_t)i * NB + b] = (nib & RF_GT) ? tm->req_gt[c.tmpl][b] : 0;
+      out->claim_req_lt[(size_t)i * NB + b] = (nib & RF_LT) ? tm->req_lt[c.tmpl][b] : 0;
+    }
+    ReqRow rr = tmpl_row(kt, tm, c.tmpl);
+    uint64_t za = ~0ull, ca = ~0ull;
+    if (kt.key_zone >= 0) { EReq qz = get(kt, rr, kt.key_zone); if (qz.f & RF_DEF) za = allowed_values(kt, kt.key_zone, qz); }
+    if (kt.key_ct >= 0) { EReq qc = get(kt, rr, kt.key_ct); if (qc.f & RF_DEF) ca = allowed_values(kt, kt.key_ct, qc); }
+    uint64_t best = ~0ull; int bs = -1, cnt = 0;
+    for (int s = 0; s < kt.n_skus; s++) {
+      if (!((cmask[s / 64] >> (s % 64)) & 1ull)) continue;
+      cnt++;
+      uint64_t pr = B200S_PRICE_NONE;
+      for (int zc = 0; zc < ZC; zc++) {
+        int z = zc / kt.n_cts, ct = zc % kt.n_cts;
+        if (!((za >> z) & 1ull) || !((ca >> ct) & 1ull)) continue;
+        pr = std::min(pr, kt.price[(size_t)zc * kt.n_skus + s]);
+      }
+      if (pr < best) { best = pr; bs = s; }
+    }
+    out->claim_sku[i] = bs;
+    out->claim_price[i] = bs >= 0 ? best : B200S_PRICE_NONE;
+    out->claim_n_options[i] = cnt;
+  }
+  return 0;
+}

@@ -207,3 +207,12 @@ def device_commands_as_oracle(enc: capi.Encoded, cmds: Dict[str, np.ndarray], i:
     return dict(decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]), n_options=int(cmds["n_options"][i]),
                 spot_required=int(cmds["spot_required"][i]), price_tie=int(cmds["price_tie"][i]),
                 head=cmds["head"][i].tolist(), mask=cmds["mask"][i].tolist())
+
+
+def emul_solve_reg(enc: capi.Encoded):
+    """host twin of the register-resident pack (selector-less pods, no existing nodes); (result, stats)"""
+    buf = capi.ResultBuffers(enc.P, enc.T, enc.R, enc.W, enc.K, enc.NB)
+    stats = np.zeros(4, np.int64)
+    rc = emul().emul_solve_reg(enc.catalog, enc.templates, enc.pods, C.byref(buf.c), _p(stats, C.c_int64))
+    assert rc == 0, rc
+    return buf.raw(), stats

@@ -51,6 +51,30 @@ def test_emulation_matches_oracle_on_fuzzed_models():
     assert ran >= 350, (ran, rejected)
 
 
+@pytest.mark.parametrize("kind,P,S", [("c2", 1500, 100), ("c2", 4000, 500), ("c2", 300, 1300), ("c2", 3000, 64)])
+def test_register_pack_twin_matches_oracle_on_config2_shapes(kind, P, S):
+    """tests/native/emul.cpp emul_solve_reg: priorities instead of positions, feasibility table instead of type masks."""
+    m = synth.config(kind, P, S)
+    enc = capi.Encoded(m)
+    raw, stats = parity.emul_solve_reg(enc)
+    parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, ob.solve(m)), f"reg twin {kind} {P}x{S}")
+    assert stats[0] == P
+
+
+def test_register_pack_twin_matches_oracle_on_fuzzed_keyless_models():
+    ran = 0
+    for seed in range(300):
+        m = fuzz_models.random_model(seed, with_nodes=False, max_pods=160, keyless=True)
+        try:
+            enc = capi.Encoded(m)
+        except capi.NotRepresentable:
+            continue
+        raw, _ = parity.emul_solve_reg(enc)
+        parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, ob.solve(m)), f"reg twin fuzz {seed}")
+        ran += 1
+    assert ran >= 250, ran
+
+
 def test_go_sort_port_of_the_pack_kernel_matches_the_oracle_port():
     rng = np.random.default_rng(7)
     for n in [1, 2, 12, 13, 30, 49, 50, 64, 200, 1000, 3000]:
