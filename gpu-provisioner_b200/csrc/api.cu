@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -29,6 +30,7 @@ struct Block {
 struct Catalog {
   KeyTab kt{};  // device pointers
   std::vector<void*> bufs;
+  std::vector<int64_t> h_dv;  // host copy of the distinct allocatable values (the register-resident pack's plan reads them)
   int S = 0, W = 0, R = 0, K = 0, NB = 0;
 };
 
@@ -107,6 +109,9 @@ struct b200s_resident {
   int32_t* sel_sku = nullptr;
   uint64_t* sel_price = nullptr;
   int32_t* sel_nopt = nullptr;
+  RegPackPlan reg_plan{};      // register-resident pack: table shape (eligible only without pod keys / nodes)
+  uint32_t* feas_bits = nullptr;
+  RegPackDev reg_dev{};
   int last_launches = 0;
   bool fit_done = false, solve_done = false;
   cudaEvent_t ev_dense0 = nullptr, ev_dense1 = nullptr;  // bracket the dense kernel of the last stage A on ctx->stream
@@ -263,6 +268,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
       pb.node_begin = eo;
       pb.node_end = eo + ((nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
       pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0;
+      pb.status = 0; pb._pad = 0;
       for (int i = 0; i < 12; i++) pb.prof[i] = 0;
       if (n_problems > 1)
         for (int i = pb.pod_begin; i < pb.pod_end; i++) { seg[i] = b; rowp[i] = b; }
@@ -389,6 +395,35 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
                   r->sel_sku, r->sel_price, r->sel_nopt};
   for (void* p : must)
     if (!p) return fail(ctx, B200S_ENOMEM, "device allocation (state)");
+  r->reg_plan.eligible = false;
+  if (r->plain && Etot == 0 && T > 0 && Ptot > 0 && !getenv("B200S_PACK_NO_REG")) {
+    // selector-less pods, no existing nodes: plan the register-resident pack (granules, tables) on the host
+    std::vector<const int64_t*> rqs(n_problems);
+    std::vector<int32_t> nqs(n_problems);
+    for (int b = 0; b < n_problems; b++) { rqs[b] = pods_in[b]->rq_requests; nqs[b] = pods_in[b]->n_reqcls; }
+    RegPackPlan& plan = r->reg_plan;
+    if (reg_pack_plan(cat->kt, cat->h_dv.data(), T, tm->daemon, n_problems, rqs.data(), nqs.data(), ctx->smem_limit, &plan)) {
+      std::vector<int32_t> rq32((size_t)REG_RT * NQ, 0);
+      size_t qoff = 0;
+      for (int b = 0; b < n_problems; b++) {
+        reg_pack_scale_requests(plan, rqs[b], nqs[b], rq32.data(), NQ, qoff);
+        qoff += (size_t)nqs[b];
+      }
+      uint8_t* d_tab = r->dalloc<uint8_t>(plan.tab.size());
+      int32_t* d_win = r->dalloc<int32_t>(plan.win.size());
+      int32_t* d_dm = r->dalloc<int32_t>(plan.daemon32.size());
+      int32_t* d_rq = r->dalloc<int32_t>(rq32.size());
+      r->feas_bits = r->dalloc<uint32_t>((size_t)T * plan.wpt);
+      if (!d_tab || !d_win || !d_dm || !d_rq || !r->feas_bits) return fail(ctx, B200S_ENOMEM, "device allocation (register pack tables)");
+      int rc = upload(ctx, d_tab, plan.tab.data(), plan.tab.size());
+      if (!rc) rc = upload(ctx, d_win, plan.win.data(), plan.win.size());
+      if (!rc) rc = upload(ctx, d_dm, plan.daemon32.data(), plan.daemon32.size());
+      if (!rc) rc = upload(ctx, d_rq, rq32.data(), rq32.size());
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (register pack tables)");  // rq32 goes out of scope
+      r->reg_dev = RegPackDev{d_tab, d_win, r->feas_bits, d_dm, d_rq};
+    }
+  }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (upload)");
   *out = r.release();
   return B200S_OK;
@@ -436,16 +471,31 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
   int nl = 0;
   CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
   *launches += nl;
-  CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0, max_pods,
-                            r->profile_pack, ctx->smem_limit, ctx->stream),
-           "pack launch");
+  bool generic_pack = true;
+  if (r->reg_plan.eligible && !r->profile_pack) {
+    // selector-less pods, no existing nodes: the register-resident form; problems it cannot hold (more claims than
+    // its threads keep) are left to the generic kernel, which skips the finished ones
+    bool may_overflow = false;
+    CUDA_TRY(ctx, launch_feas_table(cat->kt, r->tmask, r->T, r->reg_plan, r->feas_bits, ctx->stream), "feas_table launch");
+    CUDA_TRY(ctx, launch_pack_reg(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, max_pods, r->reg_plan,
+                                  r->reg_dev, &may_overflow, ctx->stream),
+             "pack_reg launch");
+    *launches += 2;
+    generic_pack = may_overflow;
+  }
+  if (generic_pack) {
+    CUDA_TRY(ctx, launch_pack(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, !r->plain, r->E > 0, max_pods,
+                              r->profile_pack, ctx->smem_limit, ctx->stream),
+             "pack launch");
+    *launches += 1;
+  }
   CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),
            "pack_finalize launch");
   CUDA_TRY(ctx, launch_select_cheapest(cat->kt, r->P, r->cout.mask, r->cout.rmask, (size_t)cat->K, 1, r->cout.rflags,
                                        r->cout.gt, r->cout.lt, (size_t)cat->NB, 1, r->sel_sku, r->sel_price, r->sel_nopt,
                                        r->problems, r->row_problem, ctx->stream),
            "select_cheapest launch");
-  *launches += 3;
+  *launches += 2;
   return 0;
 }
 
@@ -662,6 +712,7 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
   }
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (catalog)");
   cat->S = S; cat->W = W; cat->R = c->n_res; cat->K = K; cat->NB = c->n_bounded;
+  cat->h_dv.assign(c->res_dv, c->res_dv + c->n_dv);
   *catalog_id = ctx->next_id++;
   ctx->catalogs[*catalog_id] = std::move(cat);
   return B200S_OK;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "device_types.cuh"
 
 namespace b200 {
@@ -16,6 +18,7 @@ struct PackProblem {
   unsigned long long evals;
   // SM cycles thread 0 spent per phase (pop, pod row, nodes, sort, pre-filter, evaluate, commit, steps)
   unsigned long long prof[12];
+  int32_t status, _pad;  // 1: the register-resident pack (pack_reg_kernels.cu) finished this problem; pack_kernel skips it
 };
 
 // Mutable state of all problems of a launch (device pointers).
@@ -105,6 +108,34 @@ cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* mask
 cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
                         PackProblem* problems, int n_problems, bool keys, bool nodes, int max_pods, bool profile,
                         int smem_limit, cudaStream_t stream);
+// pack_reg_kernels.cu: the register-resident pack's plan for one resident problem set — granule per resource, table
+// kind per resource slot, feasibility-table shape, and host copies of the small tables it stages
+constexpr int REG_RT = 5;  // resource slots of a claim
+struct RegPackPlan {
+  bool eligible = false;
+  int32_t R = 0, cpt = 0, nwin_form = 1, cells = 0, wpt = 0;
+  int32_t perm[REG_RT], lim[REG_RT], toff[REG_RT], stride[REG_RT], row0[REG_RT], nd[REG_RT], maxv[REG_RT];
+  int64_t scale[REG_RT];
+  std::vector<uint8_t> tab;       // direct value -> rank tables
+  std::vector<int32_t> win;       // four values per window entry
+  std::vector<int32_t> daemon32;  // [MAXT][8]
+};
+struct RegPackDev {  // device copies
+  const uint8_t* tab;
+  const int32_t* win;
+  const uint32_t* bits;
+  const int32_t* daemon;
+  const int32_t* rq;  // [REG_RT][NQ]
+};
+bool reg_pack_plan(const KeyTab& kt, const int64_t* h_dv, int T, const int64_t (*daemon)[MAXR], int n_problems,
+                   const int64_t* const* rq, const int32_t* nq, int smem_limit, RegPackPlan* plan);
+void reg_pack_scale_requests(const RegPackPlan& plan, const int64_t* rq, int nq, int32_t* out, size_t out_stride,
+                             size_t out_off);
+cudaError_t launch_feas_table(const KeyTab& kt, const uint64_t* tmask, int T, const RegPackPlan& plan, uint32_t* bits,
+                              cudaStream_t stream);
+cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
+                            PackProblem* problems, int n_problems, int max_pods, const RegPackPlan& plan,
+                            const RegPackDev& dev, bool* may_overflow, cudaStream_t stream);
 cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
                                  int n_problems, ClaimOut out, cudaStream_t stream);
 

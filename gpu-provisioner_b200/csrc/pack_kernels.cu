@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
   }
 
   PackProblem& pb = problems[blockIdx.x];
+  if (pb.status == 1) return;  // finished by the register-resident form (pack_reg_kernels.cu); uniform
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
   const int E0 = pb.node_begin, E = NODES ? pb.node_end - pb.node_begin : 0;
   // this problem's slices

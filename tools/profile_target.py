@@ -68,7 +68,15 @@ for i in range(iters):
     (res.fit_matrix if mode == "fit" else res.solve)()
     ctx.record(ev1)
     print(f"{mode} {kind} {P}x{S} iter {i}: {ctx.elapsed_ms(ev0, ev1):.4f} ms", flush=True)
-    if mode == "solve":
+    if mode == "solve" and os.environ.get("B200S_REG_PROFILE"):
+        import ctypes as C
+        raw = (C.c_uint64 * 12)()
+        capi.lib().b200s_resident_pack_profile(ctx.h, res.h, raw)
+        steps = max(raw[3], 1)
+        print("   reg pack cycles/step:", {k: round(raw[i] / steps, 1) for i, k in enumerate(
+            ["claim_eval", "claim_barrier", "claim_commit", "steps", "ordw_pre", "ordw_barrier", "ordw_work", "ordw_spin",
+             "qw_pre", "qw_barrier", "full_sorts", "qw_post"])}, "steps", raw[3], "full sorts", raw[10], flush=True)
+    if mode == "solve" and not os.environ.get("B200S_NO_PROFILE"):
         pr = res.pack_profile()
         steps = max(pr["steps"], 1)
         print("   cycles/step:", {k: round(v / steps, 1) for k, v in pr.items() if k not in ("steps", "full_sorts")},
