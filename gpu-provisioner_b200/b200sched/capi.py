@@ -26,7 +26,7 @@ CMD_NONE, CMD_DELETE, CMD_REPLACE = 0, 1, 2
 WHY_OK, WHY_UNSCHEDULABLE, WHY_MANY_CLAIMS, WHY_NOT_CHEAPER, WHY_S2S_DISABLED, WHY_S2S_TOO_FEW = 0, 1, 2, 3, 4, 5
 S2S_MIN_TYPES = 15
 MAX_INSTANCE_TYPES = 600  # nodeclaimtemplate.go:41
-OK, EINVAL, ENODEVICE, ECUDA, ENOTREPRESENTABLE, ECAPACITY, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7
+OK, EINVAL, ENODEVICE, ECUDA, ENOTREPRESENTABLE, ECAPACITY, ENOMEM, ESTATE, ESTALE = 0, -1, -2, -3, -4, -5, -6, -7, -8
 CREATE_EBADNAME, CREATE_ENOTYPE, CREATE_ENOSTORAGE = -20, -21, -22
 
 _P = C.POINTER
@@ -43,7 +43,7 @@ class CatalogSoA(C.Structure):
         ("res_nd", C.c_int32 * MAX_RES), ("res_dv0", C.c_int32 * MAX_RES), ("res_row0", C.c_int32 * MAX_RES),
         ("res_dv", _P(C.c_int64)), ("n_dv", C.c_int32), ("key_row0", C.c_int32 * MAX_KEYS), ("zc_row0", C.c_int32),
         ("price", _P(C.c_uint64)), ("alloc", _P(C.c_int64)), ("capacity", _P(C.c_int64)),
-        ("price_max", _P(C.c_uint64)),
+        ("price_max", _P(C.c_uint64)), ("layout_hash", C.c_uint64),
     ]
 
 
@@ -81,7 +81,7 @@ class PodsSoA(C.Structure):
         ("sig_id", _P(C.c_int32)), ("req_id", _P(C.c_int32)), ("ts", _P(C.c_int64)), ("uid_hi", _P(C.c_uint64)),
         ("uid_lo", _P(C.c_uint64)),
         ("sig_mask", _P(C.c_uint64)), ("sig_flags", _P(C.c_uint64)), ("sig_gt", _P(C.c_int32)), ("sig_lt", _P(C.c_int32)),
-        ("sig_tolerated", _P(C.c_uint64)), ("rq_requests", _P(C.c_int64)),
+        ("sig_tolerated", _P(C.c_uint64)), ("rq_requests", _P(C.c_int64)), ("layout_hash", C.c_uint64),
     ]
 
 
@@ -89,7 +89,7 @@ class NodesSoA(C.Structure):
     _fields_ = [
         ("n_nodes", C.c_int32), ("n_res", C.c_int32), ("n_keys", C.c_int32), ("node_index", _P(C.c_int32)),
         ("available", _P(C.c_int64)), ("req_mask", _P(C.c_uint64)), ("req_flags", _P(C.c_uint64)),
-        ("taints", _P(C.c_uint64)),
+        ("taints", _P(C.c_uint64)), ("layout_hash", C.c_uint64),
     ]
 
 
@@ -218,6 +218,7 @@ class Encoded:
         self.catalog = L.b200s_encoded_catalog(h)
         self.templates = L.b200s_encoded_templates(h)
         self.pods = L.b200s_encoded_pods(h)
+        self.layout_hash = int(self.catalog.contents.layout_hash)
         self.nodes = L.b200s_encoded_nodes(h)
         c = self.catalog.contents
         self.S, self.W, self.R, self.K, self.NB = c.n_skus, c.n_words, c.n_res, c.n_keys, c.n_bounded
@@ -335,6 +336,7 @@ class Context:
             raise B200SError(rc, "b200s_init failed (no usable sm_100 device?)")
         self.h = h
         self.L = L
+        self._layouts = {}  # catalog id -> layout_hash of the encode it was uploaded from
 
     def close(self):
         if self.h:
@@ -348,9 +350,15 @@ class Context:
     def upload_catalog(self, enc: Encoded) -> int:
         cid = C.c_uint64(0)
         self._check(self.L.b200s_catalog_upload(self.h, enc.catalog, C.byref(cid)))
+        self._layouts[cid.value] = enc.layout_hash
         return cid.value
 
+    def catalog_layout(self, cid: int):
+        """layout_hash of the encode catalog `cid` was uploaded from (None when unknown)"""
+        return self._layouts.get(cid)
+
     def release_catalog(self, cid: int):
+        self._layouts.pop(cid, None)
         self._check(self.L.b200s_catalog_release(self.h, cid))
 
     def fit_matrix(self, cid: int, enc: Encoded) -> FitOut:

@@ -26,8 +26,14 @@ MAX_FLOAT64 = 1.7976931348623157e308
 MAX_PARALLEL = 100  # multinodeconsolidation.go:87
 
 
-def node_facts(model: M.Model, nodes: Sequence[int]) -> List[Tuple[int, float, bool]]:
-    """(instance type index, cheapest offering the node's labels admit or -1, is a spot node) per existing node: what
+class CandidatePriceError(RuntimeError):
+    """getCandidatePrices' "unable to determine offering" (consolidation.go:323), raised where the reference's search
+    would have hit it: on a visited probe whose simulation scheduled everything into exactly one new NodeClaim"""
+
+
+def node_facts(model: M.Model, nodes: Sequence[int]) -> List[Tuple[int, float, bool, bool]]:
+    """(instance type index, cheapest offering the node's labels admit or -1, is a spot node, is a reserved-capacity
+    node) per existing node: what
     getCandidatePrices (consolidation.go:310-328) and filterOutSameInstanceType (multinodeconsolidation.go:177-193) read
     off a candidate.  Offerings are not filtered by availability there."""
     a = model.arrays
@@ -47,7 +53,7 @@ def node_facts(model: M.Model, nodes: Sequence[int]) -> List[Tuple[int, float, b
                 ok = ok and (key not in lab or lab[key] == v)
             if ok and (best < 0 or a["off_price"][o] < best):
                 best = float(a["off_price"][o])
-        out.append((s, best, model.val_names[lab[k_ct]] == "spot"))
+        out.append((s, best, model.val_names[lab[k_ct]] == "spot", model.val_names[lab[k_ct]] == "reserved"))
     return out
 
 
@@ -59,14 +65,16 @@ def prefix_simulation(model: M.Model, node_of_pod: np.ndarray, candidates: Seque
     return M.subset(model, pods, keep)
 
 
-def prefix_price(facts: Sequence[Tuple[int, float, bool]], mid: int) -> float:
-    """getCandidatePrices: the candidates' prices added up in candidate order"""
+def prefix_price(facts: Sequence[Tuple[int, float, bool, bool]], mid: int) -> Tuple[float, bool]:
+    """getCandidatePrices (consolidation.go:310-328): the candidates' prices added up in candidate order -> (total,
+    error).  The first candidate without a compatible offering ends the walk: a reserved-capacity node makes the total
+    0.0 (free by definition, :317-320), any other is the "unable to determine offering" error (:323)."""
     price = 0.0
-    for _, p, _ in facts[:mid + 1]:
+    for _, p, _, reserved in facts[:mid + 1]:
         if p < 0:
-            raise ValueError("unable to determine offering")  # consolidation.go:323
+            return 0.0, not reserved
         price += p
-    return price
+    return price, False
 
 
 @dataclass
@@ -79,6 +87,7 @@ class Probe:
     mask: np.ndarray         # replacement instance types after filterOutSameInstanceType
     spot_required: bool
     result: capi.SolveRaw
+    price_error: bool = False  # getCandidatePrices failed on this prefix AND the reference would have called it
 
 
 def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: np.ndarray, candidates: Sequence[int],
@@ -98,11 +107,42 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
     t_sims = time.perf_counter()
     encs = [capi.Encoded(m) for m in sims]
     t1 = time.perf_counter()
+    # A prefix's pods may bring a label key, a Gt/Lt bound or a well-known flag the others do not have: b200s_encode then
+    # chooses another key layout (layout_hash) and those probes cannot share the uploaded catalog.  Probes are grouped
+    # by layout; the group of the caller's catalog runs as one batch on it, every other group on a catalog of its own.
+    uploaded = ctx.catalog_layout(cid)
+    groups = {}
+    for i, e in enumerate(encs):
+        groups.setdefault(e.layout_hash, []).append(i)
+    out: List[Optional[Probe]] = [None] * len(mids)
+    for h, idx in groups.items():
+        own = None
+        if uploaded is not None and h != uploaded:
+            own = ctx.upload_catalog(encs[idx[0]])
+        try:
+            probes = _probe_group(ctx, cid if own is None else own, [encs[i] for i in idx], [mids[i] for i in idx], facts,
+                                  ct_values, spot_to_spot)
+        finally:
+            if own is not None:
+                ctx.release_catalog(own)
+        for i, pr in zip(idx, probes):
+            out[i] = pr
+    if timing is not None:
+        timing["models_s"] = t_sims - t0   # numpy row selection of the synthetic model (the cluster-state feed's job)
+        timing["encode_s"] = t1 - t_sims   # b200s_encode of every prefix
+        timing["device_calls_s"] = time.perf_counter() - t1
+    return out
+
+
+def _probe_group(ctx: capi.Context, cid: int, encs: List[capi.Encoded], mids: List[int], facts, ct_values,
+                 spot_to_spot: bool) -> List[Probe]:
+    """the probes of one key layout, as one batch on catalog `cid`"""
     enc0 = encs[0]
     key, v_spot, v_od, v_res = ct_values
     bit_spot, bit_od, bit_res = (enc0.value_bit(key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res))
     raws = ctx.solve_batch(cid, encs)
-    prices = [prefix_price(facts, mid) for mid in mids]
+    priced = [prefix_price(facts, mid) for mid in mids]
+    prices = [p for p, _ in priced]
     spots = [all(f[2] for f in facts[:mid + 1]) for mid in mids]
     counts = [mid + 1 for mid in mids]
     cmds = ctx.consolidation_commands(cid, enc0, raws, prices, spots, counts, bit_spot, bit_od, bit_res, spot_to_spot)
@@ -116,7 +156,7 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
         rows, limits = [], []
         for i in again:
             existing, cheapest = set(), {}
-            for s, p, _ in facts[:mids[i] + 1]:
+            for s, p, _, _ in facts[:mids[i] + 1]:
                 existing.add(s)
                 if p >= 0:  # candidates without a compatible offering name a type but price nothing (:185-187)
                     cheapest[s] = min(cheapest.get(s, MAX_FLOAT64), p)
@@ -139,12 +179,12 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
         for j, i in enumerate(again):
             valid[i] = second["decision"][j] == capi.CMD_REPLACE  # something is left (:146)
             masks[i], n_opts[i] = second["mask"][j], second["n_options"][j]
-    if timing is not None:
-        timing["models_s"] = t_sims - t0   # numpy row selection of the synthetic model (the cluster-state feed's job)
-        timing["encode_s"] = t1 - t_sims   # b200s_encode of every prefix
-        timing["device_calls_s"] = time.perf_counter() - t1
-    return [Probe(mid=mids[i], decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]), valid=bool(valid[i]),
-                  n_options=int(n_opts[i]), mask=masks[i], spot_required=bool(cmds["spot_required"][i]), result=raws[i])
+    # the reference reaches getCandidatePrices only when everything was scheduled into exactly one new NodeClaim
+    # (consolidation.go:146-168): only there does a pricing error exist
+    err = [priced[i][1] and raws[i].n_unscheduled == 0 and raws[i].n_claims == 1 for i in range(len(mids))]
+    return [Probe(mid=mids[i], decision=int(cmds["decision"][i]), reason=int(cmds["reason"][i]),
+                  valid=bool(valid[i]) and not err[i], n_options=int(n_opts[i]), mask=masks[i],
+                  spot_required=bool(cmds["spot_required"][i]), result=raws[i], price_error=bool(err[i]))
             for i in range(len(mids))]
 
 
@@ -179,5 +219,9 @@ def first_n_consolidation_option(ctx: capi.Context, cid: int, model: M.Model, no
     lo, hi = search_bounds(len(candidates), min(max_parallel, len(candidates)))
     probes = multi_node_probes(ctx, cid, model, node_of_pod, candidates, range(lo, hi + 1), ct_values, spot_to_spot, timing)
     by_mid = {p.mid: p for p in probes}
-    best = replay_search(lo, hi, lambda mid: by_mid[mid].valid)
+    def valid_of(mid):
+        if by_mid[mid].price_error:  # computeConsolidation returned an error: the search ends with it (:147)
+            raise CandidatePriceError(f"unable to determine offering for a candidate of the prefix 0..{mid}")
+        return by_mid[mid].valid
+    best = replay_search(lo, hi, valid_of)
     return None if best is None else by_mid[best]

@@ -402,7 +402,7 @@ def candidate_prices(model: M.Model, nodes: Sequence[int]):
     there), and whether the node is a spot node.  Returns (prices, is_spot) per node."""
     from .consolidation import node_facts
     facts = node_facts(model, nodes)
-    for e, (_, p, _) in zip(nodes, facts):
-        if p < 0:
+    for e, (_, p, _, reserved) in zip(nodes, facts):
+        if p < 0 and not reserved:  # a reserved-capacity node without an offering is free (consolidation.go:317-320)
             raise ValueError(f"node {e}: unable to determine offering")
-    return [p for _, p, _ in facts], [sp for _, _, sp in facts]
+    return [max(p, 0.0) for _, p, _, _ in facts], [sp for _, _, sp, _ in facts]

@@ -30,6 +30,7 @@ struct Block {
 struct Catalog {
   KeyTab kt{};  // device pointers
   std::vector<void*> bufs;
+  uint64_t layout_hash = 0;   // b200s_catalog_soa_t::layout_hash of the uploaded encode
   std::vector<int64_t> h_dv;  // host copy of the distinct allocatable values (the register-resident pack's plan reads them)
   int S = 0, W = 0, R = 0, K = 0, NB = 0;
 };
@@ -152,8 +153,21 @@ int upload(b200s_ctx* ctx, Tp* dst, const Tp* src, size_t n) {
   return 0;
 }
 
+// instance-type sets handed in by the caller: no bit at or above n_skus (the kernels index price rows by bit position)
+bool masks_in_range(const uint64_t* masks, size_t n, int S, int W) {
+  if ((S & 63) == 0) return true;
+  const uint64_t tail = ~((1ull << (S & 63)) - 1ull);
+  for (size_t i = 0; i < n; i++)
+    if (masks[i * W + (W - 1)] & tail) return false;
+  return true;
+}
+
 int check_shapes(b200s_ctx* ctx, const Catalog* cat, const b200s_pods_soa_t* pods, const b200s_nodes_soa_t* nodes) {
   if (!pods) return fail(ctx, B200S_EINVAL, "pods is null");
+  if (cat->layout_hash && pods->layout_hash && cat->layout_hash != pods->layout_hash)
+    return fail(ctx, B200S_ESTALE, "pods were encoded against another key layout than the uploaded catalog: upload the catalog of the same b200s_encode");
+  if (nodes && nodes->n_nodes > 0 && cat->layout_hash && nodes->layout_hash && cat->layout_hash != nodes->layout_hash)
+    return fail(ctx, B200S_ESTALE, "nodes were encoded against another key layout than the uploaded catalog");
   if (pods->n_res != cat->R || pods->n_keys != cat->K || pods->n_bounded != cat->NB)
     return fail(ctx, B200S_EINVAL, "pods SoA does not match the catalog's R/K/NB");
   if (pods->n_pods > 0 && (pods->n_sigs <= 0 || pods->n_reqcls <= 0)) return fail(ctx, B200S_EINVAL, "pods without class tables");
@@ -713,6 +727,7 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (catalog)");
   cat->S = S; cat->W = W; cat->R = c->n_res; cat->K = K; cat->NB = c->n_bounded;
   cat->h_dv.assign(c->res_dv, c->res_dv + c->n_dv);
+  cat->layout_hash = c->layout_hash;
   *catalog_id = ctx->next_id++;
   ctx->catalogs[*catalog_id] = std::move(cat);
   return B200S_OK;
@@ -828,6 +843,7 @@ int b200s_select_cheapest(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, cons
   if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
   Catalog* cat = it->second.get();
   if (n == 0) return B200S_OK;
+  if (!masks_in_range(masks, (size_t)n, cat->S, cat->W)) return fail(ctx, B200S_EINVAL, "select_cheapest: a mask has bits beyond n_skus");
   const size_t N = (size_t)n, K = (size_t)std::max(cat->K, 1), NB = (size_t)std::max(cat->NB, 1), W = (size_t)cat->W;
   uint64_t* d_masks = (uint64_t*)ctx->alloc(N * W * 8);
   uint64_t* d_rmask = (uint64_t*)ctx->alloc(N * K * 8);
@@ -869,6 +885,7 @@ int b200s_order_by_price(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n, const
   if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
   Catalog* cat = it->second.get();
   if (n == 0) return B200S_OK;
+  if (!masks || !masks_in_range(masks, (size_t)n, cat->S, cat->W)) return fail(ctx, B200S_EINVAL, "order_by_price: a mask has bits beyond n_skus");
   const size_t N = (size_t)n, K = (size_t)cat->K, NB = (size_t)cat->NB, W = (size_t)cat->W, M = (size_t)max_types;
   std::vector<void*> held;
   auto dev = [&](size_t bytes) -> void* {
@@ -925,7 +942,11 @@ int b200s_consolidation_commands(b200s_ctx_t* ctx, uint64_t catalog_id, const b2
   if (kt.key_ct < 0 || sims->ct_spot < 0 || sims->ct_spot >= kt.n_cts || sims->ct_on_demand < 0 ||
       sims->ct_on_demand >= kt.n_cts || sims->ct_reserved >= kt.n_cts || sims->ct_spot == sims->ct_on_demand)
     return fail(ctx, B200S_ENOTREPRESENTABLE, "consolidation: spot / on-demand are not values of the catalog's capacity-type key");
+  if (sims->ct_reserved < -1 || sims->ct_reserved == sims->ct_spot || sims->ct_reserved == sims->ct_on_demand)
+    return fail(ctx, B200S_EINVAL, "consolidation: ct_reserved must be -1 or a capacity type of its own");
   if (sims->n == 0) return B200S_OK;
+  if (!sims->claim_mask || !masks_in_range(sims->claim_mask, (size_t)sims->n, cat->S, cat->W))
+    return fail(ctx, B200S_EINVAL, "consolidation: a claim mask has bits beyond n_skus");
   const size_t N = (size_t)sims->n, K = (size_t)cat->K, NB = (size_t)cat->NB, W = (size_t)cat->W;
   std::vector<uint64_t> limit(N);
   for (size_t i = 0; i < N; i++) {

@@ -352,6 +352,24 @@ void do_encode(Ctx& c) {
   cat.price_max = E->price_max.data();
   cat.alloc = E->alloc_rm.data();
   cat.capacity = E->cap_rm.data();
+  {  // the key layout this encode chose (FNV-1a): slots, value bits, numerics, well-known mask, bounded slots
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) {
+      for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xFFu; h *= 1099511628211ull; }
+    };
+    mix((uint64_t)K); mix((uint64_t)R); mix((uint64_t)(int64_t)kt.key_zone); mix((uint64_t)(int64_t)kt.key_ct);
+    mix(kt.wellknown); mix((uint64_t)NB);
+    for (int b = 0; b < NB; b++) mix((uint64_t)bounded_key[b]);
+    for (int k = 0; k < K; k++) {
+      mix((uint64_t)E->devkey_model[k]);
+      mix((uint64_t)E->devkey_values[k].size());
+      for (int v : E->devkey_values[k]) mix((uint64_t)v);
+      mix(E->val_isint[k]);
+      for (size_t b = 0; b < E->devkey_values[k].size(); b++) mix((uint64_t)E->val_int[(size_t)k * 64 + b]);
+    }
+    if (h == 0) h = 1;
+    cat.layout_hash = h;
+  }
 
   // ---- taint universe over pools + nodes ----
   std::vector<b200s_taint_t> taint_u;
@@ -588,6 +606,8 @@ void do_encode(Ctx& c) {
   Pd.sig_lt = E->sig_lt.data();
   Pd.sig_tolerated = E->sig_tolerated.data();
   Pd.rq_requests = E->rq_requests.data();
+  Pd.layout_hash = E->cat.layout_hash;
+  E->nodes.layout_hash = E->cat.layout_hash;
 }
 
 }  // namespace

@@ -63,6 +63,8 @@ extern "C" {
 #define B200S_ECAPACITY (-5)        /* caller-provided output capacity too small             */
 #define B200S_ENOMEM (-6)
 #define B200S_ESTATE (-7)           /* unknown catalog id / context misuse                   */
+#define B200S_ESTALE (-8)           /* pods / nodes were encoded against another key layout than the uploaded catalog
+                                       (layout_hash differs): upload this encode's catalog and call again */
 
 /* ---- requirement operators (corev1.NodeSelectorOperator; K/scheduling/requirement.go:47-87) ---- */
 #define B200S_OP_IN 0
@@ -219,6 +221,11 @@ typedef struct b200s_catalog_soa {
   const int64_t* capacity;   /* [R*S] raw capacity, resource-major                           */
   const uint64_t* price_max; /* [n_zones*n_cts*S] MOST expensive available offering per (zone,ct,SKU), B200S_PRICE_ABSENT if
                                 none: Offerings.MostExpensive for WorstLaunchPrice (types.go:454-474) */
+  /* The device key slots, each key's value bits, the well-known mask and the bounded-key slots are chosen by
+   * b200s_encode from the keys and Gt/Lt bounds of ONE model (SKUs, offerings, pools AND that batch's pods), so a pods /
+   * nodes SoA is only meaningful next to the catalog of the same encode.  layout_hash digests that choice; it is
+   * stamped into all three structures and the solve entry points answer B200S_ESTALE when they differ (0 = unchecked). */
+  uint64_t layout_hash;
 } b200s_catalog_soa_t;
 
 #define B200S_PRICE_NONE 0x7FEFFFFFFFFFFFFFull /* math.MaxFloat64 (types.go:224-225) */
@@ -259,6 +266,7 @@ typedef struct b200s_pods_soa {
   const uint64_t* sig_tolerated; /* [NS] bit t: tolerates taint t (taints.go:53-65) */
   /* request-class table, resource-major over NQ */
   const int64_t* rq_requests; /* [R*NQ] RequestsForPods incl. pods:1 (resources.go:30-38) */
+  uint64_t layout_hash;      /* see b200s_catalog_soa_t */
 } b200s_pods_soa_t;
 
 typedef struct b200s_nodes_soa {
@@ -269,6 +277,7 @@ typedef struct b200s_nodes_soa {
   const uint64_t* req_mask;  /* [K*E] key-major (node labels: single-value In sets) */
   const uint64_t* req_flags; /* [E] */
   const uint64_t* taints;    /* [E] */
+  uint64_t layout_hash;      /* see b200s_catalog_soa_t */
 } b200s_nodes_soa_t;
 
 /* ---- per-template attempt code written by fit_matrix / solve (parity is on the code, never on message text) ---- */

@@ -11,8 +11,9 @@ from b200sched import model as M
 def probe(model, node_of_pod, candidates, facts, mid, ct_values, spot_to_spot):
     _, v_spot, v_od, v_res = ct_values
     sim = cons.prefix_simulation(model, node_of_pod, candidates, mid)
-    return ob.consolidate(sim, cons.prefix_price(facts, mid), all(f[2] for f in facts[:mid + 1]), mid + 1, v_spot, v_od,
-                          v_res, spot_to_spot, same_type_rows=[(s, p) for s, p, _ in facts[:mid + 1]])
+    price, _ = cons.prefix_price(facts, mid)
+    return ob.consolidate(sim, price, all(f[2] for f in facts[:mid + 1]), mid + 1, v_spot, v_od,
+                          v_res, spot_to_spot, same_type_rows=[(s, p) for s, p, _, _ in facts[:mid + 1]])
 
 
 def first_n_consolidation_option(model, node_of_pod, candidates, ct_values, max_parallel=cons.MAX_PARALLEL,

@@ -14,6 +14,20 @@ NONE_BITS = int(np.float64(1.7976931348623157e308).view(np.uint64))
 
 
 class FakeContext:
+    def __init__(self):
+        self._layouts, self._next = {}, 1
+
+    def upload_catalog(self, enc):
+        self._layouts[self._next] = enc.layout_hash
+        self._next += 1
+        return self._next - 1
+
+    def release_catalog(self, cid):
+        self._layouts.pop(cid, None)
+
+    def catalog_layout(self, cid):
+        return self._layouts.get(cid)
+
     def solve_batch(self, cid, encs):
         return [parity.emul_solve(e) for e in encs]
 

@@ -232,6 +232,32 @@ def test_to_nodeclaim_instance_type_lists_match_the_oracle(gpu_ctx, kind, pods, 
         gpu_ctx.release_catalog(cid)
 
 
+def test_stale_catalog_is_refused(gpu_ctx):
+    """pods encoded against another key layout than the uploaded catalog (same K / NB, different slots) are refused
+    with B200S_ESTALE; re-uploading the catalog of the same encode makes the call go through"""
+    import test_host_helpers as th
+    ma, mb = th._team_model("example.com/team-a"), th._team_model("example.com/team-b")
+    ea, eb = capi.Encoded(ma), capi.Encoded(mb)
+    cid = gpu_ctx.upload_catalog(ea)
+    try:
+        gpu_ctx.solve(cid, ea)
+        if ea.layout_hash != eb.layout_hash:
+            with pytest.raises(capi.B200SError) as e:
+                gpu_ctx.solve(cid, eb)
+            assert e.value.code == capi.ESTALE
+            with pytest.raises(capi.B200SError) as e:
+                gpu_ctx.fit_matrix(cid, eb)
+            assert e.value.code == capi.ESTALE
+    finally:
+        gpu_ctx.release_catalog(cid)
+    cid = gpu_ctx.upload_catalog(eb)
+    try:
+        raw = gpu_ctx.solve(cid, eb)
+        parity.assert_same(parity.canon_device(eb, raw), parity.canon_oracle(mb, ob.solve(mb)), "after re-upload")
+    finally:
+        gpu_ctx.release_catalog(cid)
+
+
 @pytest.mark.gpu
 def test_consolidation_and_order_entry_points_reject_what_they_cannot_decide(gpu_ctx):
     """Error behaviour of the two widened entry points: a code, never a guess."""
@@ -266,6 +292,18 @@ def test_consolidation_and_order_entry_points_reject_what_they_cannot_decide(gpu
         with pytest.raises(capi.B200SError) as e:
             gpu_ctx.consolidation_commands(cid + 99, enc, [raw], [0.25], [False], [1], bs, bo)
         assert e.value.code == capi.ESTATE
+        # a caller mask with a bit beyond n_skus, or a reserved capacity type that is also spot / on-demand
+        import copy
+        bad = copy.copy(raw)
+        bad.claim_mask = raw.claim_mask.copy()
+        if enc.S % 64:
+            bad.claim_mask[0, -1] |= np.uint64(1) << np.uint64(63)
+            with pytest.raises(capi.B200SError) as e:
+                gpu_ctx.consolidation_commands(cid, enc, [bad], [0.25], [False], [1], bs, bo)
+            assert e.value.code == capi.EINVAL
+        with pytest.raises(capi.B200SError) as e:
+            gpu_ctx.consolidation_commands(cid, enc, [raw], [0.25], [False], [1], bs, bo, bs)
+        assert e.value.code == capi.EINVAL
     finally:
         gpu_ctx.release_catalog(cid)
 

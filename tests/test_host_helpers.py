@@ -6,7 +6,9 @@ import ctypes as C
 import numpy as np
 
 import oracle_binding as ob
-from b200sched import capi
+import pytest
+
+from b200sched import capi, synth
 
 R, PODS, MEM = 4, 3, 1  # cpu, memory, hugepages-2Mi, pods
 
@@ -101,3 +103,50 @@ def test_allocatable_random_against_oracle():
     for _ in range(300):
         allocatable(rng.integers(0, 1 << 20, R), rng.integers(0, 2, R), rng.integers(0, 1 << 10, R), rng.integers(0, 1 << 10, R),
                     rng.integers(0, 1 << 10, R), [0, 0, 1, 0])
+
+
+def _team_model(team_key):
+    """one catalog, one pool that defines both team keys, one pod that selects on `team_key`"""
+    from b200sched import model as M
+    b = synth.new_builder()
+    synth.add_catalog(b, 30)
+    for k in ("example.com/team-a", "example.com/team-b"):
+        b.key(k)
+    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"]), ("example.com/team-a", M.OP_IN, ["x"]),
+                     ("example.com/team-b", M.OP_IN, ["x"])])
+    b.add_pod([(team_key, M.OP_IN, ["x"])], [500, 1 << 30, 0, 0, 1])
+    return b.build()
+
+
+def test_layout_hash_tells_encodes_with_different_key_slots_apart():
+    """the device key slots come from the keys one model uses, pods included.  Two batches over the same
+    catalog whose pods select on different keys encode to the same K / NB but different slots; the stamp in the catalog,
+    pods and nodes SoA differs, and b200s_solve answers B200S_ESTALE instead of evaluating against stale tables
+    (tests/test_gpu.py::test_stale_catalog_is_refused)."""
+    ea, eb = capi.Encoded(_team_model("example.com/team-a")), capi.Encoded(_team_model("example.com/team-b"))
+    ea2 = capi.Encoded(_team_model("example.com/team-a"))
+    assert ea.layout_hash != 0 and ea.layout_hash == ea2.layout_hash
+    assert ea.pods.contents.layout_hash == ea.layout_hash == ea.nodes.contents.layout_hash
+    if ea.key_model != eb.key_model:
+        assert ea.K == eb.K and ea.layout_hash != eb.layout_hash
+
+
+def test_candidate_price_errors_surface_where_the_reference_would_hit_them():
+    """getCandidatePrices (consolidation.go:310-328): a reserved node without an offering makes the total 0.0, any other
+    unpriced candidate is an error -- but only for a probe whose simulation reaches the price comparison, and only when
+    the binary search visits that probe."""
+    from b200sched import consolidation as cons
+    facts = [(0, 0.5, False, False), (1, -1.0, False, True), (2, 0.25, False, False), (3, -1.0, False, False)]
+    assert cons.prefix_price(facts, 0) == (0.5, False)
+    assert cons.prefix_price(facts, 2) == (0.0, False)      # the reserved candidate ends the walk: free
+    assert cons.prefix_price(facts[2:], 1) == (0.0, True)   # unpriced and not reserved
+    visited = []
+
+    def valid_of(mid):
+        visited.append(mid)
+        if mid == 5:
+            raise cons.CandidatePriceError("x")
+        return mid < 3
+    assert cons.replay_search(1, 4, valid_of) == 2 and 5 not in visited  # the search never looks at prefix 5
+    with pytest.raises(cons.CandidatePriceError):
+        cons.replay_search(1, 9, valid_of)                   # (1 + 9) // 2 == 5 is the first probe
