@@ -241,13 +241,13 @@ def test_stale_catalog_is_refused(gpu_ctx):
     cid = gpu_ctx.upload_catalog(ea)
     try:
         gpu_ctx.solve(cid, ea)
-        if ea.layout_hash != eb.layout_hash:
-            with pytest.raises(capi.B200SError) as e:
-                gpu_ctx.solve(cid, eb)
-            assert e.value.code == capi.ESTALE
-            with pytest.raises(capi.B200SError) as e:
-                gpu_ctx.fit_matrix(cid, eb)
-            assert e.value.code == capi.ESTALE
+        assert ea.layout_hash != eb.layout_hash
+        with pytest.raises(capi.B200SError) as e:
+            gpu_ctx.solve(cid, eb)
+        assert e.value.code == capi.ESTALE
+        with pytest.raises(capi.B200SError) as e:
+            gpu_ctx.fit_matrix(cid, eb)
+        assert e.value.code == capi.ESTALE
     finally:
         gpu_ctx.release_catalog(cid)
     cid = gpu_ctx.upload_catalog(eb)

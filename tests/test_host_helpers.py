@@ -106,15 +106,15 @@ def test_allocatable_random_against_oracle():
 
 
 def _team_model(team_key):
-    """one catalog, one pool that defines both team keys, one pod that selects on `team_key`"""
+    """one catalog, one pool, one pod whose only requirement is NotIn on `team_key` -- a key nothing else uses (an
+    undefined key is forgiven for NotIn, requirements.go:183, so the pod still schedules)"""
     from b200sched import model as M
     b = synth.new_builder()
     synth.add_catalog(b, 30)
     for k in ("example.com/team-a", "example.com/team-b"):
         b.key(k)
-    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"]), ("example.com/team-a", M.OP_IN, ["x"]),
-                     ("example.com/team-b", M.OP_IN, ["x"])])
-    b.add_pod([(team_key, M.OP_IN, ["x"])], [500, 1 << 30, 0, 0, 1])
+    b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])])
+    b.add_pod([(team_key, M.OP_NOTIN, ["x"])], [500, 1 << 30, 0, 0, 1])
     return b.build()
 
 
@@ -127,8 +127,8 @@ def test_layout_hash_tells_encodes_with_different_key_slots_apart():
     ea2 = capi.Encoded(_team_model("example.com/team-a"))
     assert ea.layout_hash != 0 and ea.layout_hash == ea2.layout_hash
     assert ea.pods.contents.layout_hash == ea.layout_hash == ea.nodes.contents.layout_hash
-    if ea.key_model != eb.key_model:
-        assert ea.K == eb.K and ea.layout_hash != eb.layout_hash
+    assert ea.key_model != eb.key_model and ea.K == eb.K and ea.NB == eb.NB  # same counts, different slots
+    assert ea.layout_hash != eb.layout_hash
 
 
 def test_candidate_price_errors_surface_where_the_reference_would_hit_them():
