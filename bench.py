@@ -231,13 +231,29 @@ def dense_leg(ctx, capi, synth, kind, P, S, steps, warmup, peak, run=0):
     return out
 
 
+C5_WORKLOAD = ("config[4]: 1M pods x 2k SKUs (4 tainted NodePools, selectors), pod rows sharded over the ranks: per rank "
+               "class tables + dense pod x SKU rows of its shard, ONE NCCL all-gather of the compact per-pod results")
+
+
+def c5_config(P, S):
+    return {"workload": C5_WORKLOAD, "pods": P, "skus": S}
+
+
 def run_c5(args, rank, world, local):
-    """configs[4]: 1M pods x 2k SKUs, dense stage sharded by pod rows, one NCCL all-gather of the result rows."""
+    """configs[4] (north_star's multi-GPU partitioning): 1M pods x 2k SKUs, the pod x SKU matrix sharded by pod rows, one
+    all-gather of the compact per-pod results (first feasible template + attempt codes: 8 B/pod -- the instance-type rows
+    stay on the GPU that computed them and are re-derived from the replicated class tables where the pack opens a claim),
+    then the global packing of all pods on rank 0.  STRONG scaling: the total work is fixed.  The timed step is the
+    sharded stage + the all-gather + the import on the packing rank; the same stage on ONE GPU is timed in the same run
+    (rank 0, the others idle) so that the ratio can be read off one JSON line; the 1M-pod pack runs once, untimed steps
+    aside, and is reported with its invariants."""
     import torch
     import torch.distributed as dist
     import __graft_entry__ as g
     g.build()
     from b200sched import capi, model as M, sharding, synth
+    import oracle_binding as ob
+    import parity
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -249,77 +265,198 @@ def run_c5(args, rank, world, local):
     ctx = capi.Context(local)
     cid = ctx.upload_catalog(enc)
     res = ctx.resident(cid, enc)
+    T, W = enc.T, enc.W
+    rb = capi.compact_row_bytes(T)
     rows = max(sharding.row_shard(P, r, world)[1] - sharding.row_shard(P, r, world)[0] for r in range(world))
-    W, T = enc.W, enc.T
-    d_tmpl = torch.zeros(rows, dtype=torch.int32, device="cuda")
-    d_mask = torch.zeros(rows * W, dtype=torch.int64, device="cuda")
-    d_code = torch.zeros(rows * T, dtype=torch.uint8, device="cuda")
-    g_tmpl = torch.empty(world * rows, dtype=torch.int32, device="cuda")
-    g_mask = torch.empty(world * rows * W, dtype=torch.int64, device="cuda")
-    g_code = torch.empty(world * rows * T, dtype=torch.uint8, device="cuda")
-    ev0, ev1 = ctx.event(), ctx.event()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_send = torch.zeros(rows * rb, dtype=torch.uint8, device="cuda")
+    g_all = torch.zeros(world * rows * rb, dtype=torch.uint8, device="cuda")
+    lib_stream = torch.cuda.ExternalStream(ctx.stream())  # the collective is enqueued behind the kernels, no host sync
+    # the packing rank: all pods, per-pod results imported
+    enc_full = res_full = cid_full = None
+    if rank == 0:
+        enc_full = enc if world == 1 else capi.Encoded(full)
+        cid_full = cid if world == 1 else ctx.upload_catalog(enc_full)
+        res_full = res if world == 1 else ctx.resident(cid_full, enc_full)
+    ev0, ev1, ev2, ev3 = ctx.event(), ctx.event(), ctx.event(), ctx.event()
+
+    def gathered_rows():
+        if P % world == 0:
+            return g_all
+        v = g_all.view(world, rows, rb)
+        return torch.cat([v[r, :sharding.row_shard(P, r, world)[1] - sharding.row_shard(P, r, world)[0]] for r in range(world)]).contiguous()
 
     def step():
         ctx.flush_l2()
         ctx.record(ev0)
-        res.fit_matrix()
-        res.copy_fit_device(d_tmpl.data_ptr(), d_mask.data_ptr(), d_code.data_ptr())
+        res.fit_matrix()                      # prefilter + class tables + dense rows of this rank's shard
+        res.export_compact(d_send.data_ptr())
         ctx.record(ev1)
-        ms_fit = ctx.elapsed_ms(ev0, ev1)  # synchronises the library's stream: the send buffers are complete
-        ms_ag = 0.0
         if world > 1:
-            t0.record()
-            dist.all_gather_into_tensor(g_tmpl, d_tmpl)
-            dist.all_gather_into_tensor(g_mask, d_mask)
-            dist.all_gather_into_tensor(g_code, d_code)
-            t1.record()
-            t1.synchronize()
-            ms_ag = t0.elapsed_time(t1)
-        return ms_fit, ms_ag
+            with torch.cuda.stream(lib_stream):
+                dist.all_gather_into_tensor(g_all, d_send)
+        ctx.record(ev2)
+        if rank == 0 and world > 1:
+            res_full.import_compact(gathered_rows().data_ptr())
+        ctx.record(ev3)
+        return np.array([ctx.elapsed_ms(ev0, ev3), ctx.elapsed_ms(ev0, ev1), ctx.elapsed_ms(ev1, ev2), ctx.elapsed_ms(ev2, ev3)])
 
-    for _ in range(args.warmup):
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    acc = np.zeros(2)
+    barrier()
+    acc = np.zeros(4)
     with ClockSampler(local) as clk:
         for _ in range(args.steps):
             acc += step()
+            if world > 1:
+                dist.barrier()  # every step starts together: the time of a step is the max over the ranks
     acc /= args.steps
+    dense_k = res.dense_kernel_ms()
+    launches_stage = res.launches()
+    # end to end through host buffers: this rank's shard in, its rows out (b200s_fit_matrix), then the same all-gather
+    t_e2e = []
+    for it in range(2 + 3):
+        barrier()
+        t0 = time.perf_counter()
+        fit = ctx.fit_matrix(cid, enc)
+        if world > 1:
+            with torch.cuda.stream(lib_stream):
+                dist.all_gather_into_tensor(g_all, d_send)
+            ctx.synchronize()
+        if it >= 2:
+            t_e2e.append(1e3 * (time.perf_counter() - t0))
+    ms_e2e = float(np.mean(t_e2e))
     if world > 1:
-        t = torch.tensor(acc, device="cuda", dtype=torch.float64)
+        t = torch.tensor(list(acc) + [ms_e2e, dense_k], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        acc = t.cpu().numpy()
-    # parity spot check on this rank's shard
-    import oracle_binding as ob
-    import parity
+        v = t.cpu().numpy()
+        acc, ms_e2e, dense_k = v[:4], float(v[4]), float(v[5])
+    # parity: this rank's first and last rows (the shard boundaries) against the oracle
     fit = res.fetch_fit()
-    s0, s1 = 0, min(2000, enc.P)
-    o_tmpl, o_mask, o_code, _, _ = ob.fit_matrix(shard, s0, s1)
     cf = parity.canon_fit(enc, fit)
-    assert np.array_equal(cf["tmpl"][s0:s1], o_tmpl) and np.array_equal(cf["mask"][s0:s1], o_mask)
+    for s0, s1 in ((0, min(1000, enc.P)), (max(enc.P - 1000, 0), enc.P)):
+        o_tmpl, o_mask, o_code, _, _ = ob.fit_matrix(shard, s0, s1)
+        assert np.array_equal(cf["tmpl"][s0:s1], o_tmpl) and np.array_equal(cf["mask"][s0:s1], o_mask) and \
+            np.array_equal(cf["code"][s0:s1], o_code), f"rank {rank}: shard boundary rows differ from the oracle"
+    single = pack = None
+    cpu = None
+    if rank == 0:
+        # the same stage on ONE GPU, same run (the other ranks idle at the barrier below)
+        def one():
+            ctx.flush_l2()
+            ctx.record(ev0)
+            res_full.fit_matrix()
+            res_full.export_compact(g_all.data_ptr() if world == 1 else gathered_rows().data_ptr())
+            ctx.record(ev1)
+            return ctx.elapsed_ms(ev0, ev1)
+        if world > 1:
+            g_one = torch.zeros(P * rb, dtype=torch.uint8, device="cuda")
+            def one():  # noqa: F811
+                ctx.flush_l2()
+                ctx.record(ev0)
+                res_full.fit_matrix()
+                res_full.export_compact(g_one.data_ptr())
+                ctx.record(ev1)
+                return ctx.elapsed_ms(ev0, ev1)
+        for _ in range(3):
+            one()
+        ms_one = float(np.mean([one() for _ in range(args.steps)]))
+        single = {"ms_per_step": ms_one, "value": P * S / (ms_one * 1e-3), "dense_kernel_ms": res_full.dense_kernel_ms(),
+                  "note": "prefilter + class tables + dense rows of ALL pods + compact export on rank 0's GPU alone"}
+        if world > 1:  # the all-gathered per-pod results equal what one GPU computes for all pods
+            assert torch.equal(gathered_rows().view(P, rb)[:, :T + 1], g_one.view(P, rb)[:, :T + 1]), "gathered rows differ"
+        # "merge the global packing": FFD order + pack + cheapest SKU over all pods from the imported per-pod results
+        res_full.import_compact((gathered_rows() if world > 1 else g_all).data_ptr())
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        res_full.pack()
+        ctx.synchronize()
+        pack_s = time.perf_counter() - t0
+        raw = res_full.fetch_solve()
+        placed = int((raw.pod_place_kind == capi.PLACE_CLAIM).sum())
+        assert placed + raw.n_unscheduled == P and int(raw.claim_npods.sum()) == placed
+        assert (raw.claim_sku >= 0).all() and (raw.claim_n_options > 0).all()
+        pack = {"ms": 1e3 * pack_s, "pods": P, "nodeclaims": int(raw.n_claims), "unschedulable": int(raw.n_unscheduled),
+                "nodeclaims_per_s": raw.n_claims / pack_s, "digest": parity.digest(parity.canon_device(enc_full, raw))[:16],
+                "note": "one Solve over all pods on rank 0 from the imported per-pod results (pods with selectors: the "
+                        "generic pack kernel, one CTA); checked here by counts, bit-for-bit in tests/test_gpu.py"}
+        # CPU baseline: the reference-shaped dense pass over a bounded sample of the rows, all host threads
+        nthreads = host_threads()
+        sample = M.slice_pods(full, 0, min(P, 40_000))
+        t0 = time.perf_counter()
+        ob.fit_matrix_threads(sample, nthreads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample.n_pods * S / dt, "unit": "evals/s", "cores": nthreads, "kind": "port",
+               "sample": f"the dense pass (filterInstanceTypesByRequirements per pod x template) over the first {sample.n_pods} "
+                         "of the pods, split over all host threads", "ms": 1e3 * dt, "host_cores": os.cpu_count()}
+    barrier()
     peak, src = peaks()
-    ms = float(acc[0] + acc[1])
+    ms = float(acc[0])
     ab = dense_bytes(enc)
     line = {"metric": METRIC, "value": P * S / (ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"config[4]: {P} pods x {S} SKUs, dense stage sharded by pod rows over {world} GPU(s), "
-                                   "one NCCL all-gather of the result rows", "l2": "flushed between timed iterations"},
-            "dense_ms_max_over_ranks": float(acc[0]), "allgather_ms": float(acc[1]),
-            "allgather_bytes_per_rank": int(rows * (4 + W * 8 + T)),
-            "roofline": {"bound": "hbm", "kernel": "dense stage (per rank shard)", "achieved": ab / (acc[0] * 1e-3) / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": ab / (acc[0] * 1e-3) / 1e9 / peak, "traffic": None,
-                         "peak_source": src},
-            "clocks": clk.summary(), "parity": "first 2000 rows of the rank-0 shard identical to the CPU oracle"}
+            "dtype": "u64", "data": "synthetic", "config": c5_config(P, S),
+            "l2": "flushed between timed iterations (256 MiB memset)",
+            "stage_ms_max_over_ranks": float(acc[1]), "allgather_ms": float(acc[2]), "import_ms": float(acc[3]),
+            "dense_kernel_ms_max_over_ranks": dense_k,
+            "allgather_bytes_per_rank": int(rows * rb), "allgather_bytes_per_pod": rb,
+            "single_gpu_same_run": single, "global_pack": pack,
+            "roofline": {"bound": "hbm", "kernel": "fit_dense_vec_kernel on this rank's shard", "achieved": ab / (dense_k * 1e-3) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": ab / (dense_k * 1e-3) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes": ab, "kernel_ms": dense_k, "peak_source": src,
+                         "note": "per-shard launch: 1/N of the rows, so the launch shrinks with N (at N=8 ~11 us of a "
+                                 "~60 us stage); the single-GPU figure is in the N=1 line's roofline"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": P * S / (ms_e2e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(enc.P * 32 + enc.NS * (enc.K * 8 + 16 + enc.NB * 8) + enc.NQ * enc.R * 8),
+                    "d2h_bytes_per_step": int(enc.P * (4 + W * 8 + T)),
+                    "note": "per rank: b200s_fit_matrix with host buffers (shard in, its rows out) + the all-gather; max over ranks"},
+            "gpu_launches": int((args.steps + max(args.warmup, 3)) * (launches_stage + 1)),
+            "clocks": clk.summary(),
+            "parity": "every rank's first and last 1000 rows identical to the CPU oracle; gathered per-pod results identical to the single-GPU results"}
     res.close()
+    if res_full is not None and res_full is not res:
+        res_full.close()
     ctx.close()
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_reference_c5(args, rank):
+    """the reference arm of the multi-GPU workload: the CPU oracle's dense pass (the work the sharded stage does) on a
+    bounded sample of the 1M x 2k rows, all host threads, same metric and config"""
+    import oracle_binding as ob
+    from b200sched import model as M, synth
+    if rank != 0:
+        return
+    P, S = args.pods or 1_000_000, args.skus or 2_000
+    n = min(P, 40_000)
+    sample = synth.config("c3", n, S)  # the same generator streams: the first n pods of the 1M-pod list
+    ob.lib()
+    nthreads = host_threads()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ob.fit_matrix_threads(sample, nthreads)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+        if sum(times) > 120:
+            break
+    dt = sum(times) / len(times)
+    value = n * S / dt
+    emit({"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
+          "ms_per_step": 1e3 * dt * (P / n), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+          "data": "synthetic", "impl": "reference", "config": c5_config(P, S),
+          "cpu_baseline": {"value": value, "unit": "evals/s", "cores": nthreads, "kind": "port",
+                           "sample": f"each step: the dense pass over {n} of the {P} pods ({n * S} evaluations), split over all "
+                                     "host threads; ms_per_step is scaled to the whole workload", "host_cores": os.cpu_count()},
+          "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 def run_c4(args, rank, world, local):
@@ -498,7 +635,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c4", "c5"],
+                    help="auto: config[1] (one Solve) on one GPU, config[4] (row-sharded, strong scaling) on several")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--pods", type=int, default=0)
     ap.add_argument("--skus", type=int, default=0)
@@ -507,8 +645,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "auto":
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c5"
     if args.impl == "reference":
-        run_reference(args, rank)
+        (run_reference_c5 if args.workload == "c5" else run_reference)(args, rank)
         return
     if args.workload == "c5":
         run_c5(args, rank, world, local)
@@ -595,9 +735,11 @@ def main():
         "metric": METRIC, "value": world * credited / (ms_solve * 1e-3), "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_solve, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pods": P, "skus": S, "signatures": enc.NS, "request_classes": enc.NQ,
-                   "l2": "flushed between timed iterations (256 MiB memset)",
-                   "multi_gpu": "replicas only: one independent Solve per rank, no data-path collective (DESIGN.md section 7)"},
+        "config": {"workload": WORKLOAD, "pods": P, "skus": S},
+        "workload_detail": {"signatures": enc.NS, "request_classes": enc.NQ,
+                            "l2": "flushed between timed iterations (256 MiB memset)",
+                            "multi_gpu": "with --workload c2 under torchrun: one independent Solve per rank (replicas); the "
+                                         "default under torchrun is the row-sharded config[4] workload (--workload c5)"},
         "nodeclaims_per_s": world * raw.n_claims / (ms_solve * 1e-3), "nodeclaims": int(raw.n_claims),
         "evals_per_step": int(credited), "dense_evals_per_step": int(dense_evals),
         "step_breakdown": {"dense_stage_ms": ms_fit, "dense_stage_share": ms_fit / ms_solve,

@@ -485,6 +485,14 @@ class Context:
     def synchronize(self):
         self._check(self.L.b200s_synchronize(self.h))
 
+    def stream(self) -> int:
+        """the context's cudaStream_t as an integer (e.g. for torch.cuda.ExternalStream)"""
+        return int(self.L.b200s_stream(self.h) or 0)
+
+
+def compact_row_bytes(T: int) -> int:
+    return int(lib().b200s_compact_row_bytes(T))
+
 
 class Resident:
     def __init__(self, ctx: Context, cid: int, enc: Encoded):
@@ -504,6 +512,18 @@ class Resident:
         """Device pointers (ints) of caller-owned buffers, e.g. torch tensors' data_ptr()."""
         self.ctx._check(self.ctx.L.b200s_resident_copy_fit_device(self.ctx.h, self.h, C.c_void_p(d_tmpl), C.c_void_p(d_mask),
                                                                   C.c_void_p(d_code)))
+
+    def export_compact(self, d_out: int):
+        """compact rows (template + attempt codes, compact_row_bytes(T) each) of this resident's pods into device memory"""
+        self.ctx._check(self.ctx.L.b200s_resident_export_compact(self.ctx.h, self.h, C.c_void_p(d_out)))
+
+    def import_compact(self, d_in: int):
+        """compact rows of ALL of this resident's pods, from device memory (gathered from the ranks that evaluated them)"""
+        self.ctx._check(self.ctx.L.b200s_resident_import_compact(self.ctx.h, self.h, C.c_void_p(d_in)))
+
+    def pack(self):
+        """FFD order + pack + cheapest SKU on imported per-pod results"""
+        self.ctx._check(self.ctx.L.b200s_resident_pack(self.ctx.h, self.h))
 
     def launches(self) -> int:
         return self.ctx.L.b200s_resident_last_launches(self.h)

@@ -1,8 +1,10 @@
 """Row sharding of the dense stage across ranks.
 
 The pod x SKU matrix shards by pod rows: rows are independent, the catalog tables are replicated, and the only
-collective is ONE all-gather of the result rows (first feasible template, SKU mask, attempt codes) when a single
-pack has to see them all.  The pack itself does not shard (each placement depends on every earlier one): across
+collective is ONE all-gather of the compact per-pod results (first feasible template + attempt codes, 8 bytes a pod:
+`to_compact` / `from_compact` mirror b200s_resident_export_compact / _import_compact) when a single pack has to see
+them all; the instance-type rows stay on the GPU that computed them -- the pack re-derives a row from the replicated
+class tables when it opens a claim.  The pack itself does not shard (each placement depends on every earlier one): across
 GPUs it scales over independent Solves only ("replicas only") -- e.g. the consolidation simulations of config 4,
 dealt round-robin to the ranks, their few result words per simulation all-gathered (`deal`, `undeal`).
 """
@@ -55,3 +57,22 @@ def undeal(g: np.ndarray, n_items: int, world: int) -> np.ndarray:
         idx = deal(n_items, rank, world)
         out[idx] = g[rank, :len(idx)]
     return out
+
+
+def compact_row_bytes(T: int) -> int:
+    """b200s_compact_row_bytes: [int8 template | T code bytes | padding]"""
+    return 8 if T <= 7 else 24
+
+
+def to_compact(tmpl: np.ndarray, code: np.ndarray) -> np.ndarray:
+    """per-pod (first feasible template, attempt codes [P, T]) -> compact rows [P, compact_row_bytes(T)] uint8"""
+    P, T = code.shape
+    out = np.zeros((P, compact_row_bytes(T)), np.uint8)
+    out[:, 0] = tmpl.astype(np.int8).view(np.uint8)
+    out[:, 1:T + 1] = code
+    return out
+
+
+def from_compact(rows: np.ndarray, T: int):
+    """compact rows -> (tmpl int32 [P], code uint8 [P, T])"""
+    return rows[:, 0].view(np.int8).astype(np.int32), np.ascontiguousarray(rows[:, 1:T + 1])

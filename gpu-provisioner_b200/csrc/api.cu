@@ -114,7 +114,7 @@ struct b200s_resident {
   uint32_t* feas_bits = nullptr;
   RegPackDev reg_dev{};
   int last_launches = 0;
-  bool fit_done = false, solve_done = false;
+  bool fit_done = false, solve_done = false, rows_done = false, imported = false;
   cudaEvent_t ev_dense0 = nullptr, ev_dense1 = nullptr;  // bracket the dense kernel of the last stage A on ctx->stream
 
   template <class Tp>
@@ -359,7 +359,8 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->rqF = r->dalloc<uint64_t>(NQ * T1 * W);
   r->tm_count = r->dalloc<int32_t>(MAXT);
   r->a_tmpl = r->dalloc<int32_t>(P);
-  r->a_mask = r->dalloc<uint64_t>(P * W);
+  r->a_mask = nullptr;  // the P x W rows are materialised only for b200s_(resident_)fit_matrix: the Solve reads a row as
+                        // class row & class row when it opens a claim
   r->a_code = r->dalloc<uint8_t>(P * (size_t)std::max(T, 1));
   r->a_evals = r->dalloc<unsigned long long>(1);
   PackArrays& A = r->arr;
@@ -386,7 +387,8 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   A.queue = r->dalloc<int32_t>((size_t)r->Ppad);
   A.lastlen = r->dalloc<int32_t>(P);
   A.a_tmpl = r->a_tmpl;
-  A.a_mask = r->a_mask;
+  A.a_mask = nullptr;
+  A.sgCO = nullptr; A.rqF = nullptr; A.T = T;
   A.pod_kind = r->dalloc<int32_t>(P);
   A.pod_index = r->dalloc<int32_t>(P);
   A.pod_seq = r->dalloc<int32_t>(P);
@@ -403,7 +405,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->sel_sku = r->dalloc<int32_t>(P);
   r->sel_price = r->dalloc<uint64_t>(P);
   r->sel_nopt = r->dalloc<int32_t>(P);
-  void* must[] = {r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl, r->a_mask, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_thr, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
+  void* must[] = {r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl, r->a_code, r->a_evals, A.c_mask, A.c_req, A.c_hi, A.c_thr, A.c_rmask, A.c_rflags, A.c_gt, A.c_lt,
                   A.c_tmpl, A.c_npods, A.c_nopt, A.ord, A.ord_key, A.ord_snap, A.n_avail, A.n_rmask, A.n_rflags, A.n_npods, A.queue, A.lastlen, A.pod_kind,
                   A.pod_index, A.pod_seq, O.tmpl, O.npods, O.req, O.mask, O.rmask, O.rflags, O.gt, O.lt, O.pos_of_claim,
                   r->sel_sku, r->sel_price, r->sel_nopt};
@@ -444,7 +446,17 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
 }
 
 // stage A: template pre-filter, class tables, dense fit matrix
-int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
+// stage A.  want_rows: materialise every pod's instance-type row (b200s_fit_matrix's output); dense: run the per-pod
+// kernel at all (false when the per-pod results were imported from other GPUs: only the class tables are needed)
+int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches, bool want_rows, bool dense = true) {
+  if (want_rows && !r->a_mask) {
+    r->a_mask = r->dalloc<uint64_t>((size_t)std::max(r->P, 1) * r->cat->W);
+    if (!r->a_mask) return fail(ctx, B200S_ENOMEM, "device allocation (fit rows)");
+  }
+  r->arr.a_mask = nullptr;  // the pack always reads rows through the class tables
+  r->arr.sgCO = r->sgCO;
+  r->arr.rqF = r->rqF;
+  r->arr.T = r->T;
   CUDA_TRY(ctx, cudaMemsetAsync(r->a_evals, 0, sizeof(unsigned long long), ctx->stream), "memset");
   CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, r->tm_count, ctx->stream),
            "template_prefilter launch");
@@ -456,18 +468,19 @@ int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches) {
     CUDA_TRY(ctx, cudaEventCreate(&r->ev_dense1), "event");
   }
   CUDA_TRY(ctx, cudaEventRecord(r->ev_dense0, ctx->stream), "event record");
-  CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl,
-                                 r->a_mask, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
-           "fit_dense launch");
+  if (dense)
+    CUDA_TRY(ctx, launch_fit_dense(r->cat->kt, r->T, r->pods, r->sg_status, r->sgC, r->sgO, r->sgCO, r->rqF, r->tm_count, r->a_tmpl,
+                                   want_rows ? r->a_mask : nullptr, r->a_code, r->a_evals, ctx->n_sm, ctx->stream),
+             "fit_dense launch");
   CUDA_TRY(ctx, cudaEventRecord(r->ev_dense1, ctx->stream), "event record");
   *launches += 1 + (((long long)r->pods.NS + r->pods.NQ) * r->T > 0 ? 1 : 0) + (r->P > 0 ? 1 : 0);
   return 0;
 }
 
-int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
+int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches, bool imported = false) {
   const Catalog* cat = r->cat;
   const size_t E = (size_t)std::max(r->E, 1), P = (size_t)std::max(r->P, 1);
-  int rc = enqueue_fit(ctx, r, launches);
+  int rc = enqueue_fit(ctx, r, launches, false, !imported);
   if (rc) return rc;
   // fresh mutable state
   CUDA_TRY(ctx, cudaMemcpyAsync(r->arr.n_avail, r->n_avail0, (size_t)cat->R * E * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
@@ -515,6 +528,7 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches) {
 
 int fetch_fit(b200s_ctx* ctx, b200s_resident* r, int32_t* tmpl_out, uint64_t* mask_out, uint8_t* code_out, int64_t* evals_out) {
   const size_t P = (size_t)r->P;
+  if (P && mask_out && !r->rows_done) return fail(ctx, B200S_ESTATE, "the fit rows were not materialised: call b200s_resident_fit_matrix first");
   if (P) {
     CUDA_TRY(ctx, cudaMemcpyAsync(tmpl_out, r->a_tmpl, P * 4, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
     CUDA_TRY(ctx, cudaMemcpyAsync(mask_out, r->a_mask, P * r->cat->W * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
@@ -761,8 +775,8 @@ void b200s_resident_free(b200s_ctx_t* ctx, b200s_resident_t* r) {
 int b200s_resident_fit_matrix(b200s_ctx_t* ctx, b200s_resident_t* r) {
   if (!ctx || !r) return B200S_EINVAL;
   r->last_launches = 0;
-  int rc = enqueue_fit(ctx, r, &r->last_launches);
-  if (!rc) r->fit_done = true;
+  int rc = enqueue_fit(ctx, r, &r->last_launches, true);
+  if (!rc) { r->fit_done = true; r->rows_done = true; }
   return rc;
 }
 
@@ -791,9 +805,46 @@ int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* 
   const size_t P = (size_t)r->P;
   if (P == 0) return B200S_OK;
   if (d_tmpl) CUDA_TRY(ctx, cudaMemcpyAsync(d_tmpl, r->a_tmpl, P * 4, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
-  if (d_mask) CUDA_TRY(ctx, cudaMemcpyAsync(d_mask, r->a_mask, P * r->cat->W * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  if (d_mask) {
+    if (!r->rows_done) return fail(ctx, B200S_ESTATE, "the fit rows were not materialised: call b200s_resident_fit_matrix first");
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_mask, r->a_mask, P * r->cat->W * 8, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
+  }
   if (d_code && r->T) CUDA_TRY(ctx, cudaMemcpyAsync(d_code, r->a_code, P * r->T, cudaMemcpyDeviceToDevice, ctx->stream), "D2D");
   return B200S_OK;
+}
+
+int b200s_compact_row_bytes(int32_t n_templates) { return n_templates < 0 || n_templates > MAXT ? B200S_EINVAL : compact_row_bytes(n_templates); }
+
+/* the per-pod results another GPU needs to pack these pods: [int8 first feasible template | T attempt codes | pad] per
+ * pod, b200s_compact_row_bytes(T) bytes each, written to DEVICE memory d_out (the send buffer of the one all-gather of
+ * SURVEY.md section 8e).  The instance-type rows stay where they were computed. */
+int b200s_resident_export_compact(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_out) {
+  if (!ctx || !r || !d_out) return B200S_EINVAL;
+  if (!r->fit_done) return B200S_ESTATE;
+  CUDA_TRY(ctx, launch_compact_export(r->P, r->T, r->a_tmpl, r->a_code, (uint8_t*)d_out, ctx->n_sm, ctx->stream), "compact_export launch");
+  r->last_launches += r->P > 0 ? 1 : 0;
+  return B200S_OK;
+}
+
+/* the inverse on the GPU that packs: d_in holds compact rows for ALL of this resident's pods (gathered from the ranks
+ * that evaluated them); afterwards b200s_resident_pack runs the Solve without evaluating the pods again */
+int b200s_resident_import_compact(b200s_ctx_t* ctx, b200s_resident_t* r, const void* d_in) {
+  if (!ctx || !r || !d_in) return B200S_EINVAL;
+  CUDA_TRY(ctx, launch_compact_import(r->P, r->T, (const uint8_t*)d_in, r->a_tmpl, r->a_code, ctx->n_sm, ctx->stream), "compact_import launch");
+  r->fit_done = true;
+  r->imported = true;
+  r->last_launches = r->P > 0 ? 1 : 0;
+  return B200S_OK;
+}
+
+/* FFD order + pack + cheapest SKU on per-pod stage-A results that are already in place (imported): "merge the global
+ * packing" of the row-sharded evaluation.  The class tables are (re)built locally; rows are read through them. */
+int b200s_resident_pack(b200s_ctx_t* ctx, b200s_resident_t* r) {
+  if (!ctx || !r) return B200S_EINVAL;
+  if (!r->imported) return fail(ctx, B200S_ESTATE, "b200s_resident_pack needs b200s_resident_import_compact first");
+  int rc = enqueue_solve(ctx, r, &r->last_launches, true);
+  if (!rc) r->solve_done = true;
+  return rc;
 }
 
 int b200s_resident_last_launches(const b200s_resident_t* r) { return r ? r->last_launches : 0; }

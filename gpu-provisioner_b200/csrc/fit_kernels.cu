@@ -18,6 +18,8 @@
 #include <cstring>
 
 #include "device_types.cuh"
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace b200 {
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_kernel(int P, int T, in
 #pragma unroll
     for (int i = 0; i < WPL; i++) {
       int w = gl + i * G;
-      if (w < W) mask_out[(size_t)p * W + w] = keep[i];
+      if (w < W && mask_out) mask_out[(size_t)p * W + w] = keep[i];
     }
   }
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
@@ -371,7 +373,7 @@ __device__ __forceinline__ void dense_general_iter(const DenseArgs& a, int p, bo
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
     const unsigned v = gl + i * LPG;
-    if (live && v < (unsigned)W2) a.mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];
+    if (live && v < (unsigned)W2 && a.mask_out) a.mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];  // null: rows on demand
   }
 }
 
@@ -922,6 +924,53 @@ cudaError_t launch_consolidation(const KeyTab& kt, const ConsolidationArgs& a, i
   cudaError_t e = cudaFuncSetAttribute(consolidation_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   consolidation_kernel<<<blocks, 256, bytes, stream>>>(kt, a, key_cap);
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------------------------
+// compact stage-A rows: what another GPU needs of a pod's row to run the pack — the first feasible template and the
+// per-template attempt codes.  The instance-type row itself is a function of (signature, request class, template)
+// and the replicated class tables, so it is never sent (one all-gather of the result rows).
+// row = [int8 template | T code bytes | padding], `rb` bytes (compact_row_bytes(T))
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_export_kernel(int P, int T, int rb, const int32_t* __restrict__ tmpl,
+                                                             const uint8_t* __restrict__ code, uint8_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)P * rb; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / rb), j = (int)(i % rb);
+    uint8_t v = 0;
+    if (j == 0) v = (uint8_t)(int8_t)tmpl[p];
+    else if (j <= T) v = code[(size_t)p * T + (j - 1)];
+    out[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) compact_import_kernel(int P, int T, int rb, const uint8_t* __restrict__ in,
+                                                             int32_t* __restrict__ tmpl, uint8_t* __restrict__ code) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)P * (T + 1); i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i / (T + 1)), j = (int)(i % (T + 1));
+    const uint8_t v = in[(size_t)p * rb + j];
+    if (j == 0) tmpl[p] = (int32_t)(int8_t)v;
+    else code[(size_t)p * T + (j - 1)] = v;
+  }
+}
+
+int compact_row_bytes(int T) { return T <= 7 ? 8 : 24; }
+
+cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream) {
+  if (P == 0) return cudaSuccess;
+  const int rb = compact_row_bytes(T);
+  const long long n = (long long)P * rb;
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)n_sm * 8);
+  compact_export_kernel<<<grid, 256, 0, stream>>>(P, T, rb, tmpl, code, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_import(int P, int T, const uint8_t* in, int32_t* tmpl, uint8_t* code, int n_sm, cudaStream_t stream) {
+  if (P == 0) return cudaSuccess;
+  const int rb = compact_row_bytes(T);
+  const long long n = (long long)P * (T + 1);
+  const int grid = (int)std::min<long long>((n + 255) / 256, (long long)n_sm * 8);
+  compact_import_kernel<<<grid, 256, 0, stream>>>(P, T, rb, in, tmpl, code);
   return cudaGetLastError();
 }
 

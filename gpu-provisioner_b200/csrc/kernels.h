@@ -51,12 +51,22 @@ struct PackArrays {
   int32_t* lastlen;    // [Ptot]
   // stage A results
   const int32_t* a_tmpl;   // [Ptot]
-  const uint64_t* a_mask;  // [Ptot*W]
+  const uint64_t* a_mask;  // [Ptot*W]; null when the rows are not materialised: the row of pod p on template t is then
+                           // sgCO[sig(p), t] & rqF[rq(p), t] (stage_a_word)
+  const uint64_t* sgCO;    // [(NS*T)*W] class rows C & O
+  const uint64_t* rqF;     // [(NQ*T)*W] class rows F
+  int32_t T;
   // per pod outputs
   int32_t* pod_kind;   // [Ptot]
   int32_t* pod_index;  // [Ptot] local claim id / node row
   int32_t* pod_seq;    // [Ptot]
 };
+
+// word w of pod p's stage-A row on template t (the instance types a fresh NodeClaim of template t keeps for the pod)
+__device__ __forceinline__ uint64_t stage_a_word(const PackArrays& A, const PodsDev& pods, int p, int t, int W, int w) {
+  if (A.a_mask) return A.a_mask[(size_t)p * W + w];
+  return A.sgCO[((size_t)pods.sig_id[p] * A.T + t) * W + w] & A.rqF[((size_t)pods.req_id[p] * A.T + t) * W + w];
+}
 
 // final, ordered NodeClaim rows (what b200s_result_t carries)
 struct ClaimOut {
@@ -99,6 +109,9 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
                              int32_t* tmpl_out,
                              uint64_t* mask_out, uint8_t* code_out, unsigned long long* evals, int n_sm,
                              cudaStream_t stream);
+int compact_row_bytes(int T);
+cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream);
+cudaError_t launch_compact_import(int P, int T, const uint8_t* in, int32_t* tmpl, uint8_t* code, int n_sm, cudaStream_t stream);
 int ffd_padded(int P);
 cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, int32_t* idx, int* launches, cudaStream_t stream);
 cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* masks, const uint64_t* rmask, size_t rms,

@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
         int cnt = 0;
         for (int w = gl; w < W; w += G) {
-          uint64_t m = A.a_mask[(size_t)p * W + w];
+          uint64_t m = stage_a_word(A, pods, p, t, W, w);
           c_mask[(size_t)c * W + w] = m;
           cnt += popc64(m);
         }
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
             int mid = (lo + hi + 1) >> 1;
             unsigned hit = 0;
             for (int w = gl; w < W; w += G)
-              hit |= (A.a_mask[(size_t)p * W + w] & ldg(kt.rows + (size_t)(kt.res_row0[r] + mid) * W + w)) ? 1u : 0u;
+              hit |= (stage_a_word(A, pods, p, t, W, w) & ldg(kt.rows + (size_t)(kt.res_row0[r] + mid) * W + w)) ? 1u : 0u;
             hit = __reduce_or_sync(group_mask<G>(), hit);
             if (hit) lo = mid; else hi = mid - 1;
           }

@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     for (int c = warp; c < n; c += REG_NW) {
       const int first = c_first[c], t = c_tmpl[c];
       for (int w = lane; w < W; w += 32) {
-        uint64_t m = A.a_mask[(size_t)first * W + w];
+        uint64_t m = stage_a_word(A, pods, first, t, W, w);
         for (int r = 0; r < R; r++) m &= prm.rows[(size_t)c_rk[(size_t)c * R + r] * W + w];
         c_mask[(size_t)c * W + w] = m;
       }

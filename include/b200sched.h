@@ -477,6 +477,18 @@ int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_resu
 /* device-to-device copy of the resident dense results into caller-owned DEVICE buffers (e.g. the send buffers of
  * an NCCL all-gather when the pod rows are sharded across GPUs); enqueued on the context's stream */
 int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_tmpl, void* d_mask, void* d_code);
+/* ---- pod rows sharded across GPUs ----
+ * Each GPU evaluates its block of pod rows (b200s_resident_fit_matrix on a resident built from that block); what the
+ * GPU that runs the pack needs of a pod is its first feasible template and the per-template attempt codes — the
+ * instance-type row is a function of (signature, request class, template) and of the class tables every GPU builds from
+ * the replicated catalog, so it is never sent.  export writes the compact rows of this resident's pods to DEVICE memory
+ * (the send buffer of ONE all-gather); import takes the compact rows of ALL of a resident's pods; pack then runs FFD
+ * order + bin-pack + cheapest SKU on them without evaluating a pod again ("merge the global packing").
+ * Row: [int8 template | n_templates code bytes | padding], b200s_compact_row_bytes(n_templates) bytes. */
+int b200s_compact_row_bytes(int32_t n_templates);
+int b200s_resident_export_compact(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_out);
+int b200s_resident_import_compact(b200s_ctx_t* ctx, b200s_resident_t* r, const void* d_in);
+int b200s_resident_pack(b200s_ctx_t* ctx, b200s_resident_t* r);
 /* number of kernels the last resident_* call enqueued */
 int b200s_resident_last_launches(const b200s_resident_t* r);
 /* device time of the dense fit kernel alone in the last stage A (CUDA events on the context's stream, recorded on

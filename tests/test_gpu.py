@@ -187,6 +187,165 @@ def test_config3_full_size_properties(gpu_ctx):
     assert (d < 0).sum() <= 1
 
 
+def test_config3_full_size_solve_bit_identical(gpu_ctx):
+    """BASELINE.json configs[2] in full: 100k pods x 1k SKUs, 4 tainted NodePools, selectors -- every NodeClaim, every
+    placement, every attempt code of the whole Solve bit-identical to the oracle (which needs about half a minute)."""
+    m = synth.c3()
+    raw, o = _solve_parity(gpu_ctx, m, "config 3, full size")
+    assert raw.n_claims == o.n_claims and np.array_equal(raw.claim_sku, o.claim_sku)
+    assert o.counters["price_ties"] == 0
+
+
+def test_config4_full_size_simulation_sample(gpu_ctx):
+    """BASELINE.json configs[3] at its size: 50 000 running pods on loosely packed nodes; a spread of 24 single-node
+    consolidation simulations (each against ALL the other nodes) in one batch, their commands, and the multi-node re-pack
+    of those candidates, bit-identical to the oracle."""
+    from b200sched import model as M
+
+    def device_solve(mm):  # the loose initial packing is itself produced by the device path (as bench.py does)
+        e = capi.Encoded(mm)
+        cid0 = gpu_ctx.upload_catalog(e)
+        try:
+            r = gpu_ctx.solve(cid0, e)
+        finally:
+            gpu_ctx.release_catalog(cid0)
+
+        class R:
+            pass
+        out = R()
+        out.claim_sku, out.claim_requests = r.claim_sku, r.claim_requests
+        out.pod_place_index = np.where(r.pod_place_kind == capi.PLACE_CLAIM, r.pod_place_index, -1)
+        return out
+
+    model, node_of_pod, util = synth.c4(50_000, 500, solve=device_solve)
+    E = int(model.c.n_nodes)
+    sims = synth.c4_simulations(model, node_of_pod, util, 24, spread=True)
+    encs = [capi.Encoded(mm) for _, mm in sims]
+    prices, spot = synth.candidate_prices(model, [i for i, _ in sims])
+    key, v_spot, v_od, v_res = parity.capacity_type_values(model)
+    bits = [encs[0].value_bit(key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res)]
+    cid = gpu_ctx.upload_catalog(encs[0])
+    try:
+        outs = gpu_ctx.solve_batch(cid, encs)
+        cmds = gpu_ctx.consolidation_commands(cid, encs[0], outs, prices, spot, [1] * len(sims), bits[0], bits[1], bits[2],
+                                              spot_to_spot=True)
+        for j, ((i, mm), e, r) in enumerate(zip(sims, encs, outs)):
+            o, want = ob.consolidate(mm, prices[j], spot[j], 1, v_spot, v_od, v_res, True)
+            parity.assert_same(parity.canon_device(e, r), parity.canon_oracle(mm, o), f"c4 simulation of node {i}")
+            got = parity.device_commands_as_oracle(encs[0], cmds, j)
+            for f in ("decision", "reason", "n_options", "spot_required", "price_tie"):
+                assert got[f] == want[f], (i, f)
+            assert got["mask"] == want["mask"].tolist() and got["head"] == want["head"].tolist(), i
+        cand = np.array([i for i, _ in sims])
+        multi = M.subset(model, np.nonzero(np.isin(node_of_pod, cand))[0], np.setdiff1d(np.arange(E), cand))
+        em = capi.Encoded(multi)
+        assert em.layout_hash == encs[0].layout_hash
+        parity.assert_same(parity.canon_device(em, gpu_ctx.solve(cid, em)), parity.canon_oracle(multi, ob.solve(multi)),
+                           "c4 multi-node re-pack")
+    finally:
+        gpu_ctx.release_catalog(cid)
+
+
+def _torch_cuda():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("torch sees no GPU")
+    return torch
+
+
+def test_row_sharded_evaluation_compact_gather_and_global_pack(gpu_ctx):
+    """The multi-GPU data path on one GPU (bench.py runs it over NCCL): three "ranks" evaluate
+    their blocks of pod rows, export the compact per-pod results into one buffer (what the all-gather assembles), a
+    resident over ALL pods imports them and packs -- without evaluating a pod again, reading instance-type rows through the
+    class tables.  The Solve must be bit-identical to the oracle's and to the unsharded device Solve."""
+    torch = _torch_cuda()
+    from b200sched import model as M, sharding
+    m = synth.config("c3", 3001, 300)
+    enc_full = capi.Encoded(m)
+    rb = capi.compact_row_bytes(enc_full.T)
+    assert rb == sharding.compact_row_bytes(enc_full.T)
+    buf = torch.zeros(enc_full.P * rb, dtype=torch.uint8, device="cuda")
+    world = 3
+    for rank in range(world):
+        lo, hi = sharding.row_shard(enc_full.P, rank, world)
+        e = capi.Encoded(M.slice_pods(m, lo, hi))
+        cid = gpu_ctx.upload_catalog(e)
+        res = gpu_ctx.resident(cid, e)
+        try:
+            res.fit_matrix()
+            res.export_compact(buf.data_ptr() + lo * rb)
+            gpu_ctx.synchronize()
+        finally:
+            res.close()
+            gpu_ctx.release_catalog(cid)
+    o_tmpl, _, o_code, _, _ = ob.fit_matrix(m)
+    got_tmpl, got_code = sharding.from_compact(buf.cpu().numpy().reshape(enc_full.P, rb), enc_full.T)
+    cf = parity.canon_fit(enc_full, capi.FitOut(got_tmpl, np.zeros((enc_full.P, enc_full.W), np.uint64), got_code, 0))
+    assert np.array_equal(cf["tmpl"], o_tmpl) and np.array_equal(cf["code"], o_code)
+    cid = gpu_ctx.upload_catalog(enc_full)
+    res = gpu_ctx.resident(cid, enc_full)
+    try:
+        with pytest.raises(capi.B200SError) as e:
+            res.pack()                       # nothing imported yet
+        assert e.value.code == capi.ESTATE
+        res.import_compact(buf.data_ptr())
+        res.pack()
+        raw = res.fetch_solve()
+        direct = gpu_ctx.solve(cid, enc_full)
+    finally:
+        res.close()
+        gpu_ctx.release_catalog(cid)
+    parity.assert_same(parity.canon_device(enc_full, raw), parity.canon_oracle(m, ob.solve(m)), "pack of imported rows")
+    parity.assert_same(parity.canon_device(enc_full, raw), parity.canon_device(enc_full, direct), "imported vs direct")
+
+
+def test_config5_rows_on_every_shard_boundary_and_the_global_pack(gpu_ctx):
+    """BASELINE.json configs[4] on one GPU: 1M pods x 2k SKUs.  The dense rows around every boundary of the 8-way row
+    sharding (and of the 2- and 4-way ones: they are a subset) against the oracle, bit for bit; then the global pack of
+    all 1M pods: its digest against the committed golden of the device algorithm's host twin (tests/golden/
+    config5_digest.json, made by tests/golden/make_config5_golden.py -- the twin itself is checked against the oracle on
+    every smaller config), and the size-independent invariants of the config-3 test."""
+    import json
+    m = synth.config("c3", 1_000_000, 2_000)
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    res = gpu_ctx.resident(cid, enc)
+    try:
+        res.fit_matrix()
+        fit = res.fetch_fit()
+        res.solve()
+        raw = res.fetch_solve()
+    finally:
+        res.close()
+        gpu_ctx.release_catalog(cid)
+    cf = parity.canon_fit(enc, fit)
+    P = enc.P
+    for b in range(0, 9):
+        lo, hi = max(b * P // 8 - 250, 0), min(b * P // 8 + 250, P)
+        o_tmpl, o_mask, o_code, _, _ = ob.fit_matrix(m, lo, hi)
+        assert np.array_equal(cf["tmpl"][lo:hi], o_tmpl) and np.array_equal(cf["mask"][lo:hi], o_mask), f"boundary {b}"
+        assert np.array_equal(cf["code"][lo:hi], o_code), f"boundary {b}"
+    placed = raw.pod_place_kind == capi.PLACE_CLAIM
+    assert placed.sum() + raw.n_unscheduled == P
+    N, R = raw.n_claims, enc.R
+    assert np.array_equal(np.bincount(raw.pod_place_index[placed], minlength=N), raw.claim_npods)
+    sums = np.zeros((N, R), np.int64)
+    np.add.at(sums, raw.pod_place_index[placed], m.arrays["pod_requests"][placed])
+    assert np.array_equal(sums, raw.claim_requests)
+    assert sorted(raw.pod_seq[placed].tolist()) == list(range(int(placed.sum())))
+    alloc = m.arrays["sku_alloc"]
+    for c in range(0, N, max(1, N // 200)):
+        bits = np.unpackbits(raw.claim_mask[c].view(np.uint8), bitorder="little")[:enc.S].astype(bool)
+        assert bits.sum() == raw.claim_n_options[c] and bits[raw.claim_sku[c]]
+        assert (alloc[bits] >= raw.claim_requests[c]).all()
+    assert (np.diff(raw.claim_npods) < 0).sum() <= 1
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config5_digest.json")
+    if os.path.exists(golden):
+        want = json.load(open(golden))
+        assert [raw.n_claims, raw.n_unscheduled] == [want["n_claims"], want["n_unscheduled"]]
+        assert parity.digest(parity.canon_device(enc, raw)) == want["digest"]
+
+
 def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
     """BASELINE.json configs[3] at a size the oracle finishes quickly: running pods on loosely packed nodes, a batch of
     single-node consolidation simulations (one CTA each) and the multi-node re-pack, all bit-identical to the oracle."""

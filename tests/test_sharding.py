@@ -1,6 +1,8 @@
-"""world_size-2 gloo test of the N>1 host logic: row-shard the pods, run the dense stage per rank (the CPU oracle
-stands in for the kernel here — no GPU in this container), all-gather the result rows, compare with the unsharded
-matrix.  The GPU version of the same path is bench.py --workload c5 under torchrun."""
+"""world_size-2 gloo test of the N>1 host logic: row-shard the pods, run the dense stage per rank (the device
+algorithm compiled for the host, tests/native/emul.cpp, stands in for the kernels — no GPU in this container),
+all-gather the COMPACT per-pod results (template + attempt codes, 8 bytes a pod — the instance-type rows are not
+sent), rebuild them on rank 0 and compare with the unsharded evaluation and with the oracle.  The GPU version of
+the same path is bench.py under torchrun (b200s_resident_export_compact / _import_compact / _pack + NCCL)."""
 import os
 import socket
 import sys
@@ -18,30 +20,51 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "gpu-provisioner_b200"))
     import oracle_binding as ob
-    from b200sched import model as M, sharding, synth
+    import parity
+    from b200sched import capi, model as M, sharding, synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     m = synth.config("c3", 1001, 130)          # odd row count: ranks get unequal shards
     lo, hi = sharding.row_shard(m.n_pods, rank, world)
-    shard = M.slice_pods(m, lo, hi)
-    tmpl, mask, code, evals, T = ob.fit_matrix(shard)
+    enc = capi.Encoded(M.slice_pods(m, lo, hi))
+    fit = parity.emul_fit_matrix(enc)          # this rank's rows (they stay here) ...
+    compact = sharding.to_compact(fit.tmpl, fit.code)  # ... and what the packing rank needs of them
     rows = max(sharding.row_shard(m.n_pods, r, world)[1] - sharding.row_shard(m.n_pods, r, world)[0] for r in range(world))
-    outs = []
-    for a in (tmpl.reshape(-1, 1).astype(np.int64), mask.astype(np.int64), code.astype(np.int64)):
-        t = torch.from_numpy(sharding.pad_rows(a, rows))
-        g = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(g, t)
-        outs.append(sharding.unpad_gathered(torch.stack(g).numpy(), m.n_pods, world))
-    ev = torch.tensor([evals])
+    t = torch.from_numpy(sharding.pad_rows(compact, rows))
+    g = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(g, t)                      # the one collective
+    ev = torch.tensor([fit.evals])
     dist.all_reduce(ev)
     if rank == 0:
-        f_tmpl, f_mask, f_code, f_evals, _ = ob.fit_matrix(m)
-        ok = (np.array_equal(outs[0][:, 0], f_tmpl) and np.array_equal(outs[1].astype(np.uint64), f_mask) and
-              np.array_equal(outs[2].astype(np.uint8), f_code) and int(ev.item()) == f_evals)
+        enc_full = capi.Encoded(m)
+        got_tmpl, got_code = sharding.from_compact(sharding.unpad_gathered(torch.stack(g).numpy(), m.n_pods, world), enc_full.T)
+        full = parity.emul_fit_matrix(enc_full)
+        cf = parity.canon_fit(enc_full, capi.FitOut(got_tmpl, full.mask, got_code, int(ev.item())))
+        o_tmpl, o_mask, o_code, o_evals, _ = ob.fit_matrix(m)
+        ok = (np.array_equal(got_tmpl, full.tmpl) and np.array_equal(got_code, full.code) and int(ev.item()) == full.evals and
+              np.array_equal(cf["tmpl"], o_tmpl) and np.array_equal(cf["code"], o_code) and int(ev.item()) == o_evals)
+        # "merge the global packing": the pack over all pods (rows re-derived from the class tables) equals the oracle's
+        raw = parity.emul_solve(enc_full)
+        try:
+            parity.assert_same(parity.canon_device(enc_full, raw), parity.canon_oracle(m, ob.solve(m)), "global pack")
+        except AssertionError:
+            ok = False
         open(os.path.join(out_dir, "ok"), "w").write("1" if ok else "0")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_compact_rows_round_trip():
+    from b200sched import sharding
+    rng = np.random.default_rng(3)
+    for T in (1, 4, 7, 8, 16):
+        tmpl = rng.integers(-1, T, 50).astype(np.int32)
+        code = rng.integers(0, 256, (50, T)).astype(np.uint8)
+        rows = sharding.to_compact(tmpl, code)
+        assert rows.shape == (50, sharding.compact_row_bytes(T))
+        t2, c2 = sharding.from_compact(rows, T)
+        assert np.array_equal(t2, tmpl) and np.array_equal(c2, code)
 
 
 def test_row_shard_is_a_partition():
