@@ -143,20 +143,20 @@ def config1_latency():
     prices = [3.0 + 0.37 * ((7 * i) % 10) for i in range(10)]
     storage = 120 << 30
     n = 20000
-    got = capi.create_select("ws0123456789ab", names, storage, prices)
+    got = capi.create_select("ws0123456789", names, storage, prices)
     arr = (C.c_char_p * 10)(*[s_.encode() for s_ in names])
     pr = (C.c_double * 10)(*prices)
     ch, disk, gpu = C.c_int32(-1), C.c_int32(0), C.c_int32(0)
     f = capi.lib().b200s_create_select
     t0 = time.perf_counter()
     for _ in range(n):
-        rc = f(b"ws0123456789ab", 10, arr, pr, storage, C.byref(ch), C.byref(disk), C.byref(gpu))
+        rc = f(b"ws0123456789", 10, arr, pr, storage, C.byref(ch), C.byref(disk), C.byref(gpu))
     us = 1e6 * (time.perf_counter() - t0) / n
-    assert (rc, ch.value, disk.value, gpu.value) == got
+    assert (rc, ch.value, disk.value, gpu.value) == got and rc == 0
     f = ob.lib().oracle_create_select
     t0 = time.perf_counter()
     for _ in range(n):
-        rc = f(b"ws0123456789ab", 10, arr, pr, storage, C.byref(ch), C.byref(disk), C.byref(gpu))
+        rc = f(b"ws0123456789", 10, arr, pr, storage, C.byref(ch), C.byref(disk), C.byref(gpu))
     us_ref = 1e6 * (time.perf_counter() - t0) / n
     assert (rc, ch.value, disk.value, gpu.value) == got
     return {"metric": "NodeClaim -> vmSize selection latency", "unit": "us", "value": us, "reference_port_us": us_ref,
