@@ -43,7 +43,9 @@ class CatalogSoA(C.Structure):
         ("res_nd", C.c_int32 * MAX_RES), ("res_dv0", C.c_int32 * MAX_RES), ("res_row0", C.c_int32 * MAX_RES),
         ("res_dv", _P(C.c_int64)), ("n_dv", C.c_int32), ("key_row0", C.c_int32 * MAX_KEYS), ("zc_row0", C.c_int32),
         ("price", _P(C.c_uint64)), ("alloc", _P(C.c_int64)), ("capacity", _P(C.c_int64)),
-        ("price_max", _P(C.c_uint64)), ("layout_hash", C.c_uint64),
+        ("price_max", _P(C.c_uint64)),
+        ("cap_nd", C.c_int32 * MAX_RES), ("cap_dv0", C.c_int32 * MAX_RES), ("cap_row0", C.c_int32 * MAX_RES),
+        ("cap_dv", _P(C.c_int64)), ("n_cap_dv", C.c_int32), ("layout_hash", C.c_uint64),
     ]
 
 
@@ -70,7 +72,8 @@ class Templates(C.Structure):
         ("n_templates", C.c_int32), ("pool_index", C.c_int32 * MAX_TEMPLATES), ("taints", C.c_uint64 * MAX_TEMPLATES),
         ("req_mask", (C.c_uint64 * MAX_KEYS) * MAX_TEMPLATES), ("req_flags", C.c_uint64 * MAX_TEMPLATES),
         ("req_gt", (C.c_int64 * MAX_BOUNDED) * MAX_TEMPLATES), ("req_lt", (C.c_int64 * MAX_BOUNDED) * MAX_TEMPLATES),
-        ("daemon", (C.c_int64 * MAX_RES) * MAX_TEMPLATES), ("type_admit", _P(C.c_uint64)),
+        ("daemon", (C.c_int64 * MAX_RES) * MAX_TEMPLATES), ("limit", (C.c_int64 * MAX_RES) * MAX_TEMPLATES),
+        ("has_limit", (C.c_uint8 * MAX_RES) * MAX_TEMPLATES), ("type_admit", _P(C.c_uint64)),
     ]
 
 

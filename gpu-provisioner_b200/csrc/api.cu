@@ -76,6 +76,7 @@ struct b200s_resident {
   Catalog* cat = nullptr;
   int P = 0, Ppad = 0, E = 0, T = 0, n_problems = 0;
   bool profile_pack = false;  // b200s_resident_set_pack_profile
+  bool any_limit = false;  // some NodePool limits a resource: the new-claim template walk happens in the pack
   bool plain = true;  // no pod defines a requirement key (selects the pack kernel's form together with E == 0)
   std::vector<void*> owned;
   PodsDev pods{};
@@ -313,7 +314,15 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
       for (int k = 0; k < MAXK; k++) h->rmask[t][k] = tm->req_mask[t][k];
       for (int b = 0; b < MAXB; b++) { h->gt[t][b] = tm->req_gt[t][b]; h->lt[t][b] = tm->req_lt[t][b]; }
       for (int x = 0; x < MAXR; x++) h->daemon[t][x] = tm->daemon[t][x];
+      for (int x = 0; x < cat->R; x++)
+        if (tm->has_limit[t][x]) {
+          h->limit[t][x] = tm->limit[t][x];
+          h->limit_mask[t] |= 1u << x;
+          h->any_limit = 1;
+        }
     }
+    r->any_limit = h->any_limit != 0;
+    if (r->any_limit && !cat->kt.cap_dv) return fail(ctx, B200S_EINVAL, "templates carry NodePool limits but the catalog has no capacity rows");
     r->tmpl = r->dalloc<TmplDev>(1);
     r->tmask = r->dalloc<uint64_t>((size_t)std::max(T, 1) * W);
     r->alive = r->dalloc<int32_t>(MAXT);
@@ -412,7 +421,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   for (void* p : must)
     if (!p) return fail(ctx, B200S_ENOMEM, "device allocation (state)");
   r->reg_plan.eligible = false;
-  if (r->plain && Etot == 0 && T > 0 && Ptot > 0 && !getenv("B200S_PACK_NO_REG")) {
+  if (r->plain && Etot == 0 && T > 0 && Ptot > 0 && !r->any_limit && !getenv("B200S_PACK_NO_REG")) {
     // selector-less pods, no existing nodes: plan the register-resident pack (granules, tables) on the host
     std::vector<const int64_t*> rqs(n_problems);
     std::vector<int32_t> nqs(n_problems);
@@ -457,6 +466,15 @@ int enqueue_fit(b200s_ctx* ctx, b200s_resident* r, int* launches, bool want_rows
   r->arr.sgCO = r->sgCO;
   r->arr.rqF = r->rqF;
   r->arr.T = r->T;
+  r->arr.sg_status = r->sg_status;
+  r->arr.sgC = r->sgC;
+  r->arr.sgO = r->sgO;
+  r->arr.tmask = r->tmask;
+  r->arr.a_code = r->a_code;
+  if (r->any_limit && !r->arr.limit_rows) {
+    r->arr.limit_rows = r->dalloc<uint64_t>((size_t)r->n_problems * std::max(r->T, 1) * r->cat->W);
+    if (!r->arr.limit_rows) return fail(ctx, B200S_ENOMEM, "device allocation (limit rows)");
+  }
   CUDA_TRY(ctx, cudaMemsetAsync(r->a_evals, 0, sizeof(unsigned long long), ctx->stream), "memset");
   CUDA_TRY(ctx, launch_template_prefilter(r->cat->kt, r->tmpl, r->type_admit, r->tmask, r->alive, r->tm_count, ctx->stream),
            "template_prefilter launch");
@@ -720,6 +738,12 @@ int b200s_catalog_upload(b200s_ctx_t* ctx, const b200s_catalog_soa_t* c, uint64_
   kt.res_dv = (const int64_t*)put(c->res_dv, (size_t)c->n_dv * 8);
   kt.price = (const uint64_t*)put(c->price, (size_t)ZC * S * 8);
   kt.price_max = c->price_max ? (const uint64_t*)put(c->price_max, (size_t)ZC * S * 8) : nullptr;
+  for (int r = 0; r < MAXR; r++) { kt.cap_nd[r] = 0; kt.cap_dv0[r] = 0; kt.cap_row0[r] = 0; }
+  kt.cap_dv = nullptr;
+  if (c->cap_dv && c->n_cap_dv > 0) {
+    for (int r = 0; r < c->n_res; r++) { kt.cap_nd[r] = c->cap_nd[r]; kt.cap_dv0[r] = c->cap_dv0[r]; kt.cap_row0[r] = c->cap_row0[r]; }
+    kt.cap_dv = (const int64_t*)put(c->cap_dv, (size_t)c->n_cap_dv * 8);
+  }
   {  // rank bucket table: fit_rank of every bucket's lowest value, per resource
     std::vector<uint16_t> bkt((size_t)MAXR * (RANK_BKTS + 1), 0);
     for (int r = 0; r < c->n_res; r++) {

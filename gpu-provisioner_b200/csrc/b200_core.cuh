@@ -52,6 +52,9 @@ struct KeyTab {
   int32_t zc_row0, row_nonneg, n_rows, n_dv;
   const uint64_t* price;   // [n_zc*S]
   const uint64_t* price_max;  // [n_zc*S] most expensive available offering, B200S_PRICE_ABSENT if none (may be null)
+  // NodePool limits: ascending distinct Capacity values per resource and the rows "capacity[r] <= cap_dv[r][i]"
+  int32_t cap_nd[MAXR], cap_dv0[MAXR], cap_row0[MAXR];
+  const int64_t* cap_dv;
 };
 
 // read-only table loads: through the non-coherent (L1-cached) path on the device

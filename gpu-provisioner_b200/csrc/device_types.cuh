@@ -35,6 +35,9 @@ struct TmplDev {
   int64_t gt[MAXT][MAXB];
   int64_t lt[MAXT][MAXB];
   int64_t daemon[MAXT][MAXR];
+  int64_t limit[MAXT][MAXR];   // s.remainingResources of the template's NodePool at the start of the Solve
+  uint32_t limit_mask[MAXT];   // bit r: the NodePool limits resource r
+  uint32_t any_limit, _pad2;
 };
 
 // A requirement set + request vector + taints somewhere in (generic) memory, with element strides.

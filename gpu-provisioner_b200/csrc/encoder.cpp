@@ -36,7 +36,7 @@ struct b200s_encoded {
   b200s_pods_soa_t pods{};
   b200s_nodes_soa_t nodes{};
   // owned storage
-  std::vector<int64_t> val_int, res_dv, alloc_rm, cap_rm, rq_requests, pod_ts, node_available;
+  std::vector<int64_t> val_int, res_dv, cap_dv, alloc_rm, cap_rm, rq_requests, pod_ts, node_available;
   std::vector<uint64_t> val_isint, rows, price, price_max, type_admit, sig_mask, sig_flags, sig_tolerated, pod_uid_hi, pod_uid_lo,
       node_req_mask, node_req_flags, node_taints;
   std::vector<int32_t> sig_gt, sig_lt, pod_sig, pod_reqcls, node_index;
@@ -277,6 +277,18 @@ void do_encode(Ctx& c) {
   E->cat.zc_row0 = n_rows;
   const int ZC = kt.n_zones * kt.n_cts;
   n_rows += ZC;
+  // distinct Capacity values and prefix rows "capacity[r] <= cv[i]" (NodePool limits, scheduler.go:831-867)
+  std::vector<std::vector<int64_t>> cv(R);
+  for (int r = 0; r < R; r++) {
+    for (int s = 0; s < S; s++) cv[r].push_back(M->sku_capacity[(size_t)s * R + r]);
+    std::sort(cv[r].begin(), cv[r].end());
+    cv[r].erase(std::unique(cv[r].begin(), cv[r].end()), cv[r].end());
+    E->cat.cap_nd[r] = (int)cv[r].size();
+    E->cat.cap_dv0[r] = (int)E->cap_dv.size();
+    E->cat.cap_row0[r] = n_rows;
+    n_rows += (int)cv[r].size();
+    E->cap_dv.insert(E->cap_dv.end(), cv[r].begin(), cv[r].end());
+  }
   E->rows.assign((size_t)n_rows * W, 0);
   auto setbit = [&](int row, int s) { E->rows[(size_t)row * W + s / 64] |= 1ull << (s % 64); };
   E->alloc_rm.assign((size_t)R * S, 0);
@@ -290,6 +302,8 @@ void do_encode(Ctx& c) {
       if (a < 0) nonneg = false;
       int idx = (int)(std::lower_bound(dv[r].begin(), dv[r].end(), a) - dv[r].begin());
       for (int i = 0; i <= idx; i++) setbit(E->cat.res_row0[r] + i, s);  // alloc >= dv[i] for i <= idx
+      int cidx = (int)(std::lower_bound(cv[r].begin(), cv[r].end(), M->sku_capacity[(size_t)s * R + r]) - cv[r].begin());
+      for (int i = cidx; i < (int)cv[r].size(); i++) setbit(E->cat.cap_row0[r] + i, s);  // capacity <= cv[i] for i >= cidx
     }
     if (nonneg) setbit(0, s);
     for (int k = 0; k < K; k++) {
@@ -352,6 +366,8 @@ void do_encode(Ctx& c) {
   cat.price_max = E->price_max.data();
   cat.alloc = E->alloc_rm.data();
   cat.capacity = E->cap_rm.data();
+  cat.cap_dv = E->cap_dv.data();
+  cat.n_cap_dv = (int)E->cap_dv.size();
   {  // the key layout this encode chose (FNV-1a): slots, value bits, numerics, well-known mask, bounded slots
     uint64_t h = 1469598103934665603ull;
     auto mix = [&](uint64_t v) {
@@ -395,8 +411,12 @@ void do_encode(Ctx& c) {
   for (int t = 0; t < M->n_pools; t++) {
     int pi = order[t];
     T.pool_index[t] = pi;
+    for (int r = 0; r < MAXR; r++) { T.limit[t][r] = 0; T.has_limit[t][r] = 0; }
     for (int r = 0; r < R; r++) {
-      if (M->pool_has_limit[(size_t)pi * R + r]) reject("NodePool %d has limits (not kernelised yet)", pi);
+      if (M->pool_has_limit && M->pool_has_limit[(size_t)pi * R + r]) {  // s.remainingResources[pool] (scheduler.go:170-172)
+        T.has_limit[t][r] = 1;
+        T.limit[t][r] = M->pool_limit[(size_t)pi * R + r];
+      }
       int64_t d = M->pool_daemon[(size_t)pi * R + r];
       if (d < 0) reject("negative daemon overhead");
       T.daemon[t][r] = d;

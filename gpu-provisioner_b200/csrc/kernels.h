@@ -56,6 +56,14 @@ struct PackArrays {
   const uint64_t* sgCO;    // [(NS*T)*W] class rows C & O
   const uint64_t* rqF;     // [(NQ*T)*W] class rows F
   int32_t T;
+  // NodePool limits: the new-claim template walk happens in the pack (the limit-filtered candidate set depends on the
+  // claims opened so far), so it needs what the dense stage reads
+  const uint8_t* sg_status;  // [NS*T]
+  const uint64_t* sgC;       // [(NS*T)*W]
+  const uint64_t* sgO;       // [(NS*T)*W]
+  const uint64_t* tmask;     // [T*W] templates' pre-filtered instance types
+  uint8_t* a_code;           // [Ptot*T] per-template attempt codes (rewritten by a limited walk)
+  uint64_t* limit_rows;      // [n_problems*T*W] filterByRemainingResources rows, null without limits
   // per pod outputs
   int32_t* pod_kind;   // [Ptot]
   int32_t* pod_index;  // [Ptot] local claim id / node row

@@ -44,6 +44,8 @@ struct PackShared {
   int32_t undo_mode, undo_src, undo_dst;      // how to take the last normalisation back (see the end of the kernel)
   unsigned long long evals;
   uint64_t all_taints;  // union of the templates' taints
+  int64_t remaining[MAXT][MAXR];  // NodePool limits: s.remainingResources per template (scheduler.go:170-172)
+  int32_t t_new, _pad2;           // the template a limit-aware walk chose for the current pod, -1 none
   unsigned long long wprof[4];  // diagnostic: cycles of the commit phase by role (next pod's row, claim order, claim
                                 // state) and, in [3], full pdqsort runs (count << 40 | cycles)
 };
@@ -245,6 +247,104 @@ __device__ __forceinline__ void warp_normalise(PackShared& S, int32_t* ord, int3
   __syncwarp();
 }
 
+// ---- NodePool limits (scheduler.go:587-675, :831-867), all by one warp ----
+// filterByRemainingResources as a bit row: the instance types whose Capacity stays within the template's remaining
+// resources on every limited resource = AND over those resources of the row "capacity[r] <= largest value <= remaining"
+__device__ __forceinline__ void warp_limit_row(const KeyTab& kt, const PackShared& S, int t, int W, uint64_t* L) {
+  const int lane = threadIdx.x & 31;
+  for (int w = lane; w < W; w += 32) {
+    uint64_t m = ~0ull;
+    for (int r = 0; r < kt.n_res; r++) {
+      if (!((S.tm.limit_mask[t] >> r) & 1u)) continue;
+      const int64_t* cv = kt.cap_dv + kt.cap_dv0[r];
+      int lo = 0, hi = kt.cap_nd[r];  // number of values <= remaining
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ldg(cv + mid) <= S.remaining[t][r]) lo = mid + 1; else hi = mid; }
+      m &= lo == 0 ? 0ull : ldg(kt.rows + (size_t)(kt.cap_row0[r] + lo - 1) * W + w);
+    }
+    L[(size_t)t * W + w] = m;
+  }
+  __syncwarp();
+}
+
+// addToNewNodeClaim's template walk when NodePools have limits: the candidate set of template t is its pre-filtered
+// instance types inside the limit row, an empty one is the "exceed limits" code, and the six diagnostic flags are taken
+// over the limited set.  Writes the pod's attempt codes; returns the first template that works, or -1.
+__device__ __forceinline__ int warp_limited_walk(const KeyTab& kt, const PackShared& S, const PackArrays& A, const PodsDev& pods,
+                                                 int p, int W, const uint64_t* L) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, T = S.tm.T;
+  const size_t sig = (size_t)pods.sig_id[p], rq = (size_t)pods.req_id[p];
+  int chosen = -1;
+  for (int t = 0; t < T; t++) {
+    const uint8_t status = A.sg_status[sig * T + t];
+    uint8_t code = status == B200S_FIT_DROPPED ? (uint8_t)B200S_FIT_DROPPED : (uint8_t)B200S_FIT_NONE;
+    if (status != B200S_FIT_DROPPED && chosen < 0) {
+      const bool lim = S.tm.limit_mask[t] != 0;
+      bool any = true;
+      if (lim) {
+        bool a = false;
+        for (int w = lane; w < W; w += 32) a = a || (A.tmask[(size_t)t * W + w] & L[(size_t)t * W + w]) != 0;
+        any = __any_sync(FULL, a);
+      }
+      if (!any) {
+        code = B200S_FIT_LIMITS;  // scheduler.go:603
+      } else if (status != B200S_FIT_NONE) {
+        code = status;  // taints / incompatible requirements (nodeclaim.go:116,128)
+      } else {
+        bool nz = false, bC = false, bF = false, bO = false, bCF = false, bCO = false, bFO = false;
+        for (int w = lane; w < W; w += 32) {
+          const uint64_t l = lim ? L[(size_t)t * W + w] : ~0ull;
+          const uint64_t c = A.sgC[(sig * T + t) * W + w] & l, o = A.sgO[(sig * T + t) * W + w] & l,
+                         f = A.rqF[(rq * T + t) * W + w] & l;
+          nz = nz || (c & o & f) != 0;
+          bC = bC || c; bF = bF || f; bO = bO || o;
+          bCF = bCF || (c & f & ~o); bCO = bCO || (c & o & ~f); bFO = bFO || (f & o & ~c);
+        }
+        if (__any_sync(FULL, nz)) {
+          chosen = t;
+        } else {
+          code = filter_flags(__any_sync(FULL, bC), __any_sync(FULL, bF), __any_sync(FULL, bO), __any_sync(FULL, bCF),
+                              __any_sync(FULL, bCO), __any_sync(FULL, bFO));
+        }
+      }
+    }
+    if (lane == 0) A.a_code[(size_t)p * T + t] = code;
+  }
+  return chosen;
+}
+
+// word w of the instance types a NEW NodeClaim of template t keeps for pod p: its stage-A row, inside the template's
+// limit row when the NodePool has limits
+__device__ __forceinline__ uint64_t new_claim_word(const PackArrays& A, const PodsDev& pods, const PackShared& S, const uint64_t* L,
+                                                   int p, int t, int W, int w) {
+  uint64_t m = stage_a_word(A, pods, p, t, W, w);
+  if (S.tm.limit_mask[t]) m &= L[(size_t)t * W + w];
+  return m;
+}
+
+// subtractMax (scheduler.go:831-848) after a NodeClaim of a limited template opened: remaining -= the largest Capacity
+// among the claim's instance types, per limited resource — the smallest row "capacity <= cv[i]" that holds them all
+__device__ __forceinline__ void warp_subtract_max(const KeyTab& kt, PackShared& S, const PackArrays& A, const PodsDev& pods,
+                                                  const uint64_t* L, int p, int t, int W) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (int r = 0; r < kt.n_res; r++) {
+    if (!((S.tm.limit_mask[t] >> r) & 1u)) continue;
+    const int64_t* cv = kt.cap_dv + kt.cap_dv0[r];
+    int64_t mx = 0;
+    for (int i = kt.cap_nd[r] - 1; i >= 0; i--) {
+      bool out = false;
+      for (int w = lane; w < W; w += 32)
+        out = out || (new_claim_word(A, pods, S, L, p, t, W, w) & ~ldg(kt.rows + (size_t)(kt.cap_row0[r] + i) * W + w)) != 0;
+      if (__any_sync(FULL, out)) break;
+      mx = ldg(cv + i);
+    }
+    __syncwarp();
+    if (lane == 0) S.remaining[t][r] -= mx;
+    __syncwarp();
+  }
+}
+
 // KEYS: some pod of the batch defines a requirement key; NODES: there are existing nodes.  Without them the compiler
 // drops the requirement algebra / the node paths from the step loop (16.3 k -> 8.2 k SASS instructions without both),
 // and this kernel's speed follows its size: one CTA, every warp in a different region of ~250 KB of code
@@ -322,6 +422,8 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     for (int t = 0; t < tg->T; t++) at |= tg->taints[t];
     S.all_taints = at;
   }
+  uint64_t* lim_rows = A.limit_rows ? A.limit_rows + (size_t)blockIdx.x * tg->T * W : nullptr;
+  for (int i = tid; i < MAXT * MAXR; i += PACK_THREADS) S.remaining[i / MAXR][i % MAXR] = tg->limit[i / MAXR][i % MAXR];
   unsigned long long my_evals = 0;
   unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tick = clock64();
@@ -453,6 +555,11 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
 
   if (warp == QW) pop_and_load(0);
   __syncthreads();
+  const bool any_limit = S.tm.any_limit != 0 && lim_rows != nullptr;  // uniform
+  if (any_limit) {
+    for (int t = warp; t < S.tm.T; t += NW) warp_limit_row(kt, S, t, W, lim_rows);
+    __syncthreads();
+  }
   int cur = 0;
 
   for (;;) {
@@ -594,7 +701,19 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     // ---- commit: exactly one of (node, in-flight claim, new claim, push back).  Warp 0 handles the queue and the
     // next pod's row, the first lane group of warp 1 the claim state, warp 2 the claim order. ----
     if (tid == 0) S.best[cur ^ 1] = INT_MAX;
-    const int t_new = (!on_node && found == INT_MAX) ? A.a_tmpl[p] : -1;
+    int t_new = -1;
+    if (!on_node && found == INT_MAX) {
+      if (any_limit) {  // the walk depends on the claims opened so far: one warp does it now (uniform branch)
+        if (warp == 1) {
+          const int tw = warp_limited_walk(kt, S, A, pods, p, W, lim_rows);
+          if (lane == 0) S.t_new = tw;
+        }
+        __syncthreads();
+        t_new = S.t_new;
+      } else {
+        t_new = A.a_tmpl[p];
+      }
+    }
     if (on_node) {
       const int row = E0 + found;  // ExistingNode.Add (existingnode.go:111-119)
       if (warp == 1) {
@@ -714,7 +833,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
         }
         int cnt = 0;
         for (int w = gl; w < W; w += G) {
-          uint64_t m = stage_a_word(A, pods, p, t, W, w);
+          uint64_t m = new_claim_word(A, pods, S, lim_rows, p, t, W, w);
           c_mask[(size_t)c * W + w] = m;
           cnt += popc64(m);
         }
@@ -741,7 +860,7 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
             int mid = (lo + hi + 1) >> 1;
             unsigned hit = 0;
             for (int w = gl; w < W; w += G)
-              hit |= (stage_a_word(A, pods, p, t, W, w) & ldg(kt.rows + (size_t)(kt.res_row0[r] + mid) * W + w)) ? 1u : 0u;
+              hit |= (new_claim_word(A, pods, S, lim_rows, p, t, W, w) & ldg(kt.rows + (size_t)(kt.res_row0[r] + mid) * W + w)) ? 1u : 0u;
             hit = __reduce_or_sync(group_mask<G>(), hit);
             if (hit) lo = mid; else hi = mid - 1;
           }
@@ -787,6 +906,13 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     }
     __syncthreads();
     PROF(3);
+    if (any_limit && t_new >= 0 && S.tm.limit_mask[t_new]) {  // uniform: the new claim counts against its NodePool's limits
+      if (warp == 1) {
+        warp_subtract_max(kt, S, A, pods, lim_rows, p, t_new, W);
+        warp_limit_row(kt, S, t_new, W, lim_rows);
+      }
+      __syncthreads();
+    }
 
     // ---- what is left of the order normalisation: long rotates and the full pdqsort's bookkeeping ----
     const int mode = S.mode;  // written by warp 2 before the barrier above; nobody writes it before the next one

@@ -221,6 +221,12 @@ typedef struct b200s_catalog_soa {
   const int64_t* capacity;   /* [R*S] raw capacity, resource-major                           */
   const uint64_t* price_max; /* [n_zones*n_cts*S] MOST expensive available offering per (zone,ct,SKU), B200S_PRICE_ABSENT if
                                 none: Offerings.MostExpensive for WorstLaunchPrice (types.go:454-474) */
+  /* NodePool limits (scheduler.go:831-867): per resource the ascending distinct Capacity values and the bit rows
+   * "capacity[r] <= cap_dv[r][i]" (row cap_row0[r] + i): filterByRemainingResources is the AND of one row per limited
+   * resource, subtractMax the smallest row that contains the new NodeClaim's instance types */
+  int32_t cap_nd[B200S_MAX_RES], cap_dv0[B200S_MAX_RES], cap_row0[B200S_MAX_RES];
+  const int64_t* cap_dv;
+  int32_t n_cap_dv;
   /* The device key slots, each key's value bits, the well-known mask and the bounded-key slots are chosen by
    * b200s_encode from the keys and Gt/Lt bounds of ONE model (SKUs, offerings, pools AND that batch's pods), so a pods /
    * nodes SoA is only meaningful next to the catalog of the same encode.  layout_hash digests that choice; it is
@@ -240,6 +246,8 @@ typedef struct b200s_templates {
   int64_t req_gt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
   int64_t req_lt[B200S_MAX_TEMPLATES][B200S_MAX_BOUNDED];
   int64_t daemon[B200S_MAX_TEMPLATES][B200S_MAX_RES];
+  int64_t limit[B200S_MAX_TEMPLATES][B200S_MAX_RES];    /* s.remainingResources[pool] at the start of the Solve */
+  uint8_t has_limit[B200S_MAX_TEMPLATES][B200S_MAX_RES]; /* 1: the NodePool limits this resource (scheduler.go:170-172) */
   const uint64_t* type_admit; /* [T*W] SKUs each template's instance-type requirement admits; NULL = all */
 } b200s_templates_t;
 

@@ -28,7 +28,8 @@ def _rand_req(rng, key, allow_bounds=True):
     return (key, op, None)
 
 
-def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40, keyless: bool = False) -> M.Model:
+def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40, keyless: bool = False,
+                 limits: bool = False) -> M.Model:
     rng = np.random.default_rng(seed)
     b = M.ModelBuilder(RES)
     for k in [M.KEY_INSTANCE_TYPE, M.KEY_ZONE, M.KEY_CAPACITY_TYPE] + WK + CUSTOM + [M.KEY_NODEPOOL]:
@@ -82,7 +83,16 @@ def random_model(seed: int, with_nodes: bool = True, max_pods: int = 40, keyless
             reqs.append((M.KEY_INSTANCE_TYPE, M.OP_IN if rng.random() < 0.6 else M.OP_NOTIN, names + ["not-in-catalog"]))
         taints = [TAINTS[j] for j in range(len(TAINTS)) if rng.random() < 0.25]
         daemon = [int(rng.choice([0, 0, 100])), int(rng.choice([0, 0, 1 << 28])), 0, int(rng.choice([0, 1]))]
-        b.add_pool(f"pool-{i}", reqs, taints=taints, weight=int(rng.integers(0, 3)), daemon=daemon)
+        lim = None
+        if limits and rng.random() < 0.6:  # NodePool limits (scheduler.go:831-867): remaining cpu / memory / gpu of the pool
+            lim = {}
+            if rng.random() < 0.8:
+                lim["cpu"] = int(rng.choice([1000, 4000, 16000, 40000, 100000]))
+            if rng.random() < 0.5:
+                lim["memory"] = int(rng.choice([2, 16, 64, 200])) << 30
+            if rng.random() < 0.2:
+                lim["nvidia.com/gpu"] = int(rng.choice([0, 1, 4]))
+        b.add_pool(f"pool-{i}", reqs, taints=taints, weight=int(rng.integers(0, 3)), daemon=daemon, limits=lim)
     if with_nodes:
         for e in range(int(rng.integers(0, 6))):
             labels = {M.KEY_INSTANCE_TYPE: f"sku-{int(rng.integers(S))}", M.KEY_ZONE: str(rng.choice(ZONES)),

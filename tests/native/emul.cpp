@@ -28,6 +28,8 @@ KeyTab keytab_from(const b200s_catalog_soa_t* c) {
   kt.val_int = c->val_int; kt.rows = c->rows; kt.res_dv = c->res_dv; kt.price = c->price;
   kt.price_max = c->price_max;
   kt.zc_row0 = c->zc_row0; kt.row_nonneg = c->row_nonneg; kt.n_rows = c->n_rows; kt.n_dv = c->n_dv;
+  for (int r = 0; r < c->n_res; r++) { kt.cap_nd[r] = c->cap_nd[r]; kt.cap_dv0[r] = c->cap_dv0[r]; kt.cap_row0[r] = c->cap_row0[r]; }
+  kt.cap_dv = c->cap_dv;
   return kt;
 }
 
@@ -236,6 +238,29 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
   std::vector<int64_t> preq(R);
   std::vector<uint64_t> outw(W);
   for (int p = 0; p < P; p++) { out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED; out->pod_place_index[p] = -1; out->pod_seq[p] = -1; }
+  // NodePool limits (scheduler.go:587-675, :831-867): s.remainingResources per template; with limits the template walk of
+  // a new NodeClaim depends on the claims opened so far, so it happens here instead of in stage A
+  bool any_limit = false;
+  std::vector<std::vector<int64_t>> remaining(std::max(T, 1), std::vector<int64_t>(R, 0));
+  for (int t = 0; t < T; t++)
+    for (int r = 0; r < R; r++) {
+      remaining[t][r] = tm->limit[t][r];
+      any_limit = any_limit || tm->has_limit[t][r];
+    }
+  std::vector<uint64_t> tmask_l;
+  std::vector<int> alive_l;
+  if (any_limit) prefilter(kt, tm, &tmask_l, &alive_l);
+  // filterByRemainingResources as one bit row: instance types whose capacity stays within every limited resource
+  auto limit_row = [&](int t, std::vector<uint64_t>& L) {
+    L.assign(W, ~0ull);
+    for (int r = 0; r < R; r++) {
+      if (!tm->has_limit[t][r]) continue;
+      const int64_t* cv = kt.cap_dv + kt.cap_dv0[r];
+      int idx = -1;
+      for (int i = 0; i < kt.cap_nd[r]; i++) if (cv[i] <= remaining[t][r]) idx = i;
+      for (int w = 0; w < W; w++) L[w] &= idx < 0 ? 0ull : kt.rows[(size_t)(kt.cap_row0[r] + idx) * W + w];
+    }
+  };
   for (;;) {
     size_t len = q.size() - head;
     if (len == 0) break;
@@ -281,6 +306,36 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
     }
     if (placed) continue;
     int t = a_tmpl[p];
+    std::vector<uint64_t> new_row(a_mask.begin() + (size_t)p * W, a_mask.begin() + (size_t)(p + 1) * W);
+    if (any_limit) {  // the limit-aware walk; its codes replace stage A's for this pod
+      t = -1;
+      std::vector<uint64_t> L, cand(W), got(W);
+      for (int i = 0; i < T; i++) {
+        uint8_t code = alive_l[i] ? B200S_FIT_NONE : B200S_FIT_DROPPED;
+        if (alive_l[i] && t < 0) {
+          bool lim = false;
+          for (int r = 0; r < R; r++) lim = lim || tm->has_limit[i][r];
+          bool empty = false;
+          for (int w = 0; w < W; w++) cand[w] = tmask_l[(size_t)i * W + w];
+          if (lim) {
+            limit_row(i, L);
+            uint64_t any = 0;
+            for (int w = 0; w < W; w++) { cand[w] &= L[w]; any |= cand[w]; }
+            empty = any == 0;
+          }
+          if (empty) {
+            code = B200S_FIT_LIMITS;
+          } else {
+            ReqRow st = tmpl_row(kt, tm, i);
+            int s = can_add(kt, st, tm->daemon[i], tm->taints[i], pd, preq.data(), tol, true, cand.data(), got.data(), &code, &evals, nullptr);
+            if (s == ST_OK) { t = i; code = B200S_FIT_NONE; new_row = got; }
+            else if (s == ST_TAINT) code = B200S_FIT_TAINT;
+            else if (s == ST_INCOMPATIBLE) code = B200S_FIT_INCOMPATIBLE;
+          }
+        }
+        a_code[(size_t)p * T + i] = code;
+      }
+    }
     if (t >= 0) {  // addToNewNodeClaim
       Claim c;
       ReqRow st = tmpl_row(kt, tm, t);
@@ -288,13 +343,25 @@ int emul_solve(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, cons
       for (int k = 0; k < K; k++) put(kt, c.reqs, k, add_req(kt, k, get(kt, st, k), get(kt, pd, k)));
       c.req.resize(R);
       for (int r = 0; r < R; r++) c.req[r] = tm->daemon[t][r] + preq[r];
-      c.mask.assign(a_mask.begin() + (size_t)p * W, a_mask.begin() + (size_t)(p + 1) * W);
+      c.mask = new_row;
       c.tmpl = t;
       claims.push_back(c);
       npods.push_back(1);
       ord.push_back((int)claims.size() - 1);
       pod_claim[p] = (int)claims.size() - 1;
       out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
+      for (int r = 0; r < R; r++) {  // subtractMax (scheduler.go:831-848): the largest capacity among the claim's types
+        if (!tm->has_limit[t][r]) continue;
+        const int64_t* cv = kt.cap_dv + kt.cap_dv0[r];
+        int64_t mx = 0;
+        for (int i = kt.cap_nd[r] - 1; i >= 0; i--) {  // smallest row "capacity <= cv[i]" that holds every type
+          bool sub = true;
+          for (int w = 0; w < W; w++) sub = sub && !(new_row[w] & ~kt.rows[(size_t)(kt.cap_row0[r] + i) * W + w]);
+          if (!sub) break;
+          mx = cv[i];
+        }
+        remaining[t][r] -= mx;
+      }
     } else {
       q.push_back(p);
       lastlen[p] = (int)(q.size() - head);

@@ -75,6 +75,23 @@ def test_register_pack_twin_matches_oracle_on_fuzzed_keyless_models():
     assert ran >= 250, ran
 
 
+def test_nodepool_limits_match_oracle_on_fuzzed_models():
+    """scheduler.go:587-675, :831-867: filterByRemainingResources before every new NodeClaim, subtractMax after it, the
+    "exceed limits" attempt code — the device algorithm's host twin (bit rows over Capacity values) against the oracle"""
+    ran = limited = 0
+    for seed in range(300):
+        m = fuzz_models.random_model(seed, with_nodes=seed % 3 == 0, max_pods=60, limits=True)
+        try:
+            enc = capi.Encoded(m)
+        except capi.NotRepresentable:
+            continue
+        o = ob.solve(m)
+        parity.assert_same(parity.canon_device(enc, parity.emul_solve(enc)), parity.canon_oracle(m, o), f"limits fuzz {seed}")
+        ran += 1
+        limited += int((o.pod_fit_code == capi.FIT_LIMITS).any())
+    assert ran >= 250 and limited >= 20, (ran, limited)
+
+
 def test_go_sort_port_of_the_pack_kernel_matches_the_oracle_port():
     rng = np.random.default_rng(7)
     for n in [1, 2, 12, 13, 30, 49, 50, 64, 200, 1000, 3000]:
@@ -136,11 +153,12 @@ def test_encoder_rejects_what_it_cannot_represent_exactly():
     b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])], taints=[("k", "v", M.EFFECT_PREFERNOSCHEDULE)])
     b.add_pod([], [100, 1 << 20, 0, 0, 1])
     _reject(b.build())
-    # NodePool limits
+    # NodePool limits are representable since round 2 (bit rows over Capacity values)
     b = base()
     b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])], limits={"cpu": 100000})
     b.add_pod([], [100, 1 << 20, 0, 0, 1])
-    _reject(b.build())
+    e = capi.Encoded(b.build())
+    assert e.templates.contents.has_limit[0][0] == 1 and e.templates.contents.limit[0][0] == 100000
     # a pod selecting on the instance type
     b = base()
     b.add_pool("p", [(M.KEY_NODEPOOL, M.OP_IN, ["p"])])

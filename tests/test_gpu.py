@@ -69,6 +69,31 @@ def test_fuzzed_models_match_oracle(gpu_ctx):
     assert ran >= 120
 
 
+def test_nodepool_limits_match_oracle(gpu_ctx):
+    """NodePool limits on the device (scheduler.go:587-675, :831-867): filterByRemainingResources before every new
+    NodeClaim, subtractMax after it, the "exceed limits" attempt code -- fuzzed models and a 3 000-pod batch whose one pool
+    runs out of cpu part-way"""
+    ran = limited = 0
+    for seed in range(150):
+        m = fuzz_models.random_model(seed, with_nodes=seed % 3 == 0, max_pods=60, limits=True)
+        try:
+            capi.Encoded(m)
+        except capi.NotRepresentable:
+            continue
+        raw, o = _solve_parity(gpu_ctx, m, f"limits fuzz {seed}")
+        ran += 1
+        limited += int((o.pod_fit_code == capi.FIT_LIMITS).any())
+    assert ran >= 120 and limited >= 10, (ran, limited)
+    b = synth.new_builder()
+    synth.add_catalog(b, 300)
+    synth.add_pools(b, "c2")
+    b.pools[0]["limits"] = {"cpu": 6_000_000, "memory": 40_000 << 30}   # a few dozen nodes, then nothing
+    pods = synth.bulk_pods(b, 3000, "c2")
+    m = synth.build_model(b, pods)
+    raw, o = _solve_parity(gpu_ctx, m, "limits, 3000 pods")
+    assert 0 < o.n_unscheduled < 3000 and (o.pod_fit_code == capi.FIT_LIMITS).any()
+
+
 def test_config2_full_size_bit_identical(gpu_ctx):
     """BASELINE.json configs[1]: 10k pods x 500 SKUs — NodeClaim -> SKU selections identical to the oracle."""
     m = synth.c2()
