@@ -120,10 +120,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("B200S_LIB", LIB_PATH)  # experiments: another build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the CUDA library is the product; there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.b200s_version.restype = C.c_int
     L.b200s_init.argtypes = [C.c_int, _P(C.c_void_p)]
     L.b200s_destroy.argtypes = [C.c_void_p]

@@ -521,11 +521,12 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches, bool importe
     // selector-less pods, no existing nodes: the register-resident form; problems it cannot hold (more claims than
     // its threads keep) are left to the generic kernel, which skips the finished ones
     bool may_overflow = false;
+    int n_reg = 0;
     CUDA_TRY(ctx, launch_feas_table(cat->kt, r->tmask, r->T, r->reg_plan, r->feas_bits, ctx->stream), "feas_table launch");
     CUDA_TRY(ctx, launch_pack_reg(cat->kt, r->tmpl, r->T, r->pods, r->arr, r->problems, r->n_problems, max_pods, r->reg_plan,
-                                  r->reg_dev, &may_overflow, ctx->stream),
+                                  r->reg_dev, &may_overflow, &n_reg, ctx->stream),
              "pack_reg launch");
-    *launches += 2;
+    *launches += 1 + n_reg;
     generic_pack = may_overflow;
   }
   if (generic_pack) {

@@ -156,7 +156,7 @@ cudaError_t launch_feas_table(const KeyTab& kt, const uint64_t* tmask, int T, co
                               cudaStream_t stream);
 cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
                             PackProblem* problems, int n_problems, int max_pods, const RegPackPlan& plan,
-                            const RegPackDev& dev, bool* may_overflow, cudaStream_t stream);
+                            const RegPackDev& dev, bool* may_overflow, int* n_launched, cudaStream_t stream);
 cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
                                  int n_problems, ClaimOut out, cudaStream_t stream);
 

@@ -586,14 +586,21 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
     PROF(0);
 
     // ---- addToExistingNode ----
+    // Every thread walks ITS nodes (tid, tid + 512, ...) in ascending order and stops at its first hit: the minimum over
+    // the threads' first hits is the lowest feasible index (scheduler.go:533-540) — one barrier pair per pod instead of
+    // one per 512 nodes.  A thread also stops once its next node lies behind a hit somebody has already published.
     int found = INT_MAX;
-    for (int eb = 0; eb < E; eb += PACK_THREADS) {
-      int e = eb + tid;
-      if (e < E && node_can_add<KEYS>(kt, A, E0 + e, pd, S.zero_b)) atomicMin(&S.best[cur], e);
+    if (E > 0) {
+      for (int e = tid; e < E; e += PACK_THREADS) {
+        if (e >= PACK_THREADS && e > atomicMin(&S.best[cur], INT_MAX)) break;  // an atomic read: no hazard with the atomicMin below
+        if (node_can_add<KEYS>(kt, A, E0 + e, pd, S.zero_b)) {
+          atomicMin(&S.best[cur], e);
+          break;
+        }
+      }
       __syncthreads();
       found = S.best[cur];
       __syncthreads();
-      if (found != INT_MAX) break;
     }
     const bool on_node = found != INT_MAX;
     PROF(1);

@@ -43,7 +43,10 @@ namespace b200 {
 
 namespace {
 
-constexpr int REG_THREADS = 512;
+#ifndef B200S_REG_THREADS
+#define B200S_REG_THREADS 512
+#endif
+constexpr int REG_THREADS = B200S_REG_THREADS;
 constexpr int REG_NW = REG_THREADS / 32;
 constexpr int REG_CW = REG_NW - 2;     // claim warps; then the order warp and the queue warp
 constexpr int REG_NCT = REG_CW * 32;   // claim threads
@@ -115,6 +118,10 @@ __device__ __forceinline__ void ord_full_sort(int32_t* ord, int32_t* key, int32_
 // add() reaches the sort).
 struct OrdUndo {
   int mode, src, dst;
+  // a decided but not yet executed move: the order warp executes it at the start of the NEXT step, while the claim
+  // warps find that step's winner (pend: 0 none, 1 a claim that gained a pod passes the run behind it, 2 a new claim
+  // walks down from the end)
+  int pend, pa, pdst, pc, pk;
 };
 
 __device__ __forceinline__ void ord_move(int32_t* ord, int32_t* key, int32_t* pos_of, int src, int dst) {
@@ -245,21 +252,32 @@ __device__ __forceinline__ bool ord_win(int32_t* ord, int32_t* key, int32_t* pos
     u.mode = ORD_GENERIC;
     return true;
   }
-  // the claim passes the run of k's behind it: those move one slot down, the keys of positions [a, dst) stay k
-  for (int cb = a + 1; cb <= dst; cb += 32) {
-    const int i = cb + lane;
-    int v = 0;
-    if (i <= dst) v = ord[i];
-    __syncwarp();
-    if (i <= dst) { ord[i - 1] = v; pos_of[v] = i - 1; }
-    __syncwarp();
-  }
-  if (lane == 0) { ord[dst] = c; key[dst] = k + 1; pos_of[c] = dst; }
-  __syncwarp();
+  // the claim passes the run of k's behind it (ord_apply, next step)
+  u.pend = 1; u.pa = a; u.pdst = dst; u.pc = c; u.pk = k;
   u.mode = ORD_ROTATE;
   u.src = dst;
   u.dst = a;
   return false;
+}
+
+// executes the move ord_win / ord_append decided: by the order warp, before it looks at the arrays again
+__device__ __forceinline__ void ord_apply(int32_t* ord, int32_t* key, int32_t* pos_of, OrdUndo& u) {
+  const int lane = threadIdx.x & 31;
+  if (u.pend == 1) {  // those behind move one slot down, the keys of positions [a, dst) stay k
+    for (int cb = u.pa + 1; cb <= u.pdst; cb += 32) {
+      const int i = cb + lane;
+      int v = 0;
+      if (i <= u.pdst) v = ord[i];
+      __syncwarp();
+      if (i <= u.pdst) { ord[i - 1] = v; pos_of[v] = i - 1; }
+      __syncwarp();
+    }
+    if (lane == 0) { ord[u.pdst] = u.pc; key[u.pdst] = u.pk + 1; pos_of[u.pc] = u.pdst; }
+    __syncwarp();
+  } else if (u.pend == 2) {
+    ord_move(ord, key, pos_of, u.pa, u.pdst);
+  }
+  u.pend = 0;
 }
 
 __device__ __forceinline__ bool ord_append(int32_t* ord, int32_t* key, int32_t* pos_of, int32_t* G, int32_t* snap, int n, int c,
@@ -278,7 +296,7 @@ __device__ __forceinline__ bool ord_append(int32_t* ord, int32_t* key, int32_t* 
     return true;
   }
   const int dst = n - g1;
-  ord_move(ord, key, pos_of, n, dst);
+  u.pend = 2; u.pa = n; u.pdst = dst;
   u.mode = ORD_ROTATE;
   u.src = dst;
   u.dst = n;
@@ -402,6 +420,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin;
   if (pb.node_end != pb.node_begin) return;  // existing nodes: pack_kernel's problem (uniform)
+  if (pb.status == 1) return;                // finished by the smaller form of this kernel (uniform)
   int32_t* push_list = reinterpret_cast<int32_t*>(A.c_hi + (size_t)base * prm.R);  // scratch: pods pushed back, a ring of n_pods
   int32_t* c_first = A.c_nopt + base;  // scratch: the pod that opened the claim
   int32_t* g_snap = A.ord_snap + base;
@@ -449,7 +468,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   } while (0)
   const int OFF = 1 << (TB - 1), TBMAX = (1 << TB) - 2;
   int n = 0, seq = 0, front = OFF - 1, back = OFF;  // uniform across the CTA
-  OrdUndo undo{ORD_NONE, 0, 0};                      // order warp
+  OrdUndo undo{ORD_NONE, 0, 0, 0, 0, 0, 0, 0};       // order warp
   // queue warp: the batch being prepared (one pod per lane), staged over the steps of a batch
   int pf_p = -1, pf_rq = 0, pf_sig = 0, pf_tnew = -1;
   int32_t pf_q[RT];
@@ -552,7 +571,9 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     const bool renorm = (t > 0 && S.irr[(t - 1) & 1] != 0) || front <= 0 || back >= TBMAX;
     if (renorm) {
       // the previous step ended in a full pdqsort (or the tie-break field ran out): tie-breaks are re-derived from the
-      // explicit order, which the order warp does not touch before the barrier below
+      // explicit order, brought up to date first (a move may still be pending) and not touched before the barrier below
+      if (warp == REG_ORDW) ord_apply(s_ord, s_key, s_pos, undo);
+      __syncthreads();
       if (is_claim) {
         cand = PRIO_INF;
 #define RENORM_SLOT(j, sl)                                                            \
@@ -572,6 +593,8 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     } else {
       g = S.best[s3];
     }
+    // the move the previous step decided, beside the claim warps' search for this step's winner
+    if (warp == REG_ORDW) ord_apply(s_ord, s_key, s_pos, undo);
 
     if (g != PRIO_INF) {
       // ---- NodeClaim.Add (nodeclaim.go:168-180) by the owner; the claim moves to the front of the next bucket ----
@@ -664,7 +687,10 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 
   // ---- epilogue ----
   __syncthreads();
-  if (overflow) return;  // status stays 0
+  if (overflow) {  // status stays 0: the next form redoes the problem from a clean queue state
+    for (int i = tid; i < n_pods; i += REG_THREADS) A.lastlen[base + i] = 0;
+    return;
+  }
   {
     const int R = prm.R, W = prm.W, K = prm.K, NB = prm.NB;
     int64_t* c_req = A.c_req + (size_t)base * R;
@@ -679,6 +705,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     int32_t* g_ord = A.ord + base;
     // Results.NewNodeClaims: the order after the last sort the reference ran plus the modification that followed it
     if (warp == REG_ORDW) {
+      ord_apply(s_ord, s_key, s_pos, undo);
       if (undo.mode == ORD_ROTATE) ord_move(s_ord, s_key, s_pos, undo.src, undo.dst);
       else if (undo.mode == ORD_GENERIC)
         for (int i = lane; i < n; i += 32) s_ord[i] = g_snap[i];
@@ -922,8 +949,9 @@ cudaError_t launch_feas_table(const KeyTab& kt, const uint64_t* tmask, int T, co
 
 cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const PodsDev& pods, PackArrays arr,
                             PackProblem* problems, int n_problems, int max_pods, const RegPackPlan& plan,
-                            const RegPackDev& dev, bool* may_overflow, cudaStream_t stream) {
+                            const RegPackDev& dev, bool* may_overflow, int* n_launched, cudaStream_t stream) {
   *may_overflow = false;
+  if (n_launched) *n_launched = 0;
   if (n_problems == 0) return cudaSuccess;
   RegParams prm{};
   prm.R = kt.n_res; prm.W = kt.n_words; prm.K = kt.n_keys; prm.NB = kt.n_bounded; prm.T = T;
@@ -932,10 +960,6 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
   prm.tb = 31 - kb;
   if (prm.tb < 8) return cudaErrorInvalidValue;
   prm.wpt = plan.wpt;
-  int cpt = plan.cpt;
-  if (cpt == 4 && REG_NCT * 2 >= max_pods) cpt = 2;  // no more claims than pods
-  prm.cap = REG_NCT * cpt;
-  *may_overflow = prm.cap < max_pods;
   prm.tab_bytes = (int32_t)plan.tab.size();
   prm.win_entries = (int32_t)(plan.win.size() / 4);
   for (int s = 0; s < RT; s++) {
@@ -945,7 +969,6 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
   prm.tab = dev.tab; prm.win = reinterpret_cast<const int4*>(dev.win); prm.bits = dev.bits; prm.daemon = dev.daemon;
   prm.rq = dev.rq; prm.rows = kt.rows;
   for (int k = 0; k < MAXK; k++) prm.bslot[k] = kt.bslot[k];
-  const size_t bytes = reg_layout(prm.tab_bytes, prm.win_entries, T, plan.wpt, prm.cap).total;
   cudaError_t err = cudaSuccess;
   const bool prof = getenv("B200S_REG_PROFILE") != nullptr;
 #define REG_CALL(NWIN_, CPT_)                                                                     \
@@ -955,14 +978,30 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, REG_THREADS, bytes, stream>>>(prm, tg, pods, arr, problems);               \
   } while (0)
-  if (plan.nwin_form == 1) {
-    if (cpt == 2) REG_CALL(1, 2);
-    else REG_CALL(1, 4);
-  } else {
-    if (cpt == 2) REG_CALL(RT, 2);
-    else REG_CALL(RT, 4);
+  // Claims per thread: the two-slot form first (less code on the step's critical path); a problem that needs more
+  // claims than it holds leaves status 0 and the four-slot form — then pack_kernel — redoes it, each skipping what an
+  // earlier one finished.  A form is launched only if some problem could still need it.
+  const char* force = getenv("B200S_REG_CPT");  // experiments: "4" skips the two-slot form
+  int launched = 0;
+  for (int cpt : {2, 4}) {
+    if (cpt > plan.cpt) break;
+    if (cpt == 2 && force && atoi(force) == 4 && plan.cpt >= 4) continue;
+    if (launched && REG_NCT * (cpt / 2) >= max_pods) break;  // the smaller form cannot have overflowed
+    prm.cap = REG_NCT * cpt;
+    const size_t bytes = reg_layout(prm.tab_bytes, prm.win_entries, T, plan.wpt, prm.cap).total;
+    if (plan.nwin_form == 1) {
+      if (cpt == 2) REG_CALL(1, 2);
+      else REG_CALL(1, 4);
+    } else {
+      if (cpt == 2) REG_CALL(RT, 2);
+      else REG_CALL(RT, 4);
+    }
+    launched++;
+    *may_overflow = prm.cap < max_pods;
+    if (cudaGetLastError() != cudaSuccess) return cudaErrorLaunchFailure;
   }
 #undef REG_CALL
+  if (n_launched) *n_launched = launched;
   return cudaGetLastError();
 }
 

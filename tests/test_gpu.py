@@ -636,6 +636,25 @@ def test_solve_is_sanitizer_clean(tool, ok):
             assert "truncated 0" not in text.split("gate True")[-1], text[-2000:]
 
 
+@pytest.mark.parametrize("n_big", [1_200, 2_500])
+def test_register_pack_hands_over_when_it_runs_out_of_claim_slots(gpu_ctx, n_big):
+    """The register-resident pack holds 896 (two slots per thread) or 1 792 (four) NodeClaims.  A problem that needs more
+    is redone by the next form from a clean queue state -- 1 200 single-pod claims: the four-slot form; 2 500: the generic
+    kernel -- with pods nothing can hold pushed back in the abandoned run as well (their lastLen must not leak)."""
+    model = synth.config("c2", n_big + 600, 500)
+    req = model.arrays["pod_requests"].copy()
+    big = np.arange(model.n_pods) < n_big
+    req[big, 0], req[big, 1] = 70_000, 1 << 30      # one per node even on the largest SKU
+    req[~big, 0], req[~big, 1] = 1_000, 1 << 28
+    req[:, 2] = 0
+    req[:, 3] = 0
+    req[n_big + 500:, 0] = 10_000_000                # cpu beyond every SKU: stays in PodErrors
+    model.arrays["pod_requests"] = np.ascontiguousarray(req)
+    model.finalize()
+    raw, o = _solve_parity(gpu_ctx, model, f"claim-slot overflow {n_big}")
+    assert raw.n_claims >= n_big and raw.n_unscheduled == 100
+
+
 def test_more_claims_than_the_shared_memory_order_holds(gpu_ctx):
     """9 000 pods that each need a NodeClaim of their own push the claim order past the 8 192 entries kept in shared
     memory (it spills to global memory), and 2 500 small pods then land on the first claim of the order one after the
