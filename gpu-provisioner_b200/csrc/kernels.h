@@ -134,11 +134,11 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
 constexpr int REG_RT = 5;  // resource slots of a claim
 struct RegPackPlan {
   bool eligible = false;
-  int32_t R = 0, cpt = 0, nwin_form = 1, cells = 0, wpt = 0;
+  int32_t R = 0, cpt = 0, nwin_form = 1, cells = 0, wpt = 0, bsh = 31;
   int32_t perm[REG_RT], lim[REG_RT], toff[REG_RT], stride[REG_RT], row0[REG_RT], nd[REG_RT], maxv[REG_RT];
   int64_t scale[REG_RT];
   std::vector<uint8_t> tab;       // direct value -> rank tables
-  std::vector<int32_t> win;       // four values per window entry
+  std::vector<int32_t> win;       // four values per window entry (form RT) / {value, rank} per bucket (form 1)
   std::vector<int32_t> daemon32;  // [MAXT][8]
 };
 struct RegPackDev {  // device copies

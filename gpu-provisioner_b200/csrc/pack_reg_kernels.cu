@@ -10,13 +10,18 @@
 //   * every in-flight NodeClaim is owned by one thread and lives in its registers: the accumulated requests as
 //     32-bit multiples of each resource's granule (the gcd of every quantity of that resource in the problem — exact;
 //     a problem whose scaled values do not fit falls back to pack_kernel);
-//   * the claim ORDER is never read by the scan.  Every claim carries a priority (len(Pods), tie-break) such that
-//     "first feasible claim in s.newNodeClaims order" (scheduler.go:566-575) == "feasible claim of least priority":
-//     one warp min-reduce + one shared-memory atomicMin + one CTA barrier per pod.  The priority is updated locally:
-//     Go's sort.Slice (scheduler.go:499) puts a claim that gained a pod in front of the next bucket and a new claim
-//     at the back of bucket 1 whenever it does not take the real pdqsort path; the ORDER WARP keeps the explicit
-//     order beside the scan (exact pdqsort emulation, b200_core.cuh GoSort), tells the claim threads when a full
-//     sort happened, and they then re-derive their tie-breaks from the explicit positions;
+//   * the claim ORDER is never read by the scan.  Every claim thread knows its claims' POSITIONS in s.newNodeClaims,
+//     so "first feasible claim in order" (scheduler.go:566-575) == "feasible claim of least position": one warp
+//     min-reduce + one shared-memory atomicMin + one barrier per pod.  Positions are kept up to date locally: between
+//     two of the reference's sort.Slice calls (scheduler.go:499) one claim changed, and unless sort.Slice takes the
+//     real pdqsort path the result is that claim moving to the end of the run of claims with as many pods (a new claim:
+//     behind the last claim with one pod) — a shift by one of a range of positions, which the winner derives from a
+//     count table (claims with more than k pods) and publishes in one word for the next step;
+//   * the ORDER WARP keeps the explicit order (exact pdqsort emulation, b200_core.cuh GoSort) BESIDE the step loop,
+//     not inside it: it consumes one event word per step from a ring, at its own pace.  Only when sort.Slice could
+//     take the real pdqsort path (fewer than 50 claims, or the changed position is next to one of choosePivot's
+//     samples — decided exactly by the order warp, which has the keys) does the step loop meet it at a barrier and
+//     re-read every position; that, the final order and the un-normalisation of the last sort are what it is for;
 //   * a claim of selector-less pods keeps exactly those instance types of its template's pre-filtered set that fit
 //     its requests (nodeclaim.go:144-146, :392-423; the rows "alloc[r] >= v" are nested), so CanAdd's filter result
 //     is non-empty iff the FEASIBILITY TABLE cell of the new total's per-resource ranks is set: a bit table over
@@ -35,6 +40,7 @@
 #include <climits>
 #include <cstdlib>
 #include <numeric>
+#include <type_traits>
 
 #include "device_types.cuh"
 #include "kernels.h"
@@ -54,7 +60,6 @@ constexpr int REG_ORDW = REG_CW, REG_QW = REG_CW + 1;
 constexpr int RING = 64;
 constexpr int RT = REG_RT;             // resource slots of a claim (catalog resources, padded)
 constexpr unsigned PRIO_INF = 0xffffffffu;
-constexpr int ORD_NONE = 0, ORD_ROTATE = 1, ORD_GENERIC = 2;
 
 struct RingEnt {  // a popped pod's row: updateCachedPodData's products (scheduler.go:467-486) through its class ids
   int32_t q[8];   // request per resource slot, in granules
@@ -67,18 +72,21 @@ struct RegShared {
   int32_t daemon[MAXT][8];
   uint64_t all_taints;
   unsigned best[3], best2[3];
-  unsigned win[3];  // the step's winner: claim id | len(Pods) before the pod << 11
-  int32_t irr[2];
+  // what step t did to the order, for the claim threads (read after the next step's barrier): positions [lo, hi] move
+  // by one (mv_word); and, when sort.Slice might take the real pdqsort path on it, what the order warp needs to run
+  // that sort: the changed position, whether the claim was appended, the number of claims
+  unsigned mv[2];
+  int32_t meet_a, meet_n, done, _pad3;
   int32_t head, len, n_pushed, _pad;
   RingEnt ring[RING];
 };
 
 __host__ __device__ inline size_t reg_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-constexpr int REG_KCAP = 2048;  // pod counts below this have an entry in the order warp's count table
+constexpr int REG_KCAP = 2048;  // pod counts below this have an entry in the count table
 
 struct RegLayout {
-  size_t tab, win, bits, ord, key, pos, gt, total;
+  size_t tab, win, bits, ord, key, pos, gc, total;
 };
 
 __host__ __device__ inline RegLayout reg_layout(int tab_bytes, int win_entries, int T, int wpt, int cap) {
@@ -90,7 +98,7 @@ __host__ __device__ inline RegLayout reg_layout(int tab_bytes, int win_entries, 
   l.ord = o; o += reg_align16((size_t)cap * 4);
   l.key = o; o += reg_align16((size_t)cap * 4);
   l.pos = o; o += reg_align16((size_t)cap * 4);
-  l.gt = o; o += reg_align16((size_t)REG_KCAP * 4);
+  l.gc = o; o += reg_align16((size_t)REG_KCAP * 8);   // the claim threads' own two copies (see the loop)
   l.total = o;
   return l;
 }
@@ -103,8 +111,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // position map rebuilt after it.  One copy of the code: the step loop's instruction footprint matters.
 __device__ __forceinline__ void ord_full_sort(int32_t* ord, int32_t* key, int32_t* pos_of, int32_t* snap, int n) {
   const int lane = threadIdx.x & 31;
-  for (int i = lane; i < n; i += 32) snap[i] = ord[i];
-  __syncwarp();
+  if (snap) {
+    for (int i = lane; i < n; i += 32) snap[i] = ord[i];
+    __syncwarp();
+  }
   GoSort gs{ord, key, true};
   gs.sort(n);
   __syncwarp();
@@ -112,18 +122,8 @@ __device__ __forceinline__ void ord_full_sort(int32_t* ord, int32_t* key, int32_
   __syncwarp();
 }
 
-// The order warp's eager normalisation (see pack_kernels.cu warp_normalise for the derivation): what sort.Slice will
-// do to an order that was sorted before one element changed.  Returns true when the full pdqsort ran.  Keeps pos_of
-// (claim -> position) and how to take the normalisation back (Results.NewNodeClaims is un-normalised when no later
-// add() reaches the sort).
-struct OrdUndo {
-  int mode, src, dst;
-  // a decided but not yet executed move: the order warp executes it at the start of the NEXT step, while the claim
-  // warps find that step's winner (pend: 0 none, 1 a claim that gained a pod passes the run behind it, 2 a new claim
-  // walks down from the end)
-  int pend, pa, pdst, pc, pk;
-};
-
+// What sort.Slice (scheduler.go:499) does to an order that was sorted before one element changed (see pack_kernels.cu
+// warp_normalise for the derivation), by one warp on the explicit arrays; keeps pos_of (claim -> position).
 __device__ __forceinline__ void ord_move(int32_t* ord, int32_t* key, int32_t* pos_of, int src, int dst) {
   const int lane = threadIdx.x & 31;
   const int x = ord[src], kx = key[src];
@@ -151,10 +151,8 @@ __device__ __forceinline__ void ord_move(int32_t* ord, int32_t* key, int32_t* po
   __syncwarp();
 }
 
-__device__ __forceinline__ bool ord_normalise(int32_t* ord, int32_t* key, int32_t* pos_of, int32_t* snap, int n, int pos,
-                                              bool appended, OrdUndo& u) {
+__device__ __forceinline__ bool ord_normalise(int32_t* ord, int32_t* key, int32_t* pos_of, int n, int pos, bool appended) {
   const int lane = threadIdx.x & 31;
-  u.mode = ORD_NONE;
   if (n <= 1) return false;
   const bool sorted = appended ? !(key[n - 1] < key[n - 2]) : (pos == n - 1 || !(key[pos + 1] < key[pos]));
   if (sorted) return false;
@@ -171,8 +169,7 @@ __device__ __forceinline__ bool ord_normalise(int32_t* ord, int32_t* key, int32_
     increasing = __ballot_sync(0xffffffffu, bad) == 0;
   }
   if (!increasing) {
-    ord_full_sort(ord, key, pos_of, snap, n);
-    u.mode = ORD_GENERIC;
+    ord_full_sort(ord, key, pos_of, nullptr, n);
     return true;
   }
   // partialInsertionSort re-inserts the displaced element next to its equals
@@ -193,119 +190,31 @@ __device__ __forceinline__ bool ord_normalise(int32_t* ord, int32_t* key, int32_
       if (sb) { dst = t0 - (__ffs((int)sb) - 1) + 1; break; }
     }
   }
-  if (dst != pos) {
-    ord_move(ord, key, pos_of, pos, dst);
-    u.mode = ORD_ROTATE;
-    u.src = dst;
-    u.dst = pos;
-  }
+  if (dst != pos) ord_move(ord, key, pos_of, pos, dst);
   return false;
 }
 
-// The same decisions from the count table G[k] = number of claims with more than k pods (k < REG_KCAP), without
-// reading the order: a claim at position a that goes from k to k + 1 pods belongs at the end of the run of k's, position
-// n - G[k] - 1; a new claim with one pod belongs behind the last claim with one pod, position n - G[1].  choosePivot
-// can only see an inversion if the changed position is one of its nine samples, so the sample keys are read only
-// then (never for an appended claim: the last position is not a sample).
-__device__ __forceinline__ bool ord_win(int32_t* ord, int32_t* key, int32_t* pos_of, int32_t* G, int32_t* snap, int n, int c,
-                                        int k, OrdUndo& u) {
-  const int lane = threadIdx.x & 31;
-  const int a = pos_of[c];
-  if (k + 1 >= REG_KCAP) {  // beyond the table: the generic routine
-    if (lane == 0) key[a] = k + 1;
-    __syncwarp();
-    return ord_normalise(ord, key, pos_of, snap, n, a, false, u);
-  }
-  const int gk = G[k];
-  const int dst = n - gk - 1;
-  __syncwarp();
-  if (lane == 0) G[k] = gk + 1;
-  u.mode = ORD_NONE;
-  if (dst == a) {  // still sorted
-    if (lane == 0) key[a] = k + 1;
-    __syncwarp();
-    return false;
-  }
-  bool generic = n < 50;
-  if (!generic) {
-    const int q = n >> 2;
-    const int d1 = a - q, d2 = a - 2 * q, d3 = a - 3 * q;
-    if ((d1 >= -1 && d1 <= 1) || (d2 >= -1 && d2 <= 1) || (d3 >= -1 && d3 <= 1)) {
-      if (lane == 0) key[a] = k + 1;
-      __syncwarp();
-      int v = 0;
-      if (lane < 9) v = key[q * (lane / 3 + 1) + (lane % 3) - 1];
-      const int up = __shfl_down_sync(0xffffffffu, v, 1);
-      const int mid_next = __shfl_down_sync(0xffffffffu, v, 3);
-      bool bad = false;
-      if (lane < 9 && (lane % 3) != 2) bad = up < v;
-      if (lane == 1 || lane == 4) bad = bad || mid_next < v;
-      generic = __ballot_sync(0xffffffffu, bad) != 0;
-      __syncwarp();
-      if (!generic && lane == 0) key[a] = k;  // the move below leaves a k at position a
-    }
-  }
-  if (generic) {
-    if (lane == 0) key[a] = k + 1;
-    __syncwarp();
-    ord_full_sort(ord, key, pos_of, snap, n);
-    u.mode = ORD_GENERIC;
-    return true;
-  }
-  // the claim passes the run of k's behind it (ord_apply, next step)
-  u.pend = 1; u.pa = a; u.pdst = dst; u.pc = c; u.pk = k;
-  u.mode = ORD_ROTATE;
-  u.src = dst;
-  u.dst = a;
-  return false;
+constexpr int REG_CTHREADS = (REG_NW - 1) * 32;  // the step loop's barrier: every warp but the order warp
+__device__ __forceinline__ void step_bar() { named_bar_sync(2, REG_CTHREADS); }
+// the order warp and the claim warps (the queue warp has no part in the sort)
+__device__ __forceinline__ void meet_bar() { named_bar_sync(3, REG_CTHREADS); }
+__device__ __forceinline__ void claim_bar() { named_bar_sync(4, REG_NCT); }
+// lane 0: *p = min(*p, v) on shared memory, predicated instead of branched
+__device__ __forceinline__ void lane0_min(unsigned* p, unsigned v, int lane) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("{ .reg .pred p0; setp.eq.s32 p0, %2, 0; @p0 red.shared.min.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"(lane) : "memory");
 }
 
-// executes the move ord_win / ord_append decided: by the order warp, before it looks at the arrays again
-__device__ __forceinline__ void ord_apply(int32_t* ord, int32_t* key, int32_t* pos_of, OrdUndo& u) {
-  const int lane = threadIdx.x & 31;
-  if (u.pend == 1) {  // those behind move one slot down, the keys of positions [a, dst) stay k
-    for (int cb = u.pa + 1; cb <= u.pdst; cb += 32) {
-      const int i = cb + lane;
-      int v = 0;
-      if (i <= u.pdst) v = ord[i];
-      __syncwarp();
-      if (i <= u.pdst) { ord[i - 1] = v; pos_of[v] = i - 1; }
-      __syncwarp();
-    }
-    if (lane == 0) { ord[u.pdst] = u.pc; key[u.pdst] = u.pk + 1; pos_of[u.pc] = u.pdst; }
-    __syncwarp();
-  } else if (u.pend == 2) {
-    ord_move(ord, key, pos_of, u.pa, u.pdst);
-  }
-  u.pend = 0;
-}
-
-__device__ __forceinline__ bool ord_append(int32_t* ord, int32_t* key, int32_t* pos_of, int32_t* G, int32_t* snap, int n, int c,
-                                           OrdUndo& u) {
-  const int lane = threadIdx.x & 31;
-  const int g1 = G[1];
-  __syncwarp();
-  if (lane == 0) { ord[n] = c; key[n] = 1; pos_of[c] = n; G[0] = n + 1; }
-  __syncwarp();
-  u.mode = ORD_NONE;
-  if (g1 == 0) return false;  // every claim has one pod: sorted
-  const int n1 = n + 1;
-  if (n1 < 50) {
-    ord_full_sort(ord, key, pos_of, snap, n1);
-    u.mode = ORD_GENERIC;
-    return true;
-  }
-  const int dst = n - g1;
-  u.pend = 2; u.pa = n; u.pdst = dst;
-  u.mode = ORD_ROTATE;
-  u.src = dst;
-  u.dst = n;
-  return false;
+// the order change of a step as the claim threads see it: bits [11:0] lo, [23:12] hi, [24] the positions lo..hi move up
+// (a new claim was inserted before them) instead of down (a claim that gained a pod passed them), [25] sort.Slice may
+// take the real pdqsort path on it: the order warp runs it.  No claim sits at position 0xFFF: that is the empty range.
+constexpr unsigned MV_EMPTY = 0xFFFu | (0xFFFu << 12), MV_UP = 1u << 24, MV_MEET = 1u << 25;
+__device__ __forceinline__ unsigned mv_word(int lo, int hi, bool up, bool meet) {
+  return (lo <= hi ? ((unsigned)lo | ((unsigned)hi << 12)) : MV_EMPTY) | (up ? MV_UP : 0u) | (meet ? MV_MEET : 0u);
 }
 
 struct RegParams {
   int32_t R, W, K, NB, T;
-  int32_t tb;                 // tie-break bits of a priority; key = priority >> tb
   int32_t wpt;                // feasibility-table words per template
   int32_t cap;                // claims the CTA's threads can hold
   int32_t tab_bytes, win_entries;
@@ -315,6 +224,7 @@ struct RegParams {
   int32_t toff[RT];           // direct slot: offset into the byte table; window slot: offset into the window table
   int32_t stride[RT];         // of the slot's rank in the feasibility table
   int32_t row0[RT];           // first bit row "alloc >= dv[0]" of the slot's resource
+  int32_t bsh;                // bucket slot: log2 of the bucket width
   int64_t scale[RT];          // granule
   const uint8_t* tab;         // direct value -> rank tables (global; staged into shared memory)
   const int4* win;            // windows {dv[i], dv[i+1], dv[i+2], dv[i+3]} (global; staged)
@@ -329,71 +239,87 @@ struct RegParams {
 struct Slot {
   int32_t x[RT];       // Spec.Resources.Requests in granules
   uint64_t wrk, nwrk;  // table row (rank) of each window slot's total, 8 bits each; nwrk: after this step's pod
-  uint32_t prio;
+  uint32_t pos;        // position in s.newNodeClaims (sorted by len(Pods)) as of the last order change applied
+  uint32_t prio;       // what the step's minimum is taken over: 2 * pos + 1, except right after this claim moved
+  uint32_t cur;        // what this slot entered the step's minimum with: prio when the pod fits, else PRIO_INF
+  int32_t npods;       // len(Pods)
   int32_t tmpl;
-  bool feas;
+  uint64_t taint;      // the template's taints (bit per distinct taint)
 };
 
 __device__ __forceinline__ void slot_clear(Slot& s) {
 #pragma unroll
   for (int r = 0; r < RT; r++) s.x[r] = 0;
-  s.wrk = 0; s.nwrk = 0; s.prio = PRIO_INF; s.tmpl = 0; s.feas = false;
+  s.wrk = 0; s.nwrk = 0; s.pos = PRIO_INF; s.prio = PRIO_INF; s.npods = 0; s.tmpl = 0; s.cur = PRIO_INF; s.taint = 0;
 }
 
 // NodeClaim.CanAdd for a pod without requirement keys (nodeclaim.go:114-163): whether the filter result of the new
-// total is non-empty — the feasibility-table cell of its ranks — and the taints.  Returns the claim's priority when
-// the pod fits, PRIO_INF otherwise.  Straight-line code: the common case takes no branch.
+// total is non-empty — the feasibility-table cell of its ranks — and the taints (nodeclaim.go:116).  Returns the
+// claim's priority when the pod fits, PRIO_INF otherwise (a slot without a claim has priority PRIO_INF).  Straight-
+// line code.  NWIN == 1: the last slot's rank comes from a bucket table {the one distinct value in the bucket, ranks
+// below the bucket}; NWIN == RT: every slot tracks its rank and looks at a window of the next distinct values.
 template <int NWIN>
 __device__ __forceinline__ unsigned slot_eval(Slot& s, const RegParams& prm, const uint8_t* s_tab, const int4* s_win,
-                                              const uint32_t* s_bits, const uint64_t* taints, const int32_t (&q)[RT],
-                                              uint64_t tol, bool tol_all, bool live) {
+                                              const uint32_t* s_bits, const int32_t (&q)[RT], uint64_t tol) {
   int idx = 0;
   uint64_t nw = 0;
+  constexpr int NDIR = NWIN == RT ? 0 : RT - 1;
 #pragma unroll
-  for (int r = 0; r < RT - NWIN; r++) {
+  for (int r = 0; r < NDIR; r++) {
     // the table reaches 2 * maxv + 1 >= any claim total (<= maxv) + any pod request (clamped to maxv + 1)
     idx += (int)s_tab[prm.toff[r] + s.x[r] + q[r]] * prm.stride[r];
   }
-#pragma unroll
-  for (int r = RT - NWIN; r < RT; r++) {
-    const int sh = 8 * (r - (RT - NWIN));
+  if constexpr (NWIN == 1) {
+    constexpr int r = RT - 1;
     const int x = s.x[r] + q[r];
-    int i = (int)((s.wrk >> sh) & 0xFFull);
-    const int4 w = s_win[prm.toff[r] + i];
-    int c = (w.x < x) + (w.y < x) + (w.z < x) + (w.w < x);
-    if (c == 4) {  // more than three rows ahead (rare)
-      int j = i + 4;
-      while (s_win[prm.toff[r] + j].x < x) j++;  // the list ends in INT32_MAX
-      c = j - i;
+    const int2 b = reinterpret_cast<const int2*>(s_win)[prm.toff[r] + (x >> prm.bsh)];
+    idx += (b.y + (b.x < x ? 1 : 0)) * prm.stride[r];
+  } else {
+#pragma unroll
+    for (int r = 0; r < RT; r++) {
+      const int sh = 8 * r;
+      const int x = s.x[r] + q[r];
+      int i = (int)((s.wrk >> sh) & 0xFFull);
+      const int4 w = s_win[prm.toff[r] + i];
+      int c = (w.x < x) + (w.y < x) + (w.z < x) + (w.w < x);
+      if (c == 4) {  // more than three rows ahead (rare)
+        int j = i + 4;
+        while (s_win[prm.toff[r] + j].x < x) j++;  // the list ends in INT32_MAX
+        c = j - i;
+      }
+      i += c;
+      idx += i * prm.stride[r];
+      nw |= (uint64_t)i << sh;
     }
-    i += c;
-    idx += i * prm.stride[r];
-    nw |= (uint64_t)i << sh;
   }
-  bool f = live && ((s_bits[s.tmpl * prm.wpt + (idx >> 5)] >> (idx & 31)) & 1u);
-  if (!tol_all) f = f && (taints[s.tmpl] & ~tol) == 0;  // nodeclaim.go:116
-  s.feas = f;
+  const bool f = ((s_bits[s.tmpl * prm.wpt + (idx >> 5)] >> (idx & 31)) & 1u) != 0 && (s.taint & ~tol) == 0;
   s.nwrk = nw;
-  return f ? s.prio : PRIO_INF;
+  s.cur = f ? s.prio : PRIO_INF;
+  return s.cur;
 }
 
-// NewNodeClaim + Add (nodeclaim.go:83-109, :168-180): requests = daemon overhead + the pod; back of bucket 1
+// NewNodeClaim + Add (nodeclaim.go:83-109, :168-180): requests = daemon overhead + the pod; the claim goes behind the
+// last claim with one pod, position dst — in the not yet shifted numbering of the others: just before their dst
 template <int NWIN>
 __device__ __forceinline__ void slot_open(Slot& s, const RegParams& prm, const int4* s_win, const int32_t* daemon,
-                                          const int32_t (&q)[RT], int tnew, int TB, int back) {
+                                          const int32_t (&q)[RT], int tnew, uint64_t taint, unsigned pos, int dst) {
   uint64_t nw = 0;
 #pragma unroll
   for (int r = 0; r < RT; r++) {
     s.x[r] = daemon[r] + q[r];
-    if (r >= RT - NWIN) {
+    if (NWIN == RT) {
       int i = 0;
       while (s_win[prm.toff[r] + i].x < s.x[r]) i++;
-      nw |= (uint64_t)i << (8 * (r - (RT - NWIN)));
+      nw |= (uint64_t)i << (8 * r);
     }
   }
   s.wrk = nw;
   s.tmpl = tnew;
-  s.prio = (1u << TB) | (unsigned)back;
+  s.taint = taint;
+  s.npods = 1;
+  s.pos = pos;
+  s.prio = 2u * (unsigned)dst;
+  s.cur = PRIO_INF;
 }
 
 // PROF: cycle counters of the warp leaders into PackProblem::prof: [0] step start -> barrier, [1] wait at the
@@ -412,9 +338,8 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   int32_t* s_ord = reinterpret_cast<int32_t*>(smem + L.ord);
   int32_t* s_key = reinterpret_cast<int32_t*>(smem + L.key);
   int32_t* s_pos = reinterpret_cast<int32_t*>(smem + L.pos);
-  int32_t* s_G = reinterpret_cast<int32_t*>(smem + L.gt);
+  int32_t* s_Gc = reinterpret_cast<int32_t*>(smem + L.gc);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int TB = prm.tb;
   const bool is_claim = warp < REG_CW;
 
   PackProblem& pb = problems[blockIdx.x];
@@ -423,7 +348,6 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   if (pb.status == 1) return;                // finished by the smaller form of this kernel (uniform)
   int32_t* push_list = reinterpret_cast<int32_t*>(A.c_hi + (size_t)base * prm.R);  // scratch: pods pushed back, a ring of n_pods
   int32_t* c_first = A.c_nopt + base;  // scratch: the pod that opened the claim
-  int32_t* g_snap = A.ord_snap + base;
   const int32_t* queue = A.queue + base;
 
   // ---- stage tables ----
@@ -434,13 +358,14 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   for (int i = tid; i < prm.tab_bytes; i += REG_THREADS) s_tab[i] = prm.tab[i];
   for (int i = tid; i < prm.win_entries; i += REG_THREADS) s_win[i] = prm.win[i];
   for (int i = tid; i < prm.T * prm.wpt; i += REG_THREADS) s_bits[i] = prm.bits[i];
-  for (int i = tid; i < REG_KCAP; i += REG_THREADS) s_G[i] = 0;
+  for (int i = tid; i < REG_KCAP; i += REG_THREADS) { s_Gc[i] = 0; s_Gc[REG_KCAP + i] = 0; }
   if (tid == 0) {
     uint64_t at = 0;
     for (int t = 0; t < tg->T; t++) at |= tg->taints[t];
     S.all_taints = at;
-    for (int i = 0; i < 3; i++) { S.best[i] = PRIO_INF; S.best2[i] = PRIO_INF; S.win[i] = 0; }
-    S.irr[0] = 0; S.irr[1] = 0;
+    for (int i = 0; i < 3; i++) { S.best[i] = PRIO_INF; S.best2[i] = PRIO_INF; }
+    S.mv[0] = MV_EMPTY; S.mv[1] = MV_EMPTY;
+    S.done = 0;
     S.head = 0; S.len = 0; S.n_pushed = 0;
   }
   if (warp == REG_QW && lane < n_pods) {  // the first batch of pod rows
@@ -466,9 +391,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     if constexpr (CPT > 2) F(2, sl2);  \
     if constexpr (CPT > 3) F(3, sl3);  \
   } while (0)
-  const int OFF = 1 << (TB - 1), TBMAX = (1 << TB) - 2;
-  int n = 0, seq = 0, front = OFF - 1, back = OFF;  // uniform across the CTA
-  OrdUndo undo{ORD_NONE, 0, 0, 0, 0, 0, 0, 0};       // order warp
+  int n = 0, seq = 0;  // uniform across the CTA
   // queue warp: the batch being prepared (one pod per lane), staged over the steps of a batch
   int pf_p = -1, pf_rq = 0, pf_sig = 0, pf_tnew = -1;
   int32_t pf_q[RT];
@@ -476,7 +399,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 #pragma unroll
   for (int r = 0; r < RT; r++) pf_q[r] = 0;
   bool overflow = false;
-  unsigned long long prof[5] = {0, 0, 0, 0, 0};
+  unsigned long long prof[7] = {0, 0, 0, 0, 0, 0, 0};
   long long tick = PROF ? clock64() : 0;
 #define RPROF(i)                                    \
   do {                                              \
@@ -487,7 +410,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     }                                               \
   } while (0)
 
-  auto pop_slow = [&](int t) {  // second phase (queue warp): Queue.Pop with the lastLen rule over the pushed pods
+  auto pop_slow = [&](int t) {  // second phase (one warp): Queue.Pop with the lastLen rule over the pushed pods
     int p = -1;
     if (lane == 0 && S.len > 0) {
       const int cand = push_list[S.head];
@@ -509,43 +432,22 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     __syncwarp();
   };
 
-  int s3i = 0;  // t % 3
-  for (int t = 0;; t++) {
-    if (t == n_pods) {  // the first pass over the queue is over: what is left are the pods that were pushed back
-      __syncthreads();
-      if (S.n_pushed == 0) break;
-      __syncthreads();
-      if (warp == REG_QW) {
-        if (lane == 0) { S.head = 0; S.len = S.n_pushed; }
-        __syncwarp();
-        pop_slow(t);
-      }
-      __syncthreads();
+  unsigned t_end = 0;  // steps taken (claim warps)
+  if (warp == REG_ORDW) {
+    // ================= the order warp: runs sort.Slice when the step loop asks for it =================
+    for (;;) {
+      meet_bar();  // A: the claim threads have written the order as it was before the change, and the new pod count
+      if (S.done) break;
+      RPROF(0);
+      const int ma = S.meet_a;  // [11:0] changed position, [12] appended, [31:16] claims
+      const bool gen = ord_normalise(s_ord, s_key, s_pos, ma >> 16, ma & 0xFFF, (ma & 0x1000) != 0);
+      if (PROF && gen) prof[4]++;
+      RPROF(1);
+      meet_bar();  // B: positions are ready
     }
-    const bool phase2 = t >= n_pods;
-    const RingEnt& e = S.ring[t & (RING - 1)];
-    if (phase2 && e.p < 0) break;
-    const int s3 = s3i, s3n = s3i == 2 ? 0 : s3i + 1;
-    s3i = s3n;
-
-    // ---- before the barrier: each role its own work ----
-    int32_t q[RT];
-    unsigned cand = PRIO_INF;
-    if (is_claim) {
-      // addToInflightNode: every claim decides for itself, the least priority among the feasible ones wins
-      if (tid == 0) { S.best[s3n] = PRIO_INF; S.best2[s3n] = PRIO_INF; }
-      const uint64_t tol = e.tol;
-#pragma unroll
-      for (int r = 0; r < RT; r++) q[r] = e.q[r];
-      const bool tol_all = (S.all_taints & ~tol) == 0;
-#define EVAL_SLOT(j, sl)                                                       \
-  if ((j) * REG_NCT + (tid & ~31) < n) /* this warp holds a claim in slot j */ \
-    cand = min(cand, slot_eval<NWIN>(sl, prm, s_tab, s_win, s_bits, S.taints, q, tol, tol_all, (j) * REG_NCT + tid < n))
-      FOR_SLOTS(EVAL_SLOT);
-#undef EVAL_SLOT
-      const unsigned wmin = __reduce_min_sync(0xffffffffu, cand);
-      if (lane == 0 && wmin != PRIO_INF) atomicMin(&S.best[s3], wmin);
-    } else if (warp == REG_QW && !phase2) {  // rows of the next batch (the ring's other half), a stage every few steps
+  } else if (warp == REG_QW) {
+    // ================= the queue warp: pod rows of the next batch (the ring's other half), a stage every few steps ====
+    for (int t = 0; t < n_pods; t++) {
       const int ph = t & 31, i = (t & ~31) + 32 + lane;
       if (i < n_pods) {
         if (ph == 0) pf_p = queue[i];
@@ -563,57 +465,125 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
           d.tol = pf_tol; d.p = pf_p; d.tnew = pf_tnew;
         }
       }
+      RPROF(0);
+      step_bar();
     }
-    RPROF(0);
-    __syncthreads();  // B1
-    RPROF(1);
-    unsigned g;
-    const bool renorm = (t > 0 && S.irr[(t - 1) & 1] != 0) || front <= 0 || back >= TBMAX;
-    if (renorm) {
-      // the previous step ended in a full pdqsort (or the tie-break field ran out): tie-breaks are re-derived from the
-      // explicit order, brought up to date first (a move may still be pending) and not touched before the barrier below
-      if (warp == REG_ORDW) ord_apply(s_ord, s_key, s_pos, undo);
-      __syncthreads();
-      if (is_claim) {
-        cand = PRIO_INF;
-#define RENORM_SLOT(j, sl)                                                            \
-  if ((j) * REG_NCT + tid < n) {                                                      \
-    sl.prio = ((sl.prio >> TB) << TB) | (unsigned)(OFF + s_pos[(j) * REG_NCT + tid]); \
-    if (sl.feas) cand = min(cand, sl.prio);                                           \
-  }
-        FOR_SLOTS(RENORM_SLOT);
-#undef RENORM_SLOT
-        const unsigned wmin = __reduce_min_sync(0xffffffffu, cand);
-        if (lane == 0 && wmin != PRIO_INF) atomicMin(&S.best2[s3], wmin);
-      }
-      front = OFF - 1;
-      back = OFF + n;
-      __syncthreads();  // B2
-      g = S.best2[s3];
-    } else {
-      g = S.best[s3];
-    }
-    // the move the previous step decided, beside the claim warps' search for this step's winner
-    if (warp == REG_ORDW) ord_apply(s_ord, s_key, s_pos, undo);
+  } else {
+    // ================= claim warps: the step loop =================
+    int s3i = 0;  // t % 3
+    // one pod: returns false when the queue is exhausted (second phase) or the claims do not fit this form
+    auto step = [&](const unsigned t, auto phase2_tag) -> bool {
+      constexpr bool PHASE2 = decltype(phase2_tag)::value;
+      const RingEnt& e = S.ring[t & (RING - 1)];
+      if (PHASE2 && e.p < 0) return false;
+      const int s3 = s3i, s3n = s3i == 2 ? 0 : s3i + 1;
+      s3i = s3n;
 
-    if (g != PRIO_INF) {
-      // ---- NodeClaim.Add (nodeclaim.go:168-180) by the owner; the claim moves to the front of the next bucket ----
-      if (is_claim) {
-        // first the hand-off of (claim, pod count) to the order warp, then the owner's own update
-        int mine = -1;
-#define FIND_SLOT(j, sl) \
-  if (sl.feas && sl.prio == g) mine = (j)
-        FOR_SLOTS(FIND_SLOT);
-#undef FIND_SLOT
-        if (mine >= 0) S.win[s3] = (unsigned)(mine * REG_NCT + tid) | ((g >> TB) << 11);
-        if (__any_sync(0xffffffffu, mine >= 0)) named_bar_sync(1, 64);
+      // ---- before the barrier: addToInflightNode — every claim decides for itself, the first feasible in the order wins
+      if (tid == 0) { S.best[s3n] = PRIO_INF; S.best2[s3n] = PRIO_INF; }
+      int32_t q[RT];
+      const uint64_t tol = e.tol;
+#pragma unroll
+      for (int r = 0; r < RT; r++) q[r] = e.q[r];
+      // slots 0 and 1 unconditionally (straight-line code: the two evaluations interleave; a slot without a claim
+      // has priority PRIO_INF), the others only in warps that hold such claims
+      unsigned cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
+      if constexpr (CPT > 1) cand = min(cand, slot_eval<NWIN>(sl1, prm, s_tab, s_win, s_bits, q, tol));
+#define EVAL_SLOT(j, sl)                                                               \
+  if ((j) > 1 && (j) * REG_NCT + (tid & ~31) < n) /* this warp holds a claim in slot j */ \
+    cand = min(cand, slot_eval<NWIN>(sl, prm, s_tab, s_win, s_bits, q, tol))
+      FOR_SLOTS(EVAL_SLOT);
+#undef EVAL_SLOT
+      const unsigned wmin = __reduce_min_sync(0xffffffffu, cand);
+      lane0_min(&S.best[s3], wmin, lane);
+      RPROF(0);
+      if (PHASE2) claim_bar(); else step_bar();  // B1
+      RPROF(1);
+      // ---- the previous step's change of the order: the sort at the start of this add() (scheduler.go:499) ----
+      // The minimum above was taken over priorities that do not have it yet: every claim but the one that changed keeps
+      // its place among the others, and that one took a priority between its new neighbours' old ones.
+      const unsigned mv = S.mv[(t + 1u) & 1u];
+      unsigned g = S.best[s3];
+      if (mv & MV_MEET) {  // uniform
+        // sort.Slice may take the real pdqsort path (ties permuted): the claim threads lay out the order as it is —
+        // positions before the change, the new pod count —, the order warp sorts it, positions are re-read and the
+        // minimum is taken again.
+#define LAYOUT_SLOT(j, sl)                                 \
+  if ((j) * REG_NCT + tid < n) {                           \
+    s_ord[sl.pos] = (j) * REG_NCT + tid;                   \
+    s_key[sl.pos] = sl.npods;                              \
+    s_pos[(j) * REG_NCT + tid] = (int)sl.pos;              \
+  }
+        FOR_SLOTS(LAYOUT_SLOT);
+#undef LAYOUT_SLOT
+        meet_bar();  // A
+        meet_bar();  // B
+        cand = PRIO_INF;
+#define RELOAD_SLOT(j, sl)                               \
+  if ((j) * REG_NCT + tid < n) {                         \
+    sl.pos = (unsigned)s_pos[(j) * REG_NCT + tid];       \
+    sl.prio = 2u * sl.pos + 1u;                          \
+    sl.cur = sl.cur != PRIO_INF ? sl.prio : PRIO_INF;    \
+    cand = min(cand, sl.cur);                            \
+  }
+        FOR_SLOTS(RELOAD_SLOT);
+#undef RELOAD_SLOT
+        const unsigned wmin2 = __reduce_min_sync(0xffffffffu, cand);
+        lane0_min(&S.best2[s3], wmin2, lane);
+        claim_bar();  // B2
+        g = S.best2[s3];
+        RPROF(5);
+        if (PROF) prof[6]++;
+      }
+      // the winner is the slot whose priority entered the minimum as g; then every slot takes the previous step's shift
+      // (the claim that moved marked its position: bit 31) and its priority for the next minimum
+      int mine = -1;
+      {
+        const bool shift = (mv & MV_MEET) == 0;
+        const unsigned lo = mv & 0xFFFu, span = shift ? ((mv >> 12) & 0xFFFu) - lo : 0u;
+        const unsigned d = (mv & MV_UP) ? 1u : 0xFFFFFFFFu;
+#define SHIFT_SLOT(j, sl)                                   \
+  if (sl.cur == g) mine = (j);                              \
+  if (sl.pos - lo <= span && shift) sl.pos += d;            \
+  sl.pos &= 0x7FFFFFFFu;                                    \
+  sl.prio = 2u * sl.pos + 1u
+        FOR_SLOTS(SHIFT_SLOT);
+#undef SHIFT_SLOT
+      }
+      RPROF(3);
+
+      if (g != PRIO_INF) {
+        // ---- NodeClaim.Add (nodeclaim.go:168-180) by the owner ----
         if (mine >= 0) {
+          int a = 0, k = 0;
+#define WIN_SLOT(j, sl) \
+  if (mine == (j)) { a = (int)sl.pos; k = sl.npods; }
+          FOR_SLOTS(WIN_SLOT);
+#undef WIN_SLOT
+          // The claim now has k + 1 pods and belongs at the end of the run of claims with k pods, position dst (the
+          // claims it passes move down by one).  sort.Slice gets there by partialInsertionSort unless there are fewer
+          // than 50 claims or choosePivot's nine samples, which include the positions next to a, show an inversion; the
+          // keys are not here, so that is left to the order warp at the next step's sort.  Only winners touch the count
+          // table Gc[x] = claims with more than x pods, one per step, a barrier apart.
+          const bool big = k + 1 >= REG_KCAP;
+          const int kk = big ? REG_KCAP - 1 : k;
+          const int gk = s_Gc[kk];
+          if (!big) s_Gc[kk] = gk + 1;
+          int dst = n - gk - 1;
+          const int qq = n >> 2;
+          const bool near = (unsigned)(a - qq + 1) <= 2u || (unsigned)(a - 2 * qq + 1) <= 2u || (unsigned)(a - 3 * qq + 1) <= 2u;
+          const bool meet = big || (dst != a && (n < 50 || near));
+          if (big) dst = a;
+          S.mv[t & 1u] = mv_word(a + 1, dst, false, meet);
+          S.meet_a = a | (n << 16);
           const int p = e.p;
-#define COMMIT_SLOT(j, sl)                                          \
-  if (mine == (j)) {                                                \
-    _Pragma("unroll") for (int r = 0; r < RT; r++) sl.x[r] += q[r]; \
-    sl.wrk = sl.nwrk;                                               \
-    sl.prio = (((g >> TB) + 1u) << TB) | (unsigned)front;           \
+#define COMMIT_SLOT(j, sl)                                                   \
+  if (mine == (j)) {                                                         \
+    _Pragma("unroll") for (int r = 0; r < RT; r++) sl.x[r] += q[r];          \
+    sl.wrk = sl.nwrk;                                                        \
+    sl.npods = k + 1;                                                        \
+    sl.prio = 2u * (unsigned)dst + 2u;                                       \
+    sl.pos = meet ? (unsigned)a : (0x80000000u | (unsigned)dst);             \
   }
           FOR_SLOTS(COMMIT_SLOT);
 #undef COMMIT_SLOT
@@ -621,46 +591,38 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
           A.pod_index[p] = mine * REG_NCT + tid;
           A.pod_seq[p] = seq;
         }
-      } else if (warp == REG_ORDW) {
-        named_bar_sync(1, 64);
-        const unsigned wv = S.win[s3];
-        RPROF(3);
-        const bool gen = ord_win(s_ord, s_key, s_pos, s_G, g_snap, n, (int)(wv & 2047u), (int)(wv >> 11), undo);
-        if (lane == 0) S.irr[t & 1] = gen ? 1 : 0;
-        if (PROF && gen) prof[4]++;
-      }
-      seq++;
-      front--;
-    } else {
-      const int tnew = e.tnew, p = e.p;
-      if (tnew >= 0) {
-        // ---- addToNewNodeClaim: the template walk was done for every pod by stage A (scheduler.go:587-675) ----
-        if (n >= prm.cap) { overflow = true; break; }  // uniform: pack_kernel redoes this problem
-        const int c = n;
-        if (is_claim && tid == c % REG_NCT) {
-#define OPEN_SLOT(j, sl) \
-  if ((j) == c / REG_NCT) slot_open<NWIN>(sl, prm, s_win, S.daemon[tnew], q, tnew, TB, back)
-          FOR_SLOTS(OPEN_SLOT);
-#undef OPEN_SLOT
-          c_first[c] = p;
-          A.pod_kind[p] = B200S_PLACE_CLAIM;
-          A.pod_index[p] = c;
-          A.pod_seq[p] = seq;
-        } else if (warp == REG_ORDW) {
-          const bool gen = ord_append(s_ord, s_key, s_pos, s_G, g_snap, n, c, undo);
-          if (lane == 0) S.irr[t & 1] = gen ? 1 : 0;
-          if (PROF && gen) prof[4]++;
-        }
-        n++;
-        back++;
         seq++;
       } else {
-        // ---- Queue.Push (queue.go:63-66): the pod stays in PodErrors ----
-        if (warp == REG_QW && lane == 0) {
-          if (!phase2) {
+        const int tnew = e.tnew, p = e.p;
+        if (tnew >= 0) {
+          // ---- addToNewNodeClaim: the template walk was done for every pod by stage A (scheduler.go:587-675) ----
+          if (n >= prm.cap) { overflow = true; return false; }  // uniform: the next form redoes this problem
+          const int c = n;
+          if (tid == c % REG_NCT) {
+            // appended (scheduler.go:672); the next sort puts it behind the last claim with one pod — below 50 claims
+            // by the real pdqsort on any unsorted input, from 50 on always by re-insertion (the last position is no
+            // sample)
+            const int dst = n - s_Gc[1];
+            const bool meet = n + 1 < 50 && dst != n;
+#define OPEN_SLOT(j, sl) \
+  if ((j) == c / REG_NCT) slot_open<NWIN>(sl, prm, s_win, S.daemon[tnew], q, tnew, S.taints[tnew], meet ? (unsigned)n : (0x80000000u | (unsigned)dst), dst)
+            FOR_SLOTS(OPEN_SLOT);
+#undef OPEN_SLOT
+            S.mv[t & 1u] = mv_word(dst, n - 1, true, meet);
+            S.meet_a = n | 0x1000 | ((n + 1) << 16);
+            c_first[c] = p;
+            A.pod_kind[p] = B200S_PLACE_CLAIM;
+            A.pod_index[p] = c;
+            A.pod_seq[p] = seq;
+          }
+          n++;
+          seq++;
+        } else if (tid == 0) {
+          // ---- Queue.Push (queue.go:63-66): the pod stays in PodErrors ----
+          if (!PHASE2) {
             // the reference's queue holds the n_pods - (t + 1) pods not yet popped and the pods pushed so far
             push_list[S.n_pushed] = p;
-            A.lastlen[p] = (n_pods - (t + 1)) + S.n_pushed + 1;
+            A.lastlen[p] = (n_pods - ((int)t + 1)) + S.n_pushed + 1;
             S.n_pushed++;
           } else {
             int tail = S.head + S.len;
@@ -671,22 +633,48 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
           }
           A.pod_kind[p] = B200S_PLACE_UNSCHEDULED;
           A.pod_index[p] = -1;
-        } else if (warp == REG_ORDW) {
-          undo.mode = ORD_NONE;  // the reference sorted at the start of this add() too: the last normalisation stands
-          if (lane == 0) S.irr[t & 1] = 0;
+          S.mv[t & 1u] = MV_EMPTY;
         }
       }
+      if (PHASE2) {  // the next pod: Queue.Pop with the lastLen rule, by the warp that pushed
+        if (warp == 0) pop_slow((int)t + 1);
+        claim_bar();
+      }
+      RPROF(2);
+      if (PROF && tid == 0) prof[4]++;
+      return true;
+    };
+
+    unsigned t = 0;
+    for (; (int)t < n_pods; t++)
+      if (!step(t, std::false_type{})) break;
+    if (overflow) {
+      for (int t2 = (int)t + 1; t2 < n_pods; t2++) step_bar();  // the queue warp's remaining barriers
+    } else {
+      // the first pass over the queue is over: what is left are the pods that were pushed back
+      claim_bar();
+      if (S.n_pushed != 0) {
+        if (warp == 0) {
+          if (lane == 0) { S.head = 0; S.len = S.n_pushed; }
+          __syncwarp();
+          pop_slow((int)t);
+        }
+        claim_bar();
+        for (;; t++)
+          if (!step(t, std::true_type{})) break;
+      }
     }
-    if (phase2) {
-      if (warp == REG_QW) pop_slow(t + 1);
-      __syncthreads();
-    }
-    RPROF(2);
-    if (PROF && tid == 0) prof[4]++;
+    t_end = t;
+    // Results.NewNodeClaims is the order after the last sort the reference ran plus what the last add() did to it: the
+    // last step's change is not applied (its claim keeps its place; a new claim is last)
+    if (tid == 0) { S.done = overflow ? 2 : 1; S.meet_n = n; }
+    meet_bar();
   }
 
   // ---- epilogue ----
   __syncthreads();
+  overflow = S.done == 2;
+  n = S.meet_n;
   if (overflow) {  // status stays 0: the next form redoes the problem from a clean queue state
     for (int i = tid; i < n_pods; i += REG_THREADS) A.lastlen[base + i] = 0;
     return;
@@ -703,14 +691,20 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     int32_t* c_tmpl = A.c_tmpl + base;
     int32_t* c_npods = A.c_npods + base;
     int32_t* g_ord = A.ord + base;
-    // Results.NewNodeClaims: the order after the last sort the reference ran plus the modification that followed it
-    if (warp == REG_ORDW) {
-      ord_apply(s_ord, s_key, s_pos, undo);
-      if (undo.mode == ORD_ROTATE) ord_move(s_ord, s_key, s_pos, undo.src, undo.dst);
-      else if (undo.mode == ORD_GENERIC)
-        for (int i = lane; i < n; i += 32) s_ord[i] = g_snap[i];
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) g_ord[i] = s_ord[i];
+    if (is_claim) {
+      // the claim the very last step changed marked its position (bit 31) with where the next sort would have put it:
+      // a new claim is last, a claim that gained a pod stays where it was (one before the range it would have passed)
+      const unsigned last_mv = t_end > 0 ? S.mv[(t_end + 1u) & 1u] : MV_EMPTY;
+#define ORDER_SLOT(j, sl)                                                                                      \
+  if ((j) * REG_NCT + tid < n) {                                                                               \
+    if (sl.pos & 0x80000000u) {                                                                                \
+      if (last_mv & MV_UP) sl.pos = (unsigned)(n - 1);                                                         \
+      else sl.pos = (last_mv & 0xFFFFFFu) == MV_EMPTY ? (sl.pos & 0x7FFFFFFFu) : (last_mv & 0xFFFu) - 1u;       \
+    }                                                                                                          \
+    g_ord[sl.pos] = (j) * REG_NCT + tid;                                                                       \
+  }
+      FOR_SLOTS(ORDER_SLOT);
+#undef ORDER_SLOT
     }
     if (is_claim) {
 #define STORE_SLOT(j, sl)                                                                    \
@@ -718,13 +712,17 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     const int c = (j) * REG_NCT + tid;                                                       \
     _Pragma("unroll") for (int r = 0; r < RT; r++) if (prm.perm[r] >= 0) {                   \
       int rank;                                                                              \
-      if (r < RT - NWIN) rank = s_tab[prm.toff[r] + min(sl.x[r], prm.lim[r])];               \
-      else rank = (int)((sl.wrk >> (8 * (r < RT - NWIN ? 0 : r - (RT - NWIN)))) & 0xFFull);  \
+      if (NWIN == RT) rank = (int)((sl.wrk >> (8 * r)) & 0xFFull);                            \
+      else if (r < RT - 1) rank = s_tab[prm.toff[r] + min(sl.x[r], prm.lim[r])];             \
+      else {                                                                                 \
+        const int2 b = reinterpret_cast<const int2*>(s_win)[prm.toff[r] + (sl.x[r] >> prm.bsh)]; \
+        rank = b.y + (b.x < sl.x[r] ? 1 : 0);                                                \
+      }                                                                                      \
       c_req[(size_t)c * R + prm.perm[r]] = (int64_t)sl.x[r] * prm.scale[r];                  \
       c_rk[(size_t)c * R + prm.perm[r]] = (int64_t)(prm.row0[r] + rank);                     \
     }                                                                                        \
     c_tmpl[c] = sl.tmpl;                                                                     \
-    c_npods[c] = (int)(sl.prio >> TB);                                                       \
+    c_npods[c] = sl.npods;                                                       \
   }
       FOR_SLOTS(STORE_SLOT);
 #undef STORE_SLOT
@@ -757,10 +755,10 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     pb.n_unscheduled = S.len;
     pb.evals = 0;
     pb.status = 1;
-    if (PROF) { pb.prof[0] = prof[0]; pb.prof[1] = prof[1]; pb.prof[2] = prof[2]; pb.prof[3] = prof[4]; }
+    if (PROF) { pb.prof[0] = prof[0]; pb.prof[1] = prof[1]; pb.prof[2] = prof[2]; pb.prof[3] = prof[4]; pb.prof[7] = prof[3]; pb.prof[8] = prof[5]; pb.prof[9] = prof[6]; }
   }
-  if (PROF && warp == REG_ORDW && lane == 0) { pb.prof[4] = prof[0]; pb.prof[5] = prof[1]; pb.prof[6] = prof[2]; pb.prof[7] = prof[3]; pb.prof[10] = prof[4]; }
-  if (PROF && warp == REG_QW && lane == 0) { pb.prof[8] = prof[0]; pb.prof[9] = prof[1]; pb.prof[11] = prof[2]; }
+  if (PROF && warp == REG_ORDW && lane == 0) { pb.prof[4] = prof[0]; pb.prof[5] = prof[1]; pb.prof[6] = 0; pb.prof[10] = prof[4]; }
+  if (PROF && warp == REG_QW && lane == 0) { pb.prof[11] = prof[0]; }
 }
 
 // Feasibility table of template t: bit [sum_r i_r * stride_r] = some instance type of the template's pre-filtered
@@ -840,19 +838,37 @@ bool reg_pack_plan(const KeyTab& kt, const int64_t* h_dv, int T, const int64_t (
     direct[r] = 2 * maxv[r] + 2 <= 40960 && tab_bytes + (size_t)(2 * maxv[r] + 2) <= 65536;
     if (direct[r]) tab_bytes += (size_t)(2 * maxv[r] + 2);
   }
-  // slots: direct resources first, then padding, window resources last
-  int nwin = 0;
-  for (int r = 0; r < R; r++) nwin += direct[r] ? 0 : 1;
-  const int form = nwin <= 1 ? 1 : RT;  // compiled forms: one window slot, or every slot a window
+  // Compiled forms: (1) direct tables in slots 0 .. RT-2 and a bucket table in the last slot — for the one resource
+  // whose scaled range is too large for a direct table (memory, typically), if buckets of a power-of-two width
+  // separate its distinct values; (RT) every slot tracks its rank through windows.
+  int nwin = 0, last = -1;
+  for (int r = 0; r < R; r++)
+    if (!direct[r]) { nwin++; last = r; }
+  if (nwin == 0 && R == RT) last = R - 1;
+  int bsh = 31;
+  bool bucket_ok = nwin <= 1;
+  if (bucket_ok && last >= 0) {
+    const int64_t* dv = h_dv + kt.res_dv0[last];
+    const int nd = kt.res_nd[last];
+    bsh = 30;
+    for (; bsh >= 0; bsh--) {
+      bool ok = true;
+      for (int i = 0; i + 1 < nd && ok; i++) ok = ((dv[i] / g[last]) >> bsh) != ((dv[i + 1] / g[last]) >> bsh);
+      if (ok) break;
+    }
+    bucket_ok = bsh >= 0 && ((2 * maxv[last] + 1) >> bsh) + 1 <= 4096;
+  }
+  const int form = bucket_ok ? 1 : RT;
   int slot_of[RT];
   {
-    int d = 0, w = RT - form;
+    int d = 0, w = 0;
     for (int r = 0; r < R; r++) {
       if (form == RT) slot_of[r] = w++;
-      else if (direct[r]) slot_of[r] = d++;
-      else slot_of[r] = RT - 1;
+      else if (r == last) slot_of[r] = RT - 1;
+      else slot_of[r] = d++;
     }
   }
+  plan->bsh = bsh;
   plan->nwin_form = form;
   plan->R = R;
   plan->tab.clear();
@@ -879,9 +895,27 @@ bool reg_pack_plan(const KeyTab& kt, const int64_t* h_dv, int T, const int64_t (
   plan->cells = (int32_t)cells;
   plan->wpt = (int32_t)((cells + 31) / 32);
   for (int s = 0; s < RT; s++) {
-    const bool is_window = s >= RT - form;
+    const bool is_window = form == RT, is_bucket = form == 1 && s == RT - 1;
     const int r = plan->perm[s];
-    if (!is_window) {
+    if (is_bucket) {
+      plan->toff[s] = 0;
+      if (r < 0) {  // padding: one bucket, rank 0 (bsh = 31)
+        plan->win.push_back(INT32_MAX);
+        plan->win.push_back(0);
+        continue;
+      }
+      const int64_t* dv = h_dv + kt.res_dv0[r];
+      const int nd = kt.res_nd[r];
+      const int64_t nb = ((2 * maxv[r] + 1) >> bsh) + 1;
+      int rank = 0;
+      for (int64_t b = 0; b < nb; b++) {  // {the distinct value inside the bucket, number of distinct values below it}
+        const int64_t lo = b << bsh, hi = lo + (1ll << bsh);
+        while (rank < nd && dv[rank] / g[r] < lo) rank++;
+        const bool in = rank < nd && dv[rank] / g[r] < hi;
+        plan->win.push_back(in ? (int32_t)(dv[rank] / g[r]) : INT32_MAX);
+        plan->win.push_back(rank);
+      }
+    } else if (!is_window) {
       plan->toff[s] = (int32_t)plan->tab.size();
       if (r < 0) {  // padding: one entry, rank 0
         plan->lim[s] = 0;
@@ -905,6 +939,7 @@ bool reg_pack_plan(const KeyTab& kt, const int64_t* h_dv, int T, const int64_t (
     }
   }
   while (plan->tab.size() % 16) plan->tab.push_back(0);
+  while (plan->win.size() % 4) plan->win.push_back(0);
   plan->daemon32.assign((size_t)MAXT * 8, 0);
   for (int t = 0; t < T; t++)
     for (int s = 0; s < RT; s++)
@@ -913,7 +948,7 @@ bool reg_pack_plan(const KeyTab& kt, const int64_t* h_dv, int T, const int64_t (
         plan->daemon32[(size_t)t * 8 + s] = (int32_t)std::min<int64_t>(daemon[t][r] / g[r], maxv[r] + 1);
       }
   // claims per thread: the largest compiled form shared memory allows
-  for (int cpt : {4, 2}) {
+  for (int cpt : {4, 2, 1}) {
     const int cap = REG_NCT * cpt;
     if (reg_layout((int)plan->tab.size(), (int)(plan->win.size() / 4), T, plan->wpt, cap).total <= (size_t)smem_limit) {
       plan->cpt = cpt;
@@ -955,14 +990,15 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
   if (n_problems == 0) return cudaSuccess;
   RegParams prm{};
   prm.R = kt.n_res; prm.W = kt.n_words; prm.K = kt.n_keys; prm.NB = kt.n_bounded; prm.T = T;
-  int kb = 1;
-  while ((1 << kb) <= max_pods) kb++;  // keys up to max_pods
-  prm.tb = 31 - kb;
-  if (prm.tb < 8) return cudaErrorInvalidValue;
+  if (max_pods >= (1 << 25)) {  // a claim's pod count travels in 25 bits of an event word
+    *may_overflow = true;
+    return cudaSuccess;
+  }
   prm.wpt = plan.wpt;
   prm.tab_bytes = (int32_t)plan.tab.size();
   prm.win_entries = (int32_t)(plan.win.size() / 4);
   for (int s = 0; s < RT; s++) {
+    prm.bsh = plan.bsh;
     prm.perm[s] = plan.perm[s]; prm.lim[s] = plan.lim[s]; prm.toff[s] = plan.toff[s]; prm.stride[s] = plan.stride[s];
     prm.row0[s] = plan.row0[s]; prm.scale[s] = plan.scale[s];
   }
@@ -978,22 +1014,28 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
     if (err != cudaSuccess) return err;                                                           \
     kern<<<n_problems, REG_THREADS, bytes, stream>>>(prm, tg, pods, arr, problems);               \
   } while (0)
-  // Claims per thread: the two-slot form first (less code on the step's critical path); a problem that needs more
-  // claims than it holds leaves status 0 and the four-slot form — then pack_kernel — redoes it, each skipping what an
-  // earlier one finished.  A form is launched only if some problem could still need it.
-  const char* force = getenv("B200S_REG_CPT");  // experiments: "4" skips the two-slot form
-  int launched = 0;
-  for (int cpt : {2, 4}) {
+  // Claims per thread: the smallest form first (less code on the step's critical path); a problem that needs more
+  // claims than it holds leaves status 0 and the next form — then pack_kernel — redoes it, each skipping what an earlier
+  // one finished.  A form is launched only if some problem could still need it; batches of large problems do not try
+  // the small forms (what they do before giving up is wasted).
+  const char* force = getenv("B200S_REG_CPT");  // experiments: the first form to try
+  // (the one-slot form only where it cannot run out: every claim holds at least one pod)
+  const int first = force ? atoi(force) : (max_pods <= REG_NCT ? 1 : max_pods <= 65536 ? 2 : 4);
+  int launched = 0, prev_cap = 0;
+  for (int cpt : {1, 2, 4}) {
     if (cpt > plan.cpt) break;
-    if (cpt == 2 && force && atoi(force) == 4 && plan.cpt >= 4) continue;
-    if (launched && REG_NCT * (cpt / 2) >= max_pods) break;  // the smaller form cannot have overflowed
+    if (cpt < first && cpt < plan.cpt) continue;
+    if (launched && prev_cap >= max_pods) break;  // the smaller form cannot have overflowed
     prm.cap = REG_NCT * cpt;
+    prev_cap = prm.cap;
     const size_t bytes = reg_layout(prm.tab_bytes, prm.win_entries, T, plan.wpt, prm.cap).total;
     if (plan.nwin_form == 1) {
-      if (cpt == 2) REG_CALL(1, 2);
+      if (cpt == 1) REG_CALL(1, 1);
+      else if (cpt == 2) REG_CALL(1, 2);
       else REG_CALL(1, 4);
     } else {
-      if (cpt == 2) REG_CALL(RT, 2);
+      if (cpt == 1) REG_CALL(RT, 1);
+      else if (cpt == 2) REG_CALL(RT, 2);
       else REG_CALL(RT, 4);
     }
     launched++;

@@ -636,11 +636,12 @@ def test_solve_is_sanitizer_clean(tool, ok):
             assert "truncated 0" not in text.split("gate True")[-1], text[-2000:]
 
 
-@pytest.mark.parametrize("n_big", [1_200, 2_500])
+@pytest.mark.parametrize("n_big", [600, 1_200, 2_500])
 def test_register_pack_hands_over_when_it_runs_out_of_claim_slots(gpu_ctx, n_big):
-    """The register-resident pack holds 896 (two slots per thread) or 1 792 (four) NodeClaims.  A problem that needs more
-    is redone by the next form from a clean queue state -- 1 200 single-pod claims: the four-slot form; 2 500: the generic
-    kernel -- with pods nothing can hold pushed back in the abandoned run as well (their lastLen must not leak)."""
+    """The register-resident pack holds 448 (one slot per thread), 896 (two) or 1 792 (four) NodeClaims.  A problem that
+    needs more is redone by the next form from a clean queue state -- 600 single-pod claims: the two-slot form; 1 200:
+    the four-slot form; 2 500: the generic kernel -- with pods nothing can hold pushed back in the abandoned runs as well
+    (their lastLen must not leak)."""
     model = synth.config("c2", n_big + 600, 500)
     req = model.arrays["pod_requests"].copy()
     big = np.arange(model.n_pods) < n_big

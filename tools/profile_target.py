@@ -74,8 +74,8 @@ for i in range(iters):
         capi.lib().b200s_resident_pack_profile(ctx.h, res.h, raw)
         steps = max(raw[3], 1)
         print("   reg pack cycles/step:", {k: round(raw[i] / steps, 1) for i, k in enumerate(
-            ["claim_eval", "claim_barrier", "claim_commit", "steps", "ordw_pre", "ordw_barrier", "ordw_work", "ordw_spin",
-             "qw_pre", "qw_barrier", "full_sorts", "qw_post"])}, "steps", raw[3], "full sorts", raw[10], flush=True)
+            ["claim_eval", "claim_barrier", "claim_commit", "steps", "ordw_wait", "ordw_work", "-", "claim_post",
+             "claim_meet", "meets", "full_sorts", "qw_pre"])}, "steps", raw[3], "full sorts", raw[10], flush=True)
     if mode == "solve" and not os.environ.get("B200S_NO_PROFILE"):
         pr = res.pack_profile()
         steps = max(pr["steps"], 1)
