@@ -459,6 +459,24 @@ struct GoSort {
   }
 
   B2_HD void insertion(int a, int b) const {
+#if defined(__CUDA_ARCH__)
+    if (coop && b - a <= 32) {
+      // insertion sort with a strict comparison is the stable sort: element L goes to a + (number of elements with a
+      // smaller key, or an equal key and a smaller index)
+      const int lane = threadIdx.x & 31, len = b - a;
+      int32_t v = 0, kv = 0;
+      if (lane < len) { v = ord[a + lane]; kv = key[a + lane]; }
+      int rank = 0;
+      for (int m = 0; m < len; m++) {
+        const int32_t km = __shfl_sync(0xffffffffu, kv, m);
+        rank += (km < kv || (km == kv && m < lane)) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < len) { ord[a + rank] = v; key[a + rank] = kv; }
+      __syncwarp();
+      return;
+    }
+#endif
     for (int i = a + 1; i < b; i++)
       for (int j = i; j > a && less(j, j - 1); j--) swap(j, j - 1);
   }
@@ -497,6 +515,41 @@ struct GoSort {
   B2_HD int choose_pivot(int a, int b, int* hint) const {
     int l = b - a, swaps = 0;
     int i = a + l / 4 * 1, j = a + l / 4 * 2, k = a + l / 4 * 3;
+#if defined(__CUDA_ARCH__)
+    if (coop && l >= 8) {
+      // the same medians on (index, key) pairs in registers: the nine sample keys are read by nine lanes at once
+      const int lane = threadIdx.x & 31;
+      int32_t mine = 0;
+      if (lane < 9) mine = key[a + l / 4 * (lane / 3 + 1) + (lane % 3) - 1];
+      int ix[9];
+      int32_t kx[9];
+#pragma unroll
+      for (int m = 0; m < 9; m++) {
+        kx[m] = __shfl_sync(0xffffffffu, mine, m);
+        ix[m] = a + l / 4 * (m / 3 + 1) + (m % 3) - 1;
+      }
+      auto order2r = [&](int& ia, int32_t& ka, int& ib, int32_t& kb) {
+        if (kb < ka) {
+          swaps++;
+          const int ti = ia; ia = ib; ib = ti;
+          const int32_t tk = ka; ka = kb; kb = tk;
+        }
+      };
+      auto medianr = [&](int& ia, int32_t& ka, int& ib, int32_t& kb, int& ic, int32_t& kc) {  // result in (ib, kb)
+        order2r(ia, ka, ib, kb);
+        order2r(ib, kb, ic, kc);
+        order2r(ia, ka, ib, kb);
+      };
+      if (l >= 50) {
+        medianr(ix[0], kx[0], ix[1], kx[1], ix[2], kx[2]);
+        medianr(ix[3], kx[3], ix[4], kx[4], ix[5], kx[5]);
+        medianr(ix[6], kx[6], ix[7], kx[7], ix[8], kx[8]);
+      }
+      medianr(ix[1], kx[1], ix[4], kx[4], ix[7], kx[7]);
+      *hint = swaps == 0 ? 1 : swaps == 12 ? 2 : 0;
+      return ix[4];
+    }
+#endif
     if (l >= 8) {
       if (l >= 50) {
         i = median(i - 1, i, i + 1, swaps);
@@ -519,6 +572,13 @@ struct GoSort {
       if (i == b) return true;
       if (b - a < 50) return false;
       swap(i, i - 1);
+#if defined(__CUDA_ARCH__)
+      if (coop) {  // the two shifts below as block moves: a run of adjacent swaps carries one element across its run
+        if (i - a >= 2) shift_left_coop(i - 1);
+        if (b - i >= 2) shift_right_coop(i, b);
+        continue;
+      }
+#endif
       if (i - a >= 2)
         for (int j = i - 1; j >= 1; j--) {
           if (!less(j, j - 1)) break;
@@ -532,6 +592,59 @@ struct GoSort {
     }
     return false;
   }
+#if defined(__CUDA_ARCH__)
+  // for (j = i + 1; j < b && key[j] < key[j-1]; j++) swap(j, j-1): the element at i passes every following element
+  // smaller than itself
+  __device__ void shift_right_coop(int i, int b) const {
+    const int lane = threadIdx.x & 31;
+    const int32_t kx = key[i], x = ord[i];
+    int stop = b;
+    for (int j0 = i + 1; j0 < b; j0 += 32) {
+      const int j = j0 + lane;
+      const unsigned sb = __ballot_sync(0xffffffffu, j >= b || !(key[j] < kx));
+      if (sb) { stop = j0 + __ffs((int)sb) - 1; break; }
+    }
+    if (stop > b) stop = b;
+    const int dst = stop - 1;  // where the element ends up
+    if (dst == i) return;
+    __syncwarp();
+    for (int c0 = i + 1; c0 <= dst; c0 += 32) {
+      const int j = c0 + lane;
+      int32_t v = 0, kv = 0;
+      if (j <= dst) { v = ord[j]; kv = key[j]; }
+      __syncwarp();
+      if (j <= dst) { ord[j - 1] = v; key[j - 1] = kv; }
+      __syncwarp();
+    }
+    if (lane == 0) { ord[dst] = x; key[dst] = kx; }
+    __syncwarp();
+  }
+  // for (j = i; j >= 1 && key[j] < key[j-1]; j--) swap(j, j-1): the element at i passes every preceding element
+  // greater than itself (down to index 1: the routine's own bound, not the range's)
+  __device__ void shift_left_coop(int i) const {
+    const int lane = threadIdx.x & 31;
+    const int32_t ky = key[i], y = ord[i];
+    int dst = 0;  // where the element ends up
+    for (int j0 = i; j0 >= 1; j0 -= 32) {
+      const int j = j0 - lane;  // candidate: the element stops at j when j < 1 or !(ky < key[j-1])
+      const unsigned sb = __ballot_sync(0xffffffffu, j < 1 || !(ky < key[j - 1]));
+      if (sb) { dst = j0 - (__ffs((int)sb) - 1); break; }
+    }
+    if (dst < 0) dst = 0;
+    if (dst == i) return;
+    __syncwarp();
+    for (int c0 = i - 1; c0 >= dst; c0 -= 32) {
+      const int j = c0 - lane;
+      int32_t v = 0, kv = 0;
+      if (j >= dst) { v = ord[j]; kv = key[j]; }
+      __syncwarp();
+      if (j >= dst) { ord[j + 1] = v; key[j + 1] = kv; }
+      __syncwarp();
+    }
+    if (lane == 0) { ord[dst] = y; key[dst] = ky; }
+    __syncwarp();
+  }
+#endif
   B2_HD void break_patterns(int a, int b) const {
     int length = b - a;
     if (length >= 8) {

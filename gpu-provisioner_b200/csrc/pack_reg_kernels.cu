@@ -53,6 +53,14 @@ namespace {
 #define B200S_REG_THREADS 512
 #endif
 constexpr int REG_THREADS = B200S_REG_THREADS;
+#ifndef B200S_REG_PREFETCH
+#define B200S_REG_PREFETCH 0
+#endif
+#ifndef B200S_REG_DEFER
+#define B200S_REG_DEFER 1
+#endif
+constexpr bool REG_PREFETCH = B200S_REG_PREFETCH != 0;  // read the next pod's row before the step's barrier
+constexpr bool REG_DEFER = B200S_REG_DEFER != 0;        // the queue warp writes the winners' placements out
 constexpr int REG_NW = REG_THREADS / 32;
 constexpr int REG_CW = REG_NW - 2;     // claim warps; then the order warp and the queue warp
 constexpr int REG_NCT = REG_CW * 32;   // claim threads
@@ -77,6 +85,10 @@ struct RegShared {
   // that sort: the changed position, whether the claim was appended, the number of claims
   unsigned mv[2];
   int32_t meet_a, meet_n, done, _pad3;
+  // first pass over the queue: what step t did, for the queue warp to write out one step later (the winner's stores
+  // to global memory are off the step's critical path): claim id, or -1 nothing to write, -2 a new claim (written by
+  // its owner)
+  int32_t wlog[RING];
   int32_t head, len, n_pushed, _pad;
   RingEnt ring[RING];
 };
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     for (int i = 0; i < 3; i++) { S.best[i] = PRIO_INF; S.best2[i] = PRIO_INF; }
     S.mv[0] = MV_EMPTY; S.mv[1] = MV_EMPTY;
     S.done = 0;
+    for (int i = 0; i < RING; i++) S.wlog[i] = -1;
     S.head = 0; S.len = 0; S.n_pushed = 0;
   }
   if (warp == REG_QW && lane < n_pods) {  // the first batch of pod rows
@@ -432,6 +445,22 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
     __syncwarp();
   };
 
+  // queue warp: writes out what step t did (see RegShared::wlog)
+  auto qw_log = [&](int t) {
+    const int w = S.wlog[t & (RING - 1)];
+    if (w != -1) {
+      if (lane == 0) {
+        if (w >= 0) {
+          const int p = S.ring[t & (RING - 1)].p;
+          A.pod_kind[p] = B200S_PLACE_CLAIM;
+          A.pod_index[p] = w;
+          A.pod_seq[p] = seq;
+        }
+        S.wlog[t & (RING - 1)] = -1;
+      }
+      seq++;
+    }
+  };
   unsigned t_end = 0;  // steps taken (claim warps)
   if (warp == REG_ORDW) {
     // ================= the order warp: runs sort.Slice when the step loop asks for it =================
@@ -465,26 +494,42 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
           d.tol = pf_tol; d.p = pf_p; d.tnew = pf_tnew;
         }
       }
+      if (REG_DEFER && t > 1) qw_log(t - 2);  // this iteration runs beside step t - 1: the log of step t - 2 is complete
       RPROF(0);
       step_bar();
     }
+    if (REG_DEFER && n_pods > 1) qw_log(n_pods - 2);  // (the last step's winner writes its placement itself)
   } else {
     // ================= claim warps: the step loop =================
     int s3i = 0;  // t % 3
+    int32_t nx_q[RT];
+    uint64_t nx_tol = 0;
+    int nx_p = -1, nx_tnew = -1;
+#pragma unroll
+    for (int r = 0; r < RT; r++) nx_q[r] = 0;
     // one pod: returns false when the queue is exhausted (second phase) or the claims do not fit this form
     auto step = [&](const unsigned t, auto phase2_tag) -> bool {
       constexpr bool PHASE2 = decltype(phase2_tag)::value;
-      const RingEnt& e = S.ring[t & (RING - 1)];
-      if (PHASE2 && e.p < 0) return false;
+      // the pod's row: read during the step before in the first pass (the rows are written a batch ahead)
+      int32_t q[RT];
+      uint64_t tol;
+      int ep, etnew;
+      if (PHASE2 || t == 0 || !REG_PREFETCH) {
+        const RingEnt& e = S.ring[t & (RING - 1)];
+        tol = e.tol; ep = e.p; etnew = e.tnew;
+#pragma unroll
+        for (int r = 0; r < RT; r++) q[r] = e.q[r];
+      } else {
+        tol = nx_tol; ep = nx_p; etnew = nx_tnew;
+#pragma unroll
+        for (int r = 0; r < RT; r++) q[r] = nx_q[r];
+      }
+      if (PHASE2 && ep < 0) return false;
       const int s3 = s3i, s3n = s3i == 2 ? 0 : s3i + 1;
       s3i = s3n;
 
       // ---- before the barrier: addToInflightNode — every claim decides for itself, the first feasible in the order wins
       if (tid == 0) { S.best[s3n] = PRIO_INF; S.best2[s3n] = PRIO_INF; }
-      int32_t q[RT];
-      const uint64_t tol = e.tol;
-#pragma unroll
-      for (int r = 0; r < RT; r++) q[r] = e.q[r];
       // slots 0 and 1 unconditionally (straight-line code: the two evaluations interleave; a slot without a claim
       // has priority PRIO_INF), the others only in warps that hold such claims
       unsigned cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
@@ -496,6 +541,12 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 #undef EVAL_SLOT
       const unsigned wmin = __reduce_min_sync(0xffffffffu, cand);
       lane0_min(&S.best[s3], wmin, lane);
+      if (!PHASE2 && REG_PREFETCH) {  // the next pod's row
+        const RingEnt& e1 = S.ring[(t + 1u) & (RING - 1)];
+        nx_tol = e1.tol; nx_p = e1.p; nx_tnew = e1.tnew;
+#pragma unroll
+        for (int r = 0; r < RT; r++) nx_q[r] = e1.q[r];
+      }
       RPROF(0);
       if (PHASE2) claim_bar(); else step_bar();  // B1
       RPROF(1);
@@ -575,8 +626,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
           const bool meet = big || (dst != a && (n < 50 || near));
           if (big) dst = a;
           S.mv[t & 1u] = mv_word(a + 1, dst, false, meet);
-          S.meet_a = a | (n << 16);
-          const int p = e.p;
+          if (meet) S.meet_a = a | (n << 16);
 #define COMMIT_SLOT(j, sl)                                                   \
   if (mine == (j)) {                                                         \
     _Pragma("unroll") for (int r = 0; r < RT; r++) sl.x[r] += q[r];          \
@@ -587,13 +637,18 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   }
           FOR_SLOTS(COMMIT_SLOT);
 #undef COMMIT_SLOT
-          A.pod_kind[p] = B200S_PLACE_CLAIM;
-          A.pod_index[p] = mine * REG_NCT + tid;
-          A.pod_seq[p] = seq;
+          if (PHASE2 || !REG_DEFER || (int)t == n_pods - 1) {  // (the queue warp's last look at the log is one step earlier)
+            const int p = ep;
+            A.pod_kind[p] = B200S_PLACE_CLAIM;
+            A.pod_index[p] = mine * REG_NCT + tid;
+            A.pod_seq[p] = seq;
+          } else {
+            S.wlog[t & (RING - 1)] = mine * REG_NCT + tid;  // the queue warp writes it out
+          }
         }
         seq++;
       } else {
-        const int tnew = e.tnew, p = e.p;
+        const int tnew = etnew, p = ep;
         if (tnew >= 0) {
           // ---- addToNewNodeClaim: the template walk was done for every pod by stage A (scheduler.go:587-675) ----
           if (n >= prm.cap) { overflow = true; return false; }  // uniform: the next form redoes this problem
@@ -610,6 +665,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 #undef OPEN_SLOT
             S.mv[t & 1u] = mv_word(dst, n - 1, true, meet);
             S.meet_a = n | 0x1000 | ((n + 1) << 16);
+            if (!PHASE2 && REG_DEFER && (int)t != n_pods - 1) S.wlog[t & (RING - 1)] = -2;
             c_first[c] = p;
             A.pod_kind[p] = B200S_PLACE_CLAIM;
             A.pod_index[p] = c;

@@ -75,7 +75,7 @@ for i in range(iters):
         steps = max(raw[3], 1)
         print("   reg pack cycles/step:", {k: round(raw[i] / steps, 1) for i, k in enumerate(
             ["claim_eval", "claim_barrier", "claim_commit", "steps", "ordw_wait", "ordw_work", "-", "claim_post",
-             "claim_meet", "meets", "full_sorts", "qw_pre"])}, "steps", raw[3], "full sorts", raw[10], flush=True)
+             "claim_meet", "meets", "full_sorts", "qw_pre"])}, "steps", raw[3], "full sorts", raw[10], "meets", raw[9], flush=True)
     if mode == "solve" and not os.environ.get("B200S_NO_PROFILE"):
         pr = res.pack_profile()
         steps = max(pr["steps"], 1)
