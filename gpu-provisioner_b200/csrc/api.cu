@@ -93,6 +93,8 @@ struct b200s_resident {
   uint64_t* n_taints = nullptr;
   // class tables (per signature x template, per request vector x template)
   uint8_t* sg_status = nullptr;
+  int32_t* rq_rank = nullptr;   // [NQ] FFD rank of a request class (launch_ffd_class_rank)
+  uint64_t* ffd_k1 = nullptr;   // [P] leading sort key of a pod
   uint64_t* sgC = nullptr;
   uint64_t* sgO = nullptr;
   uint64_t* sgCO = nullptr;
@@ -269,6 +271,40 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   }
   r->pods = PodsDev{(int32_t)Ptot, (int32_t)NStot, (int32_t)NQtot, pods_in[0]->res_cpu, pods_in[0]->res_memory, d_sig, d_rq,
                     d_ts, d_uhi, d_ulo, d_smask, d_sflags, d_sgt, d_slt, d_stol, d_rq_req};
+
+  // ---- FFD: rank of every request class in (cpu desc, memory desc) order ----
+  r->rq_rank = r->dalloc<int32_t>((size_t)std::max<long long>((long long)NQtot, 1));
+  r->ffd_k1 = r->dalloc<uint64_t>((size_t)std::max<long long>((long long)Ptot, 1));
+  if (!r->rq_rank || !r->ffd_k1) return fail(ctx, B200S_ENOMEM, "device allocation (FFD keys)");
+  if (NQtot <= 16384) {
+    CUDA_TRY(ctx, launch_ffd_class_rank(r->pods, r->rq_rank, ctx->stream), "ffd_class_rank launch");
+  } else {  // many classes: sorted on the host, once per resident set
+    const size_t nqt = (size_t)NQtot;
+    std::vector<int64_t> cpu(nqt), mem(nqt);
+    size_t qo = 0;
+    for (int b = 0; b < n_problems; b++) {
+      const b200s_pods_soa_t* ps = pods_in[b];
+      const size_t nq = (size_t)ps->n_reqcls;
+      for (size_t q = 0; q < nq; q++) {
+        cpu[qo + q] = ps->rq_requests[(size_t)ps->res_cpu * nq + q];
+        mem[qo + q] = ps->rq_requests[(size_t)ps->res_memory * nq + q];
+      }
+      qo += nq;
+    }
+    std::vector<int32_t> ordq(nqt), rank(nqt);
+    for (size_t q = 0; q < nqt; q++) ordq[q] = (int32_t)q;
+    std::sort(ordq.begin(), ordq.end(), [&](int32_t x, int32_t y) {
+      return cpu[x] != cpu[y] ? cpu[x] > cpu[y] : mem[x] > mem[y];
+    });
+    for (size_t i = 0; i < nqt; i++) {
+      const int32_t q = ordq[i];
+      const bool tie = i > 0 && cpu[ordq[i - 1]] == cpu[q] && mem[ordq[i - 1]] == mem[q];
+      rank[q] = tie ? rank[ordq[i - 1]] : (int32_t)i;
+    }
+    int rc = upload(ctx, r->rq_rank, rank.data(), nqt);
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, B200S_ECUDA, "sync (ranks)");
+    if (rc) return rc;
+  }
 
   // ---- problems, segment ids ----
   r->problems_host.resize(n_problems);
@@ -509,12 +545,17 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches, bool importe
   CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_kind, 0xFF, P * 4, ctx->stream), "memset");
   CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_index, 0xFF, P * 4, ctx->stream), "memset");
   CUDA_TRY(ctx, cudaMemsetAsync(r->arr.pod_seq, 0xFF, P * 4, ctx->stream), "memset");
+  // the host copy doubles as the fetch buffer: a Solve before this one left its outputs (and status 1) in it
+  for (PackProblem& pb : r->problems_host) {
+    pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0; pb.status = 0;
+    for (unsigned long long& c : pb.prof) c = 0;
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(r->problems, r->problems_host.data(), sizeof(PackProblem) * r->n_problems,
                                 cudaMemcpyHostToDevice, ctx->stream), "H2D problems");
   int max_pods = 0;  // the largest problem of the batch
   for (const PackProblem& pb : r->problems_host) max_pods = std::max(max_pods, pb.pod_end - pb.pod_begin);
   int nl = 0;
-  CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
+  CUDA_TRY(ctx, launch_ffd_sort(r->pods, r->seg, r->rq_rank, r->ffd_k1, r->arr.queue, &nl, ctx->stream), "ffd_sort launch");
   *launches += nl;
   bool generic_pack = true;
   if (r->reg_plan.eligible && !r->profile_pack) {
@@ -535,7 +576,7 @@ int enqueue_solve(b200s_ctx* ctx, b200s_resident* r, int* launches, bool importe
              "pack launch");
     *launches += 1;
   }
-  CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, r->cout, ctx->stream),
+  CUDA_TRY(ctx, launch_pack_finalize(cat->kt, r->pods, r->arr, r->problems, r->n_problems, max_pods, r->cout, ctx->stream),
            "pack_finalize launch");
   CUDA_TRY(ctx, launch_select_cheapest(cat->kt, r->P, r->cout.mask, r->cout.rmask, (size_t)cat->K, 1, r->cout.rflags,
                                        r->cout.gt, r->cout.lt, (size_t)cat->NB, 1, r->sel_sku, r->sel_price, r->sel_nopt,

@@ -397,75 +397,120 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(const __grid
 }
 
 // -------------------------------------------------------------------------------------------------
-// FFD order: bitonic sort of pod indices.  less(a,b) is queue.go:72-108; indices >= P are +infinity.
-// `seg` (may be null) is a leading ascending key: the problem a pod belongs to in a batched solve.
+// FFD order: bitonic sort of pod indices by NewQueue's comparison (queue.go:72-108): cpu descending, memory descending,
+// creation timestamp ascending, UID ascending; indices >= P are +infinity.  The leading part of the key is folded
+// into one word per pod, k1 = (problem of a batched solve << 32) | rank of the pod's request class among the classes
+// in (cpu desc, memory desc) order (equal cpu and memory: equal rank), so that a comparison reads k1, the timestamp
+// and the UID's high word — which the chunk kernels keep in shared memory beside the index — and the UID's low word
+// only on a tie of all of those.
 // -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool ffd_less(const PodsDev& pods, const int32_t* __restrict__ seg, int a, int b) {
-  const int P = pods.P;
-  if (a >= P) return false;  // padding sorts last
-  if (b >= P) return true;
-  if (seg) {
-    int sa = seg[a], sb = seg[b];
-    if (sa != sb) return sa < sb;
+struct FfdKeys {
+  const uint64_t* k1;   // [P]
+  const int64_t* ts;    // [P]
+  const uint64_t* uh;   // [P]
+  const uint64_t* ul;   // [P]
+  int P;
+};
+
+// rank[q] = number of request classes that sort strictly before class q
+__global__ void __launch_bounds__(256) ffd_class_rank_kernel(PodsDev pods, int32_t* __restrict__ rank) {
+  __shared__ int64_t s_cpu[256], s_mem[256];
+  const int q = blockIdx.x * 256 + threadIdx.x, NQ = pods.NQ;
+  const int64_t* cpu = pods.rq_req + (size_t)pods.res_cpu * NQ;
+  const int64_t* mem = pods.rq_req + (size_t)pods.res_mem * NQ;
+  const int64_t c = q < NQ ? cpu[q] : 0, m = q < NQ ? mem[q] : 0;
+  int before = 0;
+  for (int t0 = 0; t0 < NQ; t0 += 256) {
+    const int o = t0 + threadIdx.x;
+    s_cpu[threadIdx.x] = o < NQ ? cpu[o] : INT64_MIN;
+    s_mem[threadIdx.x] = o < NQ ? mem[o] : INT64_MIN;
+    __syncthreads();
+    const int lim = min(256, NQ - t0);
+    for (int j = 0; j < lim; j++) before += (s_cpu[j] > c || (s_cpu[j] == c && s_mem[j] > m)) ? 1 : 0;
+    __syncthreads();
   }
-  const int qa = pods.req_id[a], qb = pods.req_id[b];
-  if (qa != qb) {  // equal request classes have equal cpu and memory
-    int64_t ca = pods.rq_req[(size_t)pods.res_cpu * pods.NQ + qa], cb = pods.rq_req[(size_t)pods.res_cpu * pods.NQ + qb];
-    if (ca != cb) return ca > cb;
-    int64_t ma = pods.rq_req[(size_t)pods.res_mem * pods.NQ + qa], mb = pods.rq_req[(size_t)pods.res_mem * pods.NQ + qb];
-    if (ma != mb) return ma > mb;
-  }
-  int64_t ta = pods.ts[a], tb = pods.ts[b];
-  if (ta != tb) return ta < tb;
-  uint64_t ha = pods.uid_hi[a], hb = pods.uid_hi[b];
-  if (ha != hb) return ha < hb;
-  uint64_t la = pods.uid_lo[a], lb = pods.uid_lo[b];
-  if (la != lb) return la < lb;
-  return a < b;  // identical UIDs cannot occur in a cluster; keeps the order total anyway
+  if (q < NQ) rank[q] = before;
 }
 
-constexpr int SORT_THREADS = 512;
-constexpr int SORT_CHUNK = 2 * SORT_THREADS;  // elements a CTA sorts in shared memory
-
-__global__ void ffd_init_kernel(int32_t* __restrict__ idx, int n_pad) {
+__global__ void ffd_init_kernel(PodsDev pods, const int32_t* __restrict__ seg, const int32_t* __restrict__ rank,
+                                int32_t* __restrict__ idx, uint64_t* __restrict__ k1, int n_pad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_pad) idx[i] = i;
+  if (i >= n_pad) return;
+  idx[i] = i;
+  if (i < pods.P) k1[i] = ((uint64_t)(uint32_t)(seg ? seg[i] : 0) << 32) | (uint32_t)rank[pods.req_id[i]];
 }
+
+__device__ __forceinline__ bool ffd_less_keys(const FfdKeys& K, int a, uint64_t ka, int64_t ta, uint64_t ha, int b,
+                                              uint64_t kb, int64_t tb, uint64_t hb) {
+  if (ka != kb) return ka < kb;   // padding carries the largest k1
+  if (ta != tb) return ta < tb;
+  if (ha != hb) return ha < hb;
+  if (a < K.P && b < K.P) {
+    const uint64_t la = K.ul[a], lb = K.ul[b];
+    if (la != lb) return la < lb;
+  }
+  return a < b;  // identical UIDs cannot occur in a cluster; keeps the order total anyway (and orders the padding)
+}
+
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_CHUNK = 2 * SORT_THREADS;  // elements a CTA sorts in shared memory (more per CTA: fewer launches, but the stages of a chunk run on one SM)
+constexpr size_t SORT_SMEM = (size_t)SORT_CHUNK * (4 + 8 + 8 + 8);
 
 // all bitonic stages with stride < SORT_CHUNK for merge size k (k_lo..k_hi doubling) inside shared memory
-__global__ void __launch_bounds__(SORT_THREADS) ffd_local_kernel(PodsDev pods, const int32_t* __restrict__ seg,
-                                                                 int32_t* __restrict__ idx, int k_lo, int k_hi) {
-  __shared__ int32_t s[SORT_CHUNK];
+__global__ void __launch_bounds__(SORT_THREADS) ffd_local_kernel(FfdKeys K, int32_t* __restrict__ idx, int k_lo, int k_hi) {
+  extern __shared__ __align__(16) unsigned char ffd_smem[];
+  uint64_t* s_k = reinterpret_cast<uint64_t*>(ffd_smem);
+  int64_t* s_t = reinterpret_cast<int64_t*>(s_k + SORT_CHUNK);
+  uint64_t* s_h = reinterpret_cast<uint64_t*>(s_t + SORT_CHUNK);
+  int32_t* s_i = reinterpret_cast<int32_t*>(s_h + SORT_CHUNK);
   const int base = blockIdx.x * SORT_CHUNK;
-  s[threadIdx.x] = idx[base + threadIdx.x];
-  s[threadIdx.x + SORT_THREADS] = idx[base + threadIdx.x + SORT_THREADS];
+  for (int e = threadIdx.x; e < SORT_CHUNK; e += SORT_THREADS) {
+    const int p = idx[base + e];
+    s_i[e] = p;
+    const bool real = p < K.P;
+    s_k[e] = real ? K.k1[p] : ~0ull;
+    s_t[e] = real ? K.ts[p] : 0;
+    s_h[e] = real ? K.uh[p] : 0ull;
+  }
   __syncthreads();
   for (int k = k_lo; k <= k_hi; k <<= 1) {
     for (int j = min(k >> 1, SORT_CHUNK >> 1); j > 0; j >>= 1) {
-      int t = threadIdx.x;
-      int i = ((t / j) * 2 * j) + (t % j);  // lower element of the pair
-      int l = i + j;
-      bool up = (((base + i) & k) == 0);
-      int a = s[i], b = s[l];
-      bool sw = up ? ffd_less(pods, seg, b, a) : ffd_less(pods, seg, a, b);
-      if (sw) { s[i] = b; s[l] = a; }
+#pragma unroll
+      for (int rep = 0; rep < SORT_CHUNK / (2 * SORT_THREADS); rep++) {
+        const int t = threadIdx.x + rep * SORT_THREADS;
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower element of the pair
+        const int l = i + j;
+        const bool up = (((base + i) & k) == 0);
+        const int a = s_i[i], b = s_i[l];
+        const uint64_t ka = s_k[i], kb = s_k[l], ha = s_h[i], hb = s_h[l];
+        const int64_t ta = s_t[i], tb = s_t[l];
+        const bool sw = up ? ffd_less_keys(K, b, kb, tb, hb, a, ka, ta, ha) : ffd_less_keys(K, a, ka, ta, ha, b, kb, tb, hb);
+        if (sw) {
+          s_i[i] = b; s_i[l] = a;
+          s_k[i] = kb; s_k[l] = ka;
+          s_t[i] = tb; s_t[l] = ta;
+          s_h[i] = hb; s_h[l] = ha;
+        }
+      }
       __syncthreads();
     }
   }
-  idx[base + threadIdx.x] = s[threadIdx.x];
-  idx[base + threadIdx.x + SORT_THREADS] = s[threadIdx.x + SORT_THREADS];
+  for (int e = threadIdx.x; e < SORT_CHUNK; e += SORT_THREADS) idx[base + e] = s_i[e];
 }
 
 // one global bitonic stage (stride j >= SORT_CHUNK) of merge size k
-__global__ void ffd_global_kernel(PodsDev pods, const int32_t* __restrict__ seg, int32_t* __restrict__ idx, int n_pad,
-                                  int j, int k) {
+__global__ void ffd_global_kernel(FfdKeys K, int32_t* __restrict__ idx, int n_pad, int j, int k) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pad / 2) return;
   int i = ((t / j) * 2 * j) + (t % j);
   int l = i + j;
   bool up = ((i & k) == 0);
-  int a = idx[i], b = idx[l];
-  bool sw = up ? ffd_less(pods, seg, b, a) : ffd_less(pods, seg, a, b);
+  const int a = idx[i], b = idx[l];
+  const bool ra = a < K.P, rb = b < K.P;
+  const uint64_t ka = ra ? K.k1[a] : ~0ull, kb = rb ? K.k1[b] : ~0ull;
+  const int64_t ta = ra ? K.ts[a] : 0, tb = rb ? K.ts[b] : 0;
+  const uint64_t ha = ra ? K.uh[a] : 0ull, hb = rb ? K.uh[b] : 0ull;
+  const bool sw = up ? ffd_less_keys(K, b, kb, tb, hb, a, ka, ta, ha) : ffd_less_keys(K, a, ka, ta, ha, b, kb, tb, hb);
   if (sw) { idx[i] = b; idx[l] = a; }
 }
 
@@ -864,20 +909,34 @@ static int next_pow2(int n) {
 
 int ffd_padded(int P) { return next_pow2(P < SORT_CHUNK ? SORT_CHUNK : P); }
 
-cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, int32_t* idx, int* launches, cudaStream_t stream) {
+cudaError_t launch_ffd_class_rank(const PodsDev& pods, int32_t* rank, cudaStream_t stream) {
+  if (pods.NQ <= 0) return cudaSuccess;
+  ffd_class_rank_kernel<<<(pods.NQ + 255) / 256, 256, 0, stream>>>(pods, rank);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, const int32_t* rank, uint64_t* k1, int32_t* idx,
+                            int* launches, cudaStream_t stream) {
   const int n_pad = ffd_padded(pods.P);
   int nl = 0;
-  ffd_init_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(idx, n_pad);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ffd_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  ffd_init_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(pods, seg, rank, idx, k1, n_pad);
   nl++;
+  const FfdKeys K{k1, pods.ts, pods.uid_hi, pods.uid_lo, pods.P};
   // sort every chunk in shared memory (merge sizes 2 .. SORT_CHUNK)
-  ffd_local_kernel<<<n_pad / SORT_CHUNK, SORT_THREADS, 0, stream>>>(pods, seg, idx, 2, SORT_CHUNK);
+  ffd_local_kernel<<<n_pad / SORT_CHUNK, SORT_THREADS, SORT_SMEM, stream>>>(K, idx, 2, SORT_CHUNK);
   nl++;
   for (int k = SORT_CHUNK * 2; k <= n_pad; k <<= 1) {
     for (int j = k >> 1; j >= SORT_CHUNK; j >>= 1) {
-      ffd_global_kernel<<<(n_pad / 2 + 255) / 256, 256, 0, stream>>>(pods, seg, idx, n_pad, j, k);
+      ffd_global_kernel<<<(n_pad / 2 + 255) / 256, 256, 0, stream>>>(K, idx, n_pad, j, k);
       nl++;
     }
-    ffd_local_kernel<<<n_pad / SORT_CHUNK, SORT_THREADS, 0, stream>>>(pods, seg, idx, k, k);
+    ffd_local_kernel<<<n_pad / SORT_CHUNK, SORT_THREADS, SORT_SMEM, stream>>>(K, idx, k, k);
     nl++;
   }
   if (launches) *launches = nl;

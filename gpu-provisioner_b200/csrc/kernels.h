@@ -121,7 +121,10 @@ int compact_row_bytes(int T);
 cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream);
 cudaError_t launch_compact_import(int P, int T, const uint8_t* in, int32_t* tmpl, uint8_t* code, int n_sm, cudaStream_t stream);
 int ffd_padded(int P);
-cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, int32_t* idx, int* launches, cudaStream_t stream);
+// rank[q]: request classes that sort strictly before class q in (cpu desc, memory desc) order; O(NQ^2 / threads)
+cudaError_t launch_ffd_class_rank(const PodsDev& pods, int32_t* rank, cudaStream_t stream);
+cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, const int32_t* rank, uint64_t* k1, int32_t* idx,
+                            int* launches, cudaStream_t stream);
 cudaError_t launch_select_cheapest(const KeyTab& kt, int n, const uint64_t* masks, const uint64_t* rmask, size_t rms,
                                    size_t rks, const uint64_t* rflags, const int64_t* rgt, const int64_t* rlt, size_t bms,
                                    size_t bks, int32_t* sku_out, uint64_t* price_out, int32_t* nopt_out,
@@ -158,6 +161,6 @@ cudaError_t launch_pack_reg(const KeyTab& kt, const TmplDev* tg, int T, const Po
                             PackProblem* problems, int n_problems, int max_pods, const RegPackPlan& plan,
                             const RegPackDev& dev, bool* may_overflow, int* n_launched, cudaStream_t stream);
 cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
-                                 int n_problems, ClaimOut out, cudaStream_t stream);
+                                 int n_problems, int max_pods, ClaimOut out, cudaStream_t stream);
 
 }  // namespace b200

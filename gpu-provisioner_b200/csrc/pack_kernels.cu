@@ -974,14 +974,16 @@ __global__ void __launch_bounds__(PACK_THREADS, 1) pack_kernel(const __grid_cons
 }
 
 // Results.NewNodeClaims in final order + FinalizeScheduling (nodeclaim.go:252-268: only the placeholder
-// hostname is dropped, which this encoding never materialises) + pod -> claim position.
+// hostname is dropped, which this encoding never materialises) + pod -> claim position.  gridDim.y CTAs share a
+// problem's rows and pods; every one of them writes the (identical) claim -> position map before it uses it.
 __global__ void __launch_bounds__(256) pack_finalize_kernel(KeyTab kt, PodsDev pods, PackArrays A,
                                                             const PackProblem* __restrict__ problems, ClaimOut out) {
   const PackProblem& pb = problems[blockIdx.x];
   const int base = pb.pod_begin, n_pods = pb.pod_end - pb.pod_begin, n = pb.n_claims;
   const int R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded, W = kt.n_words;
   const int row_words = W + R + K + 2 * NB;
-  for (int i = threadIdx.x; i < n * row_words; i += blockDim.x) {
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+  for (int i = tid; i < n * row_words; i += nth) {
     int pos = i / row_words, j = i - pos * row_words;
     int c = A.ord[base + pos];
     size_t src = (size_t)base + c, dst = (size_t)base + pos;
@@ -993,13 +995,15 @@ __global__ void __launch_bounds__(256) pack_finalize_kernel(KeyTab kt, PodsDev p
   }
   for (int pos = threadIdx.x; pos < n; pos += blockDim.x) {
     int c = A.ord[base + pos];
-    out.tmpl[base + pos] = A.c_tmpl[base + c];
-    out.npods[base + pos] = A.c_npods[base + c];
-    out.rflags[base + pos] = A.c_rflags[base + c];
+    if (blockIdx.y == 0) {
+      out.tmpl[base + pos] = A.c_tmpl[base + c];
+      out.npods[base + pos] = A.c_npods[base + c];
+      out.rflags[base + pos] = A.c_rflags[base + c];
+    }
     out.pos_of_claim[base + c] = pos;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n_pods; i += blockDim.x) {
+  for (int i = tid; i < n_pods; i += nth) {
     int p = base + i;  // pods of a problem are a contiguous index range (the queue ring is NOT a permutation any more)
     if (A.pod_kind[p] == B200S_PLACE_CLAIM) A.pod_index[p] = out.pos_of_claim[base + A.pod_index[p]];
   }
@@ -1062,9 +1066,13 @@ cudaError_t launch_pack(const KeyTab& kt, const TmplDev* tg, int T, const PodsDe
 }
 
 cudaError_t launch_pack_finalize(const KeyTab& kt, const PodsDev& pods, PackArrays arr, const PackProblem* problems,
-                                 int n_problems, ClaimOut out, cudaStream_t stream) {
+                                 int n_problems, int max_pods, ClaimOut out, cudaStream_t stream) {
   if (n_problems == 0) return cudaSuccess;
-  pack_finalize_kernel<<<n_problems, 256, 0, stream>>>(kt, pods, arr, problems, out);
+  // a single large Solve spreads over many CTAs, a batch of small ones keeps one each
+  int y = max_pods / 512;
+  y = y < 1 ? 1 : y > 64 ? 64 : y;
+  while (y > 1 && (long long)n_problems * y > 1184) y >>= 1;
+  pack_finalize_kernel<<<dim3((unsigned)n_problems, (unsigned)y), 256, 0, stream>>>(kt, pods, arr, problems, out);
   return cudaGetLastError();
 }
 

@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
   // queue warp: writes out what step t did (see RegShared::wlog)
   auto qw_log = [&](int t) {
     const int w = S.wlog[t & (RING - 1)];
+    __syncwarp();  // every lane has read the entry before lane 0 clears it
     if (w != -1) {
       if (lane == 0) {
         if (w >= 0) {

@@ -102,6 +102,32 @@ def test_config2_full_size_bit_identical(gpu_ctx):
     _fit_parity(gpu_ctx, m, "config 2 fit")
 
 
+def test_repeated_solves_on_resident_inputs_do_the_work_again(gpu_ctx):
+    """A resident problem set solved again (what bench.py's device-timed loop does) runs the whole pack again: same
+    result, and a device time of the same order as the first Solve's -- the fetch in between leaves the first Solve's
+    outputs in the host copy of the problem table, which must not be taken for a finished problem."""
+    m = synth.config("c2", 4000, 500)
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    res = capi.Resident(gpu_ctx, cid, enc)
+    try:
+        ev = [gpu_ctx.event() for _ in range(2)]
+        times, raws = [], []
+        for _ in range(3):
+            gpu_ctx.record(ev[0])
+            res.solve()
+            gpu_ctx.record(ev[1])
+            raws.append(res.fetch_solve())
+            times.append(gpu_ctx.elapsed_ms(ev[0], ev[1]))
+    finally:
+        res.close()
+        gpu_ctx.release_catalog(cid)
+    o = ob.solve(m)
+    for raw in raws:
+        parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, o), "repeated resident solve")
+    assert min(times[1:]) > 0.5 * times[0] or min(times[1:]) > 1.0, times  # 4 000 sequential steps take milliseconds
+
+
 def test_empty_and_ragged_inputs(gpu_ctx):
     # no pods
     m = synth.config("c2", 0, 50)
