@@ -752,10 +752,11 @@ def main():
             ctx.solve(cid, enc_i)
         ms_e2e_enc = 1e3 * (time.perf_counter() - t0) / args.steps
         ms_encode = 1e3 * t_enc / args.steps
-    res.set_pack_profile(True)  # one extra, untimed Solve with the kernel's cycle counters on
+    # one extra, untimed Solve with the register-resident pack's cycle counters on (its PROF form: ~5 % slower)
+    os.environ["B200S_REG_PROFILE"] = "1"
     res.solve()
-    prof = res.pack_profile()
-    res.set_pack_profile(False)
+    prof = res.reg_pack_profile()
+    del os.environ["B200S_REG_PROFILE"]
     barrier()
     if world > 1:
         t = torch.tensor([ms_solve, ms_fit, ms_e2e, ms_e2e_enc], device="cuda", dtype=torch.float64)
@@ -791,7 +792,10 @@ def main():
         "step_breakdown": {"dense_stage_ms": ms_fit, "dense_stage_share": ms_fit / ms_solve,
                            "pack_and_rest_ms": ms_solve - ms_fit,
                            "note": "the FFD pack is one sequential chain per Solve (latency-bound, one CTA); "
-                                   "cycles per pod step by phase (from one extra Solve with the kernel's counters on, ~3 % slower): " + json.dumps({k: round(v / max(prof['steps'], 1)) for k, v in prof.items() if k in ('start', 'nodes', 'scan', 'commit', 'normalise', 'queue_warp', 'order_warp', 'claim_group', 'full_sort_cycles')})},
+                                   "SM cycles per pod step of claim warp 0 (one extra Solve with the kernel's counters on, ~5 % slower): "
+                                   + json.dumps({k: round(v / max(prof['steps'], 1)) for k, v in prof.items()
+                                                 if k in ('claim_eval', 'claim_barrier', 'claim_post', 'claim_meet', 'claim_commit', 'order_warp_sort')})
+                                   + f"; {prof['steps']} steps, {prof['meets']} of them met the order warp, {prof['full_sorts']} full pdqsorts"},
         "roofline": {"bound": "hbm", "kernel": "fit_dense_vec_kernel (dense pod x SKU stage) on config[1]",
                      "achieved": ab / (ms_dense_k * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": ab / (ms_dense_k * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes": ab,

@@ -552,6 +552,17 @@ class Resident:
         d.pop("-"), d.pop("--")
         return d
 
+    def reg_pack_profile(self):
+        """Cycle counters of the register-resident pack (pack_reg_kernels.cu), problem 0, of the last Solve run with
+        B200S_REG_PROFILE set in the environment: per-role SM cycles, steps, order-warp meetings and full pdqsorts."""
+        out = (C.c_uint64 * 12)()
+        self.ctx._check(self.ctx.L.b200s_resident_pack_profile(self.ctx.h, self.h, out))
+        names = ["claim_eval", "claim_barrier", "claim_commit", "steps", "order_warp_wait", "order_warp_sort", "-",
+                 "claim_post", "claim_meet", "meets", "full_sorts", "queue_warp"]
+        d = dict(zip(names, [int(x) for x in out]))
+        d.pop("-")
+        return d
+
     def fetch_fit(self) -> FitOut:
         e = self.enc
         tmpl = np.zeros(max(e.P, 1), np.int32)
