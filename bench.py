@@ -529,6 +529,14 @@ def run_c4(args, rank, world, local):
     sims = [all_sims[int(j)] for j in mine]
     Bm = len(sims)
     encs = [capi.Encoded(m) for _, m in sims]
+    # the same simulations as ONE model (every node, the candidates' pods one candidate after the other): one encode, one
+    # upload of the cluster's nodes -- what b200s_solve_batch_shared takes
+    t1 = time.perf_counter()
+    shared_model, pod_off, cands = synth.c4_shared(model, node_of_pod, [i for i, _ in sims])
+    enc_all = capi.Encoded(shared_model)
+    t_encode_shared = time.perf_counter() - t1
+    assert enc_all.layout_hash == encs[0].layout_hash
+    excl = [[r] for r in enc_all.node_rows(cands)]
     sample = list(range(0, Bm, max(Bm // 32, 1)))[:32]  # a spread of this rank's simulations: parity check, CPU timing
     t_build = time.perf_counter() - t0
     cid = ctx.upload_catalog(encs[0])
@@ -547,8 +555,8 @@ def run_c4(args, rank, world, local):
     d_mine = torch.zeros((rows, 5), dtype=torch.int32, device="cuda")
     d_all = torch.zeros((world * rows, 5), dtype=torch.int32, device="cuda")
 
-    def step():
-        outs = ctx.solve_batch(cid, encs)
+    def step(separate=False):
+        outs = ctx.solve_batch(cid, encs) if separate else ctx.solve_batch_shared(cid, enc_all, pod_off, excl)
         cmds = ctx.consolidation_commands(cid, encs[0], outs, cand_price, cand_spot, [1] * Bm, ct_bits[0], ct_bits[1],
                                           ct_bits[2], spot_to_spot=True)
         table = None
@@ -592,9 +600,18 @@ def run_c4(args, rank, world, local):
         for f in ("decision", "reason", "n_options", "spot_required", "price_tie"):
             assert got[f] == want[f], (f"c4 command of node {i}", f, got, want)
         assert got["mask"] == want["mask"].tolist() and got["head"] == want["head"].tolist(), f"c4 command of node {i}"
+    # the separately flattened form of the same batch (round 1's step): against the oracle, and the shared form against it
+    step(separate=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    outs_sep, _, _ = step(separate=True)
+    torch.cuda.synchronize()
+    ms_separate = 1e3 * (time.perf_counter() - t0)
     for j, o in zip(sample, oracle_out):
-        parity.assert_same(parity.canon_device(encs[j], outs[j]), parity.canon_oracle(sims[j][1], o),
+        parity.assert_same(parity.canon_device(encs[j], outs_sep[j]), parity.canon_oracle(sims[j][1], o),
                            f"c4 simulation of node {sims[j][0]}")
+    for j in range(Bm):
+        parity.assert_shared_matches_separate(enc_all, encs[j], sims[j][0], outs_sep[j], outs[j], f"c4 simulation of node {sims[j][0]}")
     removable = (int(((table[:, 3] == 0) & (table[:, 4] == 0)).sum()) if world > 1 else
                  sum(1 for r in outs if r.n_claims == 0 and r.n_unscheduled == 0))
     # multi-node re-pack: every pod of the candidates at once against the remaining nodes
@@ -628,12 +645,17 @@ def run_c4(args, rank, world, local):
             "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "int64/u64", "data": "synthetic",
             "config": {"workload": f"config[3]: {P} running pods on {E} loosely packed nodes ({S} SKUs); {B} single-node "
-                                   "consolidation simulations per step (lowest utilisation first) through b200s_solve_batch and their commands through "
+                                   "consolidation simulations per step (lowest utilisation first) through b200s_solve_batch_shared (one pod set, the cluster's nodes handed over once) and their commands through "
                                    "b200s_consolidation_commands (host buffers in and out); plus one multi-node re-pack "
                                    "outside the timed region", "build_s": t_build,
                        "multi_gpu": "one process per GPU; the simulations are dealt round-robin to the ranks and the five "
                                     "result words per simulation all-gathered (NCCL) inside the step; wall time, max over "
                                     "ranks" if world > 1 else "single GPU"},
+            "separately_flattened": {"ms_per_step": ms_separate, "note": "the same batch as 256 separately flattened models through b200s_solve_batch (round 1's step): every simulation uploads its own copy of the cluster's nodes"},
+            "shared_encode_ms": 1e3 * t_encode_shared,
+            "e2e_with_encode": {"value": B / ((ms + 1e3 * t_encode_shared) * 1e-3), "unit": "simulations/s",
+                                "ms_per_step": ms + 1e3 * t_encode_shared,
+                                "note": "the step plus ONE b200s_encode of the batch's shared model (all nodes, every candidate's pods) -- what the shim does per batch"},
             "commands_all_ranks": {"delete": deleted_all} if world > 1 else None,
             "commands": {"delete": int((cmds["decision"] == capi.CMD_DELETE).sum()),
                          "replace": int((cmds["decision"] == capi.CMD_REPLACE).sum()),

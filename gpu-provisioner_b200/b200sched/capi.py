@@ -167,6 +167,8 @@ def lib():
                               _P(Result)]
     L.b200s_solve_batch.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(_P(PodsSoA)), _P(_P(NodesSoA)),
                                     _P(Templates), _P(SolveOpts), _P(_P(Result))]
+    L.b200s_solve_batch_shared.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(PodsSoA), _P(C.c_int32), _P(NodesSoA),
+                                           _P(C.c_int32), _P(C.c_int32), _P(Templates), _P(SolveOpts), _P(_P(Result))]
     L.b200s_resident_create.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates),
                                         _P(C.c_void_p)]
     L.b200s_resident_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -234,6 +236,11 @@ class Encoded:
         self.key_model = [L.b200s_encoded_key_model_id(h, k) for k in range(self.K)]
         self.bounded_key = [c.bounded_key[b] for b in range(self.NB)]
         self.pool_index = [self.templates.contents.pool_index[t] for t in range(self.T)]
+
+    def node_rows(self, model_nodes: Sequence[int]) -> List[int]:
+        """rows of the encoded node set (sortExistingNodes order) that hold the given model nodes"""
+        row_of = {int(self.nodes.contents.node_index[r]): r for r in range(self.E)}
+        return [row_of[int(i)] for i in model_nodes]
 
     def value_bit(self, model_key: int, model_value: int) -> int:
         """device bit of a model value inside its key's word, -1 when the encoding does not carry it"""
@@ -329,6 +336,66 @@ class ResultBuffers:
             claim_n_options=a["claim_n_options"][:N].copy())
 
 
+class BatchResultBuffers:
+    """Output buffers of a batch of Solves in one allocation per field (problem b's rows start at its first pod, the way
+    the library lays them out itself) and the b200s_result_t structs as one structured array: a batch of hundreds of small
+    simulations spends its host time here otherwise."""
+    _FIELDS = [("pod_place_kind", np.int32, "P", 1), ("pod_place_index", np.int32, "P", 1), ("pod_seq", np.int32, "P", 1),
+               ("pod_fit_code", np.uint8, "P", "T"), ("claim_template", np.int32, "C", 1), ("claim_npods", np.int32, "C", 1),
+               ("claim_requests", np.int64, "C", "R"), ("claim_mask", np.uint64, "C", "W"), ("claim_req_mask", np.uint64, "C", "K"),
+               ("claim_req_flags", np.uint64, "C", 1), ("claim_req_gt", np.int64, "C", "NB"), ("claim_req_lt", np.int64, "C", "NB"),
+               ("claim_sku", np.int32, "C", 1), ("claim_price", np.uint64, "C", 1), ("claim_n_options", np.int32, "C", 1)]
+
+    def __init__(self, pods_per_problem: Sequence[int], T: int, R: int, W: int, K: int, NB: int):
+        n = len(pods_per_problem)
+        self.n = n
+        self.P = np.asarray(pods_per_problem, np.int64)
+        self.cap = np.maximum(self.P, 1)
+        self.off = np.zeros(n + 1, np.int64)
+        self.off[1:] = np.cumsum(self.cap)           # rows of problem b: off[b] .. off[b] + cap[b]
+        total = int(self.off[-1])
+        self.width = {"T": max(T, 1), "R": R, "W": W, "K": max(K, 1), "NB": max(NB, 1), 1: 1}
+        self.dims = (T, R, W, K, NB)
+        dt = np.dtype([("cap_claims", np.int32), ("n_claims", np.int32), ("n_unscheduled", np.int32), ("_pad", np.int32),
+                       ("fit_evals", np.int64)] + [(f, np.uint64) for f, _, _, _ in self._FIELDS])
+        assert dt.itemsize == C.sizeof(Result)
+        self.res = np.zeros(n, dt)
+        self.res["cap_claims"] = self.cap
+        self.a = {}
+        for f, t, _, w in self._FIELDS:
+            wd = self.width[w]
+            arr = np.zeros(total * wd, t)
+            self.a[f] = arr
+            self.res[f] = arr.ctypes.data + self.off[:-1] * (wd * arr.itemsize)
+        self.ptrs = (self.res.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(dt.itemsize)).astype(np.uint64)
+
+    def out_pointers(self):
+        return self.ptrs.ctypes.data_as(_P(_P(Result)))
+
+    def raws(self) -> List[SolveRaw]:
+        T, R, W, K, NB = self.dims
+        out = []
+        a = self.a
+        for b in range(self.n):
+            o, P, N = int(self.off[b]), int(self.P[b]), int(self.res["n_claims"][b])
+
+            def rows(f, n_rows, w):
+                wd = self.width[w]
+                v = a[f][o * wd:(o + n_rows) * wd]
+                return v.copy() if w == 1 else v.reshape(n_rows, wd).copy()
+            out.append(SolveRaw(
+                n_claims=N, n_unscheduled=int(self.res["n_unscheduled"][b]), fit_evals=int(self.res["fit_evals"][b]),
+                pod_place_kind=rows("pod_place_kind", P, 1), pod_place_index=rows("pod_place_index", P, 1),
+                pod_seq=rows("pod_seq", P, 1), pod_fit_code=rows("pod_fit_code", P, "T")[:, :T],
+                claim_template=rows("claim_template", N, 1), claim_npods=rows("claim_npods", N, 1),
+                claim_requests=rows("claim_requests", N, "R"), claim_mask=rows("claim_mask", N, "W"),
+                claim_req_mask=rows("claim_req_mask", N, "K")[:, :K], claim_req_flags=rows("claim_req_flags", N, 1),
+                claim_req_gt=rows("claim_req_gt", N, "NB")[:, :NB], claim_req_lt=rows("claim_req_lt", N, "NB")[:, :NB],
+                claim_sku=rows("claim_sku", N, 1), claim_price=rows("claim_price", N, 1),
+                claim_n_options=rows("claim_n_options", N, 1)))
+        return out
+
+
 class Context:
     """b200s_init on one device.  Raises B200SError(ENODEVICE) when there is no sm_100 GPU."""
 
@@ -385,14 +452,29 @@ class Context:
 
     def solve_batch(self, cid: int, encs: Sequence[Encoded]) -> List[SolveRaw]:
         n = len(encs)
-        bufs = [ResultBuffers(e.P, e.T, e.R, e.W, e.K, e.NB) for e in encs]
+        e0 = encs[0]
+        bufs = BatchResultBuffers([e.P for e in encs], e0.T, e0.R, e0.W, e0.K, e0.NB)
         pods = (_P(PodsSoA) * n)(*[e.pods for e in encs])
         nodes = (_P(NodesSoA) * n)(*[e.nodes for e in encs])
-        outs = (_P(Result) * n)(*[C.pointer(b.c) for b in bufs])
         opts = SolveOpts()
         opts.want_masks = 1
-        self._check(self.L.b200s_solve_batch(self.h, cid, n, pods, nodes, encs[0].templates, C.byref(opts), outs))
-        return [b.raw() for b in bufs]
+        self._check(self.L.b200s_solve_batch(self.h, cid, n, pods, nodes, e0.templates, C.byref(opts), bufs.out_pointers()))
+        return bufs.raws()
+
+    def solve_batch_shared(self, cid: int, enc: Encoded, pod_off: Sequence[int], excluded: Sequence[Sequence[int]]) -> List[SolveRaw]:
+        """b200s_solve_batch_shared: problem b = pods pod_off[b]..pod_off[b+1] of `enc` against enc's nodes without the
+        node ROWS excluded[b] (rows of enc.nodes, i.e. sortExistingNodes order)."""
+        n = len(pod_off) - 1
+        po = np.ascontiguousarray(pod_off, np.int32)
+        eo = np.zeros(n + 1, np.int32)
+        eo[1:] = np.cumsum([len(x) for x in excluded])
+        er = np.ascontiguousarray([r for x in excluded for r in x] or [0], np.int32)
+        bufs = BatchResultBuffers(np.diff(po), enc.T, enc.R, enc.W, enc.K, enc.NB)
+        opts = SolveOpts()
+        opts.want_masks = 1
+        self._check(self.L.b200s_solve_batch_shared(self.h, cid, n, enc.pods, _p(po, C.c_int32), enc.nodes, _p(eo, C.c_int32),
+                                                    _p(er, C.c_int32), enc.templates, C.byref(opts), bufs.out_pointers()))
+        return bufs.raws()
 
     def select_cheapest(self, cid: int, enc: Encoded, masks: np.ndarray, req_mask: np.ndarray, req_flags: np.ndarray,
                         req_gt: np.ndarray, req_lt: np.ndarray):

@@ -396,6 +396,19 @@ def c4_simulations(model: M.Model, node_of_pod: np.ndarray, util: np.ndarray, n_
     return sims
 
 
+def c4_shared(model: M.Model, node_of_pod: np.ndarray, candidates: Sequence[int]):
+    """The same simulations as ONE model for b200s_solve_batch_shared: every node of the cluster, the candidates' pods
+    pending one candidate after the other.  Returns (model, pod_off, candidates): problem b = pods
+    pod_off[b]..pod_off[b+1] against all nodes but candidates[b] (model node indices; the node ROW of a model node is
+    found through the encoded nodes' node_index)."""
+    pods, off = [], [0]
+    for i in candidates:
+        pods.append(np.nonzero(node_of_pod == i)[0])
+        off.append(off[-1] + len(pods[-1]))
+    allp = np.concatenate(pods) if pods else np.zeros(0, np.int64)
+    return M.subset(model, allp, np.arange(int(model.c.n_nodes))), np.asarray(off, np.int32), [int(i) for i in candidates]
+
+
 def candidate_prices(model: M.Model, nodes: Sequence[int]):
     """getCandidatePrices for single-node candidates (K/controllers/disruption/consolidation.go:310-328): the cheapest
     offering of the node's instance type that its zone / capacity-type labels admit (availability is NOT looked at

@@ -189,9 +189,19 @@ void free_resident(b200s_resident* r) {
   delete r;
 }
 
+// b200s_solve_batch_shared: the problems are ranges of ONE pod set (pods_in[0]) and share ONE node set, of which
+// problem b removes the rows excl_rows[excl_off[b] .. excl_off[b+1])
+struct SharedBatch {
+  const int32_t* pod_off;   // [n_problems + 1]
+  const b200s_nodes_soa_t* nodes;
+  const int32_t* excl_off;  // [n_problems + 1], may be null (nothing removed)
+  const int32_t* excl_rows;
+};
+
 // Builds every device buffer a fit / solve over `n_problems` pod sets needs.
 int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b200s_pods_soa_t* const* pods_in,
-                   const b200s_nodes_soa_t* const* nodes_in, const b200s_templates_t* tm, b200s_resident** out) {
+                   const b200s_nodes_soa_t* const* nodes_in, const b200s_templates_t* tm, b200s_resident** out,
+                   const SharedBatch* sh = nullptr) {
   auto it = ctx->catalogs.find(catalog_id);
   if (it == ctx->catalogs.end()) return fail(ctx, B200S_ESTATE, "unknown catalog id");
   Catalog* cat = it->second.get();
@@ -199,12 +209,31 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   if (n_problems < 1) return fail(ctx, B200S_EINVAL, "no problems");
   const int R = cat->R, K = cat->K, NB = cat->NB, W = cat->W, T = tm->n_templates;
   long long Ptot = 0, Etot = 0;
-  for (int b = 0; b < n_problems; b++) {
-    const b200s_nodes_soa_t* nd = nodes_in ? nodes_in[b] : nullptr;
-    int rc = check_shapes(ctx, cat, pods_in[b], nd);
+  const int n_sets = sh ? 1 : n_problems;  // pod / class-table sets to upload
+  const int E0 = sh && sh->nodes ? sh->nodes->n_nodes : 0;
+  if (sh) {
+    int rc = check_shapes(ctx, cat, pods_in[0], sh->nodes);
     if (rc) return rc;
-    Ptot += pods_in[b]->n_pods;
-    if (nd) Etot += nd->n_nodes;
+    Ptot = pods_in[0]->n_pods;
+    Etot = (long long)n_problems * E0;
+    if (!sh->pod_off || sh->pod_off[0] != 0 || sh->pod_off[n_problems] != Ptot) return fail(ctx, B200S_EINVAL, "pod_off must run from 0 to n_pods");
+    for (int b = 0; b < n_problems; b++)
+      if (sh->pod_off[b + 1] < sh->pod_off[b]) return fail(ctx, B200S_EINVAL, "pod_off must not decrease");
+    if (sh->excl_off) {
+      if (sh->excl_off[0] != 0) return fail(ctx, B200S_EINVAL, "excl_off must start at 0");
+      for (int b = 0; b < n_problems; b++)
+        if (sh->excl_off[b + 1] < sh->excl_off[b]) return fail(ctx, B200S_EINVAL, "excl_off must not decrease");
+      for (int j = 0; j < sh->excl_off[n_problems]; j++)
+        if (!sh->excl_rows || sh->excl_rows[j] < 0 || sh->excl_rows[j] >= E0) return fail(ctx, B200S_EINVAL, "excluded node row out of range");
+    }
+  } else {
+    for (int b = 0; b < n_problems; b++) {
+      const b200s_nodes_soa_t* nd = nodes_in ? nodes_in[b] : nullptr;
+      int rc = check_shapes(ctx, cat, pods_in[b], nd);
+      if (rc) return rc;
+      Ptot += pods_in[b]->n_pods;
+      if (nd) Etot += nd->n_nodes;
+    }
   }
   if (Ptot > (1ll << 30) || Etot > (1ll << 30)) return fail(ctx, B200S_EINVAL, "problem too large");
   std::unique_ptr<b200s_resident, void (*)(b200s_resident*)> r(new (std::nothrow) b200s_resident(), free_resident);
@@ -220,7 +249,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
 
   // ---- pods: per-pod ids / tie-break keys concatenated; class tables concatenated with id offsets ----
   long long NStot = 0, NQtot = 0;
-  for (int b = 0; b < n_problems; b++) { NStot += pods_in[b]->n_sigs; NQtot += pods_in[b]->n_reqcls; }
+  for (int b = 0; b < n_sets; b++) { NStot += pods_in[b]->n_sigs; NQtot += pods_in[b]->n_reqcls; }
   const size_t NS = (size_t)std::max<long long>(NStot, 1), NQ = (size_t)std::max<long long>(NQtot, 1);
   int32_t* d_sig = r->dalloc<int32_t>(P);
   int32_t* d_rq = r->dalloc<int32_t>(P);
@@ -238,11 +267,11 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   {
     size_t off = 0, soff = 0, qoff = 0;
     std::vector<int32_t> tmp;
-    for (int b = 0; b < n_problems; b++) {
+    for (int b = 0; b < n_sets; b++) {
       const b200s_pods_soa_t* ps = pods_in[b];
       const size_t n = (size_t)ps->n_pods, ns = (size_t)ps->n_sigs, nq = (size_t)ps->n_reqcls;
       int rc = 0;
-      if (n_problems == 1) {
+      if (n_sets == 1) {
         rc = upload(ctx, d_sig, ps->sig_id, n);
         if (!rc) rc = upload(ctx, d_rq, ps->req_id, n);
       } else {  // class ids of problem b are shifted by the classes of the problems before it
@@ -282,7 +311,7 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
     const size_t nqt = (size_t)NQtot;
     std::vector<int64_t> cpu(nqt), mem(nqt);
     size_t qo = 0;
-    for (int b = 0; b < n_problems; b++) {
+    for (int b = 0; b < n_sets; b++) {
       const b200s_pods_soa_t* ps = pods_in[b];
       const size_t nq = (size_t)ps->n_reqcls;
       for (size_t q = 0; q < nq; q++) {
@@ -315,9 +344,9 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
     for (int b = 0; b < n_problems; b++) {
       PackProblem& pb = r->problems_host[b];
       pb.pod_begin = po;
-      pb.pod_end = po + pods_in[b]->n_pods;
+      pb.pod_end = sh ? sh->pod_off[b + 1] : po + pods_in[b]->n_pods;
       pb.node_begin = eo;
-      pb.node_end = eo + ((nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
+      pb.node_end = eo + (sh ? E0 : (nodes_in && nodes_in[b]) ? nodes_in[b]->n_nodes : 0);
       pb.n_claims = 0; pb.n_unscheduled = 0; pb.evals = 0;
       pb.status = 0; pb._pad = 0;
       for (int i = 0; i < 12; i++) pb.prof[i] = 0;
@@ -379,7 +408,29 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->n_rflags0 = r->dalloc<uint64_t>(E);
   r->n_taints = r->dalloc<uint64_t>(E);
   if (!r->n_avail0 || !r->n_rmask0 || !r->n_rflags0 || !r->n_taints) return fail(ctx, B200S_ENOMEM, "device allocation (nodes)");
-  {
+  if (sh && E0 > 0) {  // the shared rows once, then a copy per problem on the device
+    const b200s_nodes_soa_t* nd = sh->nodes;
+    const size_t n = (size_t)E0;
+    int64_t* s_avail = r->dalloc<int64_t>((size_t)R * n);
+    uint64_t* s_rmask = r->dalloc<uint64_t>((size_t)std::max(K, 1) * n);
+    uint64_t* s_rflags = r->dalloc<uint64_t>(n);
+    uint64_t* s_taints = r->dalloc<uint64_t>(n);
+    std::vector<int64_t> rows;  // batch-wide rows of the removed nodes
+    if (sh->excl_off)
+      for (int b = 0; b < n_problems; b++)
+        for (int j = sh->excl_off[b]; j < sh->excl_off[b + 1]; j++) rows.push_back((int64_t)b * E0 + sh->excl_rows[j]);
+    int64_t* d_rows = r->dalloc<int64_t>(std::max<size_t>(rows.size(), 1));
+    if (!s_avail || !s_rmask || !s_rflags || !s_taints || !d_rows) return fail(ctx, B200S_ENOMEM, "device allocation (shared nodes)");
+    int rc = upload(ctx, s_avail, nd->available, (size_t)R * n);
+    if (!rc) rc = upload(ctx, s_rmask, nd->req_mask, (size_t)K * n);
+    if (!rc) rc = upload(ctx, s_rflags, nd->req_flags, n);
+    if (!rc) rc = upload(ctx, s_taints, nd->taints, n);
+    if (!rc) rc = upload(ctx, d_rows, rows.data(), rows.size());
+    if (rc) return rc;
+    CUDA_TRY(ctx, launch_replicate_nodes(R, K, E0, Etot, s_avail, s_rmask, s_rflags, s_taints, r->n_avail0, r->n_rmask0, r->n_rflags0,
+                                         r->n_taints, (int)rows.size(), d_rows, ctx->n_sm, ctx->stream), "replicate_nodes launch");
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (shared nodes)");  // rows goes out of scope
+  } else {
     size_t off = 0;
     for (int b = 0; b < n_problems; b++) {
       const b200s_nodes_soa_t* nd = nodes_in ? nodes_in[b] : nullptr;
@@ -459,14 +510,14 @@ int build_resident(b200s_ctx* ctx, uint64_t catalog_id, int n_problems, const b2
   r->reg_plan.eligible = false;
   if (r->plain && Etot == 0 && T > 0 && Ptot > 0 && !r->any_limit && !getenv("B200S_PACK_NO_REG")) {
     // selector-less pods, no existing nodes: plan the register-resident pack (granules, tables) on the host
-    std::vector<const int64_t*> rqs(n_problems);
-    std::vector<int32_t> nqs(n_problems);
-    for (int b = 0; b < n_problems; b++) { rqs[b] = pods_in[b]->rq_requests; nqs[b] = pods_in[b]->n_reqcls; }
+    std::vector<const int64_t*> rqs(n_sets);
+    std::vector<int32_t> nqs(n_sets);
+    for (int b = 0; b < n_sets; b++) { rqs[b] = pods_in[b]->rq_requests; nqs[b] = pods_in[b]->n_reqcls; }
     RegPackPlan& plan = r->reg_plan;
-    if (reg_pack_plan(cat->kt, cat->h_dv.data(), T, tm->daemon, n_problems, rqs.data(), nqs.data(), ctx->smem_limit, &plan)) {
+    if (reg_pack_plan(cat->kt, cat->h_dv.data(), T, tm->daemon, n_sets, rqs.data(), nqs.data(), ctx->smem_limit, &plan)) {
       std::vector<int32_t> rq32((size_t)REG_RT * NQ, 0);
       size_t qoff = 0;
-      for (int b = 0; b < n_problems; b++) {
+      for (int b = 0; b < n_sets; b++) {
         reg_pack_scale_requests(plan, rqs[b], nqs[b], rq32.data(), NQ, qoff);
         qoff += (size_t)nqs[b];
       }
@@ -650,6 +701,78 @@ int fetch_solve_all(b200s_ctx* ctx, b200s_resident* r, b200s_result_t* const* ou
   unsigned long long fit_ev = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&fit_ev, r->a_evals, 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H");
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync (solve)");
+  if (r->n_problems > 1) {
+    // A batch: every array once for all problems (their rows are ranges of the same device arrays), then host copies
+    // of each problem's slices — not fifteen device copies and a synchronisation per problem.
+    const Catalog* cat = r->cat;
+    const size_t R = (size_t)cat->R, K = (size_t)cat->K, NB = (size_t)cat->NB, W = (size_t)cat->W, T = (size_t)r->T, P = (size_t)r->P;
+    bool want_mask = false;
+    for (int b = 0; b < r->n_problems; b++) {
+      if (!outs[b]) return fail(ctx, B200S_EINVAL, "null result");
+      if (r->problems_host[b].n_claims > outs[b]->cap_claims) return fail(ctx, B200S_ECAPACITY, "cap_claims too small");
+      want_mask = want_mask || outs[b]->claim_mask != nullptr;
+    }
+    std::vector<int32_t> h_kind(P), h_index(P), h_seq(P), h_tmpl(P), h_npods(P), h_sku(P), h_nopt(P);
+    std::vector<uint8_t> h_code(P * T);
+    std::vector<int64_t> h_req(P * R), h_gt(P * NB), h_lt(P * NB);
+    std::vector<uint64_t> h_mask(want_mask ? P * W : 0), h_rmask(P * K), h_rflags(P), h_price(P);
+    cudaStream_t st = ctx->stream;
+    auto d2h = [&](void* dst, const void* src, size_t bytes) {
+      return bytes == 0 ? cudaSuccess : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CUDA_TRY(ctx, d2h(h_kind.data(), r->arr.pod_kind, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_index.data(), r->arr.pod_index, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_seq.data(), r->arr.pod_seq, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_code.data(), r->a_code, P * T), "D2H");
+    CUDA_TRY(ctx, d2h(h_tmpl.data(), r->cout.tmpl, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_npods.data(), r->cout.npods, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_req.data(), r->cout.req, P * R * 8), "D2H");
+    if (want_mask) CUDA_TRY(ctx, d2h(h_mask.data(), r->cout.mask, P * W * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_rmask.data(), r->cout.rmask, P * K * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_rflags.data(), r->cout.rflags, P * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_gt.data(), r->cout.gt, P * NB * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_lt.data(), r->cout.lt, P * NB * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_sku.data(), r->sel_sku, P * 4), "D2H");
+    CUDA_TRY(ctx, d2h(h_price.data(), r->sel_price, P * 8), "D2H");
+    CUDA_TRY(ctx, d2h(h_nopt.data(), r->sel_nopt, P * 4), "D2H");
+    CUDA_TRY(ctx, cudaStreamSynchronize(st), "sync (fetch batch)");
+    for (int b = 0; b < r->n_problems; b++) {
+      const PackProblem& pb = r->problems_host[b];
+      b200s_result_t* out = outs[b];
+      const size_t base = (size_t)pb.pod_begin, n = (size_t)(pb.pod_end - pb.pod_begin), nc = (size_t)pb.n_claims;
+      out->n_claims = pb.n_claims;
+      out->n_unscheduled = pb.n_unscheduled;
+      out->fit_evals = (int64_t)pb.evals;
+      if (n) {
+        std::memcpy(out->pod_place_kind, h_kind.data() + base, n * 4);
+        std::memcpy(out->pod_place_index, h_index.data() + base, n * 4);
+        std::memcpy(out->pod_seq, h_seq.data() + base, n * 4);
+        if (T) std::memcpy(out->pod_fit_code, h_code.data() + base * T, n * T);
+      }
+      if (nc) {
+        std::memcpy(out->claim_template, h_tmpl.data() + base, nc * 4);
+        std::memcpy(out->claim_npods, h_npods.data() + base, nc * 4);
+        std::memcpy(out->claim_requests, h_req.data() + base * R, nc * R * 8);
+        if (out->claim_mask) std::memcpy(out->claim_mask, h_mask.data() + base * W, nc * W * 8);
+        if (K) std::memcpy(out->claim_req_mask, h_rmask.data() + base * K, nc * K * 8);
+        std::memcpy(out->claim_req_flags, h_rflags.data() + base, nc * 8);
+        if (NB) {
+          std::memcpy(out->claim_req_gt, h_gt.data() + base * NB, nc * NB * 8);
+          std::memcpy(out->claim_req_lt, h_lt.data() + base * NB, nc * NB * 8);
+        }
+        std::memcpy(out->claim_sku, h_sku.data() + base, nc * 4);
+        std::memcpy(out->claim_price, h_price.data() + base, nc * 8);
+        std::memcpy(out->claim_n_options, h_nopt.data() + base, nc * 4);
+      }
+      // attempt codes are reported for pods left in PodErrors only (scheduler.go:411,419)
+      for (size_t i = 0; i < n; i++)
+        if (out->pod_place_kind[i] != B200S_PLACE_UNSCHEDULED)
+          for (size_t t = 0; t < T; t++)
+            if (out->pod_fit_code[i * T + t] != B200S_FIT_DROPPED) out->pod_fit_code[i * T + t] = B200S_FIT_NONE;
+    }
+    if (outs[0]) outs[0]->fit_evals += (int64_t)fit_ev;  // stage A ran once for the whole batch
+    return 0;
+  }
   for (int b = 0; b < r->n_problems; b++) {
     int rc = fetch_problem(ctx, r, b, r->problems_host[b], r->n_problems == 1 ? fit_ev : 0ull, outs[b]);
     if (rc) return rc;
@@ -1140,6 +1263,26 @@ int b200s_solve_batch(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems,
   cudaSetDevice(ctx->device);
   b200s_resident_t* r = nullptr;
   int rc = build_resident(ctx, catalog_id, n_problems, pods, existing, templates, &r);
+  if (rc) return rc;
+  r->last_launches = 0;
+  rc = enqueue_solve(ctx, r, &r->last_launches);
+  if (!rc) rc = fetch_solve_all(ctx, r, out);
+  cudaStreamSynchronize(ctx->stream);
+  free_resident(r);
+  return rc;
+}
+
+int b200s_solve_batch_shared(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems, const b200s_pods_soa_t* pods,
+                             const int32_t* pod_off, const b200s_nodes_soa_t* nodes, const int32_t* excl_off,
+                             const int32_t* excl_rows, const b200s_templates_t* templates, const b200s_solve_opts_t* opts,
+                             b200s_result_t* const* out) {
+  (void)opts;
+  if (!ctx || n_problems < 1 || !pods || !pod_off || !templates || !out) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  const b200s_pods_soa_t* pp[1] = {pods};
+  const SharedBatch sh{pod_off, nodes, excl_off, excl_rows};
+  b200s_resident_t* r = nullptr;
+  int rc = build_resident(ctx, catalog_id, n_problems, pp, nullptr, templates, &r, &sh);
   if (rc) return rc;
   r->last_launches = 0;
   rc = enqueue_solve(ctx, r, &r->last_launches);

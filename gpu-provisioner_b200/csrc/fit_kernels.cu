@@ -909,6 +909,41 @@ static int next_pow2(int n) {
 
 int ffd_padded(int P) { return next_pow2(P < SORT_CHUNK ? SORT_CHUNK : P); }
 
+// ExistingNodes of a batch of simulations that share one cluster (b200s_solve_batch_shared): problem b gets rows
+// [b*E0, (b+1)*E0) of the batch-wide, resource/key-major arrays — a copy of the shared rows
+__global__ void __launch_bounds__(256) replicate_nodes_kernel(int R, int K, int E0, long long Etot, const int64_t* __restrict__ s_avail,
+                                                              const uint64_t* __restrict__ s_rmask, const uint64_t* __restrict__ s_rflags,
+                                                              const uint64_t* __restrict__ s_taints, int64_t* __restrict__ d_avail,
+                                                              uint64_t* __restrict__ d_rmask, uint64_t* __restrict__ d_rflags,
+                                                              uint64_t* __restrict__ d_taints) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < Etot; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % E0);
+    for (int x = 0; x < R; x++) d_avail[(size_t)x * Etot + i] = s_avail[(size_t)x * E0 + e];
+    for (int k = 0; k < K; k++) d_rmask[(size_t)k * Etot + i] = s_rmask[(size_t)k * E0 + e];
+    d_rflags[i] = s_rflags[e];
+    d_taints[i] = s_taints[e];
+  }
+}
+
+// a node a simulation removes: nothing fits a negative Available entry (resources.go:234-243), so the row is skipped
+// exactly as if it were not in the list
+__global__ void exclude_nodes_kernel(int R, long long Etot, int n, const int64_t* __restrict__ rows, int64_t* __restrict__ d_avail) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  for (int x = 0; x < R; x++) d_avail[(size_t)x * Etot + rows[j]] = -1;
+}
+
+cudaError_t launch_replicate_nodes(int R, int K, int E0, long long Etot, const int64_t* s_avail, const uint64_t* s_rmask,
+                                   const uint64_t* s_rflags, const uint64_t* s_taints, int64_t* d_avail, uint64_t* d_rmask,
+                                   uint64_t* d_rflags, uint64_t* d_taints, int n_excl, const int64_t* excl_rows, int n_sm,
+                                   cudaStream_t stream) {
+  if (Etot <= 0) return cudaSuccess;
+  const int grid = (int)std::min<long long>((Etot + 255) / 256, (long long)n_sm * 8);
+  replicate_nodes_kernel<<<grid, 256, 0, stream>>>(R, K, E0, Etot, s_avail, s_rmask, s_rflags, s_taints, d_avail, d_rmask, d_rflags, d_taints);
+  if (n_excl > 0) exclude_nodes_kernel<<<(n_excl + 255) / 256, 256, 0, stream>>>(R, Etot, n_excl, excl_rows, d_avail);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_ffd_class_rank(const PodsDev& pods, int32_t* rank, cudaStream_t stream) {
   if (pods.NQ <= 0) return cudaSuccess;
   ffd_class_rank_kernel<<<(pods.NQ + 255) / 256, 256, 0, stream>>>(pods, rank);

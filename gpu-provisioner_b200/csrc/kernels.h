@@ -121,6 +121,11 @@ int compact_row_bytes(int T);
 cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream);
 cudaError_t launch_compact_import(int P, int T, const uint8_t* in, int32_t* tmpl, uint8_t* code, int n_sm, cudaStream_t stream);
 int ffd_padded(int P);
+// b200s_solve_batch_shared: every problem's ExistingNodes = a copy of the shared rows, minus the rows it removes
+cudaError_t launch_replicate_nodes(int R, int K, int E0, long long Etot, const int64_t* s_avail, const uint64_t* s_rmask,
+                                   const uint64_t* s_rflags, const uint64_t* s_taints, int64_t* d_avail, uint64_t* d_rmask,
+                                   uint64_t* d_rflags, uint64_t* d_taints, int n_excl, const int64_t* excl_rows, int n_sm,
+                                   cudaStream_t stream);
 // rank[q]: request classes that sort strictly before class q in (cpu desc, memory desc) order; O(NQ^2 / threads)
 cudaError_t launch_ffd_class_rank(const PodsDev& pods, int32_t* rank, cudaStream_t stream);
 cudaError_t launch_ffd_sort(const PodsDev& pods, const int32_t* seg, const int32_t* rank, uint64_t* k1, int32_t* idx,

@@ -22,6 +22,7 @@
  *   b200s_solve_batch       <- the per-candidate SimulateScheduling loop
  *                              (K/controllers/disruption/helpers.go:52-143,
  *                               singlenodeconsolidation.go:68-101)
+ *   b200s_solve_batch_shared <- the same loop with the cluster's nodes handed over once
  *   b200s_create_select     <- instance.Provider.Create's vmSize pick
  *                              (pkg/providers/instance/instance.go:76-95, :321-369)
  *
@@ -417,6 +418,21 @@ int b200s_solve_batch(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems,
                       const b200s_pods_soa_t* const* pods, const b200s_nodes_soa_t* const* existing,
                       const b200s_templates_t* templates, const b200s_solve_opts_t* opts,
                       b200s_result_t* const* out);
+
+/* The same for simulations that share one cluster — SimulateScheduling per candidate
+ * (K/controllers/disruption/helpers.go:52-143) always schedules "the candidates' pods against every other node", so
+ * the B problems differ only in which pods are pending and which few nodes are gone.  ONE pod set (one b200s_encode,
+ * one dictionary of signatures / request classes) whose rows pod_off[b] .. pod_off[b+1] are problem b's pods
+ * (pod_off[0] = 0, pod_off[n_problems] = pods->n_pods), ONE node set, of which problem b removes the rows
+ * excl_rows[excl_off[b] .. excl_off[b+1]) (excl_off may be NULL: nothing removed).  The node rows are uploaded
+ * once and copied per problem on the device; a removed row gets a negative Available entry, which nothing fits
+ * (resources.go:234-243), so every other node keeps its place in the order.  Results are those of b200s_solve_batch
+ * on the B separate problems, except that existing-node indices (pod_place_index of B200S_PLACE_NODE pods, the
+ * node rows of out[b]) count rows of the SHARED node set. */
+int b200s_solve_batch_shared(b200s_ctx_t* ctx, uint64_t catalog_id, int32_t n_problems, const b200s_pods_soa_t* pods,
+                             const int32_t* pod_off, const b200s_nodes_soa_t* nodes, const int32_t* excl_off,
+                             const int32_t* excl_rows, const b200s_templates_t* templates,
+                             const b200s_solve_opts_t* opts, b200s_result_t* const* out);
 
 /* ---- consolidation commands over a batch of simulations (SURVEY section 8f N2, config 4's consumer) ----
  * computeConsolidation (K/controllers/disruption/consolidation.go:133-307) applied to n finished simulations at

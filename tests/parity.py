@@ -216,3 +216,23 @@ def emul_solve_reg(enc: capi.Encoded):
     rc = emul().emul_solve_reg(enc.catalog, enc.templates, enc.pods, C.byref(buf.c), _p(stats, C.c_int64))
     assert rc == 0, rc
     return buf.raw(), stats
+
+
+def assert_shared_matches_separate(enc_all, enc_sep, removed_node: int, sep, shared, what: str = "") -> int:
+    """A simulation solved through b200s_solve_batch_shared (every node of the cluster in the list, the removed one
+    unusable; node indices = rows of the shared node set) against the same simulation flattened on its own (its node list
+    lacks `removed_node`, every later model node sits one index lower).  Returns the number of pods placed on nodes."""
+    E = enc_all.E
+    node_of_row = np.array([enc_all.nodes.contents.node_index[r] for r in range(E)])
+    assert (sep.n_claims, sep.n_unscheduled) == (shared.n_claims, shared.n_unscheduled), what
+    for f in ("pod_place_kind", "pod_seq", "pod_fit_code", "claim_template", "claim_npods", "claim_requests", "claim_mask",
+              "claim_req_mask", "claim_req_flags", "claim_req_gt", "claim_req_lt", "claim_sku", "claim_price", "claim_n_options"):
+        assert np.array_equal(getattr(sep, f), getattr(shared, f)), (what, f)
+    sub_node = np.array([enc_sep.nodes.contents.node_index[r] for r in range(enc_sep.E)])
+    orig = np.where(sub_node >= removed_node, sub_node + 1, sub_node)
+    k = sep.pod_place_kind
+    on_claim, on_node = k == capi.PLACE_CLAIM, k == capi.PLACE_NODE
+    assert np.array_equal(sep.pod_place_index[on_claim], shared.pod_place_index[on_claim]), what
+    assert np.array_equal(orig[sep.pod_place_index[on_node]], node_of_row[shared.pod_place_index[on_node]]), what
+    assert not np.any(node_of_row[shared.pod_place_index[on_node]] == removed_node), (what, "a pod landed on the removed node")
+    return int(on_node.sum())

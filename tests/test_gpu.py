@@ -419,6 +419,28 @@ def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
         gpu_ctx.release_catalog(cid)
 
 
+def test_shared_cluster_batch_equals_separate_simulations(gpu_ctx):
+    """b200s_solve_batch_shared -- one pod set, one node set, per simulation a pod range and the node rows it removes --
+    gives what b200s_solve_batch gives on the separately flattened simulations (which the tests above hold against the
+    oracle); existing-node indices count rows of the shared node set."""
+    model, node_of_pod, util = synth.c4(4000, 300, solve=ob.solve)
+    sims = synth.c4_simulations(model, node_of_pod, util, 24, spread=True)
+    encs = [capi.Encoded(m) for _, m in sims]
+    shared, pod_off, cands = synth.c4_shared(model, node_of_pod, [i for i, _ in sims])
+    enc_all = capi.Encoded(shared)
+    assert enc_all.layout_hash == encs[0].layout_hash
+    cid = gpu_ctx.upload_catalog(enc_all)
+    try:
+        sep = gpu_ctx.solve_batch(cid, encs)
+        got = gpu_ctx.solve_batch_shared(cid, enc_all, pod_off, [[int(r)] for r in enc_all.node_rows(cands)])
+    finally:
+        gpu_ctx.release_catalog(cid)
+    on_nodes = 0
+    for (i, _), e, a, g in zip(sims, encs, sep, got):
+        on_nodes += parity.assert_shared_matches_separate(enc_all, e, i, a, g, f"simulation of node {i}")
+    assert on_nodes > 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,pods,skus", [("c2", 2000, 300), ("c3", 3000, 700), ("c2", 300, 2000)])
 def test_to_nodeclaim_instance_type_lists_match_the_oracle(gpu_ctx, kind, pods, skus):
