@@ -302,7 +302,7 @@ struct DenseArgs {
 // candidates after a failed one, the six diagnostic flags.  Must be entered by the whole warp.
 template <int LPG, int VPL>
 __device__ __forceinline__ void dense_general_iter(const DenseArgs& a, int p, bool live, unsigned sig, unsigned rq,
-                                                   unsigned& my_evals) {
+                                                   unsigned& my_evals, ulonglong2* srow = nullptr) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr unsigned GLOW = LPG == 32 ? 0xffffffffu : ((1u << LPG) - 1u);
   const unsigned lane = threadIdx.x & 31u, gl = threadIdx.x & (LPG - 1), gshift = lane & ~(unsigned)(LPG - 1);
@@ -373,7 +373,11 @@ __device__ __forceinline__ void dense_general_iter(const DenseArgs& a, int p, bo
 #pragma unroll
   for (int i = 0; i < VPL; i++) {
     const unsigned v = gl + i * LPG;
-    if (live && v < (unsigned)W2 && a.mask_out) a.mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];  // null: rows on demand
+    if (srow) {  // staged: the warp's rows leave through one bulk copy (fit_dense_bulk_kernel)
+      if (v < (unsigned)W2) srow[v] = keep[i];
+    } else if (live && v < (unsigned)W2 && a.mask_out) {
+      a.mask_out[(unsigned)p * (unsigned)W2 + v] = keep[i];  // null: rows on demand
+    }
   }
 }
 
@@ -392,6 +396,47 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_dense_vec_kernel(const __grid
     const unsigned sig = live ? (unsigned)a.sig_id[p] : 0u, rq = live ? (unsigned)a.req_id[p] : 0u;
     dense_general_iter<LPG, VPL>(a, p, live, sig, rq, my_evals);
   }
+  for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
+  if (lane == 0 && my_evals) atomicAdd(a.evals, (unsigned long long)my_evals);
+}
+
+// The same walk with the rows staged in shared memory: the 32/LPG pods of a warp iteration are consecutive, so their
+// rows are one contiguous piece of the output, written by ONE bulk asynchronous copy (cp.async.bulk, the TMA unit)
+// issued by lane 0 — the store stream no longer shares the load/store unit's queues with the class-row gathers.
+// Two buffers per warp: a buffer is reused once the copy before the last has finished reading it.
+template <int LPG, int VPL>
+__global__ void __launch_bounds__(FIT_THREADS) fit_dense_bulk_kernel(const __grid_constant__ DenseArgs a) {
+  constexpr int NG = FIT_THREADS / LPG, PPW = 32 / LPG;
+  extern __shared__ __align__(128) unsigned char dense_smem[];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int W2 = a.W2;
+  const unsigned buf_vecs = (unsigned)(PPW * W2);  // 16-byte vectors of one buffer
+  ulonglong2* wbuf = reinterpret_cast<ulonglong2*>(dense_smem) + (size_t)warp * 2 * buf_vecs;
+  unsigned my_evals = 0;
+  const int stride = gridDim.x * NG;
+  const int warp_first = blockIdx.x * NG + threadIdx.x / LPG - (int)(lane / LPG);
+  int it = 0;
+  for (int pw = warp_first; pw < a.P; pw += stride, it++) {
+    const int p = pw + (int)(lane / LPG);
+    const bool live = p < a.P;
+    const unsigned sig = live ? (unsigned)a.sig_id[p] : 0u, rq = live ? (unsigned)a.req_id[p] : 0u;
+    ulonglong2* buf = wbuf + (size_t)(it & 1) * buf_vecs;
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the copy out of this buffer is done
+    __syncwarp();
+    dense_general_iter<LPG, VPL>(a, p, live, sig, rq, my_evals, buf + (size_t)(lane / LPG) * W2);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+      const int rows = min(PPW, a.P - pw);
+      const unsigned bytes = (unsigned)rows * (unsigned)W2 * 16u;
+      const unsigned long long dst = (unsigned long long)(a.mask_out + (size_t)pw * W2);
+      const unsigned src = (unsigned)__cvta_generic_to_shared(buf);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
   for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_down_sync(0xffffffffu, my_evals, o);
   if (lane == 0 && my_evals) atomicAdd(a.evals, (unsigned long long)my_evals);
 }
@@ -868,6 +913,9 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
                      (long long)pods.NQ * T * W2l < (1ll << 31) && (long long)pods.P * T < (1ll << 31);
   if ((kt.n_words & 1) == 0 && small) {  // 16-byte rows, 32-bit indices: the vector kernel
     const int W2 = kt.n_words / 2;
+    // Rows through bulk asynchronous copies (fit_dense_bulk_kernel): measured slower than plain 16-byte stores on
+    // 1M x 2k (stage 163 us against 153 us) — kept as an opt-in experiment, see profiles/README.md
+    const bool bulk = getenv("B200S_DENSE_BULK") != nullptr;
     DenseArgs da{pods.P, T, W2, pods.sig_id, pods.req_id, sg_status, reinterpret_cast<const ulonglong2*>(sgC),
                  reinterpret_cast<const ulonglong2*>(sgO), reinterpret_cast<const ulonglong2*>(sgCO),
                  reinterpret_cast<const ulonglong2*>(rqF), tm_count, tmpl_out, reinterpret_cast<ulonglong2*>(mask_out),
@@ -876,7 +924,12 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
   do {                                                                                                           \
     long long need = ((long long)pods.P + (FIT_THREADS / LPG_) - 1) / (FIT_THREADS / LPG_);                      \
     int grid = (int)(need < (long long)n_sm * 8 ? need : (long long)n_sm * 8);                                   \
-    fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(da);                                      \
+    const size_t bulk_smem = (size_t)(FIT_THREADS / 32) * 2 * (32 / LPG_) * W2 * 16;                             \
+    if (mask_out && bulk && bulk_smem * 8 <= 200 * 1024) {                                                       \
+      fit_dense_bulk_kernel<LPG_, VPL_><<<grid, FIT_THREADS, bulk_smem, stream>>>(da);                           \
+    } else {                                                                                                     \
+      fit_dense_vec_kernel<LPG_, VPL_><<<grid, FIT_THREADS, 0, stream>>>(da);                                    \
+    }                                                                                                            \
   } while (0)
     // few lanes per pod, two 16-byte pieces per lane; measured on 1M x 2k (W2 = 16): 8x2 78 us, 4x4 94 us,
     // 16x1 118 us, 2x8 147 us (profiles/README.md)

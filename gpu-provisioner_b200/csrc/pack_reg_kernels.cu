@@ -531,10 +531,16 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 
       // ---- before the barrier: addToInflightNode — every claim decides for itself, the first feasible in the order wins
       if (tid == 0) { S.best[s3n] = PRIO_INF; S.best2[s3n] = PRIO_INF; }
-      // slots 0 and 1 unconditionally (straight-line code: the two evaluations interleave; a slot without a claim
-      // has priority PRIO_INF), the others only in warps that hold such claims
-      unsigned cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
-      if constexpr (CPT > 1) cand = min(cand, slot_eval<NWIN>(sl1, prm, s_tab, s_win, s_bits, q, tol));
+      // slot 0 always, slots 0 and 1 together once a second slot is in use anywhere (straight-line code: the two
+      // evaluations interleave; a slot without a claim has priority PRIO_INF), the others only in warps that hold such
+      // claims
+      unsigned cand;
+      if (CPT > 1 && n > REG_NCT) {  // (uniform) some thread holds a second claim
+        cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
+        if constexpr (CPT > 1) cand = min(cand, slot_eval<NWIN>(sl1, prm, s_tab, s_win, s_bits, q, tol));
+      } else {
+        cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
+      }
 #define EVAL_SLOT(j, sl)                                                               \
   if ((j) > 1 && (j) * REG_NCT + (tid & ~31) < n) /* this warp holds a claim in slot j */ \
     cand = min(cand, slot_eval<NWIN>(sl, prm, s_tab, s_win, s_bits, q, tol))
@@ -594,11 +600,13 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
         const bool shift = (mv & MV_MEET) == 0;
         const unsigned lo = mv & 0xFFFu, span = shift ? ((mv >> 12) & 0xFFFu) - lo : 0u;
         const unsigned d = (mv & MV_UP) ? 1u : 0xFFFFFFFFu;
-#define SHIFT_SLOT(j, sl)                                   \
-  if (sl.cur == g) mine = (j);                              \
-  if (sl.pos - lo <= span && shift) sl.pos += d;            \
-  sl.pos &= 0x7FFFFFFFu;                                    \
-  sl.prio = 2u * sl.pos + 1u
+#define SHIFT_SLOT(j, sl)                                     \
+  if ((j) == 0 || (j) * REG_NCT < n) { /* uniform: the slot is in use somewhere */ \
+    if (sl.cur == g) mine = (j);                              \
+    if (sl.pos - lo <= span && shift) sl.pos += d;            \
+    sl.pos &= 0x7FFFFFFFu;                                    \
+    sl.prio = 2u * sl.pos + 1u;                               \
+  }
         FOR_SLOTS(SHIFT_SLOT);
 #undef SHIFT_SLOT
       }
