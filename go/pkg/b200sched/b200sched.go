@@ -216,6 +216,73 @@ func (c *Context) SolveBatch(ms []*Model, generation uint64) ([]*Result, error) 
 	return results, nil
 }
 
+// SolveBatchShared runs the simulations of one consolidation pass (SimulateScheduling per candidate,
+// disruption/helpers.go:52-143) from ONE model: every node of the cluster and the candidates' pods pending, one candidate
+// after the other.  podOff[b] .. podOff[b+1] are simulation b's pods, removed[b] the model nodes it deletes
+// (helpers.go:83-97).  One b200s_encode, the node rows cross the bus once; result b's pod indices count from podOff[b]
+// and its existing-node rows are rows of the shared node set (Result.NodeOrder maps them to model nodes).
+func (c *Context) SolveBatchShared(m *Model, podOff []int32, removed [][]int32, generation uint64) ([]*Result, error) {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	n := len(podOff) - 1
+	if c.ctx == nil || n < 1 || len(removed) != n {
+		return nil, fmt.Errorf("%w: nothing to do", ErrFallback)
+	}
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	enc, err := encode(m, &pin)
+	if err != nil {
+		return nil, err
+	}
+	defer enc.free()
+	id, err := c.catalogFor(enc, generation)
+	if err != nil {
+		return nil, err
+	}
+	nodes := C.b200s_encoded_nodes(enc.p)
+	rowOf := make(map[int32]int32, int(nodes.n_nodes)) // model node -> row in sortExistingNodes order
+	for i := 0; i < int(nodes.n_nodes); i++ {
+		rowOf[int32(*(*C.int32_t)(unsafeIndex(nodes.node_index, i)))] = int32(i)
+	}
+	exclOff := make([]int32, n+1)
+	exclRows := make([]int32, 0, n)
+	for b, nodesOfB := range removed {
+		for _, e := range nodesOfB {
+			row, ok := rowOf[e]
+			if !ok {
+				return nil, fmt.Errorf("%w: simulation %d removes a node that is not in the model", ErrFallback, b)
+			}
+			exclRows = append(exclRows, row)
+		}
+		exclOff[b+1] = int32(len(exclRows))
+	}
+	if len(exclRows) == 0 {
+		exclRows = append(exclRows, 0) // a valid pointer; exclOff says nothing is read
+	}
+	outs := make([]*C.b200s_result_t, n)
+	results := make([]*Result, n)
+	for b := 0; b < n; b++ {
+		results[b] = newResultRange(m, enc, int(podOff[b]), int(podOff[b+1]-podOff[b]))
+		results[b].pin(&pin)
+		outs[b] = &results[b].c
+	}
+	pin.Pin(&outs[0])
+	pin.Pin(&podOff[0])
+	pin.Pin(&exclOff[0])
+	pin.Pin(&exclRows[0])
+	opts := C.b200s_solve_opts_t{want_masks: 1}
+	if rc := C.b200s_solve_batch_shared(c.ctx, C.uint64_t(id), C.int32_t(n), C.b200s_encoded_pods(enc.p),
+		(*C.int32_t)(unsafe.Pointer(&podOff[0])), nodes, (*C.int32_t)(unsafe.Pointer(&exclOff[0])),
+		(*C.int32_t)(unsafe.Pointer(&exclRows[0])), C.b200s_encoded_templates(enc.p), &opts,
+		(**C.b200s_result_t)(unsafe.Pointer(&outs[0]))); rc != 0 {
+		return nil, fmt.Errorf("%w: b200s_solve_batch_shared=%d %s", ErrFallback, int(rc), c.lastError())
+	}
+	for _, r := range results {
+		r.decode(enc)
+	}
+	return results, nil
+}
+
 // CreateSelect is instance.Provider.Create's vmSize pick (pkg/providers/instance/instance.go:76-95) with the price order
 // the scheduler computed instead of Values()[0] (Go map order): host-only, no device (config 1).
 func CreateSelect(name string, instanceTypes []string, prices []float64, storageBytes int64) (chosen int, diskGB int32, gpu bool, err error) {

@@ -40,6 +40,10 @@ type Result struct {
 	W  int
 	K  int
 	NB int
+	// PodBase / nPods: the pods of Model this result is about (SolveBatchShared: one simulation's range of the shared
+	// model; pod indices in Claims[i].Pods, PodKind, ... count from PodBase).  nPods < 0: all pods of the model.
+	PodBase int
+	nPods   int
 
 	PodKind  []int32 // PlaceUnscheduled / PlaceNode / PlaceClaim
 	PodIndex []int32 // existing-node row (sorted order, see NodeOrder) or position in Claims
@@ -54,16 +58,22 @@ type Result struct {
 	claimMask, claimReqMask, claimReqFlags, price  []uint64
 }
 
-func newResult(m *Model, enc *encoded) *Result {
+func newResult(m *Model, enc *encoded) *Result { return newResultRange(m, enc, 0, -1) }
+
+// newResultRange sizes the buffers for the pods [base, base+nPods) of the model (nPods < 0: all of them).
+func newResultRange(m *Model, enc *encoded, base, nPods int) *Result {
 	cat := C.b200s_encoded_catalog(enc.p)
 	tm := C.b200s_encoded_templates(enc.p)
-	P, T, R := m.NumPods(), int(tm.n_templates), m.NumRes()
+	P, T, R := nPods, int(tm.n_templates), m.NumRes()
+	if P < 0 {
+		P = m.NumPods()
+	}
 	W, K, NB := int(cat.n_words), int(cat.n_keys), int(cat.n_bounded)
 	n := P // a NodeClaim holds at least one pod
 	if n == 0 {
 		n = 1
 	}
-	r := &Result{m: m, W: W, K: K, NB: NB,
+	r := &Result{m: m, W: W, K: K, NB: NB, PodBase: base, nPods: P,
 		PodKind: make([]int32, n), PodIndex: make([]int32, n), PodSeq: make([]int32, n), PodCode: make([]uint8, n*max(T, 1)),
 		claimTemplate: make([]int32, n), claimNPods: make([]int32, n), claimSku: make([]int32, n), claimNOpt: make([]int32, n),
 		claimRequests: make([]int64, n*R), claimGt: make([]int64, n*max(NB, 1)), claimLt: make([]int64, n*max(NB, 1)),
@@ -95,7 +105,7 @@ func (r *Result) pin(pin *runtime.Pinner) {
 // b200s_encoded_value_model_id) and groups the pods by NodeClaim in placement order.
 func (r *Result) decode(enc *encoded) {
 	n := int(r.c.n_claims)
-	P, R := r.m.NumPods(), r.m.NumRes()
+	P, R := r.nPods, r.m.NumRes()
 	tm := C.b200s_encoded_templates(enc.p)
 	nodes := C.b200s_encoded_nodes(enc.p)
 	r.NodeOrder = make([]int32, int(nodes.n_nodes))
