@@ -531,14 +531,16 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
 
       // ---- before the barrier: addToInflightNode — every claim decides for itself, the first feasible in the order wins
       if (tid == 0) { S.best[s3n] = PRIO_INF; S.best2[s3n] = PRIO_INF; }
-      // slot 0 always, slots 0 and 1 together once a second slot is in use anywhere (straight-line code: the two
-      // evaluations interleave; a slot without a claim has priority PRIO_INF), the others only in warps that hold such
-      // claims
-      unsigned cand;
-      if (CPT > 1 && n > REG_NCT) {  // (uniform) some thread holds a second claim
+      // slot 0, or slots 0 and 1 together once a second slot is in use anywhere (straight-line code: the two evaluations
+      // interleave; a slot without a claim has priority PRIO_INF), the others only in warps that hold such claims
+      unsigned cand = PRIO_INF;
+      // Guards are CTA-wide (is the slot in use anywhere), not per warp: with per-warp guards the warps drift apart
+      // and the step got slower (6.93 against 6.66 ms in one run)
+      const int wbase = 0;
+      if (CPT > 1 && REG_NCT + wbase < n) {  // (uniform) some thread holds a second claim
         cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
         if constexpr (CPT > 1) cand = min(cand, slot_eval<NWIN>(sl1, prm, s_tab, s_win, s_bits, q, tol));
-      } else {
+      } else if (wbase < n) {  // only first claims
         cand = slot_eval<NWIN>(sl0, prm, s_tab, s_win, s_bits, q, tol);
       }
 #define EVAL_SLOT(j, sl)                                                               \
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_c
         const unsigned lo = mv & 0xFFFu, span = shift ? ((mv >> 12) & 0xFFFu) - lo : 0u;
         const unsigned d = (mv & MV_UP) ? 1u : 0xFFFFFFFFu;
 #define SHIFT_SLOT(j, sl)                                     \
-  if ((j) == 0 || (j) * REG_NCT < n) { /* uniform: the slot is in use somewhere */ \
+  if ((j) * REG_NCT + wbase < n) { /* uniform: the slot is in use somewhere */ \
     if (sl.cur == g) mine = (j);                              \
     if (sl.pos - lo <= span && shift) sl.pos += d;            \
     sl.pos &= 0x7FFFFFFFu;                                    \
