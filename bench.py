@@ -312,24 +312,49 @@ def run_c5(args, rank, world, local):
         res_full = res if world == 1 else ctx.resident(cid_full, enc_full)
     ev0, ev1, ev2, ev3 = ctx.event(), ctx.event(), ctx.event(), ctx.event()
 
+    # The exchange fused with the export: every rank maps every rank's gathered buffer (CUDA IPC) and stores its rows
+    # straight into all of them, then a flag barrier (b200s_resident_export_compact_peers).  Falls back to the NCCL
+    # collective if the mapping fails, a peer times out, or the rows differ from the collective's.
+    p2p = None
+    if world > 1 and world <= 8 and not args.no_p2p:
+        try:
+            buf, flg, tmo = ctx.device_alloc(P * rb), ctx.device_alloc(64), ctx.device_alloc(4)
+            handles = [None] * world
+            dist.all_gather_object(handles, (ctx.ipc_export(buf), ctx.ipc_export(flg)))
+            p2p = {"buf": buf, "tmo": tmo, "epoch": 0,
+                   "out": [buf if q == rank else ctx.ipc_open(handles[q][0]) for q in range(world)],
+                   "flags": [flg if q == rank else ctx.ipc_open(handles[q][1]) for q in range(world)]}
+        except Exception as e:  # noqa: BLE001 -- any failure here means "use the collective"
+            print(f"[bench] rank {rank}: peer mapping unavailable ({e}); NCCL all-gather only", file=sys.stderr)
+            p2p = None
+        ok = torch.tensor([1 if p2p else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            p2p = None
+
     def gathered_rows():
         if P % world == 0:
             return g_all
         v = g_all.view(world, rows, rb)
         return torch.cat([v[r, :sharding.row_shard(P, r, world)[1] - sharding.row_shard(P, r, world)[0]] for r in range(world)]).contiguous()
 
-    def step():
+    def step(peers=False):
         ctx.flush_l2()
         ctx.record(ev0)
         res.fit_matrix()                      # prefilter + class tables + dense rows of this rank's shard
-        res.export_compact(d_send.data_ptr())
-        ctx.record(ev1)
-        if world > 1:
-            with torch.cuda.stream(lib_stream):
-                dist.all_gather_into_tensor(g_all, d_send)
+        if peers:                             # rows stored into every rank's buffer + flag barrier: export and exchange in one
+            ctx.record(ev1)
+            p2p["epoch"] += 1
+            res.export_compact_peers(p2p["out"], p2p["flags"], rank, lo, p2p["epoch"], p2p["tmo"])
+        else:
+            res.export_compact(d_send.data_ptr())
+            ctx.record(ev1)
+            if world > 1:
+                with torch.cuda.stream(lib_stream):
+                    dist.all_gather_into_tensor(g_all, d_send)
         ctx.record(ev2)
         if rank == 0 and world > 1:
-            res_full.import_compact(gathered_rows().data_ptr())
+            res_full.import_compact(p2p["buf"] if peers else gathered_rows().data_ptr())
         ctx.record(ev3)
         return np.array([ctx.elapsed_ms(ev0, ev3), ctx.elapsed_ms(ev0, ev1), ctx.elapsed_ms(ev1, ev2), ctx.elapsed_ms(ev2, ev3)])
 
@@ -348,6 +373,44 @@ def run_c5(args, rank, world, local):
             if world > 1:
                 dist.barrier()  # every step starts together: the time of a step is the max over the ranks
     acc /= args.steps
+    acc_nccl = acc.copy()
+    collective = "one NCCL all_gather_into_tensor of the compact rows" if world > 1 else "none (one GPU)"
+    if p2p:
+        # the same step with the peer-store export; valid only if no rank timed out and every rank's buffer equals the
+        # collective's result
+        for _ in range(3):
+            step(peers=True)
+            dist.barrier()
+        check = torch.zeros(P * rb, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.copy_device(check.data_ptr(), p2p["buf"], P * rb)
+        tmo_host = torch.zeros(1, dtype=torch.int32, device="cuda")
+        ctx.copy_device(tmo_host.data_ptr(), p2p["tmo"], 4)
+        ctx.synchronize()
+        same = torch.equal(check.view(P, rb)[:, :T + 1], gathered_rows().view(P, rb)[:, :T + 1]) and int(tmo_host.item()) == 0
+        ok = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            acc_p = np.zeros(4)
+            for _ in range(args.steps):
+                acc_p += step(peers=True)
+                dist.barrier()
+            acc_p /= args.steps
+            t = torch.tensor(acc_p, device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            acc_p = t.cpu().numpy()
+            t = torch.tensor(acc_nccl, device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if acc_p[0] < float(t[0].item()):
+                acc = acc_p
+                collective = ("none: every rank stores its 8 B/pod rows into every rank's buffer through CUDA-IPC peer mappings "
+                              "(NVLink) and the ranks meet at a flag barrier (b200s_resident_export_compact_peers)")
+            else:
+                p2p["slower"] = acc_p
+            p2p["acc"] = acc_p
+        else:
+            print(f"[bench] rank {rank}: peer-store export rejected (rows differ or a peer timed out)", file=sys.stderr)
+            p2p = None
     dense_k = res.dense_kernel_ms()
     launches_stage = res.launches()
     # end to end through host buffers: this rank's shard in, its rows out (b200s_fit_matrix), then the same all-gather
@@ -363,11 +426,12 @@ def run_c5(args, rank, world, local):
         if it >= 2:
             t_e2e.append(1e3 * (time.perf_counter() - t0))
     ms_e2e = float(np.mean(t_e2e))
+    acc_nccl_max = acc_nccl
     if world > 1:
-        t = torch.tensor(list(acc) + [ms_e2e, dense_k], device="cuda", dtype=torch.float64)
+        t = torch.tensor(list(acc) + [ms_e2e, dense_k] + list(acc_nccl), device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         v = t.cpu().numpy()
-        acc, ms_e2e, dense_k = v[:4], float(v[4]), float(v[5])
+        acc, ms_e2e, dense_k, acc_nccl_max = v[:4], float(v[4]), float(v[5]), v[6:10]
     # parity: this rank's first and last rows (the shard boundaries) against the oracle
     fit = res.fetch_fit()
     cf = parity.canon_fit(enc, fit)
@@ -403,20 +467,23 @@ def run_c5(args, rank, world, local):
         if world > 1:  # the all-gathered per-pod results equal what one GPU computes for all pods
             assert torch.equal(gathered_rows().view(P, rb)[:, :T + 1], g_one.view(P, rb)[:, :T + 1]), "gathered rows differ"
         # "merge the global packing": FFD order + pack + cheapest SKU over all pods from the imported per-pod results
-        res_full.import_compact((gathered_rows() if world > 1 else g_all).data_ptr())
-        ctx.synchronize()
-        t0 = time.perf_counter()
-        res_full.pack()
-        ctx.synchronize()
-        pack_s = time.perf_counter() - t0
-        raw = res_full.fetch_solve()
-        placed = int((raw.pod_place_kind == capi.PLACE_CLAIM).sum())
-        assert placed + raw.n_unscheduled == P and int(raw.claim_npods.sum()) == placed
-        assert (raw.claim_sku >= 0).all() and (raw.claim_n_options > 0).all()
-        pack = {"ms": 1e3 * pack_s, "pods": P, "nodeclaims": int(raw.n_claims), "unschedulable": int(raw.n_unscheduled),
-                "nodeclaims_per_s": raw.n_claims / pack_s, "digest": parity.digest(parity.canon_device(enc_full, raw))[:16],
-                "note": "one Solve over all pods on rank 0 from the imported per-pod results (pods with selectors: the "
-                        "generic pack kernel, one CTA); checked here by counts, bit-for-bit in tests/test_gpu.py"}
+        if args.no_global_pack:
+            pack = {"skipped": "--no-global-pack"}
+        else:
+            res_full.import_compact(p2p["buf"] if (p2p and "acc" in p2p) else (gathered_rows() if world > 1 else g_all).data_ptr())
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            res_full.pack()
+            ctx.synchronize()
+            pack_s = time.perf_counter() - t0
+            raw = res_full.fetch_solve()
+            placed = int((raw.pod_place_kind == capi.PLACE_CLAIM).sum())
+            assert placed + raw.n_unscheduled == P and int(raw.claim_npods.sum()) == placed
+            assert (raw.claim_sku >= 0).all() and (raw.claim_n_options > 0).all()
+            pack = {"ms": 1e3 * pack_s, "pods": P, "nodeclaims": int(raw.n_claims), "unschedulable": int(raw.n_unscheduled),
+                    "nodeclaims_per_s": raw.n_claims / pack_s, "digest": parity.digest(parity.canon_device(enc_full, raw))[:16],
+                    "note": "one Solve over all pods on rank 0 from the imported per-pod results (pods with selectors: the "
+                            "generic pack kernel, one CTA); checked here by counts, bit-for-bit in tests/test_gpu.py"}
         # CPU baseline: the reference-shaped dense pass over a bounded sample of the rows, all host threads
         nthreads = host_threads()
         sample = M.slice_pods(full, 0, min(P, 40_000))
@@ -435,6 +502,14 @@ def run_c5(args, rank, world, local):
             "dtype": "u64", "data": "synthetic", "config": c5_config(P, S),
             "l2": "flushed between timed iterations (256 MiB memset)",
             "stage_ms_max_over_ranks": float(acc[1]), "allgather_ms": float(acc[2]), "import_ms": float(acc[3]),
+            "exchange": collective,
+            "exchange_nccl": None if world == 1 else {"ms_per_step": float(acc_nccl_max[0]), "stage_ms": float(acc_nccl_max[1]),
+                                                      "allgather_ms": float(acc_nccl_max[2]), "import_ms": float(acc_nccl_max[3]),
+                                                      "note": "stage = prefilter + class tables + dense rows + compact export; then one all_gather_into_tensor"},
+            "exchange_peer_store": None if not (p2p and "acc" in p2p) else {
+                "ms_per_step": float(p2p["acc"][0]), "stage_ms": float(p2p["acc"][1]), "export_and_exchange_ms": float(p2p["acc"][2]),
+                "import_ms": float(p2p["acc"][3]),
+                "note": "stage = prefilter + class tables + dense rows; then ONE launch pair stores the rows into every rank's buffer and runs the flag barrier; rows checked equal to the collective's on every rank"},
             "dense_kernel_ms_max_over_ranks": dense_k,
             "allgather_bytes_per_rank": int(rows * rb), "allgather_bytes_per_pod": rb,
             "single_gpu_same_run": single, "global_pack": pack,
@@ -696,6 +771,10 @@ def main():
     ap.add_argument("--pods", type=int, default=0)
     ap.add_argument("--skus", type=int, default=0)
     ap.add_argument("--large", action="store_true", help="also time the dense stage on 1M pods x 2k SKUs")
+    ap.add_argument("--no-p2p", dest="no_p2p", action="store_true",
+                    help="multi-GPU: only the NCCL all-gather, not the peer-store export over CUDA-IPC mappings")
+    ap.add_argument("--no-global-pack", dest="no_global_pack", action="store_true",
+                    help="multi-GPU: skip the 1M-pod global pack after the gather (70 s on one CTA)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -169,6 +169,14 @@ def lib():
                                     _P(Templates), _P(SolveOpts), _P(_P(Result))]
     L.b200s_solve_batch_shared.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, _P(PodsSoA), _P(C.c_int32), _P(NodesSoA),
                                            _P(C.c_int32), _P(C.c_int32), _P(Templates), _P(SolveOpts), _P(_P(Result))]
+    L.b200s_device_alloc.argtypes = [C.c_void_p, C.c_uint64, _P(C.c_void_p)]
+    L.b200s_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_ipc_export.argtypes = [C.c_void_p, C.c_void_p, _P(C.c_uint8)]
+    L.b200s_ipc_open.argtypes = [C.c_void_p, _P(C.c_uint8), _P(C.c_void_p)]
+    L.b200s_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+    L.b200s_copy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.b200s_resident_export_compact_peers.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, _P(C.c_void_p), _P(C.c_void_p),
+                                                      C.c_int64, C.c_uint32, C.c_void_p]
     L.b200s_resident_create.argtypes = [C.c_void_p, C.c_uint64, _P(PodsSoA), _P(NodesSoA), _P(Templates),
                                         _P(C.c_void_p)]
     L.b200s_resident_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -568,6 +576,32 @@ class Context:
     def flush_l2(self, nbytes: int = 256 << 20):
         self._check(self.L.b200s_flush_l2(self.h, nbytes))
 
+    # ---- plumbing for the peer-store export (b200s_resident_export_compact_peers) ----
+    def device_alloc(self, nbytes: int) -> int:
+        out = C.c_void_p()
+        self._check(self.L.b200s_device_alloc(self.h, C.c_uint64(int(nbytes)), C.byref(out)))
+        return int(out.value)
+
+    def device_free(self, ptr: int) -> None:
+        self._check(self.L.b200s_device_free(self.h, C.c_void_p(int(ptr))))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self.L.b200s_ipc_export(self.h, C.c_void_p(int(ptr)), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self._check(self.L.b200s_ipc_open(self.h, buf, C.byref(out)))
+        return int(out.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        self._check(self.L.b200s_ipc_close(self.h, C.c_void_p(int(ptr))))
+
+    def copy_device(self, dst: int, src: int, nbytes: int) -> None:
+        self._check(self.L.b200s_copy_device(self.h, C.c_void_p(int(dst)), C.c_void_p(int(src)), C.c_uint64(int(nbytes))))
+
     def synchronize(self):
         self._check(self.L.b200s_synchronize(self.h))
 
@@ -602,6 +636,17 @@ class Resident:
     def export_compact(self, d_out: int):
         """compact rows (template + attempt codes, compact_row_bytes(T) each) of this resident's pods into device memory"""
         self.ctx._check(self.ctx.L.b200s_resident_export_compact(self.ctx.h, self.h, C.c_void_p(d_out)))
+
+    def export_compact_peers(self, peer_out: Sequence[int], peer_flags: Sequence[int], me: int, row_offset: int, epoch: int,
+                             d_timed_out: int):
+        """b200s_resident_export_compact_peers: this shard's compact rows stored into every rank's gathered buffer (device
+        pointers valid in this process: own memory or CUDA-IPC mappings) + the flag barrier of epoch `epoch`"""
+        n = len(peer_out)
+        po = (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in peer_out])
+        pf = (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in peer_flags])
+        self.ctx._check(self.ctx.L.b200s_resident_export_compact_peers(self.ctx.h, self.h, n, int(me), po, pf,
+                                                                       C.c_int64(int(row_offset)), C.c_uint32(int(epoch)),
+                                                                       C.c_void_p(int(d_timed_out))))
 
     def import_compact(self, d_in: int):
         """compact rows of ALL of this resident's pods, from device memory (gathered from the ranks that evaluated them)"""

@@ -1015,6 +1015,73 @@ int b200s_resident_export_compact(b200s_ctx_t* ctx, b200s_resident_t* r, void* d
   return B200S_OK;
 }
 
+/* device memory another process of the node can map (CUDA IPC): what the peer-store export writes into */
+int b200s_device_alloc(b200s_ctx_t* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out || bytes == 0) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(ctx, B200S_ENOMEM, "cudaMalloc");
+  CUDA_TRY(ctx, cudaMemsetAsync(p, 0, bytes, ctx->stream), "memset");
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+  *out = p;
+  return B200S_OK;
+}
+
+int b200s_device_free(b200s_ctx_t* ctx, void* p) {
+  if (!ctx) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  if (p && cudaFree(p) != cudaSuccess) return fail(ctx, B200S_ECUDA, "cudaFree");
+  return B200S_OK;
+}
+
+int b200s_ipc_export(b200s_ctx_t* ctx, void* dptr, uint8_t handle[64]) {
+  if (!ctx || !dptr || !handle) return B200S_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaSetDevice(ctx->device);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, dptr), "cudaIpcGetMemHandle");
+  std::memcpy(handle, &h, 64);
+  return B200S_OK;
+}
+
+int b200s_ipc_open(b200s_ctx_t* ctx, const uint8_t handle[64], void** out) {
+  if (!ctx || !handle || !out) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  CUDA_TRY(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  return B200S_OK;
+}
+
+int b200s_ipc_close(b200s_ctx_t* ctx, void* p) {
+  if (!ctx || !p) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaIpcCloseMemHandle(p), "cudaIpcCloseMemHandle");
+  return B200S_OK;
+}
+
+int b200s_copy_device(b200s_ctx_t* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx || !dst || !src) return B200S_EINVAL;
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream), "D2D copy");
+  return B200S_OK;
+}
+
+/* export fused with the exchange: the rows go straight into every rank's gathered buffer through peer mappings, then a
+ * flag barrier (see include/b200sched.h) */
+int b200s_resident_export_compact_peers(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t n_peers, int32_t me, void* const* peer_out,
+                                        void* const* peer_flags, int64_t row_offset, uint32_t epoch, int32_t* d_timed_out) {
+  if (!ctx || !r || !peer_out || !peer_flags || !d_timed_out || n_peers < 1 || n_peers > 8 || me < 0 || me >= n_peers || row_offset < 0)
+    return B200S_EINVAL;
+  for (int q = 0; q < n_peers; q++)
+    if (!peer_out[q] || !peer_flags[q]) return B200S_EINVAL;
+  if (!r->fit_done) return B200S_ESTATE;
+  CUDA_TRY(ctx, launch_compact_export_peers(r->P, r->T, r->a_tmpl, r->a_code, n_peers, me, peer_out, peer_flags, row_offset, epoch,
+                                            d_timed_out, ctx->n_sm, ctx->stream), "compact_export_peers launch");
+  r->last_launches += r->P > 0 ? 2 : 1;
+  return B200S_OK;
+}
+
 /* the inverse on the GPU that packs: d_in holds compact rows for ALL of this resident's pods (gathered from the ranks
  * that evaluated them); afterwards b200s_resident_pack runs the Solve without evaluating the pods again */
 int b200s_resident_import_compact(b200s_ctx_t* ctx, b200s_resident_t* r, const void* d_in) {

@@ -1103,6 +1103,72 @@ __global__ void __launch_bounds__(256) compact_import_kernel(int P, int T, int r
 
 int compact_row_bytes(int T) { return T <= 7 ? 8 : 24; }
 
+// The same export fused with its all-gather: every rank stores its shard's rows straight into every rank's gathered
+// buffer over NVLink peer mappings (8 bytes a pod: the whole exchange is smaller than one collective's fixed cost), then
+// the ranks meet at a flag barrier — rank `me` publishes `epoch` in slot `me` of every rank's flag array once its stores
+// are out, and waits until its own array shows `epoch` in every slot.  peer.out[q] / peer.flags[q] are rank q's buffer and
+// flag array as mapped into THIS process (own memory for q == me).
+struct CompactPeers {
+  uint8_t* out[8];
+  unsigned* flags[8];
+};
+
+__global__ void __launch_bounds__(256) compact_export_peers_kernel(int P, int T, int rb, const int32_t* __restrict__ tmpl,
+                                                                   const uint8_t* __restrict__ code, CompactPeers peer, int n_peers,
+                                                                   long long row_off) {
+  const int words = rb / 8;  // 8-byte words of a row
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    unsigned long long w[3] = {0ull, 0ull, 0ull};
+    w[0] = (unsigned long long)(uint8_t)(int8_t)tmpl[p];
+    for (int j = 1; j <= T; j++) w[j >> 3] |= (unsigned long long)code[(size_t)p * T + (j - 1)] << (8 * (j & 7));
+    for (int q = 0; q < n_peers; q++) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer.out[q] + (size_t)(row_off + p) * rb);
+      for (int i = 0; i < words; i++) dst[i] = w[i];
+    }
+  }
+}
+
+// one thread per peer: signal it, then wait for it.  *timed_out is set when a peer does not show up (the caller falls back
+// to a collective); the wait is bounded so that a missing peer cannot hang the GPU.
+__global__ void compact_peers_barrier_kernel(CompactPeers peer, int n_peers, int me, unsigned epoch, int* __restrict__ timed_out) {
+  const int q = threadIdx.x;
+  if (q >= n_peers) return;
+  __threadfence_system();  // this rank's row stores (the kernel before this one) are visible system-wide before the flag
+  unsigned* theirs = peer.flags[q] + me;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const unsigned* mine = peer.flags[me] + q;
+  for (unsigned spins = 0;; spins++) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (spins > (1u << 22)) {  // ~ a second
+      *timed_out = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+cudaError_t launch_compact_export_peers(int P, int T, const int32_t* tmpl, const uint8_t* code, int n_peers, int me,
+                                        void* const* peer_out, void* const* peer_flags, long long row_off, unsigned epoch,
+                                        int* timed_out, int n_sm, cudaStream_t stream) {
+  if (n_peers < 1 || n_peers > 8 || me < 0 || me >= n_peers) return cudaErrorInvalidValue;
+  CompactPeers cp{};
+  for (int q = 0; q < n_peers; q++) {
+    cp.out[q] = static_cast<uint8_t*>(peer_out[q]);
+    cp.flags[q] = static_cast<unsigned*>(peer_flags[q]);
+  }
+  const int rb = compact_row_bytes(T);
+  if (P > 0) {
+    const int grid = (int)std::min<long long>(((long long)P + 255) / 256, (long long)n_sm * 8);
+    compact_export_peers_kernel<<<grid, 256, 0, stream>>>(P, T, rb, tmpl, code, cp, n_peers, row_off);
+  }
+  compact_peers_barrier_kernel<<<1, 32, 0, stream>>>(cp, n_peers, me, epoch, timed_out);
+  return cudaGetLastError();
+}
+
+
+
 cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream) {
   if (P == 0) return cudaSuccess;
   const int rb = compact_row_bytes(T);

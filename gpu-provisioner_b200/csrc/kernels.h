@@ -119,6 +119,9 @@ cudaError_t launch_fit_dense(const KeyTab& kt, int T, const PodsDev& pods, const
                              cudaStream_t stream);
 int compact_row_bytes(int T);
 cudaError_t launch_compact_export(int P, int T, const int32_t* tmpl, const uint8_t* code, uint8_t* out, int n_sm, cudaStream_t stream);
+cudaError_t launch_compact_export_peers(int P, int T, const int32_t* tmpl, const uint8_t* code, int n_peers, int me,
+                                        void* const* peer_out, void* const* peer_flags, long long row_off, unsigned epoch,
+                                        int* timed_out, int n_sm, cudaStream_t stream);
 cudaError_t launch_compact_import(int P, int T, const uint8_t* in, int32_t* tmpl, uint8_t* code, int n_sm, cudaStream_t stream);
 int ffd_padded(int P);
 // b200s_solve_batch_shared: every problem's ExistingNodes = a copy of the shared rows, minus the rows it removes

@@ -501,6 +501,30 @@ int b200s_resident_fetch_solve(b200s_ctx_t* ctx, b200s_resident_t* r, b200s_resu
 /* device-to-device copy of the resident dense results into caller-owned DEVICE buffers (e.g. the send buffers of
  * an NCCL all-gather when the pod rows are sharded across GPUs); enqueued on the context's stream */
 int b200s_resident_copy_fit_device(b200s_ctx_t* ctx, b200s_resident_t* r, void* d_tmpl, void* d_mask, void* d_code);
+/* Plumbing for the peer-store export below: a device allocation of the library's own (zero-initialised) whose CUDA IPC
+ * handle (64 bytes, cudaIpcMemHandle_t) another process of the same node opens on ITS device with peer access enabled;
+ * b200s_copy_device enqueues a device-to-device copy on the context's stream (to look at such a buffer from a framework
+ * tensor).  One process per GPU exchanges the handles with whatever it has (the bench: torch.distributed). */
+int b200s_device_alloc(b200s_ctx_t* ctx, uint64_t bytes, void** out);
+int b200s_device_free(b200s_ctx_t* ctx, void* p);
+int b200s_ipc_export(b200s_ctx_t* ctx, void* dptr, uint8_t handle[64]);
+int b200s_ipc_open(b200s_ctx_t* ctx, const uint8_t handle[64], void** out);
+int b200s_ipc_close(b200s_ctx_t* ctx, void* p);
+int b200s_copy_device(b200s_ctx_t* ctx, void* dst, const void* src, uint64_t bytes);
+
+/* The export fused with its all-gather, for ranks of one NVLink domain that have mapped each other's memory (CUDA IPC;
+ * torch's storage sharing does it in the bench): peer_out[q] is rank q's gathered buffer [P_total * row_bytes] and
+ * peer_flags[q] rank q's flag array (uint32[n_peers], zero-initialised) AS MAPPED INTO THIS PROCESS (q == me: own
+ * memory).  The shard's rows are stored at row_offset in every peer's buffer, then the ranks meet at a flag barrier:
+ * rank `me` publishes `epoch` (a counter the caller increments every call, starting at 1) in slot `me` of every flag
+ * array and waits for `epoch` in every slot of its own.  When the call's stream work completes, this rank's buffer holds
+ * every rank's rows of this epoch.  The wait is bounded (about a second): *d_timed_out (device int, caller-zeroed) is
+ * set instead of hanging when a peer never arrives.  The caller must not start epoch e+1 while a peer may still read
+ * epoch e's rows (the bench has a step barrier).  n_peers <= 8. */
+int b200s_resident_export_compact_peers(b200s_ctx_t* ctx, b200s_resident_t* r, int32_t n_peers, int32_t me,
+                                        void* const* peer_out, void* const* peer_flags, int64_t row_offset,
+                                        uint32_t epoch, int32_t* d_timed_out);
+
 /* ---- pod rows sharded across GPUs ----
  * Each GPU evaluates its block of pod rows (b200s_resident_fit_matrix on a resident built from that block); what the
  * GPU that runs the pack needs of a pod is its first feasible template and the per-template attempt codes — the

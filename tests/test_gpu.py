@@ -419,6 +419,36 @@ def test_config4_consolidation_simulations_in_one_batch(gpu_ctx):
         gpu_ctx.release_catalog(cid)
 
 
+def test_peer_store_export_equals_plain_export(gpu_ctx):
+    """b200s_resident_export_compact_peers with this GPU as its only peer: the rows land at the row offset exactly as
+    b200s_resident_export_compact writes them, the flag barrier passes on the own flag, nothing times out (the multi-rank
+    form of the same call is what `bench.py --gpus N` runs)."""
+    import torch
+    m = synth.config("c3", 5000, 300)
+    enc = capi.Encoded(m)
+    cid = gpu_ctx.upload_catalog(enc)
+    res = gpu_ctx.resident(cid, enc)
+    try:
+        res.fit_matrix()
+        rb = capi.compact_row_bytes(enc.T)
+        plain = torch.zeros(enc.P * rb, dtype=torch.uint8, device="cuda")
+        off = 123
+        peers = torch.full(((enc.P + off) * rb,), 0xEE, dtype=torch.uint8, device="cuda")
+        flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+        timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()  # the fills ran on torch's stream, the library has its own
+        res.export_compact(plain.data_ptr())
+        for epoch in (1, 2):
+            res.export_compact_peers([peers.data_ptr()], [flags.data_ptr()], 0, off, epoch, timed_out.data_ptr())
+        gpu_ctx.synchronize()
+        assert int(timed_out.item()) == 0 and int(flags[0].item()) == 2
+        got = peers.view(-1, rb)
+        assert torch.equal(got[off:].reshape(-1), plain) and bool((got[:off] == 0xEE).all())
+    finally:
+        res.close()
+        gpu_ctx.release_catalog(cid)
+
+
 def test_shared_cluster_batch_equals_separate_simulations(gpu_ctx):
     """b200s_solve_batch_shared -- one pod set, one node set, per simulation a pod range and the node rows it removes --
     gives what b200s_solve_batch gives on the separately flattened simulations (which the tests above hold against the
