@@ -551,17 +551,21 @@ def solve(model: M.Model):
     W = (S + 63) // 64
     mask = np.zeros((len(claims), W), np.uint64)
     sku = np.full(len(claims), -1, np.int32)
+    orders = []
     for i, nc in enumerate(claims):
-        best = math.inf
         for it in nc.instance_types:
             mask[i, it.idx // 64] |= np.uint64(1) << np.uint64(it.idx % 64)
-            # InstanceTypes.OrderByPrice (K/cloudprovider/types.go:221-240): cheapest available compatible offering
-            price = min([pr for oreq, pr, avail in it.offerings if avail and compatible(cx, nc.requirements, oreq, True)],
-                        default=math.inf)
-            if price < best:
-                best, sku[i] = price, it.idx
+        # InstanceTypes.OrderByPrice (K/cloudprovider/types.go:221-240): sort.Slice — the unstable pdqsort again — by
+        # the cheapest available offering the requirements admit (math.MaxFloat64 when there is none); equal prices end
+        # up where pdqsort leaves them.  NodeClaimTemplate.ToNodeClaim keeps the first MaxInstanceTypes
+        # (nodeclaimtemplate.go:77-82), the parity unit's cheapest SKU is element 0.
+        keyed = [(min([pr for oreq, pr, avail in it.offerings if avail and compatible(cx, nc.requirements, oreq, True)],
+                      default=1.7976931348623157e308), it.idx) for it in nc.instance_types]
+        sort_slice(keyed, lambda x, y: x[0] < y[0])
+        orders.append([idx for _, idx in keyed])
+        sku[i] = keyed[0][1] if keyed else -1
     return dict(n_claims=len(claims), n_unscheduled=int((kind < 0).sum()), pod_place_kind=kind, pod_place_index=index,
                 pod_seq=seq, claim_pool=np.array([nc.template.pool for nc in claims], np.int32),
                 claim_npods=np.array([len(nc.pods) for nc in claims], np.int32),
                 claim_requests=np.array([nc.requests for nc in claims], np.int64).reshape(len(claims), R),
-                claim_mask=mask, claim_sku=sku, node_npods=np.array([len(n.pods) for n in nodes], np.int32))
+                claim_mask=mask, claim_sku=sku, claim_order=orders, node_npods=np.array([len(n.pods) for n in nodes], np.int32))

@@ -52,3 +52,23 @@ def test_python_restatement_agrees_on_consolidation_simulations():
         o = _same(sim, f"simulation of node {i}")
         on_nodes += int((o.pod_place_kind == 0).sum())
     assert on_nodes > 0
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_price_ties_fall_where_pdqsort_leaves_them(block):
+    """Equal prices make OrderByPrice's result — hence the cheapest SKU of a NodeClaim and ToNodeClaim's instance-type
+    list — depend on Go's unstable sort.  With the prices of fuzzed catalogs squeezed onto a handful of values, the
+    oracle's list and the Python restatement's (a third port of pdqsort) must still be the same list."""
+    ties = 0
+    for seed in range(block * 40, block * 40 + 40):
+        m = fuzz_models.random_model(9000 + seed, with_nodes=False, max_pods=50, keyless=seed % 2 == 0)
+        pr = m.arrays["off_price"]
+        pr[:] = np.round(pr * 1.5, 0) / 1.5 + 0.25   # a few distinct prices per catalog (in place: the C model aliases it)
+        o, order, count, tie = ob.solve_ordered(m, 600)
+        r = solve_ref.solve(m)
+        assert o.n_claims == r["n_claims"] and np.array_equal(o.pod_place_index, r["pod_place_index"]), seed
+        assert np.array_equal(o.claim_sku, r["claim_sku"]), seed
+        for i in range(o.n_claims):
+            assert order[i, :count[i]].tolist() == r["claim_order"][i][:600], (seed, i)
+        ties += int(tie.sum())
+    assert ties >= 10
