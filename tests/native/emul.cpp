@@ -511,7 +511,7 @@ struct OrderEmu {  // the order warp's arrays and its eager normalisation with u
 }  // namespace
 
 extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templates_t* tm, const b200s_pods_soa_t* pods,
-                              b200s_result_t* out, int64_t* stats) {
+                              b200s_result_t* out, int64_t* stats, int32_t kcap) {
   KeyTab kt = keytab_from(cat);
   const int W = kt.n_words, T = tm->n_templates, P = pods->n_pods, R = kt.n_res, K = kt.n_keys, NB = kt.n_bounded;
   for (int s = 0; s < pods->n_sigs; s++)
@@ -555,27 +555,56 @@ extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templa
       }
       table[t][(size_t)cell] = any;
     }
-  struct Claim { std::vector<int64_t> req, thr; std::vector<int> rk; int tmpl; int64_t prio; int npods; int first; };
+  // The order, as pack_reg_kernel keeps it: every claim knows its POSITION in s.newNodeClaims; a step's change of the
+  // order is one range of positions moving by one (the shift word), applied by everyone one step late; the minimum of a
+  // step is taken over priorities 2 * pos + 1 that do not have the previous step's shift yet, in which the claim that
+  // changed took a value between its new neighbours' old ones; only when sort.Slice could take the real pdqsort path is
+  // the explicit order laid out and sorted (OrderEmu::normalise), lazily, at the start of the NEXT add() — which is when
+  // the reference sorts, so the last step's change is simply never applied.
+  struct Claim { std::vector<int64_t> req, thr; std::vector<int> rk; int tmpl; uint32_t pos, prio; int npods; int first; };
   std::vector<Claim> claims;
   OrderEmu oe;
-  const int TB = 24;
-  const int64_t OFF = 1ll << 23;
-  int64_t front = OFF - 1, back = OFF;
+  const int KCAP = kcap > 0 ? kcap : 2048;  // pod counts with an entry in the count table G[x] = claims with more than x pods
+  std::vector<int> G(KCAP, 0);
+  struct Shift { int lo = 1, hi = 0; bool up = false, meet = false; int meet_a = 0, meet_n = 0; bool meet_app = false; } rec;
+  const uint32_t MARK = 0x80000000u;
   std::vector<int> lastlen(P, 0), pod_claim(P, -1);
   size_t head = 0;
   int seq = 0;
   std::vector<int64_t> preq(R), x(R);
   int64_t n_generic = 0, n_resolve = 0, n_steps = 0;
   for (int p = 0; p < P; p++) { out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED; out->pod_place_index[p] = -1; out->pod_seq[p] = -1; }
-  auto reset_prios = [&]() {
+  int64_t n_meets = 0;
+  // the sort at the start of an add(): the previous step's shift, or — when it asked for it — the real sort.Slice
+  auto start_of_add = [&]() {
     const int n = (int)claims.size();
-    for (int c = 0; c < n; c++) claims[c].prio = ((int64_t)claims[c].npods << TB) | (OFF + oe.pos_of[c]);
-    front = OFF - 1;
-    back = OFF + n;
+    if (rec.meet) {
+      n_meets++;
+      oe.ord.assign(n, 0); oe.key.assign(n, 0); oe.pos_of.assign(n, 0);
+      for (int c = 0; c < n; c++) {  // the order as it is: positions before the change, the new pod count
+        oe.ord[claims[c].pos] = c; oe.key[claims[c].pos] = claims[c].npods; oe.pos_of[c] = (int)claims[c].pos;
+      }
+      oe.normalise(rec.meet_a, rec.meet_app);
+      if (oe.generic) n_generic++;
+      for (int c = 0; c < n; c++) claims[c].pos = (uint32_t)oe.pos_of[c];
+    } else {
+      for (int c = 0; c < n; c++) {
+        uint32_t& ps = claims[c].pos;
+        if (!(ps & MARK) && (int)ps >= rec.lo && (int)ps <= rec.hi) ps += rec.up ? 1u : 0xFFFFFFFFu;
+        ps &= ~MARK;  // the claim that moved had marked where it went
+      }
+    }
+    for (int c = 0; c < n; c++) claims[c].prio = 2u * claims[c].pos + 1u;
+    rec = Shift{};
   };
-  auto check_order = [&]() -> bool {  // the priorities order the claims exactly as the explicit array does
-    for (size_t i = 1; i < oe.ord.size(); i++)
-      if (!(claims[oe.ord[i - 1]].prio < claims[oe.ord[i]].prio)) return false;
+  auto positions_are_a_permutation = [&]() -> bool {
+    const int n = (int)claims.size();
+    std::vector<char> seen(n, 0);
+    for (int c = 0; c < n; c++) {
+      const uint32_t ps = claims[c].pos & ~MARK;
+      if (ps >= (uint32_t)n || seen[ps]) return false;
+      seen[ps] = 1;
+    }
     return true;
   };
   for (;;) {
@@ -585,13 +614,14 @@ extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templa
     if (lastlen[p] == (int)len) break;
     head++;
     n_steps++;
-    oe.undo_mode = 0;  // the reference sorts at the start of this add() too: the last normalisation stands
     const uint64_t tol = pod_tolerated(pods, p);
     for (int r = 0; r < R; r++) preq[r] = req(r, p);
     // in-flight: every claim classified independently, least priority among the feasible ones wins
     int win = -1;
     std::vector<int> win_rk, nrk(R);
     bool win_moved = false;
+    std::vector<char> feasible(claims.size(), 0), is_moved(claims.size(), 0);
+    std::vector<std::vector<int>> moved_rk(claims.size());
     for (int c = 0; c < (int)claims.size(); c++) {
       Claim& cl = claims[c];
       if (tm->taints[cl.tmpl] & ~tol) continue;
@@ -617,29 +647,51 @@ extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templa
         }
         if (!ok || !table[cl.tmpl][(size_t)cell]) continue;
       }
-      if (win < 0 || cl.prio < claims[win].prio) {
-        win = c;
-        win_moved = moved;
-        if (moved) win_rk = nrk;
-      }
+      feasible[c] = 1;
+      if (moved) moved_rk[c] = nrk;
+      is_moved[c] = moved;
     }
+    // the kernel takes the minimum before it knows the previous step's shift; when that step asked for the real sort
+    // the minimum is taken again afterwards over the re-read positions
+    auto least = [&]() {
+      int w = -1;
+      for (int c = 0; c < (int)claims.size(); c++)
+        if (feasible[c] && (w < 0 || claims[c].prio < claims[w].prio)) w = c;
+      return w;
+    };
+    const bool resorted = rec.meet;
+    win = least();
+    start_of_add();
+    if (resorted) win = least();
+    else if (win >= 0 && least() != win) return -3000;  // the stale priorities and the true positions must agree
+    if (!positions_are_a_permutation()) return -3001;
     if (win >= 0) {
+      win_moved = is_moved[win];
+      if (win_moved) win_rk = moved_rk[win];
       Claim& cl = claims[win];
       if (win_moved) {
         cl.rk = win_rk;
         for (int r = 0; r < R; r++) cl.thr[r] = kt.res_dv[kt.res_dv0[r] + cl.rk[r]];
       }
       for (int r = 0; r < R; r++) cl.req[r] += preq[r];
-      cl.npods++;
-      cl.prio = ((int64_t)cl.npods << TB) | front;
-      front--;
+      // the claim now has k + 1 pods and belongs at the end of the run of claims with k pods (pack_reg_kernel's winner)
+      const int n = (int)claims.size(), a = (int)cl.pos, k = cl.npods;
+      const bool big = k + 1 >= KCAP;
+      const int kk = big ? KCAP - 1 : k;
+      const int gk = G[kk];
+      if (!big) G[kk] = gk + 1;
+      int dst = n - gk - 1;
+      const int qq = n >> 2;
+      const bool near = (unsigned)(a - qq + 1) <= 2u || (unsigned)(a - 2 * qq + 1) <= 2u || (unsigned)(a - 3 * qq + 1) <= 2u;
+      const bool meet = big || (dst != a && (n < 50 || near));
+      if (big) dst = a;
+      rec.lo = a + 1; rec.hi = dst; rec.up = false; rec.meet = meet;
+      rec.meet_a = a; rec.meet_app = false; rec.meet_n = n;
+      cl.npods = k + 1;
+      cl.prio = 2u * (uint32_t)dst + 2u;
+      cl.pos = meet ? (uint32_t)a : (MARK | (uint32_t)dst);
       pod_claim[p] = win;
       out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
-      const int a = oe.pos_of[win];
-      oe.key[a]++;
-      oe.normalise(a, false);
-      if (oe.generic) { n_generic++; reset_prios(); }
-      if (!check_order()) return -1000 - (int)n_steps % 1000;
       continue;
     }
     int t = a_tmpl[p];
@@ -654,15 +706,16 @@ extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templa
       c.first = p;
       c.tmpl = t;
       c.npods = 1;
-      c.prio = ((int64_t)1 << TB) | back;
-      back++;
+      // appended (scheduler.go:672); the next sort puts it behind the last claim with one pod
+      const int n = (int)claims.size();
+      const int dst = n - (KCAP > 1 ? G[1] : 0);
+      const bool meet = (n + 1 < 50 && dst != n) || KCAP <= 1;
+      c.pos = meet ? (uint32_t)n : (MARK | (uint32_t)dst);
+      c.prio = 2u * (uint32_t)dst;
+      rec.lo = dst; rec.hi = n - 1; rec.up = true; rec.meet = meet;
+      rec.meet_a = n; rec.meet_app = true; rec.meet_n = n + 1;
       claims.push_back(c);
       const int cid = (int)claims.size() - 1;
-      oe.ord.push_back(cid); oe.key.push_back(1); oe.pos_of.push_back(cid);
-      oe.pos_of[cid] = (int)oe.ord.size() - 1;
-      oe.normalise((int)oe.ord.size() - 1, true);
-      if (oe.generic) { n_generic++; reset_prios(); }
-      if (!check_order()) return -2000;
       pod_claim[p] = cid;
       out->pod_place_kind[p] = B200S_PLACE_CLAIM; out->pod_seq[p] = seq++;
     } else {
@@ -671,9 +724,17 @@ extern "C" int emul_solve_reg(const b200s_catalog_soa_t* cat, const b200s_templa
       out->pod_place_kind[p] = B200S_PLACE_UNSCHEDULED;
     }
   }
-  oe.undo();
-  if (stats) { stats[0] = n_steps; stats[1] = n_generic; stats[2] = n_resolve; }
+  // Results.NewNodeClaims: the order after the last sort the reference ran plus what the last add() did — the last
+  // step's change is not applied: its claim keeps its place (one before the range it would have passed), a new claim is last
   const int n = (int)claims.size();
+  for (int c = 0; c < n; c++) {
+    uint32_t& ps = claims[c].pos;
+    if (ps & MARK) ps = rec.up ? (uint32_t)(n - 1) : (rec.lo <= rec.hi ? (uint32_t)(rec.lo - 1) : (ps & ~MARK));
+  }
+  if (!positions_are_a_permutation()) return -3002;
+  oe.ord.assign(n, 0);
+  for (int c = 0; c < n; c++) oe.ord[claims[c].pos] = c;
+  if (stats) { stats[0] = n_steps; stats[1] = n_generic; stats[2] = n_resolve; stats[3] = n_meets; }
   if (n > out->cap_claims) return B200S_ECAPACITY;
   out->n_claims = n;
   out->n_unscheduled = (int)(q.size() - head);

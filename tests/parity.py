@@ -209,11 +209,13 @@ def device_commands_as_oracle(enc: capi.Encoded, cmds: Dict[str, np.ndarray], i:
                 head=cmds["head"][i].tolist(), mask=cmds["mask"][i].tolist())
 
 
-def emul_solve_reg(enc: capi.Encoded):
-    """host twin of the register-resident pack (selector-less pods, no existing nodes); (result, stats)"""
+def emul_solve_reg(enc: capi.Encoded, kcap: int = 0):
+    """host twin of the register-resident pack (selector-less pods, no existing nodes): positions, shift words, the
+    real sort only on demand, exactly as pack_reg_kernel does it; (result, stats = steps, full pdqsorts, rank look-ups,
+    meetings with the order warp).  kcap: size of the count table (0: the kernel's 2 048)"""
     buf = capi.ResultBuffers(enc.P, enc.T, enc.R, enc.W, enc.K, enc.NB)
     stats = np.zeros(4, np.int64)
-    rc = emul().emul_solve_reg(enc.catalog, enc.templates, enc.pods, C.byref(buf.c), _p(stats, C.c_int64))
+    rc = emul().emul_solve_reg(enc.catalog, enc.templates, enc.pods, C.byref(buf.c), _p(stats, C.c_int64), C.c_int32(kcap))
     assert rc == 0, rc
     return buf.raw(), stats
 

@@ -53,12 +53,31 @@ def test_emulation_matches_oracle_on_fuzzed_models():
 
 @pytest.mark.parametrize("kind,P,S", [("c2", 1500, 100), ("c2", 4000, 500), ("c2", 300, 1300), ("c2", 3000, 64)])
 def test_register_pack_twin_matches_oracle_on_config2_shapes(kind, P, S):
-    """tests/native/emul.cpp emul_solve_reg: priorities instead of positions, feasibility table instead of type masks."""
+    """tests/native/emul.cpp emul_solve_reg, the serial twin of pack_reg_kernel: claims know their positions, a step's
+    change of the order is one shift word applied a step late, the minimum is taken over priorities that do not have it
+    yet, sort.Slice runs only when it could take the real pdqsort path, and the last change is never applied.  The twin
+    also checks at every step that the stale priorities pick the claim the true positions pick."""
     m = synth.config(kind, P, S)
     enc = capi.Encoded(m)
+    o = ob.solve(m)
     raw, stats = parity.emul_solve_reg(enc)
-    parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, ob.solve(m)), f"reg twin {kind} {P}x{S}")
+    parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, o), f"reg twin {kind} {P}x{S}")
     assert stats[0] == P
+    if o.n_claims > 60:  # most steps need no sort at all once there are 50 claims
+        assert 0 < stats[3] < P // 3 and stats[1] <= stats[3], stats
+    # a count table of three entries: every claim with two or more pods takes the "beyond the table" path (real sort)
+    raw, stats = parity.emul_solve_reg(enc, kcap=3)
+    parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, o), f"reg twin {kind} {P}x{S} kcap 3")
+
+
+def test_register_pack_twin_reproduces_config2_digest_and_the_kernels_counters():
+    """BASELINE config[1] at full size on the serial twin: the golden digest, and the two counters pack_reg_kernel reports
+    for the same workload (bench.py step_breakdown: 318 of the 10 000 steps meet the order warp, 284 run the full
+    pdqsort) -- the kernel and its twin take the same path, not only reach the same result."""
+    enc = capi.Encoded(synth.c2())
+    raw, stats = parity.emul_solve_reg(enc)
+    assert parity.digest(parity.canon_device(enc, raw))[:16] == "1423b60e3481b574"
+    assert (int(stats[0]), int(stats[1]), int(stats[3])) == (10_000, 284, 318)
 
 
 def test_register_pack_twin_matches_oracle_on_fuzzed_keyless_models():
@@ -69,8 +88,10 @@ def test_register_pack_twin_matches_oracle_on_fuzzed_keyless_models():
             enc = capi.Encoded(m)
         except capi.NotRepresentable:
             continue
-        raw, _ = parity.emul_solve_reg(enc)
-        parity.assert_same(parity.canon_device(enc, raw), parity.canon_oracle(m, ob.solve(m)), f"reg twin fuzz {seed}")
+        o = parity.canon_oracle(m, ob.solve(m))
+        for kcap in (0, 3, 5):  # 0: the kernel's 2 048; small tables send claims down the "beyond the table" path (3 is the least that still counts single-pod claims)
+            raw, _ = parity.emul_solve_reg(enc, kcap=kcap)
+            parity.assert_same(parity.canon_device(enc, raw), o, f"reg twin fuzz {seed} kcap {kcap}")
         ran += 1
     assert ran >= 250, ran
 
