@@ -519,15 +519,54 @@ void do_encode(Ctx& c) {
   // ---- pods: dictionary-encode requirement signatures and request vectors ----
   // Replicas of one workload share both, so the pod arrays shrink to two ids per pod and the kernels
   // evaluate each distinct signature / request vector once.  Exact: a class is a bit-for-bit equal row.
-  struct VecHash {
-    size_t operator()(const std::vector<uint64_t>& v) const {
-      uint64_t h = 0x9E3779B97F4A7C15ull;
-      for (uint64_t x : v) { h ^= x + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; }
-      return (size_t)h;
+  // A dictionary of fixed-width rows: open addressing over the row hash, rows kept in one flat array (the per-pod cost of
+  // the encode is these two look-ups; a node-based map with vector keys was half of b200s_encode's time).
+  struct RowDict {
+    size_t width = 0;
+    std::vector<uint64_t> rows;   // [n * width]
+    std::vector<int32_t> slot;    // id or -1
+    size_t n = 0, mask = 0;
+    void init(size_t w, size_t expect) {
+      width = w;
+      size_t cap = 64;
+      while (cap < 2 * expect) cap <<= 1;
+      slot.assign(cap, -1);
+      mask = cap - 1;
     }
+    static uint64_t hash(const uint64_t* v, size_t w) {
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (size_t i = 0; i < w; i++) { h ^= v[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; }
+      return h ^ (h >> 29);
+    }
+    void grow() {
+      std::vector<int32_t> ns(slot.size() * 2, -1);
+      const size_t nm = ns.size() - 1;
+      for (size_t id = 0; id < n; id++) {
+        size_t i = (size_t)hash(rows.data() + id * width, width) & nm;
+        while (ns[i] >= 0) i = (i + 1) & nm;
+        ns[i] = (int32_t)id;
+      }
+      slot.swap(ns);
+      mask = nm;
+    }
+    int32_t id_of(const uint64_t* v) {
+      size_t i = (size_t)hash(v, width) & mask;
+      for (;; i = (i + 1) & mask) {
+        const int32_t id = slot[i];
+        if (id < 0) break;
+        if (std::memcmp(rows.data() + (size_t)id * width, v, width * 8) == 0) return id;
+      }
+      slot[i] = (int32_t)n;
+      rows.insert(rows.end(), v, v + width);
+      n++;
+      if (2 * n > slot.size()) grow();
+      return (int32_t)(n - 1);
+    }
+    const uint64_t* row(size_t id) const { return rows.data() + id * width; }
   };
-  std::unordered_map<std::vector<uint64_t>, int32_t, VecHash> sig_of, rq_of;
-  std::vector<std::vector<uint64_t>> sig_rows, rq_rows;
+  RowDict sig_of, rq_of;
+  rq_of.init((size_t)R, 1024);
+  sig_of.init((size_t)K + 2 + 2 * (size_t)NB, 1024);
   const size_t Pz = (size_t)std::max(P, 1);
   E->pod_sig.assign(Pz, 0);
   E->pod_reqcls.assign(Pz, 0);
@@ -539,7 +578,7 @@ void do_encode(Ctx& c) {
   E->pod_uid_lo.resize(Pz);
   std::vector<long double> sums(R, 0);
   std::vector<uint64_t> row;
-  // memo of the signature of an identical raw requirement + toleration list (cheap path for replicas)
+  int32_t plain_sig = -1;  // signature id of a pod without requirements and tolerations, once one has been seen
   for (int p = 0; p < P; p++) {
     row.assign((size_t)R, 0);
     for (int r = 0; r < R; r++) {
@@ -548,15 +587,14 @@ void do_encode(Ctx& c) {
       row[r] = (uint64_t)q;
       sums[r] += (long double)q;
     }
-    auto itq = rq_of.find(row);
-    if (itq == rq_of.end()) {
-      itq = rq_of.emplace(row, (int32_t)rq_rows.size()).first;
-      rq_rows.push_back(row);
-    }
-    E->pod_reqcls[p] = itq->second;
+    E->pod_reqcls[p] = rq_of.id_of(row.data());
 
-    ReqSet rs;
     int r0 = M->pod_req_off[p], r1 = M->pod_req_off[p + 1];
+    if (r1 == r0 && M->pod_tol_off[p + 1] == M->pod_tol_off[p] && plain_sig >= 0) {
+      E->pod_sig[p] = plain_sig;  // no requirement, no toleration: the signature the first such pod got
+      continue;
+    }
+    ReqSet rs;
     if (r1 > r0) build_set(r0, r1, &rs, "a pod", nullptr);
     row.assign((size_t)K + 2 + 2 * (size_t)NB, 0);
     uint64_t f = 0;
@@ -580,26 +618,22 @@ void do_encode(Ctx& c) {
       if (ok) tol |= 1ull << ti;
     }
     row[(size_t)K + 1] = tol;
-    auto its = sig_of.find(row);
-    if (its == sig_of.end()) {
-      its = sig_of.emplace(row, (int32_t)sig_rows.size()).first;
-      sig_rows.push_back(row);
-    }
-    E->pod_sig[p] = its->second;
+    E->pod_sig[p] = sig_of.id_of(row.data());
+    if (r1 == r0 && t1 == t0) plain_sig = E->pod_sig[p];
   }
   for (int r = 0; r < R; r++) {
     long double mx = 0;
     for (int t = 0; t < M->n_pools; t++) mx = std::max(mx, (long double)T.daemon[t][r]);
     if (sums[r] + mx > 9.0e18L) reject("accumulated requests of resource %d could overflow int64", r);
   }
-  const size_t NS = sig_rows.size(), NQ = rq_rows.size(), NS1 = std::max<size_t>(NS, 1), NQ1 = std::max<size_t>(NQ, 1);
+  const size_t NS = sig_of.n, NQ = rq_of.n, NS1 = std::max<size_t>(NS, 1), NQ1 = std::max<size_t>(NQ, 1);
   E->sig_mask.assign((size_t)std::max(K, 1) * NS1, 0);
   E->sig_flags.assign(NS1, 0);
   E->sig_tolerated.assign(NS1, 0);
   E->sig_gt.assign((size_t)std::max(NB, 1) * NS1, 0);
   E->sig_lt.assign((size_t)std::max(NB, 1) * NS1, 0);
   for (size_t i = 0; i < NS; i++) {
-    const auto& rw = sig_rows[i];
+    const uint64_t* rw = sig_of.row(i);
     for (int k = 0; k < K; k++) E->sig_mask[(size_t)k * NS + i] = rw[k];
     E->sig_flags[i] = rw[K];
     E->sig_tolerated[i] = rw[(size_t)K + 1];
@@ -610,7 +644,7 @@ void do_encode(Ctx& c) {
   }
   E->rq_requests.assign((size_t)R * NQ1, 0);
   for (size_t i = 0; i < NQ; i++)
-    for (int r = 0; r < R; r++) E->rq_requests[(size_t)r * NQ + i] = (int64_t)rq_rows[i][r];
+    for (int r = 0; r < R; r++) E->rq_requests[(size_t)r * NQ + i] = (int64_t)rq_of.row(i)[r];
   b200s_pods_soa_t& Pd = E->pods;
   Pd.n_pods = P; Pd.n_res = R; Pd.n_keys = K; Pd.n_bounded = NB;
   Pd.res_cpu = M->res_cpu; Pd.res_memory = M->res_memory;
