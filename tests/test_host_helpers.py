@@ -150,3 +150,38 @@ def test_candidate_price_errors_surface_where_the_reference_would_hit_them():
     assert cons.replay_search(1, 4, valid_of) == 2 and 5 not in visited  # the search never looks at prefix 5
     with pytest.raises(cons.CandidatePriceError):
         cons.replay_search(1, 9, valid_of)                   # (1 + 9) // 2 == 5 is the first probe
+
+
+def test_batch_result_buffers_alias_their_arrays():
+    """capi.BatchResultBuffers lays the b200s_result_t structs of a batch out as one structured array whose pointer fields
+    aim into one allocation per field, problem b's rows starting at its first pod: what the library writes through a struct
+    is what raws() hands back."""
+    import ctypes as C
+    pods = [3, 0, 5]
+    T, R, W, K, NB = 2, 4, 3, 2, 1
+    b = capi.BatchResultBuffers(pods, T, R, W, K, NB)
+    ptrs = b.out_pointers()
+    for i, P in enumerate(pods):
+        res = ptrs[i].contents
+        assert res.cap_claims == max(P, 1)
+        res.n_claims, res.n_unscheduled, res.fit_evals = min(P, 2), P - min(P, 2), 1000 + i
+        for p in range(P):
+            res.pod_place_kind[p] = 10 * i + p
+            for t in range(T):
+                res.pod_fit_code[p * T + t] = i + p + t
+        for c in range(min(P, 2)):
+            res.claim_npods[c] = 7 * i + c
+            for w in range(W):
+                res.claim_mask[c * W + w] = (i << 8) | (c << 4) | w
+            for r in range(R):
+                res.claim_requests[c * R + r] = -(i * 100 + c * 10 + r)
+    raws = b.raws()
+    for i, (P, raw) in enumerate(zip(pods, raws)):
+        N = min(P, 2)
+        assert (raw.n_claims, raw.n_unscheduled, raw.fit_evals) == (N, P - N, 1000 + i)
+        assert raw.pod_place_kind.tolist() == [10 * i + p for p in range(P)]
+        assert raw.pod_fit_code.shape == (P, T) and raw.pod_fit_code.tolist() == [[i + p + t for t in range(T)] for p in range(P)]
+        assert raw.claim_npods.tolist() == [7 * i + c for c in range(N)]
+        assert raw.claim_mask.tolist() == [[(i << 8) | (c << 4) | w for w in range(W)] for c in range(N)]
+        assert raw.claim_requests.tolist() == [[-(i * 100 + c * 10 + r) for r in range(R)] for c in range(N)]
+        assert raw.claim_req_mask.shape == (N, K) and raw.claim_req_gt.shape == (N, NB)
