@@ -710,6 +710,18 @@ def run_c4(args, rank, world, local):
     search_t = {}
     cons.first_n_consolidation_option(ctx, cid, model, node_of_pod, cand100, ctv)  # warm-up (device block cache)
     got = cons.first_n_consolidation_option(ctx, cid, model, node_of_pod, cand100, ctv, timing=search_t)
+    # the same search with every prefix as ranges of ONE model (one encode, the nodes once: b200s_solve_batch_shared)
+    search_shared = None
+    try:
+        ts = {}
+        cons.first_n_consolidation_option(ctx, cid, model, node_of_pod, cand100, ctv, shared=True)
+        one = cons.first_n_consolidation_option(ctx, cid, model, node_of_pod, cand100, ctv, timing=ts, shared=True)
+        same = (one is None) == (got is None) and (one is None or (one.mid, one.decision, one.n_options, one.mask.tolist()) ==
+                                                   (got.mid, got.decision, got.n_options, got.mask.tolist()))
+        search_shared = {"same_result": bool(same), "one_model_numpy_s": ts["models_s"], "b200s_encode_s": ts["encode_s"],
+                         "library_calls_s": ts["device_calls_s"]}
+    except Exception as e:  # noqa: BLE001 -- a secondary measurement must not take the line down
+        search_shared = {"error": repr(e)[:200]}
     t0 = time.perf_counter()
     want_mid, probed = cref.first_n_consolidation_option(model, node_of_pod, cand100, ctv)
     t_search_cpu = time.perf_counter() - t0
@@ -747,6 +759,7 @@ def run_c4(args, rank, world, local):
                                   "prefix_models_numpy_s": search_t.get("models_s"),
                                   "b200s_encode_s": search_t.get("encode_s"),
                                   "library_calls_s": search_t.get("device_calls_s"),
+                                  "as_one_shared_model": search_shared,
                                   "cpu_sequential_search_s": t_search_cpu, "cpu_probes": len(probed)},
             "cpu_baseline": {"value": 1.0 / t_cpu, "unit": "simulations/s", "cores": 1, "kind": "port",
                              "sample": "32 of the same simulations (every 8th) on one host core", "evals_per_simulation": evals_cpu},

@@ -90,19 +90,56 @@ class Probe:
     price_error: bool = False  # getCandidatePrices failed on this prefix AND the reference would have called it
 
 
+def shared_prefix_model(model: M.Model, node_of_pod: np.ndarray, candidates: Sequence[int], mids: Sequence[int]):
+    """Every prefix of `mids` as ONE model for b200s_solve_batch_shared: all nodes of the cluster, and for each prefix, one
+    after the other, the pods of candidates[0..mid] (a pod of an early candidate appears once per prefix that holds it; in
+    the order prefix_simulation gives them).  Returns (model, pod_off, removed): prefix i = pods pod_off[i]..pod_off[i+1]
+    against every node but the model nodes removed[i]."""
+    cand = np.asarray(candidates, np.int64)
+    pods, off, removed = [], [0], []
+    for mid in mids:
+        gone = cand[:mid + 1]
+        pods.append(np.nonzero(np.isin(node_of_pod, gone))[0])
+        off.append(off[-1] + len(pods[-1]))
+        removed.append([int(e) for e in gone])
+    allp = np.concatenate(pods) if pods else np.zeros(0, np.int64)
+    return M.subset(model, allp, np.arange(int(model.c.n_nodes))), np.asarray(off, np.int32), removed
+
+
 def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: np.ndarray, candidates: Sequence[int],
                       mids: Sequence[int], ct_values: Tuple[int, int, int, int], spot_to_spot: bool = False,
-                      timing: Optional[dict] = None) -> List[Probe]:
+                      timing: Optional[dict] = None, shared: bool = False) -> List[Probe]:
     """computeConsolidation + filterOutSameInstanceType for the prefixes `mids`, as one batch.
     ct_values = (model key of the capacity type, model value ids of spot, on-demand, reserved or -1).
     timing, when given, receives the wall seconds of building the prefix models ("models_s"), of b200s_encode
-    ("encode_s") and of the device calls ("device_calls_s": host buffers in, results out)."""
+    ("encode_s") and of the device calls ("device_calls_s": host buffers in, results out).
+    shared: hand the prefixes over as one model (shared_prefix_model, ONE b200s_encode, the cluster's nodes once:
+    b200s_solve_batch_shared) instead of one model per prefix; existing-node indices in Probe.result then count rows of
+    the whole cluster's node set."""
     import time
     mids = list(mids)
     if not mids:
         return []
     t0 = time.perf_counter()
     facts = node_facts(model, candidates)
+    if shared:
+        one, pod_off, removed = shared_prefix_model(model, node_of_pod, candidates, mids)
+        t_sims = time.perf_counter()
+        enc = capi.Encoded(one)
+        t1 = time.perf_counter()
+        uploaded = ctx.catalog_layout(cid)
+        own = ctx.upload_catalog(enc) if (uploaded is not None and enc.layout_hash != uploaded) else None
+        try:
+            use = cid if own is None else own
+            raws = ctx.solve_batch_shared(use, enc, pod_off, [enc.node_rows(r) for r in removed])
+            out = _commands(ctx, use, enc, raws, mids, facts, ct_values, spot_to_spot)
+        finally:
+            if own is not None:
+                ctx.release_catalog(own)
+        if timing is not None:
+            timing["models_s"], timing["encode_s"] = t_sims - t0, t1 - t_sims
+            timing["device_calls_s"] = time.perf_counter() - t1
+        return out
     sims = [prefix_simulation(model, node_of_pod, candidates, mid) for mid in mids]
     t_sims = time.perf_counter()
     encs = [capi.Encoded(m) for m in sims]
@@ -137,10 +174,14 @@ def multi_node_probes(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: 
 def _probe_group(ctx: capi.Context, cid: int, encs: List[capi.Encoded], mids: List[int], facts, ct_values,
                  spot_to_spot: bool) -> List[Probe]:
     """the probes of one key layout, as one batch on catalog `cid`"""
-    enc0 = encs[0]
+    return _commands(ctx, cid, encs[0], ctx.solve_batch(cid, encs), mids, facts, ct_values, spot_to_spot)
+
+
+def _commands(ctx: capi.Context, cid: int, enc0: capi.Encoded, raws, mids: List[int], facts, ct_values,
+              spot_to_spot: bool) -> List[Probe]:
+    """computeConsolidation (+ filterOutSameInstanceType) on finished simulations `raws` of the prefixes `mids`"""
     key, v_spot, v_od, v_res = ct_values
     bit_spot, bit_od, bit_res = (enc0.value_bit(key, v) if v >= 0 else -1 for v in (v_spot, v_od, v_res))
-    raws = ctx.solve_batch(cid, encs)
     priced = [prefix_price(facts, mid) for mid in mids]
     prices = [p for p, _ in priced]
     spots = [all(f[2] for f in facts[:mid + 1]) for mid in mids]
@@ -212,12 +253,13 @@ def replay_search(lo: int, hi: int, valid_of) -> Optional[int]:
 def first_n_consolidation_option(ctx: capi.Context, cid: int, model: M.Model, node_of_pod: np.ndarray,
                                  candidates: Sequence[int], ct_values: Tuple[int, int, int, int],
                                  max_parallel: int = MAX_PARALLEL, spot_to_spot: bool = False,
-                                 timing: Optional[dict] = None) -> Optional[Probe]:
+                                 timing: Optional[dict] = None, shared: bool = False) -> Optional[Probe]:
     """firstNConsolidationOption: candidates are already in disruption-cost order and capped by the budgets."""
     if len(candidates) < 2:
         return None
     lo, hi = search_bounds(len(candidates), min(max_parallel, len(candidates)))
-    probes = multi_node_probes(ctx, cid, model, node_of_pod, candidates, range(lo, hi + 1), ct_values, spot_to_spot, timing)
+    probes = multi_node_probes(ctx, cid, model, node_of_pod, candidates, range(lo, hi + 1), ct_values, spot_to_spot, timing,
+                               shared=shared)
     by_mid = {p.mid: p for p in probes}
     def valid_of(mid):
         if by_mid[mid].price_error:  # computeConsolidation returned an error: the search ends with it (:147)

@@ -34,6 +34,29 @@ class FakeContext:
     def solve(self, cid, enc):
         return parity.emul_solve(enc)
 
+    def solve_batch_shared(self, cid, enc, pod_off, excluded):
+        """b200s_solve_batch_shared's contract on the host: problem b = pods pod_off[b]..pod_off[b+1] of enc's model
+        against its nodes without the node ROWS excluded[b]; node indices of the results count rows of enc's node set."""
+        from b200sched import model as M
+        m = enc.model
+        E = enc.E
+        node_of_row = np.array([enc.nodes.contents.node_index[r] for r in range(E)])
+        row_of_node = np.zeros(max(E, 1), np.int64)
+        row_of_node[node_of_row] = np.arange(E)
+        out = []
+        for b in range(len(pod_off) - 1):
+            gone = set(int(node_of_row[r]) for r in excluded[b])
+            keep = np.array([e for e in range(E) if e not in gone], np.int64)
+            sub = M.subset(m, np.arange(int(pod_off[b]), int(pod_off[b + 1])), keep)
+            es = capi.Encoded(sub)
+            assert es.layout_hash == enc.layout_hash
+            raw = parity.emul_solve(es)
+            sub_rows = np.array([es.nodes.contents.node_index[r] for r in range(es.E)], np.int64)  # sub-model node per row
+            on_node = raw.pod_place_kind == capi.PLACE_NODE
+            raw.pod_place_index[on_node] = row_of_node[keep[sub_rows[raw.pod_place_index[on_node]]]]
+            out.append(raw)
+        return out
+
     def _allowed(self, enc, k, row):
         f = parity.emul().emul_allowed_values
         f.restype = C.c_uint64

@@ -506,11 +506,22 @@ def test_multi_node_search_driver_on_the_host_stand_in():
         want_mid, _ = ref.first_n_consolidation_option(sub, nop, cand, ctv)
         got = cons.first_n_consolidation_option(ctx, 0, sub, nop, cand, ctv)
         assert (got.mid if got is not None else None) == want_mid
+        # the same search with every prefix in ONE model (b200s_solve_batch_shared's input): same end, same command
+        one = cons.first_n_consolidation_option(ctx, 0, sub, nop, cand, ctv, shared=True)
+        assert (one.mid if one is not None else None) == want_mid
+        if got is not None:
+            assert (one.decision, one.reason, one.valid, one.n_options, one.mask.tolist(), one.spot_required) == (
+                got.decision, got.reason, got.valid, got.n_options, got.mask.tolist(), got.spot_required)
+            assert (one.result.n_claims, one.result.n_unscheduled) == (got.result.n_claims, got.result.n_unscheduled)
         if take < 2:
             continue
         lo_, hi_ = cons.search_bounds(take, take)
         facts = cons.node_facts(sub, cand)
-        for p in cons.multi_node_probes(ctx, 0, sub, nop, cand, range(lo_, hi_ + 1), ctv):
+        separate = cons.multi_node_probes(ctx, 0, sub, nop, cand, range(lo_, hi_ + 1), ctv)
+        for p, q in zip(separate, cons.multi_node_probes(ctx, 0, sub, nop, cand, range(lo_, hi_ + 1), ctv, shared=True)):
+            assert (p.mid, p.decision, p.reason, p.valid, p.n_options, p.mask.tolist()) == (
+                q.mid, q.decision, q.reason, q.valid, q.n_options, q.mask.tolist()), (take, off, p.mid)
+        for p in separate:
             _, cmd = ref.probe(sub, nop, cand, facts, p.mid, ctv, False)
             assert (p.decision, p.reason, p.valid, p.n_options, p.mask.tolist()) == (
                 cmd["decision"], cmd["reason"], bool(cmd["valid"]), cmd["n_options"], cmd["mask"].tolist()), (take, off, p.mid)

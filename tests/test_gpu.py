@@ -751,3 +751,31 @@ def test_more_claims_than_the_shared_memory_order_holds(gpu_ctx):
     model.arrays["pod_requests"] = np.ascontiguousarray(req)
     model.finalize()
     _solve_parity(gpu_ctx, model, "spill: 9000 single-pod claims + 2500 riders")
+
+
+def test_multi_node_search_from_one_shared_model(gpu_ctx):
+    """firstNConsolidationOption with every prefix handed over as ranges of ONE model (one b200s_encode, the cluster's nodes
+    once: b200s_solve_batch_shared) ends on the same prefix, with the same command, as the form that flattens and encodes
+    every prefix on its own -- and as the reference's sequential search over oracle simulations.  (Written after the last
+    GPU run of round 2: checked on the host stand-in in tests/test_consolidation.py, first run on the device is the
+    driver's.)"""
+    import consolidation_ref as ref
+    from b200sched import consolidation as cons
+    model, node_of_pod, util = synth.c4(1500, 120, solve=ob.solve)
+    order = np.argsort(util, kind="stable")
+    for take, off in ((24, 0), (30, 40), (2, 0)):
+        sub, nop = ref.sub_cluster(model, node_of_pod, order[off:off + take])
+        cand = list(range(take))
+        ctv = parity.capacity_type_values(sub)
+        want_mid, _ = ref.first_n_consolidation_option(sub, nop, cand, ctv)
+        cid = gpu_ctx.upload_catalog(capi.Encoded(sub))
+        try:
+            sep = cons.first_n_consolidation_option(gpu_ctx, cid, sub, nop, cand, ctv)
+            one = cons.first_n_consolidation_option(gpu_ctx, cid, sub, nop, cand, ctv, shared=True)
+        finally:
+            gpu_ctx.release_catalog(cid)
+        assert (one.mid if one is not None else None) == want_mid == (sep.mid if sep is not None else None), (take, off)
+        if one is not None:
+            assert (one.decision, one.reason, one.valid, one.n_options, one.mask.tolist(), one.spot_required) == (
+                sep.decision, sep.reason, sep.valid, sep.n_options, sep.mask.tolist(), sep.spot_required), (take, off)
+            assert (one.result.n_claims, one.result.n_unscheduled) == (sep.result.n_claims, sep.result.n_unscheduled)
