@@ -753,6 +753,8 @@ def test_more_claims_than_the_shared_memory_order_holds(gpu_ctx):
     _solve_parity(gpu_ctx, model, "spill: 9000 single-pod claims + 2500 riders")
 
 
+@pytest.mark.xfail(strict=False, reason="written after round 2's last GPU minute: checked on the host stand-in "
+                                        "(tests/test_consolidation.py), never yet run on a device")
 def test_multi_node_search_from_one_shared_model(gpu_ctx):
     """firstNConsolidationOption with every prefix handed over as ranges of ONE model (one b200s_encode, the cluster's nodes
     once: b200s_solve_batch_shared) ends on the same prefix, with the same command, as the form that flattens and encodes
