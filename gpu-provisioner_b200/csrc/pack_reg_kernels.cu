@@ -4,8 +4,9 @@
 //
 // pack_kernels.cu walks s.newNodeClaims in order, lane group per claim, claim state in global memory.  A step there
 // is a chain of dependent loads (order -> claim state -> tables -> type mask) and several CTA barriers.  On this
-// machine a warp's dependent instruction stream runs at 4-5 cycles per instruction whatever it does, so a step costs
-// what its longest role ISSUES; this form is built to issue little:
+// machine a warp's dependent instruction stream runs at 6-10 cycles per instruction whatever it does, so a step costs
+// what its longest role ISSUES (and, with sixteen warps on one SM, what all of them issue together: the kernel fills
+// 42 % of its SM's issue slots); this form is built to issue little:
 //
 //   * every in-flight NodeClaim is owned by one thread and lives in its registers: the accumulated requests as
 //     32-bit multiples of each resource's granule (the gcd of every quantity of that resource in the problem — exact;
@@ -17,25 +18,32 @@
 //     real pdqsort path the result is that claim moving to the end of the run of claims with as many pods (a new claim:
 //     behind the last claim with one pod) — a shift by one of a range of positions, which the winner derives from a
 //     count table (claims with more than k pods) and publishes in one word for the next step;
-//   * the ORDER WARP keeps the explicit order (exact pdqsort emulation, b200_core.cuh GoSort) BESIDE the step loop,
-//     not inside it: it consumes one event word per step from a ring, at its own pace.  Only when sort.Slice could
-//     take the real pdqsort path (fewer than 50 claims, or the changed position is next to one of choosePivot's
-//     samples — decided exactly by the order warp, which has the keys) does the step loop meet it at a barrier and
-//     re-read every position; that, the final order and the un-normalisation of the last sort are what it is for;
+//   * the minimum of a step is taken BEFORE the previous step's shift is known (that costs no second barrier): over
+//     priorities 2 * pos + 1 in which the claim that changed took a value between its new neighbours' old ones — every
+//     other claim keeps its place among the others, so the order of the priorities is the order of the true positions;
+//   * the ORDER WARP does nothing in an ordinary step.  Only when sort.Slice could take the real pdqsort path — fewer
+//     than 50 claims and an unsorted order, the changed position next to one of choosePivot's nine samples (the keys
+//     decide, and nobody holds them), or a pod count beyond the count table — do the claim threads lay the order out
+//     in shared memory as it is, the order warp runs the exact emulation (b200_core.cuh GoSort), positions are re-read
+//     and the minimum is taken again.  That is lazy in the reference's own way: its sort runs at the start of the
+//     NEXT add(), so the last step's change is simply never applied and Results.NewNodeClaims needs no undo;
 //   * a claim of selector-less pods keeps exactly those instance types of its template's pre-filtered set that fit
 //     its requests (nodeclaim.go:144-146, :392-423; the rows "alloc[r] >= v" are nested), so CanAdd's filter result
 //     is non-empty iff the FEASIBILITY TABLE cell of the new total's per-resource ranks is set: a bit table over
 //     rank space, built once per Solve by feas_table_kernel from the bit rows.  The rank of a total is one byte load
-//     from a direct value -> rank table (resources with a small scaled range) or one 16-byte window of the next
-//     distinct allocatable values and four compares (the others).  No type mask is read or written in the loop; the
+//     from a direct value -> rank table (resources with a small scaled range), one 8-byte bucket entry for the one
+//     resource whose range is too large (memory), or — when the catalog's values do not bucket — a 16-byte window of the
+//     next distinct allocatable values and four compares per resource.  No type mask is read or written in the loop; the
 //     final InstanceTypeOptions are the first pod's stage-A row inside the rows of the final totals;
 //   * the queue warp prepares pod rows 32 at a time, a batch ahead (Queue.Pop, queue.go:46-60: until the first
 //     pass over the queue is over the pop order is the FFD order), and appends pushed-back pods (queue.go:63-66) to
 //     a side list that the second phase then cycles through with the lastLen rule.
 //
-// The host twin (tests/native/emul.cpp emul_solve_reg) runs the same algorithm serially and is checked against the
-// oracle on the CPU; the kernel is checked against the oracle in tests/test_gpu.py.  A problem that needs more claims
-// than the threads hold leaves status 0 and pack_kernel (launched right after, skipping finished problems) redoes it.
+// The host twin (tests/native/emul.cpp emul_solve_reg) runs the same algorithm serially — positions, shift words, the
+// minimum over priorities that lack the last shift, the sort on demand — and is checked against the oracle on the CPU
+// (fuzz, and config[1] with the kernel's own counters: 318 meetings, 284 full pdqsorts); the kernel is checked against
+// the oracle in tests/test_gpu.py.  A problem that needs more claims than the threads hold leaves status 0 and the next
+// form, then pack_kernel (launched right after, skipping finished problems), redoes it.
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
@@ -334,9 +342,10 @@ __device__ __forceinline__ void slot_open(Slot& s, const RegParams& prm, const i
   s.cur = PRIO_INF;
 }
 
-// PROF: cycle counters of the warp leaders into PackProblem::prof: [0] step start -> barrier, [1] wait at the
-// barrier, [2] barrier -> end of step, [3] steps for warp 0; the same three for the order warp in [4..6] with its
-// wait for the winner's id in [7] and the full pdqsorts in [10]; for the queue warp in [8], [9], [11]
+// PROF: cycle counters of the warp leaders into PackProblem::prof.  Claim warp 0: [0] step start -> barrier (evaluate),
+// [1] wait at the barrier, [7] barrier -> winner known (read the minimum, shift positions), [2] the rest of the step
+// (commit), [8] cycles in steps that met the order warp, [9] such steps, [3] steps.  Order warp: [4] waiting for a
+// meeting, [5] sorting, [10] full pdqsorts.  Queue warp: [11] its own work before the barrier.
 template <int NWIN, int CPT, bool PROF>
 __global__ void __launch_bounds__(REG_THREADS, 1) pack_reg_kernel(const __grid_constant__ RegParams prm,
                                                                   const TmplDev* __restrict__ tg, PodsDev pods, PackArrays A,
