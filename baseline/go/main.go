@@ -10,7 +10,7 @@
 //
 // Call shape: scheduling.NewTopology + scheduling.NewScheduler + (*Scheduler).Solve, the way
 // Provisioner.NewScheduler / Schedule do (pkg/controllers/provisioning/provisioner.go:236-345), with NodePools in
-// OrderByWeight order and no existing nodes, no daemonsets, no volumes.  It also times Solve, which is the true
+// OrderByWeight order, existing nodes as state.StateNode fixtures, one daemonset pod per pool with overhead, no volumes.  It also times Solve, which is the true
 // "Go on host cores" baseline SURVEY.md section 8d (4) asks for.
 package main
 
@@ -76,10 +76,22 @@ type instanceTypeJSON struct {
 }
 
 type nodePoolJSON struct {
-	Name         string      `json:"name"`
-	Weight       int32       `json:"weight"`
-	Requirements []reqJSON   `json:"requirements"`
-	Taints       []taintJSON `json:"taints"`
+	Name           string            `json:"name"`
+	Weight         int32             `json:"weight"`
+	Requirements   []reqJSON         `json:"requirements"`
+	Taints         []taintJSON       `json:"taints"`
+	Limits         map[string]string `json:"limits"`          // remaining resources of the pool at the start of the Solve
+	DaemonOverhead map[string]string `json:"daemon_overhead"` // what getDaemonOverhead must come to for this pool
+}
+
+// an existing node: becomes a state.StateNode (Node only when initialized; Node + NodeClaim, registered but not
+// initialized, otherwise — StateNode.Initialized, statenode.go:342-349)
+type nodeJSON struct {
+	Name        string            `json:"name"`
+	Labels      map[string]string `json:"labels"`
+	Available   map[string]string `json:"available"`
+	Taints      []taintJSON       `json:"taints"`
+	Initialized bool              `json:"initialized"`
 }
 
 type podJSON struct {
@@ -97,6 +109,7 @@ type modelJSON struct {
 	InstanceTypes  []instanceTypeJSON `json:"instance_types"`
 	NodePools      []nodePoolJSON     `json:"node_pools"`
 	Pods           []podJSON          `json:"pods"`
+	Nodes          []nodeJSON         `json:"nodes"`
 }
 
 type claimJSON struct {
@@ -114,9 +127,10 @@ type reqOutput struct {
 }
 
 type resultJSON struct {
-	SolveSeconds  float64     `json:"solve_seconds"`
-	NewNodeClaims []claimJSON `json:"new_node_claims"`
-	Unschedulable []int       `json:"unschedulable"`
+	SolveSeconds  float64          `json:"solve_seconds"`
+	NewNodeClaims []claimJSON      `json:"new_node_claims"`
+	Unschedulable []int            `json:"unschedulable"`
+	ExistingNodes map[string][]int `json:"existing_nodes"` // Results.ExistingNodes: node name -> pods it took
 }
 
 // the scheduler only stores the provider on state.Cluster; nothing on the Solve path calls it
@@ -227,10 +241,34 @@ func main() {
 		pool.Spec.Template.Spec.Requirements = reqs
 		pool.Spec.Template.Spec.Taints = taints
 		pool.Spec.Template.Spec.NodeClassRef = &v1.NodeClassReference{Group: "karpenter.test.sh", Kind: "TestNodeClass", Name: "default"}
+		if len(np.Limits) > 0 { // NewScheduler: remainingResources[pool] = Spec.Limits (scheduler.go:170-172)
+			pool.Spec.Limits = v1.Limits(resourceList(np.Limits, ""))
+		}
 		nodePools = append(nodePools, pool)
 		byPool[np.Name] = instanceTypes
 	}
 	nodepoolutils.OrderByWeight(nodePools)
+
+	// ---- daemon overhead (getDaemonOverhead, scheduler.go:773-783): one daemonset pod per pool that asks for it, bound
+	// to the pool by a node selector on karpenter.sh/nodepool and tolerating everything.  RequestsForPods counts the pod
+	// itself as pods: 1, so an overhead is expressible only if its pods entry is 1 (tools/dump_model.py checks).
+	daemonSetPods := []*corev1.Pod{}
+	for _, np := range m.NodePools {
+		reqs := resourceList(np.DaemonOverhead, "pods")
+		nonZero := false
+		for _, q := range reqs {
+			nonZero = nonZero || !q.IsZero()
+		}
+		if !nonZero && np.DaemonOverhead["pods"] != "1" {
+			continue
+		}
+		daemonSetPods = append(daemonSetPods, &corev1.Pod{
+			ObjectMeta: metav1.ObjectMeta{Name: "daemon-" + np.Name, Namespace: "kube-system", UID: types.UID("daemon-" + np.Name)},
+			Spec: corev1.PodSpec{
+				NodeSelector: map[string]string{v1.NodePoolLabelKey: np.Name},
+				Tolerations:  []corev1.Toleration{{Operator: corev1.TolerationOpExists}},
+				Containers:   []corev1.Container{{Name: "d", Resources: corev1.ResourceRequirements{Requests: reqs}}}}})
+	}
 
 	// ---- pods: requests on one container (RequestsForPods adds pods: 1 itself, resources.go:36), the requirement
 	// set as the one required node-affinity term, tolerations as given
@@ -254,14 +292,42 @@ func main() {
 		indexOf[pod.UID] = p.Index
 	}
 
+	// ---- existing nodes as state.StateNode fixtures.  Available() = Allocatable - PodRequests (statenode.go:386-388)
+	// and no pod is tracked on the fixture, so Allocatable carries the dumped remaining resources; Capacity is the same
+	// (it is read only by updateRemainingResources, for nodes that carry a limited pool's label).  An initialized node
+	// is an unmanaged one (no NodeClaim: always Registered and Initialized); an uninitialized node gets an empty
+	// NodeClaim and the registered label only.
+	stateNodes := []*state.StateNode{}
+	for _, n := range m.Nodes {
+		labels := map[string]string{}
+		for k, v := range n.Labels {
+			labels[k] = v
+		}
+		taints := []corev1.Taint{}
+		for _, t := range n.Taints {
+			taints = append(taints, corev1.Taint{Key: t.Key, Value: t.Value, Effect: corev1.TaintEffect(t.Effect)})
+		}
+		sn := state.NewNode()
+		if !n.Initialized {
+			labels[v1.NodeRegisteredLabelKey] = "true"
+			sn.NodeClaim = &v1.NodeClaim{ObjectMeta: metav1.ObjectMeta{Name: n.Name}}
+		}
+		avail := resourceList(n.Available, "")
+		sn.Node = &corev1.Node{
+			ObjectMeta: metav1.ObjectMeta{Name: n.Name, Labels: labels},
+			Spec:       corev1.NodeSpec{Taints: taints, ProviderID: "b200://" + n.Name},
+			Status:     corev1.NodeStatus{Allocatable: avail, Capacity: avail}}
+		stateNodes = append(stateNodes, sn)
+	}
+
 	kubeClient := fake.NewClientBuilder().Build()
 	clk := clock.RealClock{}
 	cluster := state.NewCluster(clk, kubeClient, stubProvider{})
-	topology, err := scheduling.NewTopology(ctx, kubeClient, cluster, nil, nodePools, byPool, pods)
+	topology, err := scheduling.NewTopology(ctx, kubeClient, cluster, stateNodes, nodePools, byPool, pods)
 	if err != nil {
 		panic(err)
 	}
-	scheduler := scheduling.NewScheduler(ctx, kubeClient, nodePools, cluster, nil, topology, byPool, nil, test.NewEventRecorder(), clk)
+	scheduler := scheduling.NewScheduler(ctx, kubeClient, nodePools, cluster, stateNodes, topology, byPool, daemonSetPods, test.NewEventRecorder(), clk)
 	start := time.Now()
 	results, err := scheduler.Solve(ctx, pods)
 	elapsed := time.Since(start)
@@ -269,7 +335,13 @@ func main() {
 		panic(err)
 	}
 
-	out := resultJSON{SolveSeconds: elapsed.Seconds(), NewNodeClaims: []claimJSON{}, Unschedulable: []int{}}
+	out := resultJSON{SolveSeconds: elapsed.Seconds(), NewNodeClaims: []claimJSON{}, Unschedulable: []int{}, ExistingNodes: map[string][]int{}}
+	for _, en := range results.ExistingNodes {
+		for _, p := range en.Pods {
+			out.ExistingNodes[en.Name()] = append(out.ExistingNodes[en.Name()], indexOf[p.UID])
+		}
+		sort.Ints(out.ExistingNodes[en.Name()])
+	}
 	for _, nc := range results.NewNodeClaims {
 		c := claimJSON{NodePool: nc.NodePoolName, Pods: []int{}, InstanceTypes: []string{}, Requests: map[string]string{},
 			Requirements: map[string]reqOutput{}}

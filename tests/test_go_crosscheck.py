@@ -44,3 +44,29 @@ def test_comparison_accepts_the_oracles_view_and_sees_a_change():
     bad = copy.deepcopy(got)
     bad["unschedulable"] = bad["unschedulable"] + [12345]
     assert cg.compare(m, want, bad)
+
+
+def test_models_with_existing_nodes_round_trip_through_the_dump_and_the_comparison():
+    """config[3]-style simulations and fuzzed models: the dump names every node (labels, remaining resources, taints,
+    initialized), limits and daemon overheads; the oracle's view lists the pods each existing node took; the comparison
+    accepts it and notices a pod moved to another node."""
+    checked = on_nodes = 0
+    for gen in ([{"kind": "c4sim", "pods": 600, "skus": 60, "sim": j} for j in range(3)] +
+                [{"kind": "fuzz", "seed": 1000 + s} for s in range(40)]):
+        m = dump_model.generate(gen)
+        if dump_model.expressible(m) is not None:
+            continue
+        d = json.loads(json.dumps(dump_model.dump(m, gen)))
+        assert len(d["nodes"]) == int(m.c.n_nodes) and all(set(n) == {"name", "labels", "available", "taints", "initialized"} for n in d["nodes"])
+        assert all("limits" in p and "daemon_overhead" in p for p in d["node_pools"])
+        want = cg.oracle_view(m, ob.solve(m))
+        got = json.loads(json.dumps(want))
+        assert cg.compare(m, want, got) == []
+        checked += 1
+        if want["existing_nodes"]:
+            on_nodes += 1
+            bad = copy.deepcopy(got)
+            name = next(iter(bad["existing_nodes"]))
+            bad["existing_nodes"]["some-other-node"] = bad["existing_nodes"].pop(name)
+            assert cg.compare(m, want, bad)
+    assert checked >= 15 and on_nodes >= 5, (checked, on_nodes)

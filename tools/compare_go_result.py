@@ -61,7 +61,13 @@ def oracle_view(model, o):
             "requests": {r: dump_model.quantity(r, o.claim_requests[c, i]) for i, r in enumerate(model.res_names)},
             "requirements": reqs})
     unsched = sorted(int(p) for p in range(model.n_pods) if o.pod_place_kind[p] == capi.PLACE_UNSCHEDULED)
-    return {"new_node_claims": claims, "unschedulable": unsched}
+    # Results.ExistingNodes: the pods each existing node took (rows of the oracle's result are sortExistingNodes order)
+    on_nodes = {}
+    for p in range(model.n_pods):
+        if o.pod_place_kind[p] == capi.PLACE_NODE:
+            on_nodes.setdefault(model.node_names[int(o.node_order[int(o.pod_place_index[p])])], []).append(int(p))
+    return {"new_node_claims": claims, "unschedulable": unsched,
+            "existing_nodes": {n: sorted(ps) for n, ps in sorted(on_nodes.items())}}
 
 
 def compare(model, want, got):
@@ -69,6 +75,8 @@ def compare(model, want, got):
     diffs = []
     if want["unschedulable"] != got["unschedulable"]:
         diffs.append(f"unschedulable pods differ: oracle {len(want['unschedulable'])}, go {len(got['unschedulable'])}")
+    if want.get("existing_nodes", {}) != {n: sorted(ps) for n, ps in (got.get("existing_nodes") or {}).items() if ps}:
+        diffs.append("pods placed on existing nodes differ")
     if len(want["new_node_claims"]) != len(got["new_node_claims"]):
         diffs.append(f"NewNodeClaims: oracle {len(want['new_node_claims'])}, go {len(got['new_node_claims'])}")
     keys = set(model.key_names)
@@ -91,7 +99,7 @@ if __name__ == "__main__":
     dumped = json.load(open(sys.argv[1]))
     got = json.load(open(sys.argv[2]))
     gen = dumped["generator"]
-    model = synth.config(gen["kind"], gen["pods"], gen["skus"])
+    model = dump_model.generate(gen)
     again = json.loads(json.dumps(dump_model.dump(model, gen)))
     if again != dumped:
         raise SystemExit("the model regenerated here differs from the dump the Go harness read")

@@ -1,11 +1,13 @@
 """Write a synthetic scheduling model as string-level JSON for the off-box Go cross-check (baseline/go/main.go).
 
   python tools/dump_model.py {c2|c3} PODS SKUS out.json
+  python tools/dump_model.py c4sim PODS SKUS out.json [SIMULATION]     # a consolidation simulation: existing nodes
+  python tools/dump_model.py fuzz SEED 0 out.json                      # tests/fuzz_models.py, with existing nodes
 
 The dump carries what the Go harness needs to rebuild Karpenter objects (InstanceTypes with Offerings, NodePools,
-Pods) from the very arrays the encoder and the oracle consume, plus the generator arguments, so that
-tools/compare_go_result.py can regenerate the same model here and hold the Go scheduler's result against the oracle's.
-Existing nodes are not dumped: configs 2, 3 and 5 have none (config 4's simulations need state.StateNode fixtures).
+Pods, existing nodes as state.StateNode fixtures) from the very arrays the encoder and the oracle consume, plus the
+generator arguments, so that tools/compare_go_result.py can regenerate the same model here and hold the Go scheduler's
+result against the oracle's.
 """
 import json
 import os
@@ -83,15 +85,68 @@ def dump(model: M.Model, generator: dict) -> dict:
         pods.append({"index": p, "uid": f"{h[:8]}-{h[8:12]}-{h[12:16]}-{h[16:20]}-{h[20:]}",
                      "creation_timestamp": int(a["pod_ts"][p]), "requests": resources(a["pod_requests"][p]),
                      "requirements": reqs(a["pod_req_off"][p], a["pod_req_off"][p + 1]), "tolerations": tols})
+    # existing nodes: labels (the model keeps them as single-value In requirements), what is left of their allocatable
+    # (ExistingNode.remainingResources, existingnode.go:57), taints, and whether the node is initialized
+    nodes = []
+    for e in range(int(model.c.n_nodes)):
+        labels = {r["key"]: r["values"][0] for r in reqs(a["node_req_off"][e], a["node_req_off"][e + 1])}
+        nodes.append({"name": model.node_names[e], "labels": labels, "available": resources(a["node_available"][e]),
+                      "taints": taints(a["node_taint_off"][e], a["node_taint_off"][e + 1]),
+                      "initialized": bool(a["node_initialized"][e])})
+    limits = []
+    for p in range(int(model.c.n_pools)):
+        limits.append({res: quantity(res, a["pool_limit"][p][r]) for r, res in enumerate(model.res_names) if a["pool_has_limit"][p][r]})
+    for pool, lim in zip(pools, limits):
+        pool["limits"] = lim
+        pool["daemon_overhead"] = resources(a["pool_daemon"][model.pool_names.index(pool["name"])])
     return {"generator": generator, "resources": list(model.res_names),
-            "wellknown_extra": sorted(model.wellknown_extra), "instance_types": its, "node_pools": pools, "pods": pods}
+            "wellknown_extra": sorted(model.wellknown_extra), "instance_types": its, "node_pools": pools, "pods": pods,
+            "nodes": nodes}
+
+
+def expressible(model: M.Model):
+    """None, or why baseline/go/main.go cannot rebuild this model as Karpenter objects"""
+    a = model.arrays
+    pods_res = model.res_names.index("pods") if "pods" in model.res_names else -1
+    for p in range(int(model.c.n_pools)):
+        d = [int(x) for x in a["pool_daemon"][p]]
+        if any(d) and (pods_res < 0 or d[pods_res] != 1):
+            return (f"pool {model.pool_names[p]}: a daemon overhead is the requests of daemonset pods, and RequestsForPods counts "
+                    "each of them as pods: 1 (resources.go:36) -- an overhead whose pods entry is not 1 has no pod set")
+    for e in range(int(model.c.n_nodes)):
+        if any(int(x) < 0 for x in a["node_available"][e]):
+            return f"node {model.node_names[e]}: negative available resources need tracked pods on the StateNode fixture"
+    return None
+
+
+def generate(gen: dict) -> M.Model:
+    """the model a dump's generator arguments name"""
+    kind = gen["kind"]
+    if kind in ("c2", "c3"):
+        return synth.config(kind, gen["pods"], gen["skus"])
+    if kind == "fuzz":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import fuzz_models
+        return fuzz_models.random_model(gen["seed"], with_nodes=True, max_pods=gen.get("max_pods", 60))
+    if kind == "c4sim":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob
+        model, node_of_pod, util = synth.c4(gen["pods"], gen["skus"], solve=ob.solve)
+        return synth.c4_simulations(model, node_of_pod, util, gen["sim"] + 1)[gen["sim"]][1]
+    raise SystemExit(f"unknown generator {kind}")
 
 
 if __name__ == "__main__":
     kind, P, S, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
-    m = synth.config(kind, P, S)
-    if int(m.c.n_nodes):
-        raise SystemExit("existing nodes are not part of this dump")
+    gen = {"kind": kind, "pods": P, "skus": S}
+    if kind == "fuzz":
+        gen = {"kind": "fuzz", "seed": P}
+    elif kind == "c4sim":
+        gen["sim"] = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    m = generate(gen)
+    why = expressible(m)
+    if why:
+        raise SystemExit("not expressible for the Go harness: " + why)
     with open(out, "w") as f:
-        json.dump(dump(m, {"kind": kind, "pods": P, "skus": S}), f)
-    print(f"{out}: {P} pods, {S} instance types, {int(m.c.n_pools)} node pools")
+        json.dump(dump(m, gen), f)
+    print(f"{out}: {m.n_pods} pods, {m.n_skus} instance types, {int(m.c.n_pools)} node pools, {int(m.c.n_nodes)} existing nodes")
